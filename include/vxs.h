@@ -1,0 +1,166 @@
+/* vxs.h — C-ABI of the B200-native Voxel-SLAM bundle-adjustment hot path (libvxs.so).
+ *
+ * The reference (hku-mars/Voxel-SLAM, one ROS C++ executable) has no plugin/FFI layer: the boundary of this path is
+ * the C++ call surface used by VoxelSLAM/src/voxelslam.cpp.  Every entry point below names the reference interface it
+ * replaces (file:line into /root/reference/VoxelSLAM/src/).  A header-only C++ shim with the reference's class names
+ * on top of this ABI is in voxel_slam_b200/csrc/shim/voxel_ba_shim.hpp; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *  - plain C types only; all pointers are HOST pointers unless the name says _dev; caller owns every buffer.
+ *  - every function returns an int status (VXS_OK = 0, <0 error, >0 warning); nothing ever calls exit()
+ *    (the reference printf+exit(0)s, voxel_map.hpp:345-348, 1211-1215).
+ *  - one vxs_ctx per calling thread (the reference runs local BA and global BA on two threads concurrently,
+ *    voxelslam.cpp:2617-2619); a ctx owns its CUDA stream(s) and scratch memory; calls on one ctx are synchronous.
+ *  - there is NO CPU fallback: without a CUDA device vxs_ctx_create fails with VXS_ERR_CUDA.
+ *  - layouts: pose12 = R row-major (9) | p (3).  state24 = R (9) | p | v | bg | ba | g  (tools.hpp:135-145 IMUST without t, cov).
+ *    cluster10 = Pxx Pxy Pxz Pyy Pyz Pzz vx vy vz N  (tools.hpp:304-310 PointCluster, symmetric P packed, N as double).
+ *    eig12 = lambda0..2 (ascending) | U row-major 3x3, eigenvectors in COLUMNS (Eigen convention, voxel_map.hpp:163-168).
+ *    Hessians are column-major n x n like Eigen::MatrixXd.
+ */
+#ifndef VXS_H
+#define VXS_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VXS_OK 0
+#define VXS_ERR_CUDA (-1)
+#define VXS_ERR_ARG (-2)
+#define VXS_ERR_TOO_FEW_VOXELS (-3) /* reference: "Too Less Voxel" exit(0), voxel_map.hpp:345-348 */
+#define VXS_ERR_COMM (-4)
+#define VXS_ERR_NOMEM (-5)
+#define VXS_ERR_RANGE (-6)   /* voxel coordinate outside the packable range (see vxs_build_*) */
+#define VXS_ERR_CALLBACK (-7)
+#define VXS_WARN_SINGULAR 1  /* a zero pivot was met in the LDLT (Eigen would continue with zeros) */
+
+typedef struct vxs_ctx vxs_ctx;
+typedef struct vxs_factor vxs_factor;
+
+/* ---------------------------------------------------------------- context */
+int vxs_version(void);
+int vxs_ctx_create(int device, vxs_ctx** out);
+int vxs_ctx_destroy(vxs_ctx* ctx);
+const char* vxs_ctx_last_error(const vxs_ctx* ctx);
+/* pinned host memory for callers that want full-speed H2D/D2H (optional) */
+int vxs_host_alloc(void** out, uint64_t bytes);
+int vxs_host_free(void* p);
+/* kernels launched by this ctx since creation (bench.py's gpu_launches) */
+int64_t vxs_ctx_launch_count(const vxs_ctx* ctx);
+/* per-stage CUDA-event timing on the ctx stream: enable, run calls, then read the accumulated stages.
+ * names: up to cap stage names (static strings), ms_total / calls per stage.  Stage names are the kernel names. */
+int vxs_ctx_timing_enable(vxs_ctx* ctx, int on);
+int vxs_ctx_timing_read(vxs_ctx* ctx, int cap, const char** names, double* ms_total, int64_t* calls, int* n_out);
+int vxs_ctx_timing_reset(vxs_ctx* ctx);
+
+/* ---------------------------------------------------------------- multi-GPU (one process per GPU; NCCL over NVLink)
+ * Voxel-sharded BA: every rank holds the factor voxels it owns and the replicated poses; [H_lidar, g, r] are
+ * all-reduced once per Hessian build and the scalar residual once per residual evaluation. */
+int vxs_comm_unique_id(unsigned char id[128]);
+int vxs_ctx_comm_init(vxs_ctx* ctx, const unsigned char id[128], int rank, int nranks);
+int vxs_ctx_comm_destroy(vxs_ctx* ctx);
+
+/* ---------------------------------------------------------------- LidarFactor  (voxel_map.hpp:109-290) */
+int vxs_factor_create(vxs_ctx* ctx, int win_size, vxs_factor** out);          /* LidarFactor(int _w)      :120 */
+int vxs_factor_destroy(vxs_factor* f);
+int vxs_factor_clear(vxs_factor* f);                                            /* LidarFactor::clear       :281 */
+int vxs_factor_set_win_size(vxs_factor* f, int win_size);                       /* voxhess.win_size = ...   voxelslam.cpp:1609 */
+/* Batched LidarFactor::push_voxel (:122-130).  CSR over the frames that observe each voxel (N != 0), frames ascending
+ * within a voxel.  fix10 may be NULL (all-zero fix clusters), coe may be NULL (all 1.0, voxel_map.hpp:1316). */
+int vxs_factor_push_voxels(vxs_factor* f, int64_t n_vox, const int64_t* entry_ptr, const int32_t* entry_frame,
+                           const double* entry_cluster10, const double* fix10, const double* coe, const double* eig12,
+                           const double* sum10);
+/* Same, in the reference's dense layout vector<vector<PointCluster>>: clusters10 is [n_vox][win_size][10], N==0 = absent. */
+int vxs_factor_push_voxels_dense(vxs_factor* f, int64_t n_vox, const double* clusters10, const double* fix10,
+                                 const double* coe, const double* eig12, const double* sum10);
+int vxs_factor_counts(const vxs_factor* f, int64_t* n_vox, int64_t* n_entries, int* win_size);
+/* eig_values / eig_vectors / pcr_adds as left by the last residual evaluation (read by OctoTree::margi :1217-1222) */
+int vxs_factor_read_back(vxs_factor* f, double* eig12, double* sum10);
+/* the stored structure (for tests and for callers that keep the factor device-resident) */
+int vxs_factor_read_structure(vxs_factor* f, int64_t* entry_ptr, int32_t* entry_frame, double* entry_cluster10,
+                              double* fix10, double* coe);
+
+/* LidarFactor::evaluate_only_residual(xs, 0, size, residual)  :243-279 — overwrites the cached eig / sum */
+int vxs_factor_evaluate_residual(vxs_ctx* ctx, vxs_factor* f, const double* poses12, double* residual);
+/* LidarFactor::acc_evaluate2(xs, 0, size, Hess, JacT, residual)  :132-241 — uses the CACHED eig / sum.
+ * hess: (6W x 6W) column-major, jact: 6W. */
+int vxs_factor_evaluate_hessian(vxs_ctx* ctx, vxs_factor* f, const double* poses12, double* hess, double* jact,
+                                double* residual);
+
+/* ---------------------------------------------------------------- LM solvers */
+typedef struct vxs_lm_trace { double r1, r2, u, v, q1; int32_t accepted; int32_t hess_built; } vxs_lm_trace;
+
+/* Lidar_BA_Optimizer::damping_iter(x_stats, voxhess, hess, resis, max_iter)  voxel_map.hpp:367-442.
+ * poses12 in/out (W x 12).  hess_out (6W x 6W col-major, may be NULL) = raw Hessian of the last build (:391).
+ * resis[2] = {first residual1, last residual2} (:394-395,440).  thd_num only reproduces the reference's
+ * "voxels < threads" error (VXS_ERR_TOO_FEW_VOXELS); pass Lidar_BA_Optimizer::thd_num (:296).
+ * trace (may be NULL): up to trace_cap entries, *trace_len written. */
+int vxs_lidar_ba(vxs_ctx* ctx, vxs_factor* f, double* poses12, int max_iter, int thd_num, double* hess_out,
+                 double resis[2], int* is_converge, vxs_lm_trace* trace, int trace_cap, int* trace_len);
+
+/* The IMU factor stays on the CPU (preintegration.hpp, out of scope); the LI solvers call back into it.
+ *  eval     : sum over the W-1 factors of IMU_PRE::give_evaluate (:137) or give_evaluate_g (:214).  states: W x 24.
+ *             if want_jac: blocks[(W-1)][bs*bs] column-major and gvec[(W-1)][bs], bs = 30 (33 with gravity);
+ *             *cost = sum of r^T cov^-1 r (unscaled; the solver applies imu_coef, voxel_map.hpp:505-507).
+ *  update   : IMU_PRE::update_state(dxi.block<15,1>(15 j)) for every factor j (:296; voxel_map.hpp:608-609)
+ *  rollback : dbg = dbg_buf, dba = dba_buf (voxel_map.hpp:639-643)
+ * Callbacks return 0 on success. */
+typedef struct vxs_imu_hooks {
+  void* user;
+  int (*eval)(void* user, const double* states24, int W, int with_gravity, int want_jac, double* blocks, double* gvec, double* cost);
+  int (*update)(void* user, const double* dxi, int W);
+  int (*rollback)(void* user);
+} vxs_imu_hooks;
+
+/* LI_BA_Optimizer::damping_iter (voxel_map.hpp:562-653; with_gravity=0, n=15W, the reference hard-codes 3 iterations)
+ * and LI_BA_OptimizerGravity::damping_iter (:775-862; with_gravity=1, n=15W+3, max_iter default 2).
+ * states24 in/out (W x 24); hess_out (n x n col-major, may be NULL); resis[2] as above; imu_coef = voxel_map.hpp:446. */
+int vxs_li_ba(vxs_ctx* ctx, vxs_factor* f, double* states24, int with_gravity, int max_iter, double imu_coef,
+              const vxs_imu_hooks* imu, double* hess_out, double resis[2], vxs_lm_trace* trace, int trace_cap,
+              int* trace_len);
+
+/* ---------------------------------------------------------------- voxel map (build-from-scratch semantics) */
+typedef struct vxs_map_params {
+  double voxel_size;        /* voxel_map.hpp:87 / gba_voxel_size loop_refine.hpp:271 */
+  double min_eigen_value;   /* voxel_map.hpp:84 / loop_refine.hpp:270 */
+  double plane_thre[4];     /* plane_eigen_value_thre, already inverted (voxelslam.cpp:825 / :2490) */
+  double min_point[4];      /* voxel_map.hpp:83 min_point (voxelslam.cpp:812 sets 5,5,5,5); ignored by the GBA map (literal 10) */
+  int32_t max_layer;        /* voxel_map.hpp:85 */
+  int32_t reserved;
+} vxs_map_params;
+
+/* voxel quantisation + hash, bit-exact (voxel_map.hpp:1511-1518, tools.hpp:24-49): xyz[n][3], hash[n] */
+int vxs_voxel_keys(vxs_ctx* ctx, const double* pw, int64_t n, double voxel_size, int64_t* xyz, uint64_t* hash);
+
+/* Identity of a factor voxel for order-independent comparison: root cell + layer + octant path (sum leaf_l * 8^(depth-l)). */
+typedef struct vxs_voxel_id { int64_t x, y, z; int32_t layer; int32_t path; } vxs_voxel_id;
+
+/* cut_voxel for every scan of the window (voxel_map.hpp:1504-1540) then OctoTree::recut + tras_opt on every root
+ * (voxel_map.hpp:1148-1194, 1308-1333) — the from-scratch sequence of voxelslam.cpp:600-628 / 1171-1180.
+ * pts_body: all scans concatenated (fp64 xyz, body frame), scan_offsets[W+1]; poses12: W x 12.
+ * fix_pts (may be NULL): already-world fixed map points (cut_voxel :1641-1671).  The factor `out` is cleared and refilled
+ * (device-resident; nothing is copied back unless ids_out / vxs_factor_read_* are used).
+ * ids_out (may be NULL, capacity ids_cap): identity of every factor voxel in factor order; *n_out = number of voxels. */
+int vxs_build_window_factor(vxs_ctx* ctx, const vxs_map_params* mp, const double* pts_body, const int64_t* scan_offsets,
+                            const double* poses12, int W, const double* fix_pts, int64_t n_fix, vxs_factor* out,
+                            vxs_voxel_id* ids_out, int64_t ids_cap, int64_t* n_out);
+
+/* OctreeGBA::cut_voxel for every keyframe + OctreeGBA_multi_recut (loop_refine.hpp:446-479, 483-537).
+ * xyz: float points of all keyframes concatenated (x,y,z per point, stride_floats between points: 3 for packed xyz,
+ * 12 for pcl::PointXYZINormal), kf_offsets[W+1] in points. */
+int vxs_build_gba_factor(vxs_ctx* ctx, const vxs_map_params* mp, const float* xyz, int stride_floats,
+                         const int64_t* kf_offsets, const double* poses12, int W, vxs_factor* out, vxs_voxel_id* ids_out,
+                         int64_t ids_cap, int64_t* n_out);
+
+/* The BA loop of HBA_add_edge (voxelslam.cpp:2360-2399): per outer iteration rebuild the GBA map at the current poses,
+ * recut, Lidar_BA_Optimizer::damping_iter(up=4); coarse-to-fine switch to `fine` on convergence / last iteration.
+ * poses12 in/out; hess_out (6W x 6W) = raw Hessian of the last build (consumed by the PGO edge extraction :2405-2427).
+ * resis_log (may be NULL, 2 doubles per outer iteration); *outer_iters = iterations run. */
+int vxs_hba_window(vxs_ctx* ctx, const vxs_map_params* coarse, const vxs_map_params* fine, const float* xyz,
+                   int stride_floats, const int64_t* kf_offsets, double* poses12, int W, int max_iter, int thread_num,
+                   double* hess_out, double* resis_log, int* outer_iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VXS_H */

@@ -1,0 +1,396 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see vxo_core.hpp header; parity unpinned).
+//
+// Voxel-map side of the hot path, restated from /root/reference/VoxelSLAM/src/:
+//   voxel_map.hpp:1511-1518 (= loop_refine.hpp:452-459)  float quantisation      -> voxel_key
+//   tools.hpp:24-49          VOXEL_LOC + hash                                    -> VoxelLoc, voxel_hash
+//   voxel_map.hpp:896-930    SlideWindow
+//   voxel_map.hpp:935-1333   OctoTree: push/push_fix*/plane_judge/allocate/allocate_fix/fix_divide/
+//                            subdivide/recut/tras_opt      (margi/plane_update/match are "next" scope)
+//   voxel_map.hpp:1504-1540  cut_voxel (window)   :1641-1671 cut_voxel (fixed map points)
+//   voxelslam.cpp:600-628    build-from-scratch sequence (cut all scans, then recut + tras_opt)
+//   loop_refine.hpp:273-537  OctreeGBA, OctreeGBA_multi_recut
+//   voxelslam.cpp:2360-2427  HBA_add_edge BA loop + PGO edge extraction
+#pragma once
+#include <unordered_map>
+#include "vxo_core.hpp"
+
+namespace vxo {
+
+struct VoxelLoc {
+  int64_t x, y, z;
+  bool operator==(const VoxelLoc& o) const { return x == o.x && y == o.y && z == o.z; }
+};
+// tools.hpp:39-48 with HASH_P=116101, MAX_N=10000000000 (tools.hpp:9-10); size_t wrap-around arithmetic
+inline uint64_t voxel_hash(const VoxelLoc& s) {
+  const uint64_t HP = 116101ull, MN = 10000000000ull;
+  return (((uint64_t(s.z) * HP) % MN + uint64_t(s.y)) * HP) % MN + uint64_t(s.x);
+}
+struct VoxelLocHash { size_t operator()(const VoxelLoc& s) const { return size_t(voxel_hash(s)); } };
+
+// voxel_map.hpp:1511-1518: float loc = pw/voxel_size; if(loc<0) loc -= 1; (int64_t)loc   (trap B#1)
+inline VoxelLoc voxel_key(const V3& pw, double voxel_size) {
+  int64_t k[3];
+  for (int j = 0; j < 3; j++) {
+    float loc = float(pw[j] / voxel_size);
+    if (loc < 0) loc -= 1;
+    k[j] = int64_t(loc);
+  }
+  return VoxelLoc{k[0], k[1], k[2]};
+}
+
+struct MapParams {
+  double voxel_size = 1.0;           // voxel_map.hpp:87
+  double min_eigen_value = 0.0025;   // voxel_map.hpp:84
+  int max_layer = 2;                 // voxel_map.hpp:85
+  double min_point[4] = {5, 5, 5, 5};              // voxelslam.cpp:812
+  double plane_thre[8] = {.25, .25, .25, .25, .25, .25, .25, .25};  // plane_eigen_value_thre (already inverted, voxelslam.cpp:825)
+  bool with_cov_add = false;         // voxel_map.hpp:990-992 by-product used only by plane_update (odometry)
+};
+
+struct PV { V3 pnt; M3 var; };  // voxel_map.hpp:14-19 pointVar
+
+// voxel_map.hpp:91-106
+inline void bf_var(const PV& pv, double bcov[81], const V3& vec) {
+  double Bi[6][3] = {{2 * vec[0], 0, 0}, {vec[1], vec[0], 0}, {vec[2], 0, vec[0]}, {0, 2 * vec[1], 0}, {0, vec[2], vec[1]}, {0, 0, 2 * vec[2]}};
+  double Biup[6][3];
+  for (int r = 0; r < 6; r++) for (int c = 0; c < 3; c++) Biup[r][c] = (Bi[r][0] * pv.var(0, c) + Bi[r][1] * pv.var(1, c)) + Bi[r][2] * pv.var(2, c);
+  for (int r = 0; r < 6; r++) for (int c = 0; c < 6; c++) bcov[r * 9 + c] = (Biup[r][0] * Bi[c][0] + Biup[r][1] * Bi[c][1]) + Biup[r][2] * Bi[c][2];
+  for (int r = 0; r < 6; r++) for (int c = 0; c < 3; c++) { bcov[r * 9 + 6 + c] = Biup[r][c]; bcov[(6 + c) * 9 + r] = Biup[r][c]; }
+  for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) bcov[(6 + r) * 9 + 6 + c] = pv.var(r, c);
+}
+
+struct SlideWindow {  // voxel_map.hpp:896-930
+  std::vector<std::vector<PV>> points;
+  std::vector<PC> pcrs_local;
+  explicit SlideWindow(int w) : points(w), pcrs_local(w) { for (auto& p : points) p.reserve(20); }
+  void clear() { for (auto& p : points) p.clear(); for (auto& c : pcrs_local) c.clear(); }
+};
+
+// identification of a factor voxel for order-independent comparison in tests
+struct VoxelId { int64_t x, y, z; int layer; int path; };  // path = sum leafnum_l * 8^(l-1)
+
+struct OctoTree {  // voxel_map.hpp:935-1502
+  SlideWindow* sw = nullptr;
+  PC pcr_add;
+  double cov_add[81];
+  PC pcr_fix;
+  std::vector<PV> point_fix;
+  int layer, octo_state = 0, wdsize;
+  OctoTree* leaves[8];
+  double voxel_center[3];
+  float quater_length;
+  bool is_plane = false, isexist = false;
+  V3 eig_value; M3 eig_vector;
+  int opt_state = -1;
+  VoxelLoc root{0, 0, 0}; int path = 0;  // bookkeeping for tests only
+
+  OctoTree(int l, int w) : layer(l), wdsize(w) { for (auto& p : leaves) p = nullptr; std::memset(cov_add, 0, sizeof cov_add); }
+  ~OctoTree() { for (auto p : leaves) delete p; delete sw; }
+
+  void push(int ord, const PV& pv, const V3& pw, const MapParams& mp_) {  // :969-994 (mp[] ring map = identity in a from-scratch build)
+    if (!sw) sw = new SlideWindow(wdsize);
+    isexist = true;
+    if (layer < mp_.max_layer) sw->points[ord].push_back(pv);
+    sw->pcrs_local[ord].push(pv.pnt);
+    pcr_add.push(pw);
+    if (mp_.with_cov_add) { double Bi[81]; bf_var(pv, Bi, pw); for (int i = 0; i < 81; i++) cov_add[i] += Bi[i]; }
+  }
+  void push_fix(const PV& pv, const MapParams& mp_) {  // :996-1005
+    if (layer < mp_.max_layer) point_fix.push_back(pv);
+    pcr_fix.push(pv.pnt); pcr_add.push(pv.pnt);
+    if (mp_.with_cov_add) { double Bi[81]; bf_var(pv, Bi, pv.pnt); for (int i = 0; i < 81; i++) cov_add[i] += Bi[i]; }
+  }
+  void push_fix_novar(const PV& pv, const MapParams& mp_) {  // :1007-1013
+    if (layer < mp_.max_layer) point_fix.push_back(pv);
+    pcr_fix.push(pv.pnt); pcr_add.push(pv.pnt);
+  }
+  bool plane_judge(const V3& ev, const MapParams& mp_) const {  // :1015-1019
+    return ev[0] < mp_.min_eigen_value && (ev[0] / ev[2]) < mp_.plane_thre[layer];
+  }
+  OctoTree* child_for(const V3& pw) {  // :1029-1041 (same code at :1056-1068, :1078-1089, :1101-1112)
+    int xyz[3] = {0, 0, 0};
+    for (int k = 0; k < 3; k++) if (pw[k] > voxel_center[k]) xyz[k] = 1;
+    int leafnum = 4 * xyz[0] + 2 * xyz[1] + xyz[2];
+    if (!leaves[leafnum]) {
+      OctoTree* c = new OctoTree(layer + 1, wdsize);
+      for (int k = 0; k < 3; k++) c->voxel_center[k] = voxel_center[k] + (2 * xyz[k] - 1) * quater_length;  // int*float -> float, then double +
+      c->quater_length = quater_length / 2;
+      c->root = root; c->path = path * 8 + leafnum;
+      leaves[leafnum] = c;
+    }
+    return leaves[leafnum];
+  }
+  void allocate(int ord, const PV& pv, const V3& pw, const MapParams& mp_) {  // :1021-1046
+    if (octo_state == 0) push(ord, pv, pw, mp_);
+    else child_for(pw)->allocate(ord, pv, pw, mp_);
+  }
+  void allocate_fix(const PV& pv, const MapParams& mp_) {  // :1048-1072
+    if (octo_state == 0) push_fix_novar(pv, mp_);
+    else if (layer < mp_.max_layer) child_for(pv.pnt)->allocate_fix(pv, mp_);
+  }
+  void fix_divide(const MapParams& mp_) { for (const PV& pv : point_fix) child_for(pv.pnt)->push_fix(pv, mp_); }  // :1074-1094
+  void subdivide(int si, const State& xx, const MapParams& mp_) {  // :1096-1116 — world point re-derived with the CURRENT pose
+    for (const PV& pv : sw->points[si]) {
+      V3 pw = xx.R * pv.pnt + xx.p;
+      child_for(pw)->push(si, pv, pw, mp_);
+    }
+  }
+  void recut(int win_count, const std::vector<State>& x_buf, const MapParams& mp_) {  // :1148-1194
+    if (octo_state == 0) {
+      if (layer >= 0) {
+        opt_state = -1;
+        if (pcr_add.N <= mp_.min_point[layer]) { is_plane = false; return; }
+        if (!isexist || sw == nullptr) return;
+        eig3_sym(pcr_add.cov(), eig_value, eig_vector);
+        is_plane = plane_judge(eig_value, mp_);
+        if (is_plane) return;
+        else if (layer >= mp_.max_layer) return;
+      }
+      if (pcr_fix.N != 0) { fix_divide(mp_); std::vector<PV>().swap(point_fix); }
+      for (int i = 0; i < win_count; i++) subdivide(i, x_buf[i], mp_);
+      sw->clear(); delete sw; sw = nullptr;
+      octo_state = 1;
+    }
+    for (auto c : leaves) if (c) c->recut(win_count, x_buf, mp_);
+  }
+  void tras_opt(LidarFactor& vox_opt, std::vector<VoxelId>* ids) {  // :1308-1333
+    if (octo_state == 0) {
+      if (layer >= 0 && isexist && is_plane && sw != nullptr) {
+        if (eig_value[0] / eig_value[1] > 0.12) return;
+        std::vector<PC> pcrs(wdsize);
+        for (int i = 0; i < wdsize; i++) pcrs[i] = sw->pcrs_local[i];
+        opt_state = int(vox_opt.size());
+        vox_opt.push_voxel(pcrs, pcr_fix, 1.0, eig_value, eig_vector, pcr_add);
+        if (ids) ids->push_back(VoxelId{root.x, root.y, root.z, layer, path});
+      }
+    } else
+      for (auto c : leaves) if (c) c->tras_opt(vox_opt, ids);
+  }
+};
+
+using LocalMap = std::unordered_map<VoxelLoc, OctoTree*, VoxelLocHash>;
+inline void local_map_free(LocalMap& m) { for (auto& kv : m) delete kv.second; m.clear(); }
+
+// voxel_map.hpp:1504-1540 (feat_tem_map bookkeeping dropped: in a from-scratch build slide map == map)
+inline void cut_voxel(LocalMap& feat_map, const std::vector<PV>& pvec, int win_count, int wdsize, const std::vector<V3>& pwld, const MapParams& mp_) {
+  for (size_t i = 0; i < pvec.size(); i++) {
+    VoxelLoc position = voxel_key(pwld[i], mp_.voxel_size);
+    auto it = feat_map.find(position);
+    if (it != feat_map.end()) { it->second->allocate(win_count, pvec[i], pwld[i], mp_); it->second->isexist = true; }
+    else {
+      OctoTree* ot = new OctoTree(0, wdsize);
+      ot->root = position;
+      ot->allocate(win_count, pvec[i], pwld[i], mp_);
+      ot->voxel_center[0] = (0.5 + position.x) * mp_.voxel_size;
+      ot->voxel_center[1] = (0.5 + position.y) * mp_.voxel_size;
+      ot->voxel_center[2] = (0.5 + position.z) * mp_.voxel_size;
+      ot->quater_length = float(mp_.voxel_size / 4.0);
+      feat_map[position] = ot;
+    }
+  }
+}
+// voxel_map.hpp:1641-1671 — fixed (already-world) map points
+inline void cut_voxel_fix(LocalMap& feat_map, const std::vector<PV>& pvec, int wdsize, const MapParams& mp_) {
+  for (const PV& pv : pvec) {
+    VoxelLoc position = voxel_key(pv.pnt, mp_.voxel_size);
+    auto it = feat_map.find(position);
+    if (it != feat_map.end()) it->second->allocate_fix(pv, mp_);
+    else {
+      OctoTree* ot = new OctoTree(0, wdsize);
+      ot->root = position;
+      ot->push_fix_novar(pv, mp_);
+      ot->voxel_center[0] = (0.5 + position.x) * mp_.voxel_size;
+      ot->voxel_center[1] = (0.5 + position.y) * mp_.voxel_size;
+      ot->voxel_center[2] = (0.5 + position.z) * mp_.voxel_size;
+      ot->quater_length = float(mp_.voxel_size / 4.0);
+      feat_map[position] = ot;
+    }
+  }
+}
+
+// voxelslam.cpp:600-628 (motion_init) / :1171-1180 (loop_update): cut every scan of the window with the
+// current poses, then recut(win_size) + tras_opt on every root.  `threads`>1 mirrors multi_recut
+// (voxelslam.cpp:1398-1453: roots split into ranges, recut in threads, serial tras_opt).
+inline void build_window_factor(LocalMap& map, const std::vector<std::vector<PV>>& scans, const std::vector<State>& xs, const MapParams& mp_,
+                                int threads, LidarFactor& out, std::vector<VoxelId>* ids) {
+  const int W = int(scans.size());
+  std::vector<V3> pwld;
+  for (int i = 0; i < W; i++) {
+    pwld.resize(scans[i].size());
+    for (size_t k = 0; k < scans[i].size(); k++) pwld[k] = xs[i].R * scans[i][k].pnt + xs[i].p;  // voxelslam.cpp:616
+    cut_voxel(map, scans[i], i, W, pwld, mp_);
+  }
+  std::vector<OctoTree*> roots;
+  for (auto& kv : map) roots.push_back(kv.second);
+  if (threads <= 1 || int(roots.size()) < threads) {
+    for (auto r : roots) r->recut(W, xs, mp_);
+  } else {
+    std::vector<std::vector<OctoTree*>> octss(threads);
+    double part = 1.0 * roots.size() / threads;
+    int cnt = 0;
+    for (auto r : roots) { octss[cnt].push_back(r); if (octss[cnt].size() >= part && cnt < threads - 1) cnt++; }
+    std::vector<std::thread> th;
+    for (int i = 1; i < threads; i++) th.emplace_back([&, i] { for (auto r : octss[i]) r->recut(W, xs, mp_); });
+    for (auto r : octss[0]) r->recut(W, xs, mp_);
+    for (auto& t : th) t.join();
+  }
+  for (auto r : roots) r->tras_opt(out, ids);
+}
+
+// ------------------------------------------------------------------ global-BA map  loop_refine.hpp:269-537
+struct GbaParams {
+  double voxel_size = 1.0;          // gba_voxel_size
+  double min_eigen_value = 0.01;    // gba_min_eigen_value
+  double eigen_value_array[8] = {.25, .25, .25, .25, .25, .25, .25, .25};  // gba_eigen_value_array (inverted, voxelslam.cpp:2490)
+  int max_layer = 2;                // shares the global max_layer (loop_refine.hpp:391)
+};
+
+struct OctreeGBA {  // loop_refine.hpp:273-481
+  std::vector<std::vector<V3>> locals, worlds;
+  PC pcr_add;
+  int layer, octo_state = 0, wdsize;
+  OctreeGBA* leaves[8];
+  double voxel_center[3];
+  float quater_length;
+  bool is_plane = false;
+  VoxelLoc root{0, 0, 0}; int path = 0;
+  OctreeGBA(int l, int w) : locals(w), worlds(w), layer(l), wdsize(w) { for (auto& p : leaves) p = nullptr; }
+  ~OctreeGBA() { for (auto p : leaves) delete p; }
+  void push(int ord, const V3& local, const V3& world) { locals[ord].push_back(local); worlds[ord].push_back(world); pcr_add.push(world); }  // :316-321
+  void subdivide() {  // :323-356 — uses the STORED world points
+    for (int i = 0; i < wdsize; i++)
+      for (size_t j = 0; j < locals[i].size(); j++) {
+        const V3& pw = worlds[i][j];
+        int xyz[3] = {0, 0, 0};
+        for (int k = 0; k < 3; k++) if (pw[k] > voxel_center[k]) xyz[k] = 1;
+        int leafnum = 4 * xyz[0] + 2 * xyz[1] + xyz[2];
+        if (!leaves[leafnum]) {
+          OctreeGBA* c = new OctreeGBA(layer + 1, wdsize);
+          for (int k = 0; k < 3; k++) c->voxel_center[k] = voxel_center[k] + (2 * xyz[k] - 1) * quater_length;
+          c->quater_length = quater_length / 2;
+          c->root = root; c->path = path * 8 + leafnum;
+          leaves[leafnum] = c;
+        }
+        leaves[leafnum]->push(i, locals[i][j], pw);
+      }
+  }
+  void recut(LidarFactor& vox_opt, const GbaParams& gp, std::vector<VoxelId>* ids) {  // :358-405
+    if (pcr_add.N <= 10) return;
+    V3 ev; M3 evec;
+    eig3_sym(pcr_add.cov(), ev, evec);
+    is_plane = ev[0] < gp.min_eigen_value && (ev[0] / ev[2]) < gp.eigen_value_array[layer];
+    if (is_plane) {
+      if (pcr_add.N < 10) return;
+      int exi = 0;
+      for (int i = 0; i < wdsize; i++) if (!locals[i].empty()) exi++;
+      if (exi <= 1) return;
+      if (ev[0] / ev[1] > 0.12) return;
+      std::vector<PC> pcrs(wdsize);
+      for (int i = 0; i < wdsize; i++) for (const V3& v : locals[i]) pcrs[i].push(v);
+      PC pcr_fix;
+      vox_opt.push_voxel(pcrs, pcr_fix, 1.0, ev, evec, pcr_add);
+      if (ids) ids->push_back(VoxelId{root.x, root.y, root.z, layer, path});
+      return;
+    } else if (layer >= gp.max_layer) return;
+    else { subdivide(); octo_state = 1; }
+    for (auto c : leaves) if (c) c->recut(vox_opt, gp, ids);
+  }
+};
+using GbaMap = std::unordered_map<VoxelLoc, OctreeGBA*, VoxelLocHash>;
+
+// loop_refine.hpp:446-479.  xyz are the keyframe's float points (pcl::PointXYZINormal x,y,z).
+inline void gba_cut_voxel(GbaMap& feat_map, const State& xc, const float* xyz, size_t npts, int win_count, int wdsize, const GbaParams& gp) {
+  for (size_t k = 0; k < npts; k++) {
+    V3 local = v3(xyz[3 * k], xyz[3 * k + 1], xyz[3 * k + 2]);
+    V3 world = xc.R * local + xc.p;
+    VoxelLoc position = voxel_key(world, gp.voxel_size);
+    auto it = feat_map.find(position);
+    if (it != feat_map.end()) it->second->push(win_count, local, world);
+    else {
+      OctreeGBA* ot = new OctreeGBA(0, wdsize);
+      ot->root = position;
+      ot->push(win_count, local, world);
+      ot->voxel_center[0] = (0.5 + position.x) * gp.voxel_size;
+      ot->voxel_center[1] = (0.5 + position.y) * gp.voxel_size;
+      ot->voxel_center[2] = (0.5 + position.z) * gp.voxel_size;
+      ot->quater_length = float(gp.voxel_size / 4.0);
+      feat_map[position] = ot;
+    }
+  }
+}
+// loop_refine.hpp:483-537: roots split into ranges, thread-private factors concatenated in thread order; the map is consumed.
+inline void gba_multi_recut(GbaMap& feat_map, LidarFactor& voxhess, int thd_num, const GbaParams& gp, std::vector<VoxelId>* ids) {
+  std::vector<std::vector<OctreeGBA*>> octss(thd_num);
+  std::vector<LidarFactor> facs(thd_num, LidarFactor(voxhess.win_size));
+  std::vector<std::vector<VoxelId>> idss(thd_num);
+  double part = 1.0 * feat_map.size() / thd_num;
+  int cnt = 0;
+  for (auto& kv : feat_map) { octss[cnt].push_back(kv.second); if (octss[cnt].size() >= part && cnt < thd_num - 1) cnt++; }
+  auto fn = [&](int i) { for (OctreeGBA* oc : octss[i]) { oc->recut(facs[i], gp, ids ? &idss[i] : nullptr); delete oc; } };
+  std::vector<std::thread> th;
+  for (int i = 1; i < thd_num; i++) th.emplace_back(fn, i);
+  fn(0);
+  for (auto& t : th) t.join();
+  feat_map.clear();
+  for (int i = 0; i < thd_num; i++) {
+    for (size_t a = 0; a < facs[i].size(); a++)
+      voxhess.push_voxel(facs[i].plvec_voxels[a], facs[i].sig_vecs[a], facs[i].coeffs[a], facs[i].eig_values[a], facs[i].eig_vectors[a], facs[i].pcr_adds[a]);
+    if (ids) ids->insert(ids->end(), idss[i].begin(), idss[i].end());
+  }
+}
+
+struct Keyframes {  // the cloud of each keyframe (float xyz, as PointXYZINormal stores them)
+  std::vector<const float*> xyz;
+  std::vector<size_t> npts;
+};
+struct PgoEdge { int i, j; double rot[9], tra[3], v6[6]; };
+
+// voxelslam.cpp:2360-2427 — the BA loop of HBA_add_edge (coarse-to-fine switch to the LocalBA voxel parameters) and the
+// PGO edge extraction from the last raw Hessian.  `fine` = {voxel_size, plane_eigen_value_thre, min_eigen_value} of LocalBA.
+inline int hba_window(std::vector<State>& xs, const Keyframes& kf, GbaParams gp, const GbaParams& fine, int max_iter, int thread_num, Mat& hess,
+                      std::vector<PgoEdge>* edges, std::vector<double>* resis_log) {
+  const int wdsize = int(xs.size());
+  int up = 4, converge_flag = 0, iters_run = 0;
+  double converge_thre = 0.05;
+  for (int iterCnt = 0; iterCnt < max_iter; iterCnt++) {
+    if (converge_flag == 1 || iterCnt == max_iter - 1) {
+      gp.voxel_size = fine.voxel_size; gp.min_eigen_value = fine.min_eigen_value;
+      for (int k = 0; k < 8; k++) gp.eigen_value_array[k] = fine.eigen_value_array[k];
+    }
+    GbaMap oct_map;
+    for (int i = 0; i < wdsize; i++) gba_cut_voxel(oct_map, xs[i], kf.xyz[i], kf.npts[i], i, wdsize, gp);
+    LidarFactor voxhess(wdsize);
+    gba_multi_recut(oct_map, voxhess, thread_num, gp, nullptr);
+    std::vector<double> resis;
+    int status = 0;
+    bool is_converge = lidar_ba_damping_iter(xs, voxhess, &hess, resis, up, thread_num, nullptr, &status);
+    iters_run++;
+    if (status != 0) return -1;
+    if (resis_log) { resis_log->push_back(resis[0]); resis_log->push_back(resis[1]); }
+    if ((std::fabs(resis[0] - resis[1]) / resis[0] < converge_thre && is_converge) || (iterCnt == max_iter - 2 && converge_flag == 0)) {
+      converge_thre = 0.01;
+      if (converge_flag == 0) converge_flag = 1;
+      else if (converge_flag == 1) break;
+    }
+  }
+  if (edges) {
+    for (int i = 0; i < wdsize - 1; i++)
+      for (int j = i + 1; j < wdsize; j++) {
+        bool isAdd = true;
+        PgoEdge e; e.i = i; e.j = j;
+        for (int k = 0; k < 6; k++) {
+          double hc = std::fabs(hess(6 * i + k, 6 * j + k));
+          if (hc < 1e-6) { isAdd = false; break; }
+          e.v6[k] = 1.0 / hc;
+        }
+        if (!isAdd) continue;
+        V3 t = tr(xs[i].R) * (xs[j].p - xs[i].p);
+        M3 r = tr(xs[i].R) * xs[j].R;
+        for (int a = 0; a < 3; a++) { e.tra[a] = t[a]; for (int b = 0; b < 3; b++) e.rot[3 * a + b] = r(a, b); }
+        edges->push_back(e);
+      }
+  }
+  return iters_run;
+}
+
+}  // namespace vxo

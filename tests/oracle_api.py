@@ -1,0 +1,194 @@
+"""ctypes wrapper around oracle/_build/liboracle.so — the CPU restatement of the reference (TEST INFRASTRUCTURE ONLY)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from voxel_slam_b200.api import LM_TRACE_DTYPE, VOXEL_ID_DTYPE, LmTrace, MapParams, VoxelId, _dp, _f64
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_PATH = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(ORACLE_PATH)
+        _lib.vxo_factor_create.restype = C.c_void_p
+        _lib.vxo_build_window_factor.restype = C.c_void_p
+        _lib.vxo_build_gba_factor.restype = C.c_void_p
+        _lib.vxo_factor_size.restype = C.c_int64
+        for fn in ("vxo_factor_residual", "vxo_factor_hessian", "vxo_time_hessian", "vxo_time_residual"):
+            getattr(_lib, fn).restype = C.c_double
+    return _lib
+
+
+def eig3(A):
+    A = _f64(A).reshape(3, 3)
+    w, U = np.zeros(3), np.zeros((3, 3))
+    lib().vxo_eig3(_dp(A), _dp(w), _dp(U))
+    return w, U
+
+
+def hostmath_eig3(sym6):
+    s = _f64(sym6)
+    w, U = np.zeros(3), np.zeros((3, 3))
+    lib().vxo_hostmath_eig3(_dp(s), _dp(w), _dp(U))
+    return w, U
+
+
+def voxel_keys(pw, voxel_size):
+    p = _f64(pw).reshape(-1, 3)
+    n = p.shape[0]
+    xyz = np.zeros((n, 3), dtype=np.int64)
+    h = np.zeros(n, dtype=np.uint64)
+    lib().vxo_voxel_keys(_dp(p), C.c_int64(n), C.c_double(voxel_size), xyz.ctypes.data_as(C.POINTER(C.c_int64)), h.ctypes.data_as(C.POINTER(C.c_uint64)))
+    return xyz, h
+
+
+def cluster_from_points(pts):
+    p = _f64(pts).reshape(-1, 3)
+    out = np.zeros(10)
+    lib().vxo_cluster_from_points(_dp(p), C.c_int64(p.shape[0]), _dp(out))
+    return out
+
+
+def cluster_transform(c10, pose12, hostmath=False):
+    c, p, out = _f64(c10), _f64(pose12), np.zeros(10)
+    (lib().vxo_hostmath_transform if hostmath else lib().vxo_cluster_transform)(_dp(c), _dp(p), _dp(out))
+    return out
+
+
+def so3_exp(w):
+    w = _f64(w)
+    R = np.zeros((3, 3))
+    lib().vxo_so3_exp(_dp(w), _dp(R))
+    return R
+
+
+def ldlt_solve(A, b):
+    A = np.asfortranarray(A, dtype=np.float64)
+    b = _f64(b)
+    x = np.zeros_like(b)
+    rc = lib().vxo_ldlt_solve(_dp(A), _dp(b), C.c_int(b.shape[0]), _dp(x))
+    return x, rc
+
+
+class OracleFactor:
+    def __init__(self, handle, W):
+        self._h = C.c_void_p(handle)
+        self.W = W
+
+    @staticmethod
+    def from_dense(W, clusters10, fix10, coe, eig12, sum10):
+        h = lib().vxo_factor_create(C.c_int(W))
+        f = OracleFactor(h, W)
+        cl, e, s = _f64(clusters10), _f64(eig12), _f64(sum10)
+        fx = _f64(fix10) if fix10 is not None else None
+        co = _f64(coe) if coe is not None else None
+        n = e.reshape(-1, 12).shape[0]
+        lib().vxo_factor_push_dense(f._h, C.c_int64(n), _dp(cl), _dp(fx), _dp(co), _dp(e), _dp(s))
+        return f
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().vxo_factor_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def size(self):
+        return int(lib().vxo_factor_size(self._h))
+
+    def export(self):
+        n, W = self.size(), self.W
+        cl, fx, co, e, s = np.zeros((n, W, 10)), np.zeros((n, 10)), np.zeros(n), np.zeros((n, 12)), np.zeros((n, 10))
+        ids = np.zeros(n, dtype=VOXEL_ID_DTYPE)
+        lib().vxo_factor_export(self._h, _dp(cl), _dp(fx), _dp(co), _dp(e), _dp(s), ids.ctypes.data_as(C.POINTER(VoxelId)))
+        return dict(clusters10=cl, fix10=fx, coe=co, eig12=e, sum10=s, ids=ids)
+
+    def residual(self, poses12):
+        p = _f64(poses12)
+        return float(lib().vxo_factor_residual(self._h, _dp(p)))
+
+    def hessian(self, poses12, hostmath=False):
+        p = _f64(poses12)
+        n = 6 * self.W
+        H, J = np.zeros((n, n), order="F"), np.zeros(n)
+        if hostmath:
+            lib().vxo_hostmath_hessian(self._h, _dp(p), _dp(H), _dp(J))
+            return H, J, None
+        r = lib().vxo_factor_hessian(self._h, _dp(p), _dp(H), _dp(J))
+        return H, J, float(r)
+
+    def time_hessian(self, poses12, threads, reps=1):
+        p = _f64(poses12)
+        r = C.c_double(0)
+        return float(lib().vxo_time_hessian(self._h, _dp(p), C.c_int(threads), C.c_int(reps), C.byref(r))), r.value
+
+    def time_residual(self, poses12, threads, reps=1):
+        p = _f64(poses12)
+        r = C.c_double(0)
+        return float(lib().vxo_time_residual(self._h, _dp(p), C.c_int(threads), C.c_int(reps), C.byref(r))), r.value
+
+    def lidar_ba(self, poses12, max_iter=3, thd_num=2, trace_cap=64):
+        p = _f64(poses12).copy()
+        n = 6 * self.W
+        H, resis = np.zeros((n, n), order="F"), np.zeros(2)
+        conv, tl = C.c_int(0), C.c_int(0)
+        tr = np.zeros(trace_cap, dtype=LM_TRACE_DTYPE)
+        rc = lib().vxo_lidar_ba(self._h, _dp(p), C.c_int(max_iter), C.c_int(thd_num), _dp(H), _dp(resis), C.byref(conv), tr.ctypes.data_as(C.POINTER(LmTrace)),
+                                C.c_int(trace_cap), C.byref(tl))
+        return dict(poses=p, hess=H, resis=resis, is_converge=bool(conv.value), trace=tr[: tl.value], status=rc)
+
+    def li_ba(self, states24, imu, with_gravity=False, max_iter=3, imu_coef=1e-4, trace_cap=64):
+        s = _f64(states24).copy()
+        n = 15 * self.W + (3 if with_gravity else 0)
+        H, resis = np.zeros((n, n), order="F"), np.zeros(2)
+        tl = C.c_int(0)
+        tr = np.zeros(trace_cap, dtype=LM_TRACE_DTYPE)
+        rc = lib().vxo_li_ba(self._h, _dp(s), C.c_int(int(with_gravity)), C.c_int(max_iter), C.c_double(imu_coef), C.byref(imu.hooks), _dp(H), _dp(resis),
+                             tr.ctypes.data_as(C.POINTER(LmTrace)), C.c_int(trace_cap), C.byref(tl))
+        return dict(states=s, hess=H, resis=resis, trace=tr[: tl.value], status=rc)
+
+
+def build_window_factor(mp, pts_body, scan_offsets, poses12, fix_pts=None, threads=1, var_diag=0.0):
+    pts = _f64(pts_body).reshape(-1, 3)
+    off = np.ascontiguousarray(scan_offsets, dtype=np.int64)
+    W = off.shape[0] - 1
+    p = _f64(poses12)
+    fx = _f64(fix_pts).reshape(-1, 3) if fix_pts is not None else None
+    secs = C.c_double(0)
+    h = lib().vxo_build_window_factor(C.byref(mp), _dp(pts), off.ctypes.data_as(C.POINTER(C.c_int64)), _dp(p), C.c_int(W), _dp(fx), C.c_int64(0 if fx is None else fx.shape[0]),
+                                      C.c_int(threads), C.c_double(var_diag), C.byref(secs))
+    f = OracleFactor(h, W)
+    f.build_seconds = secs.value
+    return f
+
+
+def build_gba_factor(mp, xyz_f32, kf_offsets, poses12, threads=2, stride_floats=3):
+    x = np.ascontiguousarray(xyz_f32, dtype=np.float32)
+    off = np.ascontiguousarray(kf_offsets, dtype=np.int64)
+    W = off.shape[0] - 1
+    p = _f64(poses12)
+    secs = C.c_double(0)
+    h = lib().vxo_build_gba_factor(C.byref(mp), x.ctypes.data_as(C.POINTER(C.c_float)), C.c_int(stride_floats), off.ctypes.data_as(C.POINTER(C.c_int64)), _dp(p), C.c_int(W),
+                                   C.c_int(threads), C.byref(secs))
+    f = OracleFactor(h, W)
+    f.build_seconds = secs.value
+    return f
+
+
+def hba_window(coarse, fine, xyz_f32, kf_offsets, poses12, max_iter, thread_num=2, stride_floats=3):
+    x = np.ascontiguousarray(xyz_f32, dtype=np.float32)
+    off = np.ascontiguousarray(kf_offsets, dtype=np.int64)
+    W = off.shape[0] - 1
+    p = _f64(poses12).copy()
+    H = np.zeros((6 * W, 6 * W), order="F")
+    log = np.zeros(2 * max(max_iter, 1))
+    it = C.c_int(0)
+    rc = lib().vxo_hba_window(C.byref(coarse), C.byref(fine), x.ctypes.data_as(C.POINTER(C.c_float)), C.c_int(stride_floats), off.ctypes.data_as(C.POINTER(C.c_int64)), _dp(p),
+                              C.c_int(W), C.c_int(max_iter), C.c_int(thread_num), _dp(H), _dp(log), C.byref(it))
+    return dict(poses=p, hess=H, resis_log=log[: 2 * it.value], outer_iters=it.value, status=rc)

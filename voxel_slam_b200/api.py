@@ -1,0 +1,394 @@
+"""ctypes mirror of include/vxs.h (libvxs.so) and of the synthetic-workload harness (libvxs_harness.so).
+
+Names follow the reference's call surface: ``Factor`` = LidarFactor (voxel_map.hpp:109-290), ``Context.lidar_ba`` =
+Lidar_BA_Optimizer::damping_iter (voxel_map.hpp:367), ``Context.li_ba`` = LI_BA_Optimizer(+Gravity)::damping_iter
+(voxel_map.hpp:562, 775), ``Context.build_window_factor`` = cut_voxel + recut + tras_opt (voxel_map.hpp:1504, 1148, 1308).
+"""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libvxs.so")
+HARNESS_PATH = os.path.join(_HERE, "lib", "libvxs_harness.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "vxs.h")
+
+VXS_OK = 0
+VXS_WARN_SINGULAR = 1
+VXS_ERR_TOO_FEW_VOXELS = -3
+
+
+class VxsError(RuntimeError):
+    def __init__(self, code, what=""):
+        super().__init__(f"libvxs error {code}: {what}")
+        self.code = code
+
+
+class MapParams(C.Structure):
+    _fields_ = [("voxel_size", C.c_double), ("min_eigen_value", C.c_double), ("plane_thre", C.c_double * 4),
+                ("min_point", C.c_double * 4), ("max_layer", C.c_int32), ("reserved", C.c_int32)]
+
+    @staticmethod
+    def make(voxel_size=1.0, min_eigen_value=0.0025, plane_thre=(0.25,) * 4, min_point=(5.0,) * 4, max_layer=2):
+        p = MapParams()
+        p.voxel_size, p.min_eigen_value, p.max_layer = voxel_size, min_eigen_value, max_layer
+        for i in range(4):
+            p.plane_thre[i] = plane_thre[i]
+            p.min_point[i] = min_point[i]
+        return p
+
+
+class LmTrace(C.Structure):
+    _fields_ = [("r1", C.c_double), ("r2", C.c_double), ("u", C.c_double), ("v", C.c_double), ("q1", C.c_double),
+                ("accepted", C.c_int32), ("hess_built", C.c_int32)]
+
+
+class VoxelId(C.Structure):
+    _fields_ = [("x", C.c_int64), ("y", C.c_int64), ("z", C.c_int64), ("layer", C.c_int32), ("path", C.c_int32)]
+
+
+VOXEL_ID_DTYPE = np.dtype([("x", "<i8"), ("y", "<i8"), ("z", "<i8"), ("layer", "<i4"), ("path", "<i4")])
+LM_TRACE_DTYPE = np.dtype([("r1", "<f8"), ("r2", "<f8"), ("u", "<f8"), ("v", "<f8"), ("q1", "<f8"), ("accepted", "<i4"), ("hess_built", "<i4")])
+
+IMU_EVAL = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double))
+IMU_UPDATE = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_int)
+IMU_ROLLBACK = C.CFUNCTYPE(C.c_int, C.c_void_p)
+
+
+class ImuHooks(C.Structure):
+    _fields_ = [("user", C.c_void_p), ("eval", IMU_EVAL), ("update", IMU_UPDATE), ("rollback", IMU_ROLLBACK)]
+
+
+def declared_symbols(header=HEADER_PATH):
+    """Every function name include/vxs.h declares (used by the ABI test)."""
+    txt = open(header).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(vxs_[a-z0-9_]+)\s*\(", txt)))
+
+
+_lib = None
+_harness = None
+
+
+def lib():
+    """Load libvxs.so (fails loudly if the CUDA extension has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise VxsError(-100, f"{LIB_PATH} is missing — run __graft_entry__.build(); there is no CPU fallback")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.vxs_ctx_last_error.restype = C.c_char_p
+        _lib.vxs_ctx_launch_count.restype = C.c_int64
+    return _lib
+
+
+def harness():
+    global _harness
+    if _harness is None:
+        if not os.path.exists(HARNESS_PATH):
+            raise VxsError(-100, f"{HARNESS_PATH} is missing — run __graft_entry__.build()")
+        _harness = C.CDLL(HARNESS_PATH)
+        _harness.vxh_imu_create.restype = C.c_void_p
+    return _harness
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+# ---------------------------------------------------------------------------------------------- harness
+def true_pose(L, i):
+    out = np.zeros(12)
+    harness().vxh_true_pose(C.c_double(L), C.c_int(i), _dp(out))
+    return out
+
+
+def perturb_pose(pose12, seed, rot_sigma, pos_sigma):
+    out = np.zeros(12)
+    p = _f64(pose12)
+    harness().vxh_perturb_pose(_dp(p), C.c_uint64(seed), C.c_double(rot_sigma), C.c_double(pos_sigma), _dp(out))
+    return out
+
+
+def gen_scan(L, frame, n, pose12_true, seed=0x5EED0000, off=0.37, sigma=0.01, max_range=0.0, dtype=np.float64, out=None):
+    p = _f64(pose12_true)
+    if dtype == np.float32:
+        xyz = np.empty((n, 3), dtype=np.float32) if out is None else out
+        harness().vxh_gen_scan_f32(C.c_double(L), C.c_double(off), C.c_double(sigma), C.c_double(max_range), C.c_uint64(seed), C.c_int(frame), C.c_int64(n), _dp(p),
+                                   xyz.ctypes.data_as(C.POINTER(C.c_float)))
+    else:
+        xyz = np.empty((n, 3), dtype=np.float64) if out is None else out
+        harness().vxh_gen_scan(C.c_double(L), C.c_double(off), C.c_double(sigma), C.c_double(max_range), C.c_uint64(seed), C.c_int(frame), C.c_int64(n), _dp(p), _dp(xyz))
+    return xyz
+
+
+class ImuWindow:
+    """W-1 synthetic IMU preintegration factors (stand-in for the reference's unchanged IMU_PRE objects)."""
+
+    def __init__(self, poses12_true, T=0.1, samples=20, gyr_noise=1e-3, acc_noise=1e-2, seed=7):
+        p = _f64(poses12_true).reshape(-1, 12)
+        self.W = p.shape[0]
+        self._h = C.c_void_p(harness().vxh_imu_create(_dp(p), C.c_int(self.W), C.c_double(T), C.c_int(samples), C.c_double(gyr_noise), C.c_double(acc_noise), C.c_uint64(seed)))
+        self.hooks = ImuHooks()
+        harness().vxh_imu_hooks(self._h, C.byref(self.hooks))
+
+    def reset(self):
+        harness().vxh_imu_reset(self._h)
+
+    def eval(self, states24, with_gravity=False, want_jac=True):
+        s = _f64(states24)
+        bs = 33 if with_gravity else 30
+        blocks = np.zeros((self.W - 1, bs * bs))
+        gvec = np.zeros((self.W - 1, bs))
+        cost = C.c_double(0)
+        harness().vxh_imu_eval(self._h, _dp(s), C.c_int(self.W), C.c_int(int(with_gravity)), C.c_int(int(want_jac)), _dp(blocks), _dp(gvec), C.byref(cost))
+        return cost.value, blocks, gvec
+
+    def __del__(self):
+        try:
+            if self._h:
+                harness().vxh_imu_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+# ---------------------------------------------------------------------------------------------- libvxs
+class Context:
+    def __init__(self, device=0):
+        self._p = C.c_void_p()
+        rc = lib().vxs_ctx_create(C.c_int(device), C.byref(self._p))
+        if rc != 0:
+            raise VxsError(rc, "vxs_ctx_create failed (no CUDA device? libvxs has no CPU fallback)")
+        self.device = device
+
+    def close(self):
+        if self._p:
+            lib().vxs_ctx_destroy(self._p)
+            self._p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc < 0:
+            raise VxsError(rc, (lib().vxs_ctx_last_error(self._p) or b"").decode())
+        return rc
+
+    @property
+    def launches(self):
+        return int(lib().vxs_ctx_launch_count(self._p))
+
+    def timing(self, on=True):
+        self._check(lib().vxs_ctx_timing_enable(self._p, C.c_int(int(on))))
+
+    def timing_reset(self):
+        self._check(lib().vxs_ctx_timing_reset(self._p))
+
+    def timing_read(self):
+        cap = 64
+        names = (C.c_char_p * cap)()
+        ms = (C.c_double * cap)()
+        calls = (C.c_int64 * cap)()
+        n = C.c_int(0)
+        self._check(lib().vxs_ctx_timing_read(self._p, C.c_int(cap), names, ms, calls, C.byref(n)))
+        return {names[i].decode(): (ms[i], calls[i]) for i in range(n.value)}
+
+    # --- multi-GPU
+    @staticmethod
+    def comm_unique_id():
+        buf = (C.c_ubyte * 128)()
+        rc = lib().vxs_comm_unique_id(buf)
+        if rc != 0:
+            raise VxsError(rc, "vxs_comm_unique_id")
+        return bytes(buf)
+
+    def comm_init(self, uid, rank, nranks):
+        buf = (C.c_ubyte * 128).from_buffer_copy(uid)
+        self._check(lib().vxs_ctx_comm_init(self._p, buf, C.c_int(rank), C.c_int(nranks)))
+
+    # --- evaluation
+    def evaluate_residual(self, f, poses12):
+        p = _f64(poses12)
+        r = C.c_double(0)
+        self._check(lib().vxs_factor_evaluate_residual(self._p, f._p, _dp(p), C.byref(r)))
+        return r.value
+
+    def evaluate_hessian(self, f, poses12):
+        p = _f64(poses12)
+        n = 6 * f.win_size
+        H = np.zeros((n, n), order="F")
+        J = np.zeros(n)
+        r = C.c_double(0)
+        self._check(lib().vxs_factor_evaluate_hessian(self._p, f._p, _dp(p), _dp(H), _dp(J), C.byref(r)))
+        return H, J, r.value
+
+    # --- solvers
+    def lidar_ba(self, f, poses12, max_iter=3, thd_num=2, want_hess=True, trace_cap=64):
+        p = _f64(poses12).copy()
+        n = 6 * f.win_size
+        H = np.zeros((n, n), order="F") if want_hess else None
+        resis = np.zeros(2)
+        conv = C.c_int(0)
+        tr = np.zeros(trace_cap, dtype=LM_TRACE_DTYPE)
+        tl = C.c_int(0)
+        rc = self._check(lib().vxs_lidar_ba(self._p, f._p, _dp(p), C.c_int(max_iter), C.c_int(thd_num), _dp(H), _dp(resis), C.byref(conv),
+                                            tr.ctypes.data_as(C.POINTER(LmTrace)), C.c_int(trace_cap), C.byref(tl)))
+        return dict(poses=p, hess=H, resis=resis, is_converge=bool(conv.value), trace=tr[: tl.value], status=rc)
+
+    def li_ba(self, f, states24, imu, with_gravity=False, max_iter=3, imu_coef=1e-4, want_hess=True, trace_cap=64):
+        s = _f64(states24).copy()
+        n = 15 * f.win_size + (3 if with_gravity else 0)
+        H = np.zeros((n, n), order="F") if want_hess else None
+        resis = np.zeros(2)
+        tr = np.zeros(trace_cap, dtype=LM_TRACE_DTYPE)
+        tl = C.c_int(0)
+        rc = self._check(lib().vxs_li_ba(self._p, f._p, _dp(s), C.c_int(int(with_gravity)), C.c_int(max_iter), C.c_double(imu_coef), C.byref(imu.hooks), _dp(H), _dp(resis),
+                                         tr.ctypes.data_as(C.POINTER(LmTrace)), C.c_int(trace_cap), C.byref(tl)))
+        return dict(states=s, hess=H, resis=resis, trace=tr[: tl.value], status=rc)
+
+    # --- voxel map
+    def voxel_keys(self, pw, voxel_size):
+        p = _f64(pw).reshape(-1, 3)
+        n = p.shape[0]
+        xyz = np.zeros((n, 3), dtype=np.int64)
+        h = np.zeros(n, dtype=np.uint64)
+        self._check(lib().vxs_voxel_keys(self._p, _dp(p), C.c_int64(n), C.c_double(voxel_size), xyz.ctypes.data_as(C.POINTER(C.c_int64)), h.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return xyz, h
+
+    def build_window_factor(self, mp, pts_body, scan_offsets, poses12, out, fix_pts=None, want_ids=False, ids_cap=0):
+        pts = _f64(pts_body).reshape(-1, 3)
+        off = np.ascontiguousarray(scan_offsets, dtype=np.int64)
+        W = off.shape[0] - 1
+        p = _f64(poses12)
+        fx = _f64(fix_pts).reshape(-1, 3) if fix_pts is not None else None
+        ids = np.zeros(ids_cap, dtype=VOXEL_ID_DTYPE) if want_ids else None
+        n_out = C.c_int64(0)
+        self._check(lib().vxs_build_window_factor(self._p, C.byref(mp), _dp(pts), off.ctypes.data_as(C.POINTER(C.c_int64)), _dp(p), C.c_int(W), _dp(fx),
+                                                  C.c_int64(0 if fx is None else fx.shape[0]), out._p,
+                                                  ids.ctypes.data_as(C.POINTER(VoxelId)) if want_ids else None, C.c_int64(ids_cap), C.byref(n_out)))
+        return (n_out.value, ids[: n_out.value]) if want_ids else n_out.value
+
+    def build_gba_factor(self, mp, xyz_f32, kf_offsets, poses12, out, stride_floats=3, want_ids=False, ids_cap=0):
+        x = np.ascontiguousarray(xyz_f32, dtype=np.float32)
+        off = np.ascontiguousarray(kf_offsets, dtype=np.int64)
+        W = off.shape[0] - 1
+        p = _f64(poses12)
+        ids = np.zeros(ids_cap, dtype=VOXEL_ID_DTYPE) if want_ids else None
+        n_out = C.c_int64(0)
+        self._check(lib().vxs_build_gba_factor(self._p, C.byref(mp), x.ctypes.data_as(C.POINTER(C.c_float)), C.c_int(stride_floats), off.ctypes.data_as(C.POINTER(C.c_int64)),
+                                               _dp(p), C.c_int(W), out._p, ids.ctypes.data_as(C.POINTER(VoxelId)) if want_ids else None, C.c_int64(ids_cap), C.byref(n_out)))
+        return (n_out.value, ids[: n_out.value]) if want_ids else n_out.value
+
+    def hba_window(self, coarse, fine, xyz_f32, kf_offsets, poses12, max_iter, thread_num=2, stride_floats=3):
+        x = np.ascontiguousarray(xyz_f32, dtype=np.float32)
+        off = np.ascontiguousarray(kf_offsets, dtype=np.int64)
+        W = off.shape[0] - 1
+        p = _f64(poses12).copy()
+        H = np.zeros((6 * W, 6 * W), order="F")
+        log = np.zeros(2 * max(max_iter, 1))
+        it = C.c_int(0)
+        self._check(lib().vxs_hba_window(self._p, C.byref(coarse), C.byref(fine), x.ctypes.data_as(C.POINTER(C.c_float)), C.c_int(stride_floats),
+                                         off.ctypes.data_as(C.POINTER(C.c_int64)), _dp(p), C.c_int(W), C.c_int(max_iter), C.c_int(thread_num), _dp(H), _dp(log), C.byref(it)))
+        return dict(poses=p, hess=H, resis_log=log[: 2 * it.value], outer_iters=it.value)
+
+
+class Factor:
+    """Device-resident LidarFactor."""
+
+    def __init__(self, ctx, win_size):
+        self.ctx = ctx
+        self._p = C.c_void_p()
+        ctx._check(lib().vxs_factor_create(ctx._p, C.c_int(win_size), C.byref(self._p)))
+
+    def close(self):
+        if self._p:
+            lib().vxs_factor_destroy(self._p)
+            self._p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def clear(self):
+        self.ctx._check(lib().vxs_factor_clear(self._p))
+
+    def counts(self):
+        v, e, w = C.c_int64(0), C.c_int64(0), C.c_int(0)
+        self.ctx._check(lib().vxs_factor_counts(self._p, C.byref(v), C.byref(e), C.byref(w)))
+        return v.value, e.value, w.value
+
+    @property
+    def win_size(self):
+        return self.counts()[2]
+
+    def push_voxels(self, entry_ptr, entry_frame, entry_cluster10, eig12, sum10, fix10=None, coe=None):
+        ptr = np.ascontiguousarray(entry_ptr, dtype=np.int64)
+        fr = np.ascontiguousarray(entry_frame, dtype=np.int32)
+        cl, e, s = _f64(entry_cluster10), _f64(eig12), _f64(sum10)
+        fx = _f64(fix10) if fix10 is not None else None
+        co = _f64(coe) if coe is not None else None
+        self.ctx._check(lib().vxs_factor_push_voxels(self._p, C.c_int64(ptr.shape[0] - 1), ptr.ctypes.data_as(C.POINTER(C.c_int64)), fr.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                     _dp(cl), _dp(fx), _dp(co), _dp(e), _dp(s)))
+
+    def push_voxels_raw(self, n_vox, ptr_p, frame_p, cl_p, fix_p, coe_p, eig_p, sum_p):
+        """Raw-pointer variant (pinned buffers from vxs_host_alloc) used by bench.py's end-to-end leg."""
+        self.ctx._check(lib().vxs_factor_push_voxels(self._p, C.c_int64(n_vox), ptr_p, frame_p, cl_p, fix_p, coe_p, eig_p, sum_p))
+
+    def push_voxels_dense(self, clusters10, eig12, sum10, fix10=None, coe=None):
+        cl, e, s = _f64(clusters10), _f64(eig12), _f64(sum10)
+        n = e.reshape(-1, 12).shape[0]
+        fx = _f64(fix10) if fix10 is not None else None
+        co = _f64(coe) if coe is not None else None
+        self.ctx._check(lib().vxs_factor_push_voxels_dense(self._p, C.c_int64(n), _dp(cl), _dp(fx), _dp(co), _dp(e), _dp(s)))
+
+    def read_back(self):
+        v = self.counts()[0]
+        eig, s = np.zeros((v, 12)), np.zeros((v, 10))
+        self.ctx._check(lib().vxs_factor_read_back(self._p, _dp(eig), _dp(s)))
+        return eig, s
+
+    def read_structure(self):
+        v, e, _ = self.counts()
+        ptr = np.zeros(v + 1, dtype=np.int64)
+        fr = np.zeros(e, dtype=np.int32)
+        cl, fx, co = np.zeros((e, 10)), np.zeros((v, 10)), np.zeros(v)
+        self.ctx._check(lib().vxs_factor_read_structure(self._p, ptr.ctypes.data_as(C.POINTER(C.c_int64)), fr.ctypes.data_as(C.POINTER(C.c_int32)), _dp(cl), _dp(fx), _dp(co)))
+        return ptr, fr, cl, fx, co
+
+
+def host_alloc(nbytes):
+    p = C.c_void_p()
+    rc = lib().vxs_host_alloc(C.byref(p), C.c_uint64(nbytes))
+    if rc != 0:
+        raise VxsError(rc, "vxs_host_alloc")
+    return p
+
+
+def host_free(p):
+    lib().vxs_host_free(p)
+
+
+_PINNED = []
+
+
+def pinned_array(shape, dtype):
+    """numpy view over pinned (page-locked) host memory."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape))
+    p = host_alloc(max(n * dtype.itemsize, 16))
+    buf = (C.c_char * (n * dtype.itemsize)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+    _PINNED.append(p)  # freed at interpreter exit
+    return arr

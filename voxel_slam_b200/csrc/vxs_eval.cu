@@ -1,0 +1,520 @@
+// LidarFactor evaluation kernels (sm_100a): evaluate_only_residual and acc_evaluate2 of the reference
+// (voxel_map.hpp:243-279, 132-241), re-designed for the GPU:
+//
+//   k_cluster_sum   sub-warp group per voxel, lanes over the voxel's CSR entries; coalesced SoA fp64 loads of the clusters,
+//                   pose gather through the read-only path, cluster transform in registers, shuffle reduction of the
+//                   10 sums, one SoA store per voxel.                                      HBM-bound: (k+1)*80 B / voxel
+//   k_eig_residual  thread per voxel: covariance + fp64 Jacobi eigensolve, SoA store of (lambda,U); deterministic
+//                   two-level reduction of sum coe*lambda0 ("last block" pattern).         176 B / voxel
+//   k_jac           group per voxel, lane per entry: g_i, D_i and the three scaled rank-1 rows x^m_i,
+//                   rows stored for the SYRK, g/D accumulated with fp64 RED.                 k*80+176 B read, k*144 B written / voxel
+//   k_syrk          H -= X^T X over frame pairs: CTA tile 16x16 frames, each thread two 6x6 blocks (72 fp64 accumulators),
+//                   warp tile 8x8 frames so every shared-memory read is a broadcast/128-B wavefront; rows staged with
+//                   cp.async (zero-fill beyond W), 3-stage pipeline; split over voxel chunks, fp64 RED epilogue.
+//                   fp64-FMA bound for k >~ 4.
+//   k_pairs         sparse windows (k << W, top-level global BA): group per voxel, block pairs straight to RED.
+//   k_assemble      dense n x n system from the block accumulators (+ the CPU-evaluated IMU 30x30 blocks), mirror of the lower triangle.
+#include <algorithm>
+#include "vxs_internal.h"
+#include "vxs_math.cuh"
+
+using namespace vxs;
+
+struct FactorView {
+  const int32_t* ptr; const int32_t* frame;
+  const double* cl; size_t Ecap;
+  const double* fix; const double* coe;
+  double* eig; double* sum; size_t Vcap;
+  int V; int W; int has_fix;
+};
+static FactorView make_view(const vxs_factor* f) {
+  FactorView v;
+  v.ptr = f->ptr; v.frame = f->frame; v.cl = f->cl; v.Ecap = f->Ecap; v.fix = f->fix; v.coe = f->coe; v.eig = f->eig; v.sum = f->sum;
+  v.Vcap = f->Vcap; v.V = int(f->V); v.W = f->W; v.has_fix = f->has_fix ? 1 : 0;
+  return v;
+}
+
+__device__ __forceinline__ cluster load_cluster_soa(const double* __restrict__ base, size_t stride, size_t i) {
+  cluster c;
+  c.P.xx = __ldg(base + i); c.P.xy = __ldg(base + stride + i); c.P.xz = __ldg(base + 2 * stride + i);
+  c.P.yy = __ldg(base + 3 * stride + i); c.P.yz = __ldg(base + 4 * stride + i); c.P.zz = __ldg(base + 5 * stride + i);
+  c.v.x = __ldg(base + 6 * stride + i); c.v.y = __ldg(base + 7 * stride + i); c.v.z = __ldg(base + 8 * stride + i);
+  c.n = __ldg(base + 9 * stride + i);
+  return c;
+}
+__device__ __forceinline__ void load_pose(const double* __restrict__ poses, int stride, int fr, rot3& R, d3& t) {
+  const double* p = poses + size_t(fr) * stride;
+  R.r00 = __ldg(p); R.r01 = __ldg(p + 1); R.r02 = __ldg(p + 2); R.r10 = __ldg(p + 3); R.r11 = __ldg(p + 4); R.r12 = __ldg(p + 5);
+  R.r20 = __ldg(p + 6); R.r21 = __ldg(p + 7); R.r22 = __ldg(p + 8);
+  t = mk3(__ldg(p + 9), __ldg(p + 10), __ldg(p + 11));
+}
+
+// ------------------------------------------------------------------ residual: transform + sum
+template <int G>
+__global__ void __launch_bounds__(256) k_cluster_sum(FactorView f, const double* __restrict__ poses, int pstride) {
+  const int lane = threadIdx.x & (G - 1);
+  const int group = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+  const int ngroups = (gridDim.x * blockDim.x) / G;
+  const int iters = (f.V + ngroups - 1) / ngroups;
+  for (int it = 0; it < iters; it++) {
+    const int v = group + it * ngroups;
+    const bool valid = v < f.V;
+    int beg = 0, end = 0;
+    if (valid) { beg = f.ptr[v]; end = f.ptr[v + 1]; }
+    cluster acc;
+    acc.P.xx = acc.P.xy = acc.P.xz = acc.P.yy = acc.P.yz = acc.P.zz = 0.0; acc.v = mk3(0, 0, 0); acc.n = 0.0;
+    for (int e = beg + lane; e < end; e += G) {
+      cluster c = load_cluster_soa(f.cl, f.Ecap, size_t(e));
+      rot3 R; d3 t;
+      load_pose(poses, pstride, __ldg(f.frame + e), R, t);
+      cluster_transform_acc(c, R, t, acc);
+    }
+#pragma unroll
+    for (int off = G / 2; off > 0; off >>= 1) {
+      acc.P.xx += __shfl_xor_sync(0xffffffffu, acc.P.xx, off); acc.P.xy += __shfl_xor_sync(0xffffffffu, acc.P.xy, off);
+      acc.P.xz += __shfl_xor_sync(0xffffffffu, acc.P.xz, off); acc.P.yy += __shfl_xor_sync(0xffffffffu, acc.P.yy, off);
+      acc.P.yz += __shfl_xor_sync(0xffffffffu, acc.P.yz, off); acc.P.zz += __shfl_xor_sync(0xffffffffu, acc.P.zz, off);
+      acc.v.x += __shfl_xor_sync(0xffffffffu, acc.v.x, off); acc.v.y += __shfl_xor_sync(0xffffffffu, acc.v.y, off);
+      acc.v.z += __shfl_xor_sync(0xffffffffu, acc.v.z, off); acc.n += __shfl_xor_sync(0xffffffffu, acc.n, off);
+    }
+    if (valid && lane == 0) {
+      if (f.has_fix) {  // PointCluster sig = sig_vecs[a]  (voxel_map.hpp:255)
+        cluster fx = load_cluster_soa(f.fix, f.Vcap, size_t(v));
+        acc.P.xx += fx.P.xx; acc.P.xy += fx.P.xy; acc.P.xz += fx.P.xz; acc.P.yy += fx.P.yy; acc.P.yz += fx.P.yz; acc.P.zz += fx.P.zz;
+        acc.v = acc.v + fx.v; acc.n += fx.n;
+      }
+      double* s = f.sum + v; const size_t st = f.Vcap;
+      s[0] = acc.P.xx; s[st] = acc.P.xy; s[2 * st] = acc.P.xz; s[3 * st] = acc.P.yy; s[4 * st] = acc.P.yz; s[5 * st] = acc.P.zz;
+      s[6 * st] = acc.v.x; s[7 * st] = acc.v.y; s[8 * st] = acc.v.z; s[9 * st] = acc.n;
+    }
+  }
+}
+
+// deterministic block + grid reduction of one double per thread; result[0] written by the last block
+__device__ __forceinline__ void block_grid_sum(double val, double* partial, unsigned int* counter, double* result) {
+  __shared__ double sh[256];
+  __shared__ bool is_last;
+  const int tid = threadIdx.x;
+  sh[tid] = val;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) { if (tid < s) sh[tid] += sh[tid + s]; __syncthreads(); }
+  if (tid == 0) {
+    partial[blockIdx.x] = sh[0];
+    __threadfence();
+    unsigned int t = atomicAdd(counter, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    double a = 0.0;
+    for (unsigned int i = tid; i < gridDim.x; i += blockDim.x) a += __ldcg(partial + i);
+    sh[tid] = a;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) { if (tid < s) sh[tid] += sh[tid + s]; __syncthreads(); }
+    if (tid == 0) { result[0] = sh[0]; *counter = 0u; }
+  }
+}
+
+// RECOMPUTE = true : evaluate_only_residual tail (voxel_map.hpp:264-276): cov, eigensolve, cache, r += coe*lambda0
+// RECOMPUTE = false: residual += coe * lmbd[kk] of acc_evaluate2 (voxel_map.hpp:234) from the cached eigenvalues
+template <bool RECOMPUTE>
+__global__ void __launch_bounds__(256) k_eig_residual(FactorView f, double* partial, unsigned int* counter, double* result) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  double contrib = 0.0;
+  if (v < f.V) {
+    const size_t st = f.Vcap;
+    double lam0;
+    if (RECOMPUTE) {
+      cluster s = load_cluster_soa(f.sum, st, size_t(v));
+      sym3 C = cov_from_sum(s);
+      double w[3]; d3 u0, u1, u2;
+      eig3_jacobi(C, w, u0, u1, u2);
+      double* e = f.eig + v;
+      e[0] = w[0]; e[st] = w[1]; e[2 * st] = w[2];
+      e[3 * st] = u0.x; e[4 * st] = u1.x; e[5 * st] = u2.x;
+      e[6 * st] = u0.y; e[7 * st] = u1.y; e[8 * st] = u2.y;
+      e[9 * st] = u0.z; e[10 * st] = u1.z; e[11 * st] = u2.z;
+      lam0 = w[0];
+    } else {
+      lam0 = f.eig[v];
+    }
+    contrib = f.coe[v] * lam0;
+  }
+  block_grid_sum(contrib, partial, counter, result);
+}
+
+// ------------------------------------------------------------------ Hessian part 1: per-entry Jacobian rows
+__device__ __forceinline__ void store_zero_rows(double* dst, int nframes) {
+  double2* p = reinterpret_cast<double2*>(dst);
+  for (int i = 0; i < nframes * 9; i++) p[i] = make_double2(0.0, 0.0);
+}
+
+template <int G, bool DENSE>
+__global__ void __launch_bounds__(128) k_jac(FactorView f, const double* __restrict__ poses, int pstride, double* __restrict__ X, double* __restrict__ gD) {
+  const int lane = threadIdx.x & (G - 1);
+  const int group = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+  const int ngroups = (gridDim.x * blockDim.x) / G;
+  const int W = f.W;
+  double* gbuf = gD;
+  double* Dbuf = gD + size_t(W) * 6;
+  for (int v = group; v < f.V; v += ngroups) {
+    const int beg = f.ptr[v], end = f.ptr[v + 1];
+    if (DENSE && beg == end && lane == 0) store_zero_rows(X + size_t(v) * W * 18, W);
+    if (beg + lane >= end) continue;
+    const size_t st = f.Vcap;
+    const double* e = f.eig + v;
+    double lam[3] = {__ldg(e), __ldg(e + st), __ldg(e + 2 * st)};
+    d3 u0 = mk3(__ldg(e + 3 * st), __ldg(e + 6 * st), __ldg(e + 9 * st));
+    d3 u1 = mk3(__ldg(e + 4 * st), __ldg(e + 7 * st), __ldg(e + 10 * st));
+    d3 u2 = mk3(__ldg(e + 5 * st), __ldg(e + 8 * st), __ldg(e + 11 * st));
+    const double* s = f.sum + v;
+    d3 sv = mk3(__ldg(s + 6 * st), __ldg(s + 7 * st), __ldg(s + 8 * st));
+    const double NN = __ldg(s + 9 * st);
+    const voxel_consts kc = make_voxel_consts(lam, u0, u1, u2, sv, NN, __ldg(f.coe + v));
+    for (int en = beg + lane; en < end; en += G) {
+      cluster c = load_cluster_soa(f.cl, f.Ecap, size_t(en));
+      const int fr = __ldg(f.frame + en);
+      rot3 R; d3 t;
+      load_pose(poses, pstride, fr, R, t);
+      entry_out o;
+      entry_jacobian(kc, c, R, t, o);
+      double* xd = DENSE ? X + (size_t(v) * W + fr) * 18 : X + size_t(en) * 18;
+      double2* x2 = reinterpret_cast<double2*>(xd);
+#pragma unroll
+      for (int i = 0; i < 9; i++) x2[i] = make_double2(o.x[2 * i], o.x[2 * i + 1]);
+      if (DENSE) {  // zero the slots of frames that do not observe this voxel
+        const int prev = (en > beg) ? __ldg(f.frame + en - 1) : -1;
+        if (fr - prev > 1) store_zero_rows(X + (size_t(v) * W + prev + 1) * 18, fr - prev - 1);
+        if (en == end - 1 && fr < W - 1) store_zero_rows(X + (size_t(v) * W + fr + 1) * 18, W - 1 - fr);
+      }
+      double* g = gbuf + fr * 6;
+#pragma unroll
+      for (int i = 0; i < 6; i++) atomicAdd(g + i, kc.coe * o.g[i]);
+      double* D = Dbuf + fr * 24;
+#pragma unroll
+      for (int i = 0; i < 9; i++) atomicAdd(D + i, o.Drr[i]);
+#pragma unroll
+      for (int i = 0; i < 9; i++) atomicAdd(D + 9 + i, o.Drt[i]);
+#pragma unroll
+      for (int i = 0; i < 6; i++) atomicAdd(D + 18 + i, o.Dtt[i]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ Hessian part 2a: sparse windows, block pairs -> RED
+template <int G>
+__global__ void __launch_bounds__(128) k_pairs(FactorView f, const double* __restrict__ X, double* __restrict__ C) {
+  const int lane = threadIdx.x & (G - 1);
+  const int group = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+  const int ngroups = (gridDim.x * blockDim.x) / G;
+  const int nl = f.W * 6;
+  for (int v = group; v < f.V; v += ngroups) {
+    const int beg = f.ptr[v], k = f.ptr[v + 1] - beg;
+    const int total = k * k * 36;
+    for (int idx = lane; idx < total; idx += G) {
+      const int a = idx / (36 * k), rem = idx - a * 36 * k, b = rem / 36, el = rem - b * 36;
+      if (b < a) continue;
+      const int r = el / 6, c = el - r * 6;
+      const double* xa = X + size_t(beg + a) * 18 + r;
+      const double* xb = X + size_t(beg + b) * 18 + c;
+      const double val = xa[0] * xb[0] + xa[6] * xb[6] + xa[12] * xb[12];
+      const int fa = __ldg(f.frame + beg + a), fb = __ldg(f.frame + beg + b);
+      atomicAdd(C + size_t(6 * fb + c) * nl + 6 * fa + r, -val);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ Hessian part 2b: dense windows, SYRK over frame pairs
+#define SYRK_FT 16      // frames per CTA tile side
+#define SYRK_VB 4       // voxels per pipeline stage
+#define SYRK_STAGES 3
+#define SYRK_THREADS 128
+#define SYRK_PART (SYRK_FT * 18)                 // doubles per (voxel, part)
+#define SYRK_STAGE_DOUBLES (SYRK_VB * 2 * SYRK_PART)
+
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, bool pred) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  int sz = pred ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gsrc), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__global__ void __launch_bounds__(SYRK_THREADS, 2) k_syrk(const double* __restrict__ X, double* __restrict__ C, int V, int W, int ntiles, int NG, int vox_per_chunk) {
+  extern __shared__ __align__(16) double smem[];
+  const int tile = blockIdx.x % ntiles, chunk = blockIdx.x / ntiles;
+  // decode tile -> (I,J), I <= J
+  int I = 0, rem = tile;
+  while (rem >= NG - I) { rem -= NG - I; I++; }
+  const int J = I + rem;
+  const int v_begin = chunk * vox_per_chunk, v_end = min(V, v_begin + vox_per_chunk);
+  if (v_begin >= v_end) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wy = warp >> 1, wx = warp & 1;
+  const int li0 = wy * 8 + (lane >> 3), li1 = li0 + 4, lj = wx * 8 + (lane & 7);   // local frame indices within the tile
+  const int fi0 = I * SYRK_FT + li0, fi1 = I * SYRK_FT + li1, fj = J * SYRK_FT + lj;
+  // warp-uniform skip: unit entirely below the diagonal of a diagonal tile, or entirely in the padding
+  const bool warp_active = !((I == J) && (wy > wx)) && (I * SYRK_FT + wy * 8 < W) && (J * SYRK_FT + wx * 8 < W);
+
+  double acc0[36], acc1[36];
+#pragma unroll
+  for (int i = 0; i < 36; i++) { acc0[i] = 0.0; acc1[i] = 0.0; }
+
+  const int nsteps = (v_end - v_begin + SYRK_VB - 1) / SYRK_VB;
+  const size_t rowW = size_t(W) * 18;
+  // chunks of 16 B per stage: VB voxels x 2 parts x (FT*18/2) double2
+  constexpr int CH_PER_PART = SYRK_PART / 2;            // 144
+  constexpr int CH_PER_STAGE = SYRK_VB * 2 * CH_PER_PART;
+  auto issue = [&](int step) {
+    double* sbase = smem + size_t(step % SYRK_STAGES) * SYRK_STAGE_DOUBLES;
+    const int v0 = v_begin + step * SYRK_VB;
+    for (int ch = tid; ch < CH_PER_STAGE; ch += SYRK_THREADS) {
+      const int vb = ch / (2 * CH_PER_PART), r2 = ch - vb * 2 * CH_PER_PART, part = r2 / CH_PER_PART, off2 = r2 - part * CH_PER_PART;
+      const int fr_local = off2 / 9;                     // 9 double2 per frame
+      const int gframe = (part == 0 ? I : J) * SYRK_FT + fr_local;
+      const int v = v0 + vb;
+      const bool ok = (v < v_end) && (gframe < W);
+      const double* src = X + size_t(ok ? v : v_begin) * rowW + size_t(ok ? gframe : 0) * 18 + size_t(off2 - fr_local * 9) * 2;
+      cp_async16_zfill(sbase + (size_t(vb) * 2 + part) * SYRK_PART + size_t(off2) * 2, src, ok);
+    }
+  };
+  for (int s = 0; s < SYRK_STAGES - 1; s++) { if (s < nsteps) issue(s); cp_async_commit(); }
+  for (int step = 0; step < nsteps; step++) {
+    cp_async_wait<SYRK_STAGES - 2>();
+    __syncthreads();
+    if (step + SYRK_STAGES - 1 < nsteps) issue(step + SYRK_STAGES - 1);
+    cp_async_commit();
+    if (warp_active) {
+      const double* sbase = smem + size_t(step % SYRK_STAGES) * SYRK_STAGE_DOUBLES;
+#pragma unroll
+      for (int vb = 0; vb < SYRK_VB; vb++) {
+        const double* A = sbase + size_t(vb) * 2 * SYRK_PART;
+        const double* B = A + SYRK_PART;
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+          const double2* pa0 = reinterpret_cast<const double2*>(A + li0 * 18 + m * 6);
+          const double2* pa1 = reinterpret_cast<const double2*>(A + li1 * 18 + m * 6);
+          const double2* pb = reinterpret_cast<const double2*>(B + lj * 18 + m * 6);
+          double a0[6], a1[6], b[6];
+#pragma unroll
+          for (int q = 0; q < 3; q++) {
+            double2 t0 = pa0[q], t1 = pa1[q], tb = pb[q];
+            a0[2 * q] = t0.x; a0[2 * q + 1] = t0.y; a1[2 * q] = t1.x; a1[2 * q + 1] = t1.y; b[2 * q] = tb.x; b[2 * q + 1] = tb.y;
+          }
+#pragma unroll
+          for (int r = 0; r < 6; r++)
+#pragma unroll
+            for (int c = 0; c < 6; c++) { acc0[r * 6 + c] = fma(a0[r], b[c], acc0[r * 6 + c]); acc1[r * 6 + c] = fma(a1[r], b[c], acc1[r * 6 + c]); }
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+  // epilogue: H_ij -= sum x_i x_j^T for i <= j
+  const int nl = W * 6;
+  if (warp_active && fj < W) {
+    if (fi0 < W && fi0 <= fj) {
+#pragma unroll
+      for (int r = 0; r < 6; r++)
+#pragma unroll
+        for (int c = 0; c < 6; c++) atomicAdd(C + size_t(6 * fj + c) * nl + 6 * fi0 + r, -acc0[r * 6 + c]);
+    }
+    if (fi1 < W && fi1 <= fj) {
+#pragma unroll
+      for (int r = 0; r < 6; r++)
+#pragma unroll
+        for (int c = 0; c < 6; c++) atomicAdd(C + size_t(6 * fj + c) * nl + 6 * fi1 + r, -acc1[r * 6 + c]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ dense system assembly
+// H (n x n col-major) from the lidar block accumulator C (upper block triangle), block-diagonal D, gradient g, and the
+// host-evaluated IMU part (already summed over factors, unscaled).  S = dofs per frame (6 or 15); rows >= W*S are the gravity dofs.
+// Mirrors hess_plus (voxel_map.hpp:455-463) + "Hess.block(6i,6j) = Hess.block(6j,6i)^T" (voxel_map.hpp:237-239).
+__global__ void k_assemble(const double* __restrict__ C, const double* __restrict__ gD, const double* __restrict__ blocks, const double* __restrict__ gvec, int bs,
+                           double imu_coef, int W, int S, int n, double* __restrict__ H, double* __restrict__ jact) {
+  const size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= size_t(n) * n) return;
+  const int row = int(idx % n), col = int(idx / n);
+  const int nl = 6 * W, nfs = W * S;
+  const double* Dbuf = gD + size_t(W) * 6;
+  double val = 0.0;
+  if (row < nfs && col < nfs) {
+    const int fi = row / S, a = row - fi * S, fj = col / S, b = col - fj * S;
+    if (a < 6 && b < 6) {
+      if (fi < fj) val = C[size_t(6 * fj + b) * nl + 6 * fi + a];
+      else if (fi > fj) val = C[size_t(6 * fi + a) * nl + 6 * fj + b];
+      else {
+        val = C[size_t(6 * fi + b) * nl + 6 * fi + a];
+        const double* D = Dbuf + fi * 24;
+        if (a < 3 && b < 3) val += D[3 * a + b];
+        else if (a < 3) val += D[9 + 3 * a + (b - 3)];
+        else if (b < 3) val += D[9 + 3 * b + (a - 3)];
+        else {
+          const int p = a - 3, q = b - 3, lo = p < q ? p : q, hi = p < q ? q : p;
+          val += D[18 + (lo == 0 ? hi : (lo == 1 ? 2 + hi : 5))];
+        }
+      }
+    }
+  }
+  if (blocks) {  // IMU factor i couples frames (i, i+1) [and the 3 gravity dofs]: voxel_map.hpp:493-499 / 701-712, then *= imu_coef
+    const size_t bb = size_t(bs) * bs;
+    double imu = 0.0;
+    const bool rg = row >= nfs, cg = col >= nfs;
+    if (!rg && !cg) {
+      const int fi = row / S, a = row - fi * S, fj = col / S, b = col - fj * S;
+      if (fi == fj) {
+        if (fi >= 1) imu += blocks[size_t(fi - 1) * bb + size_t(15 + b) * bs + 15 + a];
+        if (fi <= W - 2) imu += blocks[size_t(fi) * bb + size_t(b) * bs + a];
+      } else if (fi + 1 == fj) imu += blocks[size_t(fi) * bb + size_t(15 + b) * bs + a];
+      else if (fj + 1 == fi) imu += blocks[size_t(fj) * bb + size_t(b) * bs + 15 + a];
+    } else if (rg && cg) {
+      for (int i = 0; i < W - 1; i++) imu += blocks[size_t(i) * bb + size_t(30 + col - nfs) * bs + 30 + row - nfs];
+    } else if (rg) {
+      const int fj = col / S, b = col - fj * S, lr = 30 + row - nfs;
+      if (fj >= 1) imu += blocks[size_t(fj - 1) * bb + size_t(15 + b) * bs + lr];
+      if (fj <= W - 2) imu += blocks[size_t(fj) * bb + size_t(b) * bs + lr];
+    } else {
+      const int fi = row / S, a = row - fi * S, lc = 30 + col - nfs;
+      if (fi >= 1) imu += blocks[size_t(fi - 1) * bb + size_t(lc) * bs + 15 + a];
+      if (fi <= W - 2) imu += blocks[size_t(fi) * bb + size_t(lc) * bs + a];
+    }
+    val += imu_coef * imu;
+  }
+  H[idx] = val;
+  if (col == 0) {
+    double g = 0.0;
+    if (row < nfs) { const int fi = row / S, a = row - fi * S; if (a < 6) g = gD[fi * 6 + a]; }
+    if (gvec) {
+      double gi = 0.0;
+      if (row < nfs) {
+        const int fi = row / S, a = row - fi * S;
+        if (fi >= 1) gi += gvec[size_t(fi - 1) * bs + 15 + a];
+        if (fi <= W - 2) gi += gvec[size_t(fi) * bs + a];
+      } else {
+        for (int i = 0; i < W - 1; i++) gi += gvec[size_t(i) * bs + 30 + row - nfs];
+      }
+      g += imu_coef * gi;
+    }
+    jact[row] = g;
+  }
+}
+
+// ------------------------------------------------------------------ host drivers
+static inline unsigned nblk(size_t n, unsigned b) { return unsigned((n + b - 1) / b); }
+static int pick_group(const vxs_factor* f) {
+  const double avg = f->V > 0 ? double(f->E) / double(f->V) : 1.0;
+  return avg > 16.0 ? 32 : (avg > 8.0 ? 16 : 8);
+}
+
+// layout of the all-reducible accumulator block: [ C (6W)^2 | g 6W | D 24W | r1 ]
+static size_t hess_block_doubles(int W) { return size_t(6 * W) * size_t(6 * W) + size_t(30) * W + 1; }
+
+int vxs_eval_residual_dev(vxs_ctx* ctx, vxs_factor* f, const double* poses_dev, int pstride, double* residual_dev) {
+  if (f->V == 0) { VXS_CUDA(ctx, cudaMemsetAsync(residual_dev, 0, 8, ctx->stream)); return VXS_OK; }
+  FactorView fv = make_view(f);
+  const int G = pick_group(f);
+  const unsigned blocks_v = nblk(size_t(f->V), 256);
+  VXS_CUDA(ctx, f->partial.reserve(blocks_v));
+  if (!f->counter.p) { VXS_CUDA(ctx, f->counter.reserve(4)); VXS_CUDA(ctx, cudaMemsetAsync(f->counter.p, 0, 16, ctx->stream)); }
+  {
+    const size_t groups_needed = size_t(f->V);
+    unsigned grid = unsigned(std::min<size_t>((groups_needed * G + 255) / 256, size_t(ctx->sm_count) * 8));
+    if (G == 32) { auto kp = k_cluster_sum<32>; VXS_LAUNCH(ctx, "k_cluster_sum", kp, grid, 256, 0, fv, poses_dev, pstride); }
+    else if (G == 16) { auto kp = k_cluster_sum<16>; VXS_LAUNCH(ctx, "k_cluster_sum", kp, grid, 256, 0, fv, poses_dev, pstride); }
+    else { auto kp = k_cluster_sum<8>; VXS_LAUNCH(ctx, "k_cluster_sum", kp, grid, 256, 0, fv, poses_dev, pstride); }
+  }
+  { auto kp = k_eig_residual<true>; VXS_LAUNCH(ctx, "k_eig_residual", kp, blocks_v, 256, 0, fv, f->partial.p, f->counter.p, residual_dev); }
+  if (ctx->nranks > 1) return vxs_comm_allreduce(ctx, residual_dev, 1);
+  return VXS_OK;
+}
+
+// Builds C / g / D / r1 in f->C (layout above).  Dense windows go through the SYRK, sparse ones through k_pairs.
+int vxs_eval_hessian_dev(vxs_ctx* ctx, vxs_factor* f, const double* poses_dev, int pstride, double* /*unused*/) {
+  const int W = f->W;
+  const size_t nl = size_t(6) * W, tot = hess_block_doubles(W);
+  VXS_CUDA(ctx, f->C.reserve(tot));
+  double* C = f->C.p; double* gD = C + nl * nl; double* r1 = gD + size_t(30) * W;
+  VXS_CUDA(ctx, cudaMemsetAsync(C, 0, tot * 8, ctx->stream));
+  if (f->V > 0) {
+    FactorView fv = make_view(f);
+    const int G = pick_group(f);
+    // dense-slot rows when the window is reasonably covered (SURVEY §5 "long-context" row): V*W*144 B vs E*144 B
+    const bool dense = (double(f->V) * W <= 4.0 * double(f->E)) && (double(f->V) * W * 144.0 <= 24e9);
+    const size_t xdoubles = dense ? size_t(f->V) * W * 18 : size_t(f->E) * 18;
+    VXS_CUDA(ctx, f->X.reserve(xdoubles));
+    const unsigned blocks_v = nblk(size_t(f->V), 256);
+    VXS_CUDA(ctx, f->partial.reserve(blocks_v));
+    if (!f->counter.p) { VXS_CUDA(ctx, f->counter.reserve(4)); VXS_CUDA(ctx, cudaMemsetAsync(f->counter.p, 0, 16, ctx->stream)); }
+    unsigned grid = unsigned(std::min<size_t>((size_t(f->V) * G + 127) / 128, size_t(ctx->sm_count) * 16));
+#define LAUNCH_JAC(GG, DD) { auto kp = k_jac<GG, DD>; VXS_LAUNCH(ctx, "k_jac", kp, grid, 128, 0, fv, poses_dev, pstride, f->X.p, gD); }
+    if (dense) { if (G == 32) LAUNCH_JAC(32, true) else if (G == 16) LAUNCH_JAC(16, true) else LAUNCH_JAC(8, true) }
+    else { if (G == 32) LAUNCH_JAC(32, false) else if (G == 16) LAUNCH_JAC(16, false) else LAUNCH_JAC(8, false) }
+#undef LAUNCH_JAC
+    if (dense) {
+      const int NG = (W + SYRK_FT - 1) / SYRK_FT, ntiles = NG * (NG + 1) / 2;
+      // enough chunks to fill the machine a few times over; tiles of one chunk are adjacent in launch order (L2 reuse of X)
+      int target_ctas = ctx->sm_count * 2 * 4;
+      int nchunks = std::max(1, std::min<int>((target_ctas + ntiles - 1) / ntiles, int((f->V + SYRK_VB * 8 - 1) / (SYRK_VB * 8))));
+      int vpc = int((f->V + nchunks - 1) / nchunks);
+      vpc = ((vpc + SYRK_VB - 1) / SYRK_VB) * SYRK_VB;
+      nchunks = int((f->V + vpc - 1) / vpc);
+      const size_t smem = size_t(SYRK_STAGES) * SYRK_STAGE_DOUBLES * 8;
+      VXS_CUDA(ctx, cudaFuncSetAttribute(k_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+      VXS_LAUNCH(ctx, "k_syrk", k_syrk, unsigned(nchunks * ntiles), SYRK_THREADS, smem, f->X.p, C, int(f->V), W, ntiles, NG, vpc);
+    } else {
+      if (G == 32) { auto kp = k_pairs<32>; VXS_LAUNCH(ctx, "k_pairs", kp, grid, 128, 0, fv, f->X.p, C); }
+      else if (G == 16) { auto kp = k_pairs<16>; VXS_LAUNCH(ctx, "k_pairs", kp, grid, 128, 0, fv, f->X.p, C); }
+      else { auto kp = k_pairs<8>; VXS_LAUNCH(ctx, "k_pairs", kp, grid, 128, 0, fv, f->X.p, C); }
+    }
+    { auto kp = k_eig_residual<false>; VXS_LAUNCH(ctx, "k_lambda_sum", kp, blocks_v, 256, 0, fv, f->partial.p, f->counter.p, r1); }
+  }
+  if (ctx->nranks > 1) return vxs_comm_allreduce(ctx, C, tot);
+  return VXS_OK;
+}
+
+// assemble into ctx->Hraw / ctx->jact (n = W*S + extra).  Himu/gimu device pointers or null.
+int vxs_assemble_dev(vxs_ctx* ctx, vxs_factor* f, int S, int n, const double* blocks, const double* gvec, int bs, double imu_coef) {
+  const int W = f->W;
+  const size_t nl = size_t(6) * W;
+  VXS_CUDA(ctx, ctx->Hraw.reserve(size_t(n) * n));
+  VXS_CUDA(ctx, ctx->jact.reserve(size_t(n)));
+  const double* C = f->C.p; const double* gD = C + nl * nl;
+  VXS_LAUNCH(ctx, "k_assemble", k_assemble, nblk(size_t(n) * n, 256), 256, 0, C, gD, blocks, gvec, bs, imu_coef, W, S, n, ctx->Hraw.p, ctx->jact.p);
+  return VXS_OK;
+}
+double* vxs_hess_r1_dev(vxs_factor* f) { return f->C.p + size_t(6 * f->W) * size_t(6 * f->W) + size_t(30) * f->W; }
+
+// ------------------------------------------------------------------ public evaluation entry points
+extern "C" int vxs_factor_evaluate_residual(vxs_ctx* ctx, vxs_factor* f, const double* poses12, double* residual) {
+  if (!ctx || !f || !poses12 || !residual || f->ctx != ctx) return VXS_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  const int W = f->W;
+  VXS_CUDA(ctx, ctx->states_a.reserve(size_t(W) * 24));
+  VXS_CUDA(ctx, cudaMemcpyAsync(ctx->states_a.p, poses12, size_t(W) * 12 * 8, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = vxs_eval_residual_dev(ctx, f, ctx->states_a.p, 12, ctx->scal.p);
+  if (rc) return rc;
+  VXS_CUDA(ctx, cudaMemcpyAsync(residual, ctx->scal.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  VXS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return VXS_OK;
+}
+
+extern "C" int vxs_factor_evaluate_hessian(vxs_ctx* ctx, vxs_factor* f, const double* poses12, double* hess, double* jact, double* residual) {
+  if (!ctx || !f || !poses12 || f->ctx != ctx) return VXS_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  const int W = f->W, n = 6 * W;
+  VXS_CUDA(ctx, ctx->states_a.reserve(size_t(W) * 24));
+  VXS_CUDA(ctx, cudaMemcpyAsync(ctx->states_a.p, poses12, size_t(W) * 12 * 8, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = vxs_eval_hessian_dev(ctx, f, ctx->states_a.p, 12, nullptr);
+  if (rc) return rc;
+  rc = vxs_assemble_dev(ctx, f, 6, n, nullptr, nullptr, 0, 0.0);
+  if (rc) return rc;
+  if (hess) VXS_CUDA(ctx, cudaMemcpyAsync(hess, ctx->Hraw.p, size_t(n) * n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (jact) VXS_CUDA(ctx, cudaMemcpyAsync(jact, ctx->jact.p, size_t(n) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (residual) VXS_CUDA(ctx, cudaMemcpyAsync(residual, vxs_hess_r1_dev(f), 8, cudaMemcpyDeviceToHost, ctx->stream));
+  VXS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return VXS_OK;
+}

@@ -1,0 +1,132 @@
+// Internal structures of libvxs (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/vxs.h"
+
+#define VXS_SM_COUNT_FALLBACK 148
+
+struct vxs_stage {
+  const char* name;
+  double ms_total;
+  int64_t calls;
+};
+struct vxs_pending_event {
+  int stage;
+  cudaEvent_t a, b;
+};
+
+template <typename T>
+struct DevBuf {  // grow-only device buffer
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc((void**)&p, n * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct vxs_ctx {
+  int device = 0;
+  int sm_count = VXS_SM_COUNT_FALLBACK;
+  cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copy = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  // timing
+  bool timing = false;
+  std::vector<vxs_stage> stages;
+  std::vector<vxs_pending_event> pending;
+  std::vector<cudaEvent_t> event_pool;
+  // NCCL
+  void* comm = nullptr;
+  int rank = 0, nranks = 1;
+  // solver scratch (n = system size)
+  DevBuf<double> Hraw, Mp, Lm, himu, gimu, jact, dvec, rhs, dx, dtmp, states_a, states_b;
+  DevBuf<int> perm;
+  DevBuf<double> scal;   // small scalar slots on device
+  DevBuf<int> flags;
+  DevBuf<double> stage;   // H2D/D2H staging for AoS<->SoA conversion
+  DevBuf<int64_t> stage_i64;
+  // pinned host staging
+  double* h_pin = nullptr;
+  size_t h_pin_cap = 0;
+  // voxeliser scratch lives in vxs_voxelize.cu (opaque)
+  void* vox_scratch = nullptr;
+};
+
+struct vxs_factor {
+  vxs_ctx* ctx = nullptr;
+  int W = 0;
+  int64_t V = 0, E = 0;
+  size_t Vcap = 0, Ecap = 0;     // SoA strides
+  int32_t* ptr = nullptr;        // [Vcap+1]
+  int32_t* frame = nullptr;      // [Ecap]
+  int32_t* vox = nullptr;        // [Ecap] entry -> voxel
+  double* cl = nullptr;          // [10][Ecap] SoA clusters
+  double* fix = nullptr;         // [10][Vcap]
+  double* coe = nullptr;         // [Vcap]
+  double* eig = nullptr;         // [12][Vcap]
+  double* sum = nullptr;         // [10][Vcap]
+  bool has_fix = false;
+  // evaluation workspaces (sized lazily)
+  DevBuf<double> X;              // scaled rank-3 rows: dense-slot [V][W][18] or compact [E][18]
+  DevBuf<double> C;              // lidar Hessian accumulator, (6W)^2 column-major, upper block triangle
+  DevBuf<double> gD;             // [W][6] gradient + [W][24] block-diagonal remainder
+  DevBuf<double> partial;        // block partial sums for the residual
+  DevBuf<unsigned int> counter;
+};
+
+inline int vxs_fail(vxs_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) {
+  if (c) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s%s%s", what, e != cudaSuccess ? ": " : "", e != cudaSuccess ? cudaGetErrorString(e) : "");
+    c->err = buf;
+  }
+  return code;
+}
+#define VXS_CUDA(ctx, call)                                                   \
+  do {                                                                        \
+    cudaError_t _e = (call);                                                  \
+    if (_e != cudaSuccess) return vxs_fail((ctx), VXS_ERR_CUDA, #call, _e);   \
+  } while (0)
+
+int vxs_stage_id(vxs_ctx* c, const char* name);
+void vxs_stage_begin(vxs_ctx* c, int stage);
+void vxs_stage_end(vxs_ctx* c);
+
+// Launch a kernel on the ctx stream, count it, optionally bracket it with events under the given stage name.
+#define VXS_LAUNCH(ctx, stage_name_, kern, grid, block, smem, ...)                    \
+  do {                                                                               \
+    if ((ctx)->timing) vxs_stage_begin((ctx), vxs_stage_id((ctx), stage_name_));     \
+    kern<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                    \
+    (ctx)->launches++;                                                               \
+    if ((ctx)->timing) vxs_stage_end((ctx));                                         \
+    cudaError_t _le = cudaGetLastError();                                            \
+    if (_le != cudaSuccess) return vxs_fail((ctx), VXS_ERR_CUDA, stage_name_, _le);  \
+  } while (0)
+
+// factor internals shared between translation units
+int vxs_factor_reserve(vxs_factor* f, size_t Vneed, size_t Eneed);
+int vxs_factor_finish_push(vxs_factor* f);  // builds entry->voxel map, sets flags
+
+// evaluation (vxs_eval.cu): all device-side, results stay on device
+struct vxs_eval_out {
+  double* C;    // (6W)^2 lidar Hessian (upper block triangle valid, diag blocks full), column-major
+  double* gD;   // [W][6] g, then [W][24] D
+};
+int vxs_eval_residual_dev(vxs_ctx* ctx, vxs_factor* f, const double* poses_dev, int pose_stride, double* residual_dev);
+int vxs_eval_hessian_dev(vxs_ctx* ctx, vxs_factor* f, const double* poses_dev, int pose_stride, double* r1_dev);
+int vxs_comm_allreduce(vxs_ctx* ctx, double* buf, size_t n);
+
+// solver (vxs_solve.cu)
+int vxs_solve_damped(vxs_ctx* ctx, const double* Hraw, const double* jact, int n, int gauge, double u, double* dx_dev, double* D_dev, double* rhs_dev, int* singular_flag_host);

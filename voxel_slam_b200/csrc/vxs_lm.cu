@@ -1,0 +1,276 @@
+// Levenberg–Marquardt drivers of the reference, host-orchestrated over the CUDA kernels:
+//   Lidar_BA_Optimizer::damping_iter        voxel_map.hpp:367-442   -> vxs_lidar_ba
+//   LI_BA_Optimizer::damping_iter           voxel_map.hpp:562-653   -> vxs_li_ba(with_gravity = 0)
+//   LI_BA_OptimizerGravity::damping_iter    voxel_map.hpp:775-862   -> vxs_li_ba(with_gravity = 1)
+// Per iteration the GPU does Hessian build, assembly, damped LDL^T solve and the residual-only evaluation; the host does the
+// scalar accept/reject logic, the (tiny) state retraction x [+] dx and the IMU callbacks.  3n+1 doubles come back per
+// iteration; the factor, the Hessian and all workspaces stay in HBM.
+// Multi-GPU (voxel-sharded factor): [C | g | D | r1] is all-reduced once per Hessian build and r2 once per residual
+// evaluation (vxs_eval.cu); every rank then runs the identical replicated solve.
+#include <dlfcn.h>
+#include <math.h>
+#include <string.h>
+#include <vector>
+#include "vxs_internal.h"
+#include "vxs_math.cuh"
+
+using namespace vxs;
+
+int vxs_assemble_dev(vxs_ctx* ctx, vxs_factor* f, int S, int n, const double* blocks, const double* gvec, int bs, double imu_coef);
+double* vxs_hess_r1_dev(vxs_factor* f);
+
+// ------------------------------------------------------------------ NCCL (dlopen'ed: libvxs has no link-time dependency on it)
+typedef struct { char internal[128]; } vxs_nccl_uid;
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(vxs_nccl_uid*) = nullptr;
+  int (*CommInitRank)(void**, int, vxs_nccl_uid, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi* nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) { api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (api.lib) break; }
+    if (api.lib) {
+      api.GetUniqueId = (int (*)(vxs_nccl_uid*))dlsym(api.lib, "ncclGetUniqueId");
+      api.CommInitRank = (int (*)(void**, int, vxs_nccl_uid, int))dlsym(api.lib, "ncclCommInitRank");
+      api.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(api.lib, "ncclAllReduce");
+      api.CommDestroy = (int (*)(void*))dlsym(api.lib, "ncclCommDestroy");
+      api.GetErrorString = (const char* (*)(int))dlsym(api.lib, "ncclGetErrorString");
+      if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy) api.lib = nullptr;
+    }
+  }
+  return api.lib ? &api : nullptr;
+}
+extern "C" int vxs_comm_unique_id(unsigned char id[128]) {
+  NcclApi* a = nccl_api();
+  if (!a || !id) return VXS_ERR_COMM;
+  vxs_nccl_uid u;
+  if (a->GetUniqueId(&u) != 0) return VXS_ERR_COMM;
+  memcpy(id, u.internal, 128);
+  return VXS_OK;
+}
+extern "C" int vxs_ctx_comm_init(vxs_ctx* ctx, const unsigned char id[128], int rank, int nranks) {
+  if (!ctx || !id || rank < 0 || nranks < 1 || rank >= nranks) return VXS_ERR_ARG;
+  NcclApi* a = nccl_api();
+  if (!a) return vxs_fail(ctx, VXS_ERR_COMM, "libnccl.so.2 not loadable");
+  cudaSetDevice(ctx->device);
+  vxs_nccl_uid u; memcpy(u.internal, id, 128);
+  void* comm = nullptr;
+  int rc = a->CommInitRank(&comm, nranks, u, rank);
+  if (rc != 0) return vxs_fail(ctx, VXS_ERR_COMM, a->GetErrorString ? a->GetErrorString(rc) : "ncclCommInitRank failed");
+  ctx->comm = comm; ctx->rank = rank; ctx->nranks = nranks;
+  return VXS_OK;
+}
+extern "C" int vxs_ctx_comm_destroy(vxs_ctx* ctx) {
+  if (!ctx) return VXS_ERR_ARG;
+  if (ctx->comm) { NcclApi* a = nccl_api(); if (a) a->CommDestroy(ctx->comm); ctx->comm = nullptr; }
+  ctx->rank = 0; ctx->nranks = 1;
+  return VXS_OK;
+}
+int vxs_comm_allreduce(vxs_ctx* ctx, double* buf, size_t n) {
+  if (ctx->nranks <= 1) return VXS_OK;
+  NcclApi* a = nccl_api();
+  if (!a || !ctx->comm) return vxs_fail(ctx, VXS_ERR_COMM, "communicator not initialised");
+  if (ctx->timing) { vxs_stage_begin(ctx, vxs_stage_id(ctx, "nccl_allreduce")); }
+  int rc = a->AllReduce(buf, buf, n, /*ncclFloat64*/ 8, /*ncclSum*/ 0, ctx->comm, ctx->stream);
+  if (ctx->timing) vxs_stage_end(ctx);
+  if (rc != 0) return vxs_fail(ctx, VXS_ERR_COMM, a->GetErrorString ? a->GetErrorString(rc) : "ncclAllReduce failed");
+  return VXS_OK;
+}
+
+// ------------------------------------------------------------------ host-side state retraction
+// x_temp = x [+] dxi   (voxel_map.hpp:405-409, 599-606, 813-822);  state stride sst (12 or 24), dof stride dst (6 or 15)
+static void retract(const double* x, double* xt, const double* dxi, int W, int sst, int dst) {
+  for (int j = 0; j < W; j++) {
+    const double* s = x + size_t(j) * sst; double* o = xt + size_t(j) * sst; const double* d = dxi + size_t(j) * dst;
+    rot3 R = load_rot(s);
+    rot3 Rn = rot_mul(R, so3_exp(mk3(d[0], d[1], d[2])));
+    o[0] = Rn.r00; o[1] = Rn.r01; o[2] = Rn.r02; o[3] = Rn.r10; o[4] = Rn.r11; o[5] = Rn.r12; o[6] = Rn.r20; o[7] = Rn.r21; o[8] = Rn.r22;
+    for (int k = 0; k < 3; k++) o[9 + k] = s[9 + k] + d[3 + k];
+    if (dst == 15) for (int k = 0; k < 9; k++) o[12 + k] = s[12 + k] + d[6 + k];  // v, bg, ba
+  }
+}
+
+struct LmCommon {
+  vxs_ctx* ctx; vxs_factor* f;
+  int W, n, S, gauge, sst;
+  std::vector<double> x, xt, dx, D, rhs;
+};
+
+// one Hessian build on the device (+ optional IMU blocks already on the host), returns lidar r1 pointer on device
+static int build_hessian(LmCommon& c, const double* blocks_h, const double* gvec_h, int bs, double imu_coef) {
+  vxs_ctx* ctx = c.ctx;
+  VXS_CUDA(ctx, cudaMemcpyAsync(ctx->states_a.p, c.x.data(), c.x.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = vxs_eval_hessian_dev(ctx, c.f, ctx->states_a.p, c.sst, nullptr);
+  if (rc) return rc;
+  const double *bd = nullptr, *gd = nullptr;
+  if (blocks_h) {
+    const size_t nb = size_t(c.W - 1) * bs * bs, ng = size_t(c.W - 1) * bs;
+    VXS_CUDA(ctx, ctx->himu.reserve(nb + ng));
+    VXS_CUDA(ctx, cudaMemcpyAsync(ctx->himu.p, blocks_h, nb * 8, cudaMemcpyHostToDevice, ctx->stream));
+    VXS_CUDA(ctx, cudaMemcpyAsync(ctx->himu.p + nb, gvec_h, ng * 8, cudaMemcpyHostToDevice, ctx->stream));
+    bd = ctx->himu.p; gd = ctx->himu.p + nb;
+  }
+  return vxs_assemble_dev(ctx, c.f, c.S, c.n, bd, gd, bs, imu_coef);
+}
+
+// solve + bring dx, D, rhs (and one extra device scalar) back
+static int solve_and_fetch(LmCommon& c, double u, const double* extra_dev, double* extra_host, int* singular) {
+  vxs_ctx* ctx = c.ctx;
+  const int n = c.n;
+  VXS_CUDA(ctx, ctx->dx.reserve(size_t(n)));
+  VXS_CUDA(ctx, ctx->dvec.reserve(size_t(n)));
+  VXS_CUDA(ctx, ctx->rhs.reserve(size_t(n)));
+  int rc = vxs_solve_damped(ctx, ctx->Hraw.p, ctx->jact.p, n, c.gauge, u, ctx->dx.p, ctx->dvec.p, ctx->rhs.p, singular);
+  if (rc) return rc;
+  VXS_CUDA(ctx, cudaMemcpyAsync(c.dx.data(), ctx->dx.p, size_t(n) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  VXS_CUDA(ctx, cudaMemcpyAsync(c.D.data(), ctx->dvec.p, size_t(n) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  VXS_CUDA(ctx, cudaMemcpyAsync(c.rhs.data(), ctx->rhs.p, size_t(n) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (extra_dev) VXS_CUDA(ctx, cudaMemcpyAsync(extra_host, extra_dev, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  VXS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return VXS_OK;
+}
+
+static int lm_prepare(LmCommon& c) {
+  vxs_ctx* ctx = c.ctx;
+  cudaSetDevice(ctx->device);
+  VXS_CUDA(ctx, ctx->states_a.reserve(size_t(c.W) * 24));
+  VXS_CUDA(ctx, ctx->states_b.reserve(size_t(c.W) * 24));
+  c.dx.assign(c.n, 0.0); c.D.assign(c.n, 0.0); c.rhs.assign(c.n, 0.0);
+  return VXS_OK;
+}
+
+// ------------------------------------------------------------------ Lidar_BA_Optimizer::damping_iter
+extern "C" int vxs_lidar_ba(vxs_ctx* ctx, vxs_factor* f, double* poses12, int max_iter, int thd_num, double* hess_out, double resis[2],
+                            int* is_converge_out, vxs_lm_trace* trace, int trace_cap, int* trace_len) {
+  if (!ctx || !f || !poses12 || f->ctx != ctx || max_iter < 0) return VXS_ERR_ARG;
+  LmCommon c;
+  c.ctx = ctx; c.f = f; c.W = f->W; c.S = 6; c.n = 6 * f->W; c.gauge = 6; c.sst = 12;
+  int rc = lm_prepare(c);
+  if (rc) return rc;
+  const int W = c.W, n = c.n;
+  c.x.assign(poses12, poses12 + size_t(W) * 12);
+  c.xt = c.x;
+  double u = 0.01, v = 2, residual1 = 0, residual2 = 0, q;
+  bool is_calc_hess = true, is_converge = true;
+  int ntrace = 0, warn = 0, singular = 0;
+  if (trace_len) *trace_len = 0;
+  for (int i = 0; i < max_iter; i++) {
+    const bool built = is_calc_hess;
+    if (is_calc_hess) { rc = build_hessian(c, nullptr, nullptr, 0, 0.0); if (rc) return rc; }
+    rc = solve_and_fetch(c, u, built ? vxs_hess_r1_dev(f) : nullptr, &residual1, &singular);
+    if (rc) return rc;
+    if (singular) warn = VXS_WARN_SINGULAR;
+    if (i == 0 && resis) resis[0] = residual1;
+    retract(c.x.data(), c.xt.data(), c.dx.data(), W, 12, 6);
+    double q1 = 0;
+    for (int k = 0; k < n; k++) q1 += c.dx[k] * (u * c.D[k] * c.dx[k] + c.rhs[k]);   // rhs = -JacT (gauged)
+    q1 *= 0.5;
+    if (ctx->nranks == 1 && f->V < thd_num) return vxs_fail(ctx, VXS_ERR_TOO_FEW_VOXELS, "Too Less Voxel (voxel_map.hpp:345-348)");
+    VXS_CUDA(ctx, cudaMemcpyAsync(ctx->states_b.p, c.xt.data(), size_t(W) * 12 * 8, cudaMemcpyHostToDevice, ctx->stream));
+    rc = vxs_eval_residual_dev(ctx, f, ctx->states_b.p, 12, ctx->scal.p);
+    if (rc) return rc;
+    VXS_CUDA(ctx, cudaMemcpyAsync(&residual2, ctx->scal.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    VXS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    q = residual1 - residual2;
+    if (trace && ntrace < trace_cap) { vxs_lm_trace t = {residual1, residual2, u, v, q1, q > 0 ? 1 : 0, built ? 1 : 0}; trace[ntrace++] = t; }
+    if (q > 0) {
+      c.x = c.xt;
+      const double one_three = 1.0 / 3;
+      q = q / q1; v = 2; q = 1 - pow(2 * q - 1, 3);
+      u *= (q < one_three ? one_three : q);
+      is_calc_hess = true;
+    } else { u = u * v; v = 2 * v; is_calc_hess = false; is_converge = false; }
+    if (fabs((residual1 - residual2) / residual1) < 1e-6) break;
+  }
+  if (resis) resis[1] = residual2;
+  if (is_converge_out) *is_converge_out = is_converge ? 1 : 0;
+  if (trace_len) *trace_len = ntrace;
+  memcpy(poses12, c.x.data(), size_t(W) * 12 * 8);
+  if (hess_out && max_iter > 0) {
+    VXS_CUDA(ctx, cudaMemcpyAsync(hess_out, ctx->Hraw.p, size_t(n) * n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    VXS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return warn;
+}
+
+// ------------------------------------------------------------------ LI_BA_Optimizer(+Gravity)::damping_iter
+extern "C" int vxs_li_ba(vxs_ctx* ctx, vxs_factor* f, double* states24, int with_gravity, int max_iter, double imu_coef, const vxs_imu_hooks* imu,
+                         double* hess_out, double resis[2], vxs_lm_trace* trace, int trace_cap, int* trace_len) {
+  if (!ctx || !f || !states24 || !imu || !imu->eval || !imu->update || !imu->rollback || f->ctx != ctx || max_iter < 0) return VXS_ERR_ARG;
+  LmCommon c;
+  c.ctx = ctx; c.f = f; c.W = f->W; c.S = 15; c.n = 15 * f->W + (with_gravity ? 3 : 0); c.gauge = with_gravity ? 6 : 15; c.sst = 24;
+  int rc = lm_prepare(c);
+  if (rc) return rc;
+  const int W = c.W, n = c.n, bs = with_gravity ? 33 : 30;
+  c.x.assign(states24, states24 + size_t(W) * 24);
+  c.xt = c.x;
+  std::vector<double> blocks(size_t(W - 1) * bs * bs), gvec(size_t(W - 1) * bs);
+  double u = 0.01, v = 2, residual1 = 0, residual2 = 0, q, r_imu1 = 0;
+  bool is_calc_hess = true;
+  int ntrace = 0, warn = 0, singular = 0;
+  if (trace_len) *trace_len = 0;
+  for (int it = 0; it < max_iter; it++) {
+    const bool built = is_calc_hess;
+    double r1_lidar = 0;
+    if (is_calc_hess) {
+      // divide_thread (voxel_map.hpp:465-523): the IMU factors are evaluated by the caller's code on the CPU
+      double cost = 0;
+      if (imu->eval(imu->user, c.x.data(), W, with_gravity, 1, blocks.data(), gvec.data(), &cost) != 0) return vxs_fail(ctx, VXS_ERR_CALLBACK, "imu eval");
+      r_imu1 = cost * (imu_coef * 0.5);
+      rc = build_hessian(c, blocks.data(), gvec.data(), bs, imu_coef);
+      if (rc) return rc;
+    }
+    rc = solve_and_fetch(c, u, built ? vxs_hess_r1_dev(f) : nullptr, &r1_lidar, &singular);
+    if (rc) return rc;
+    if (singular) warn = VXS_WARN_SINGULAR;
+    if (built) residual1 = r_imu1 + r1_lidar;
+    if (it == 0 && resis) resis[0] = residual1;
+    if (with_gravity) {  // x_stats_temp[0].g += dxi.tail(3) accumulates on the TEMP state (voxel_map.hpp:813), then is broadcast (:821)
+      for (int k = 0; k < 3; k++) c.xt[21 + k] += c.dx[n - 3 + k];
+    }
+    const double g0[3] = {c.xt[21], c.xt[22], c.xt[23]};
+    retract(c.x.data(), c.xt.data(), c.dx.data(), W, 24, 15);
+    for (int j = 0; j < W; j++) for (int k = 0; k < 3; k++) c.xt[size_t(j) * 24 + 21 + k] = with_gravity ? g0[k] : c.x[size_t(j) * 24 + 21 + k];
+    if (imu->update(imu->user, c.dx.data(), W) != 0) return vxs_fail(ctx, VXS_ERR_CALLBACK, "imu update");
+    double q1 = 0;
+    for (int k = 0; k < n; k++) q1 += c.dx[k] * (u * c.D[k] * c.dx[k] + c.rhs[k]);
+    q1 *= 0.5;
+    // only_residual (voxel_map.hpp:525-560): GPU evaluates the lidar part while the host evaluates the IMU part
+    VXS_CUDA(ctx, cudaMemcpyAsync(ctx->states_b.p, c.xt.data(), size_t(W) * 24 * 8, cudaMemcpyHostToDevice, ctx->stream));
+    rc = vxs_eval_residual_dev(ctx, f, ctx->states_b.p, 24, ctx->scal.p);
+    if (rc) return rc;
+    double r2_lidar = 0, cost2 = 0;
+    VXS_CUDA(ctx, cudaMemcpyAsync(&r2_lidar, ctx->scal.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (imu->eval(imu->user, c.xt.data(), W, with_gravity, 0, nullptr, nullptr, &cost2) != 0) return vxs_fail(ctx, VXS_ERR_CALLBACK, "imu eval");
+    VXS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    residual2 = cost2 * (imu_coef * 0.5) + r2_lidar;
+    q = residual1 - residual2;
+    if (trace && ntrace < trace_cap) { vxs_lm_trace t = {residual1, residual2, u, v, q1, q > 0 ? 1 : 0, built ? 1 : 0}; trace[ntrace++] = t; }
+    if (q > 0) {
+      c.x = c.xt;
+      const double one_three = 1.0 / 3;
+      q = q / q1; v = 2; q = 1 - pow(2 * q - 1, 3);
+      u *= (q < one_three ? one_three : q);
+      is_calc_hess = true;
+    } else {
+      u = u * v; v = 2 * v; is_calc_hess = false;
+      if (imu->rollback(imu->user) != 0) return vxs_fail(ctx, VXS_ERR_CALLBACK, "imu rollback");
+    }
+    if (fabs((residual1 - residual2) / residual1) < 1e-6) break;
+  }
+  if (resis) resis[1] = residual2;
+  if (trace_len) *trace_len = ntrace;
+  memcpy(states24, c.x.data(), size_t(W) * 24 * 8);
+  if (hess_out && max_iter > 0) {
+    VXS_CUDA(ctx, cudaMemcpyAsync(hess_out, ctx->Hraw.p, size_t(n) * n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    VXS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return warn;
+}
