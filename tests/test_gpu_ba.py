@@ -183,10 +183,11 @@ def test_two_concurrent_callers(ctx):
 
     def work(i):
         c = vx.Context(0)
-        f = gpu_factor(c, sc)
         for _ in range(3):
+            f = gpu_factor(c, sc)     # a solve overwrites the factor's cached eig/sums (voxel_map.hpp:271-273), so start fresh
             outs[i] = c.lidar_ba(f, sc["poses_est"], max_iter=3)
-        f.close(); c.close()
+            f.close()
+        c.close()
 
     th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
     [t.start() for t in th]

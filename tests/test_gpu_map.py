@@ -1,0 +1,152 @@
+"""GPU parity tests for the voxel-map construction (cut_voxel + recut + tras_opt; OctreeGBA) through the C-ABI.
+Bit-exact: voxel keys, hash values, point-to-voxel assignment (per-(voxel, frame) point counts and the voxel identity set).
+Floating point: cluster sums 1e-12 relative (summation order differs), eigenvalues 1e-7 of lambda_max."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_api as oa
+import scenes
+import voxel_slam_b200 as vx
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORDER = ["x", "y", "z", "layer", "path"]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = vx.Context(0)
+    yield c
+    c.close()
+
+
+def test_voxel_keys_golden_and_oracle(ctx):
+    cases = json.load(open(os.path.join(HERE, "golden", "voxel_keys.json")))
+    for vs in sorted({c["voxel_size"] for c in cases}):
+        sub = [c for c in cases if c["voxel_size"] == vs]
+        p = np.array([[float.fromhex(h) for h in c["p"]] for c in sub])
+        xyz, h = ctx.voxel_keys(p, vs)
+        assert xyz.tolist() == [c["key"] for c in sub]
+        assert [int(v) for v in h] == [int(c["hash"]) for c in sub]
+    rng = np.random.default_rng(7)
+    p = np.concatenate([rng.uniform(-500, 500, (200000, 3)), np.round(rng.uniform(-50, 50, (5000, 3))), rng.uniform(-1e-6, 1e-6, (1000, 3))])
+    for vs in (0.3, 1.0, 2.0):
+        a, ha = ctx.voxel_keys(p, vs)
+        b, hb = oa.voxel_keys(p, vs)
+        assert np.array_equal(a, b) and np.array_equal(ha, hb)
+
+
+def compare_factors(f_gpu, ids_gpu, of, W):
+    ex = of.export()
+    assert len(ids_gpu) == of.size(), (len(ids_gpu), of.size())
+    pg, po = np.argsort(ids_gpu, order=ORDER), np.argsort(ex["ids"], order=ORDER)
+    assert np.array_equal(ids_gpu[pg], ex["ids"][po])                       # identical voxel set (root cell, layer, octant path)
+    ptr, fr, cl, fx, co = f_gpu.read_structure()
+    eig, s = f_gpu.read_back()
+    dense = np.zeros((len(ids_gpu), W, 10))
+    vox = np.repeat(np.arange(len(ids_gpu)), np.diff(ptr))
+    dense[vox, fr] = cl
+    assert np.all(np.diff(fr)[np.diff(vox) == 0] > 0)                        # frames ascending within a voxel
+    dg, do = dense[pg], ex["clusters10"][po]
+    assert np.array_equal(dg[:, :, 9], do[:, :, 9])                          # bit-exact per-(voxel, frame) point counts
+    assert np.max(np.abs(dg - do) / (np.abs(do) + 1e-6)) < 1e-12
+    assert np.array_equal(s[pg][:, 9], ex["sum10"][po][:, 9])
+    assert np.max(np.abs(s[pg] - ex["sum10"][po]) / (np.abs(ex["sum10"][po]) + 1e-6)) < 1e-12
+    assert np.max(np.abs(fx[pg] - ex["fix10"][po]) / (np.abs(ex["fix10"][po]) + 1e-6)) < 1e-12
+    assert np.all(co == 1.0)
+    lam_g, lam_o = eig[pg][:, :3], ex["eig12"][po][:, :3]
+    assert np.max(np.abs(lam_g - lam_o) / np.max(np.abs(lam_o), axis=1, keepdims=True)) < 1e-7
+    return pg, po
+
+
+@pytest.mark.parametrize("W,pts,L,max_layer,vs", [(4, 6000, 5.0, 2, 1.0), (10, 20000, 12.0, 2, 1.0), (6, 8000, 6.0, 0, 1.0), (5, 8000, 6.0, 3, 2.0), (7, 5000, 5.0, 1, 0.5)])
+def test_window_factor_parity(ctx, W, pts, L, max_layer, vs):
+    sc = scenes.make_window(W=W, pts_per_scan=pts, L=L, seed=17, max_layer=max_layer, voxel_size=vs)
+    f = vx.Factor(ctx, W)
+    n, ids = ctx.build_window_factor(sc["mp"], sc["pts"], sc["offsets"], sc["poses_est"], f, want_ids=True, ids_cap=sc["oracle_factor"].size() + 1000)
+    assert n == f.counts()[0]
+    compare_factors(f, ids, sc["oracle_factor"], W)
+    # the device-resident factor is directly usable by the solver and gives the oracle's answer
+    g = ctx.lidar_ba(f, sc["poses_est"], max_iter=3)
+    r = sc["oracle_factor"].lidar_ba(sc["poses_est"], max_iter=3)
+    assert np.max(np.abs(g["poses"] - r["poses"])) < 1e-6 * np.max(np.abs(r["poses"] - sc["poses_est"]))
+    assert abs(g["resis"][1] - r["resis"][1]) / r["resis"][1] < 1e-8
+
+
+def test_window_factor_negative_coordinates_and_plane_on_cell_boundary(ctx):
+    """Adversarial placement (SURVEY trap B#1): the room is shifted so that cells have negative indices and one plane sits
+    exactly on a cell boundary (x = 0)."""
+    W, pts, L = 4, 8000, 5.0
+    tr, est = scenes.poses_true_est(W, L, 23)
+    p, off = scenes.make_points(W, pts, L, 23, tr)
+    shift = np.array([-0.37 - 2.0, -7.37, -0.37])        # plane x=0.37 -> x=-2.0 (exact cell boundary), others negative
+    tr2, est2 = tr.copy(), est.copy()
+    tr2[:, 9:] += shift; est2[:, 9:] += shift
+    mp = vx.MapParams.make()
+    of = oa.build_window_factor(mp, p, off, est2)
+    f = vx.Factor(ctx, W)
+    n, ids = ctx.build_window_factor(mp, p, off, est2, f, want_ids=True, ids_cap=of.size() + 100)
+    assert (ids["x"] < 0).any() and n > 20
+    compare_factors(f, ids, of, W)
+
+
+def test_window_factor_with_fixed_map_points(ctx):
+    W, pts, L = 4, 6000, 5.0
+    sc = scenes.make_window(W=W, pts_per_scan=pts, L=L, seed=29)
+    fixp = vx.gen_scan(L, 77, 9000, vx.true_pose(L, 0), seed=99)            # body frame of pose 0 ...
+    R0, t0 = sc["poses_true"][0, :9].reshape(3, 3), sc["poses_true"][0, 9:]
+    fixw = fixp @ R0.T + t0                                                  # ... moved to the world: the "fixed map"
+    of = oa.build_window_factor(sc["mp"], sc["pts"], sc["offsets"], sc["poses_est"], fix_pts=fixw)
+    f = vx.Factor(ctx, W)
+    n, ids = ctx.build_window_factor(sc["mp"], sc["pts"], sc["offsets"], sc["poses_est"], f, fix_pts=fixw, want_ids=True, ids_cap=of.size() + 100)
+    assert np.abs(of.export()["fix10"]).max() > 0
+    compare_factors(f, ids, of, W)
+    r_g, r_o = ctx.evaluate_residual(f, sc["poses_true"]), of.residual(sc["poses_true"])
+    assert abs(r_g - r_o) / r_o < 1e-9
+
+
+def make_gba(W, pts, L, seed):
+    tr, est = scenes.poses_true_est(W, L, seed, rot_sigma=3e-3, pos_sigma=2e-2)
+    xyz, off = scenes.make_points(W, pts, L, seed, tr, dtype=np.float32)
+    return tr, est, xyz, off
+
+
+@pytest.mark.parametrize("stride", [3, 12])
+def test_gba_factor_parity(ctx, stride):
+    W = 8
+    tr, est, xyz, off = make_gba(W, 5000, 8.0, 51)
+    if stride != 3:   # pcl::PointXYZINormal layout: 48-byte points
+        wide = np.zeros((xyz.shape[0], stride), dtype=np.float32); wide[:, :3] = xyz; xyz = wide
+    mp = vx.MapParams.make(voxel_size=2.0, min_eigen_value=0.1, max_layer=2)
+    of = oa.build_gba_factor(mp, xyz, off, est, threads=2, stride_floats=stride)
+    f = vx.Factor(ctx, W)
+    n, ids = ctx.build_gba_factor(mp, xyz, off, est, f, stride_floats=stride, want_ids=True, ids_cap=of.size() + 100)
+    assert n > 10
+    compare_factors(f, ids, of, W)
+
+
+def test_hba_window_parity(ctx):
+    W = 10
+    tr, est, xyz, off = make_gba(W, 4000, 8.0, 53)
+    coarse = vx.MapParams.make(voxel_size=2.0, min_eigen_value=0.1, max_layer=2)
+    fine = vx.MapParams.make(voxel_size=1.0, min_eigen_value=0.0025, max_layer=2)
+    g = ctx.hba_window(coarse, fine, xyz, off, est, max_iter=4, thread_num=2)
+    r = oa.hba_window(coarse, fine, xyz, off, est, max_iter=4, thread_num=2)
+    assert g["outer_iters"] == r["outer_iters"]
+    assert np.max(np.abs(g["resis_log"] - r["resis_log"]) / r["resis_log"]) < 1e-6
+    inc = np.max(np.abs(r["poses"] - est))
+    assert np.max(np.abs(g["poses"] - r["poses"])) < 1e-5 * inc
+    assert np.max(np.abs(g["hess"] - r["hess"])) < 1e-6 * np.max(np.abs(r["hess"]))
+    assert np.abs(g["poses"] - tr).max() < 0.5 * np.abs(est - tr).max()
+
+
+def test_radix_sort_and_scan_at_scale(ctx):
+    """1.5 M points, multiple sort tiles and scan blocks: per-voxel counts must still match the oracle exactly."""
+    W, pts, L = 3, 500000, 30.0
+    sc = scenes.make_window(W=W, pts_per_scan=pts, L=L, seed=61, threads=8)
+    f = vx.Factor(ctx, W)
+    n, ids = ctx.build_window_factor(sc["mp"], sc["pts"], sc["offsets"], sc["poses_est"], f, want_ids=True, ids_cap=sc["oracle_factor"].size() + 1000)
+    compare_factors(f, ids, sc["oracle_factor"], W)

@@ -170,7 +170,7 @@ class Context:
 
     def close(self):
         if self._p:
-            lib().vxs_ctx_destroy(self._p)
+            lib().vxs_ctx_destroy(self._p)      # releases the device memory of any factor still alive on this ctx
             self._p = C.c_void_p()
 
     def __del__(self):

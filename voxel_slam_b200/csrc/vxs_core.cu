@@ -32,11 +32,14 @@ extern "C" int vxs_ctx_create(int device, vxs_ctx** out) {
 }
 
 void vxs_voxelize_release(vxs_ctx* c);
+static void vxs_factor_release_device(vxs_factor* f);
 
 extern "C" int vxs_ctx_destroy(vxs_ctx* c) {
   if (!c) return VXS_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  for (vxs_factor* f : c->factors) { vxs_factor_release_device(f); f->ctx = nullptr; }   // handles stay valid for vxs_factor_destroy
+  c->factors.clear();
   vxs_ctx_comm_destroy(c);
   vxs_voxelize_release(c);
   for (auto& p : c->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
@@ -97,6 +100,7 @@ extern "C" int vxs_factor_create(vxs_ctx* ctx, int win_size, vxs_factor** out) {
   if (!ctx || !out || win_size <= 0) return VXS_ERR_ARG;
   vxs_factor* f = new vxs_factor();
   f->ctx = ctx; f->W = win_size;
+  ctx->factors.push_back(f);
   *out = f;
   return VXS_OK;
 }
@@ -105,16 +109,24 @@ static void factor_free_arrays(vxs_factor* f) {
   f->ptr = f->frame = f->vox = nullptr; f->cl = f->fix = f->coe = f->eig = f->sum = nullptr;
   f->Vcap = f->Ecap = 0;
 }
-extern "C" int vxs_factor_destroy(vxs_factor* f) {
-  if (!f) return VXS_OK;
-  cudaSetDevice(f->ctx->device);
-  cudaStreamSynchronize(f->ctx->stream);
+static void vxs_factor_release_device(vxs_factor* f) {
   factor_free_arrays(f);
   f->X.release(); f->C.release(); f->gD.release(); f->partial.release(); f->counter.release();
+  f->V = f->E = 0;
+}
+extern "C" int vxs_factor_destroy(vxs_factor* f) {
+  if (!f) return VXS_OK;
+  if (f->ctx) {   // ctx still alive
+    vxs_ctx* c = f->ctx;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    vxs_factor_release_device(f);
+    for (size_t i = 0; i < c->factors.size(); i++) if (c->factors[i] == f) { c->factors.erase(c->factors.begin() + i); break; }
+  }
   delete f;
   return VXS_OK;
 }
-extern "C" int vxs_factor_clear(vxs_factor* f) { if (!f) return VXS_ERR_ARG; f->V = 0; f->E = 0; f->has_fix = false; return VXS_OK; }
+extern "C" int vxs_factor_clear(vxs_factor* f) { if (!f || !f->ctx) return VXS_ERR_ARG; f->V = 0; f->E = 0; f->has_fix = false; return VXS_OK; }
 extern "C" int vxs_factor_set_win_size(vxs_factor* f, int w) { if (!f || w <= 0 || f->V != 0) return VXS_ERR_ARG; f->W = w; return VXS_OK; }
 extern "C" int vxs_factor_counts(const vxs_factor* f, int64_t* n_vox, int64_t* n_entries, int* win_size) {
   if (!f) return VXS_ERR_ARG;
@@ -196,7 +208,7 @@ static inline unsigned nblk(size_t n, unsigned b) { return unsigned((n + b - 1) 
 extern "C" int vxs_factor_push_voxels(vxs_factor* f, int64_t n_vox, const int64_t* entry_ptr, const int32_t* entry_frame,
                                       const double* entry_cluster10, const double* fix10, const double* coe, const double* eig12,
                                       const double* sum10) {
-  if (!f || n_vox < 0 || (n_vox > 0 && (!entry_ptr || !entry_frame || !entry_cluster10 || !eig12 || !sum10))) return VXS_ERR_ARG;
+  if (!f || !f->ctx || n_vox < 0 || (n_vox > 0 && (!entry_ptr || !entry_frame || !entry_cluster10 || !eig12 || !sum10))) return VXS_ERR_ARG;
   if (n_vox == 0) return VXS_OK;
   vxs_ctx* ctx = f->ctx;
   cudaSetDevice(ctx->device);
@@ -241,7 +253,7 @@ extern "C" int vxs_factor_push_voxels(vxs_factor* f, int64_t n_vox, const int64_
 
 extern "C" int vxs_factor_push_voxels_dense(vxs_factor* f, int64_t n_vox, const double* clusters10, const double* fix10, const double* coe,
                                             const double* eig12, const double* sum10) {
-  if (!f || n_vox < 0 || (n_vox > 0 && !clusters10)) return VXS_ERR_ARG;
+  if (!f || !f->ctx || n_vox < 0 || (n_vox > 0 && !clusters10)) return VXS_ERR_ARG;
   const int W = f->W;
   std::vector<int64_t> ptr(size_t(n_vox) + 1, 0);
   std::vector<int32_t> frame;
@@ -258,7 +270,7 @@ extern "C" int vxs_factor_push_voxels_dense(vxs_factor* f, int64_t n_vox, const 
 }
 
 extern "C" int vxs_factor_read_back(vxs_factor* f, double* eig12, double* sum10) {
-  if (!f) return VXS_ERR_ARG;
+  if (!f || !f->ctx) return VXS_ERR_ARG;
   vxs_ctx* ctx = f->ctx;
   cudaSetDevice(ctx->device);
   const size_t n = size_t(f->V);
@@ -278,7 +290,7 @@ extern "C" int vxs_factor_read_back(vxs_factor* f, double* eig12, double* sum10)
 }
 
 extern "C" int vxs_factor_read_structure(vxs_factor* f, int64_t* entry_ptr, int32_t* entry_frame, double* entry_cluster10, double* fix10, double* coe) {
-  if (!f) return VXS_ERR_ARG;
+  if (!f || !f->ctx) return VXS_ERR_ARG;
   vxs_ctx* ctx = f->ctx;
   cudaSetDevice(ctx->device);
   const size_t n = size_t(f->V), ne = size_t(f->E);

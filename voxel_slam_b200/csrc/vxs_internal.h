@@ -62,6 +62,7 @@ struct vxs_ctx {
   size_t h_pin_cap = 0;
   // voxeliser scratch lives in vxs_voxelize.cu (opaque)
   void* vox_scratch = nullptr;
+  std::vector<struct vxs_factor*> factors;   // live factors created on this ctx (released with it)
 };
 
 struct vxs_factor {

@@ -103,12 +103,15 @@ struct LmCommon {
   std::vector<double> x, xt, dx, D, rhs;
 };
 
-// one Hessian build on the device (+ optional IMU blocks already on the host), returns lidar r1 pointer on device
-static int build_hessian(LmCommon& c, const double* blocks_h, const double* gvec_h, int bs, double imu_coef) {
+// one Hessian build on the device, in two halves so that the caller can evaluate the IMU factors on the CPU in between
+// (the reference does exactly that: worker threads run acc_evaluate2 while the main thread runs give_evaluate, voxel_map.hpp:487-499)
+static int hessian_launch(LmCommon& c) {
   vxs_ctx* ctx = c.ctx;
   VXS_CUDA(ctx, cudaMemcpyAsync(ctx->states_a.p, c.x.data(), c.x.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-  int rc = vxs_eval_hessian_dev(ctx, c.f, ctx->states_a.p, c.sst, nullptr);
-  if (rc) return rc;
+  return vxs_eval_hessian_dev(ctx, c.f, ctx->states_a.p, c.sst, nullptr);
+}
+static int hessian_assemble(LmCommon& c, const double* blocks_h, const double* gvec_h, int bs, double imu_coef) {
+  vxs_ctx* ctx = c.ctx;
   const double *bd = nullptr, *gd = nullptr;
   if (blocks_h) {
     const size_t nb = size_t(c.W - 1) * bs * bs, ng = size_t(c.W - 1) * bs;
@@ -163,7 +166,7 @@ extern "C" int vxs_lidar_ba(vxs_ctx* ctx, vxs_factor* f, double* poses12, int ma
   if (trace_len) *trace_len = 0;
   for (int i = 0; i < max_iter; i++) {
     const bool built = is_calc_hess;
-    if (is_calc_hess) { rc = build_hessian(c, nullptr, nullptr, 0, 0.0); if (rc) return rc; }
+    if (is_calc_hess) { rc = hessian_launch(c); if (rc) return rc; rc = hessian_assemble(c, nullptr, nullptr, 0, 0.0); if (rc) return rc; }
     rc = solve_and_fetch(c, u, built ? vxs_hess_r1_dev(f) : nullptr, &residual1, &singular);
     if (rc) return rc;
     if (singular) warn = VXS_WARN_SINGULAR;
@@ -221,10 +224,12 @@ extern "C" int vxs_li_ba(vxs_ctx* ctx, vxs_factor* f, double* states24, int with
     double r1_lidar = 0;
     if (is_calc_hess) {
       // divide_thread (voxel_map.hpp:465-523): the IMU factors are evaluated by the caller's code on the CPU
-      double cost = 0;
+      rc = hessian_launch(c);   // GPU: lidar part (asynchronous)
+      if (rc) return rc;
+      double cost = 0;          // CPU meanwhile: IMU part
       if (imu->eval(imu->user, c.x.data(), W, with_gravity, 1, blocks.data(), gvec.data(), &cost) != 0) return vxs_fail(ctx, VXS_ERR_CALLBACK, "imu eval");
       r_imu1 = cost * (imu_coef * 0.5);
-      rc = build_hessian(c, blocks.data(), gvec.data(), bs, imu_coef);
+      rc = hessian_assemble(c, blocks.data(), gvec.data(), bs, imu_coef);
       if (rc) return rc;
     }
     rc = solve_and_fetch(c, u, built ? vxs_hess_r1_dev(f) : nullptr, &r1_lidar, &singular);

@@ -1,7 +1,665 @@
-// Voxel-map construction on the GPU (placeholder translation unit; replaced by the real kernels in the next milestone).
+// Voxel-map construction on the GPU, build-from-scratch semantics (what motion_init voxelslam.cpp:600-628, loop_update
+// :1171-1180 and every HBA pass :2374-2379 do): cut every scan into root voxels, then the top-down recut of the adaptive
+// octree, then factor extraction.  Reference functions replaced (voxel_map.hpp / loop_refine.hpp):
+//   cut_voxel :1504-1540, cut_voxel(fix) :1641-1671, OctoTree::allocate/push/subdivide/fix_divide :969-1116,
+//   OctoTree::recut + plane_judge :1015-1019,1148-1194, tras_opt :1308-1333, LidarFactor::push_voxel :122-130,
+//   OctreeGBA::cut_voxel/push/subdivide/recut LR:316-405,446-479, OctreeGBA_multi_recut LR:483-537.
+//
+// GPU formulation (no pointer-chasing octree, no per-voxel mutex):
+//   * every point gets, in one pass, its root cell (bit-exact float quantisation) and the octant it would fall into at each
+//     deeper layer — child centres depend only on the root cell and the octant path, so the whole descent is known up front;
+//   * per layer: 64-bit key (node | frame) -> LSD radix sort (8-bit digits, warp match-any ranking, stable) -> contiguous
+//     (node, frame) segments -> one warp per segment accumulates the body-frame cluster (pcrs_local) and the world cluster
+//     (pcr_add) with shuffle reductions -> one thread per node: sums, covariance, fp64 Jacobi eigensolve, plane test ->
+//     dead / plane / subdivide; only the points of subdivided nodes are re-keyed for the next layer;
+//   * plane leaves passing the tras_opt filter are appended straight into the device-resident CSR factor.
+// Fixed map points are a pseudo-frame W with identity pose: their clusters become pcr_fix.
+#include <limits.h>
+#include <string.h>
+#include <algorithm>
+#include <vector>
 #include "vxs_internal.h"
-void vxs_voxelize_release(vxs_ctx*) {}
-extern "C" int vxs_voxel_keys(vxs_ctx* ctx, const double*, int64_t, double, int64_t*, uint64_t*) { return vxs_fail(ctx, VXS_ERR_ARG, "vxs_voxel_keys: not built yet"); }
-extern "C" int vxs_build_window_factor(vxs_ctx* ctx, const vxs_map_params*, const double*, const int64_t*, const double*, int, const double*, int64_t, vxs_factor*, vxs_voxel_id*, int64_t, int64_t*) { return vxs_fail(ctx, VXS_ERR_ARG, "vxs_build_window_factor: not built yet"); }
-extern "C" int vxs_build_gba_factor(vxs_ctx* ctx, const vxs_map_params*, const float*, int, const int64_t*, const double*, int, vxs_factor*, vxs_voxel_id*, int64_t, int64_t*) { return vxs_fail(ctx, VXS_ERR_ARG, "vxs_build_gba_factor: not built yet"); }
-extern "C" int vxs_hba_window(vxs_ctx* ctx, const vxs_map_params*, const vxs_map_params*, const float*, int, const int64_t*, double*, int, int, int, double*, double*, int*) { return vxs_fail(ctx, VXS_ERR_ARG, "vxs_hba_window: not built yet"); }
+#include "vxs_math.cuh"
+
+using namespace vxs;
+
+// ------------------------------------------------------------------ scratch
+struct VoxScratch {
+  DevBuf<double> pts_d; DevBuf<float> pts_f; DevBuf<double> poses; DevBuf<long long> offsets; DevBuf<long long> bbox;
+  DevBuf<unsigned long long> keysA, keysB; DevBuf<unsigned int> idxA, idxB; DevBuf<unsigned short> pathbits;
+  DevBuf<unsigned int> hist, flags, scanbuf, blocksums, totals;
+  DevBuf<unsigned int> rec_start, node_of_rec, node_rec_start, rec_node_flag;
+  DevBuf<unsigned long long> rec_key;
+  DevBuf<double> rec_local, rec_world;
+  // node arrays, two generations (current level / parent level)
+  DevBuf<int> node_state[2]; DevBuf<long long> node_root[2]; DevBuf<int> node_path[2];
+  DevBuf<double> node_eig, node_sum, node_fix; DevBuf<unsigned int> node_nent, node_sel, node_voff, node_eoff;
+  DevBuf<vxs_voxel_id> ids;
+  std::vector<vxs_voxel_id> ids_host;
+};
+static VoxScratch* scratch(vxs_ctx* c) { if (!c->vox_scratch) c->vox_scratch = new VoxScratch(); return static_cast<VoxScratch*>(c->vox_scratch); }
+void vxs_voxelize_release(vxs_ctx* c) {
+  if (!c->vox_scratch) return;
+  VoxScratch* s = static_cast<VoxScratch*>(c->vox_scratch);
+  s->pts_d.release(); s->pts_f.release(); s->poses.release(); s->offsets.release(); s->bbox.release(); s->keysA.release(); s->keysB.release();
+  s->idxA.release(); s->idxB.release(); s->pathbits.release(); s->hist.release(); s->flags.release(); s->scanbuf.release(); s->blocksums.release();
+  s->totals.release(); s->rec_start.release(); s->node_of_rec.release(); s->node_rec_start.release(); s->rec_node_flag.release(); s->rec_key.release();
+  s->rec_local.release(); s->rec_world.release();
+  for (int g = 0; g < 2; g++) { s->node_state[g].release(); s->node_root[g].release(); s->node_path[g].release(); }
+  s->node_eig.release(); s->node_sum.release(); s->node_fix.release(); s->node_nent.release(); s->node_sel.release(); s->node_voff.release(); s->node_eoff.release();
+  s->ids.release();
+  delete s;
+  c->vox_scratch = nullptr;
+}
+static inline unsigned nblk(size_t n, unsigned b) { return unsigned((n + b - 1) / b); }
+
+// ------------------------------------------------------------------ bit-exact point -> cell arithmetic (no FMA contraction)
+// world = R*p + t with the oracle's summation order ((r0*x + r1*y) + r2*z) + t   (voxelslam.cpp:616, loop_refine.hpp:451)
+__device__ __forceinline__ double dot3_rn(double a0, double a1, double a2, double x, double y, double z, double t) {
+  return __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(a0, x), __dmul_rn(a1, y)), __dmul_rn(a2, z)), t);
+}
+__device__ __forceinline__ d3 world_point(const double* __restrict__ pose, d3 p) {
+  return mk3(dot3_rn(pose[0], pose[1], pose[2], p.x, p.y, p.z, pose[9]), dot3_rn(pose[3], pose[4], pose[5], p.x, p.y, p.z, pose[10]),
+             dot3_rn(pose[6], pose[7], pose[8], p.x, p.y, p.z, pose[11]));
+}
+// voxel_map.hpp:1511-1518: float loc = pw/voxel_size; if(loc<0) loc -= 1; (int64_t)loc
+__device__ __forceinline__ long long quantise(double pw, double voxel_size) {
+  float loc = __double2float_rn(__ddiv_rn(pw, voxel_size));
+  if (loc < 0.0f) loc = __fsub_rn(loc, 1.0f);
+  return __float2ll_rz(loc);
+}
+// tools.hpp:39-48
+__device__ __forceinline__ unsigned long long voxel_hash(long long x, long long y, long long z) {
+  const unsigned long long HP = 116101ull, MN = 10000000000ull;
+  return (((((unsigned long long)z * HP) % MN + (unsigned long long)y) * HP) % MN) + (unsigned long long)x;
+}
+// octant path down to max_layer: 3 bits per layer, layer 1 in the low bits (voxel_map.hpp:1029-1040)
+__device__ __forceinline__ unsigned int octant_bits(d3 pw, long long kx, long long ky, long long kz, double voxel_size, int max_layer) {
+  double cx = __dmul_rn(__dadd_rn(0.5, (double)kx), voxel_size), cy = __dmul_rn(__dadd_rn(0.5, (double)ky), voxel_size), cz = __dmul_rn(__dadd_rn(0.5, (double)kz), voxel_size);
+  float q = __double2float_rn(__ddiv_rn(voxel_size, 4.0));
+  unsigned int bits = 0;
+  for (int l = 0; l < max_layer; l++) {
+    const int bx = pw.x > cx, by = pw.y > cy, bz = pw.z > cz;
+    bits |= (unsigned int)(4 * bx + 2 * by + bz) << (3 * l);
+    cx = __dadd_rn(cx, (double)__fmul_rn((float)(2 * bx - 1), q));
+    cy = __dadd_rn(cy, (double)__fmul_rn((float)(2 * by - 1), q));
+    cz = __dadd_rn(cz, (double)__fmul_rn((float)(2 * bz - 1), q));
+    q = __fdiv_rn(q, 2.0f);
+  }
+  return bits;
+}
+
+struct PointSrc {
+  const double* pd; const float* pf; int fstride;  // exactly one of pd / pf
+  const long long* offsets;                        // [nframes+1] (nframes = W or W+1 with the fix pseudo-frame)
+  const double* poses;                             // [nframes][12]
+  int nframes;
+  long long n;
+};
+__device__ __forceinline__ d3 load_point(const PointSrc& s, long long i) {
+  if (s.pd) return mk3(s.pd[3 * i], s.pd[3 * i + 1], s.pd[3 * i + 2]);
+  const float* p = s.pf + size_t(i) * s.fstride;
+  return mk3((double)p[0], (double)p[1], (double)p[2]);
+}
+__device__ __forceinline__ int frame_of(const PointSrc& s, long long i) {
+  int lo = 0, hi = s.nframes;  // offsets[lo] <= i < offsets[hi]
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s.offsets[mid] <= i) lo = mid; else hi = mid; }
+  return lo;
+}
+
+__global__ void k_voxel_keys(const double* __restrict__ pw, long long n, double voxel_size, long long* __restrict__ xyz, unsigned long long* __restrict__ hash) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long x = quantise(pw[3 * i], voxel_size), y = quantise(pw[3 * i + 1], voxel_size), z = quantise(pw[3 * i + 2], voxel_size);
+  xyz[3 * i] = x; xyz[3 * i + 1] = y; xyz[3 * i + 2] = z;
+  hash[i] = voxel_hash(x, y, z);
+}
+
+__global__ void __launch_bounds__(256) k_bbox(PointSrc s, double voxel_size, long long* __restrict__ bbox) {
+  long long mn[3] = {LLONG_MAX, LLONG_MAX, LLONG_MAX}, mx[3] = {LLONG_MIN, LLONG_MIN, LLONG_MIN};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < s.n; i += (long long)gridDim.x * blockDim.x) {
+    const int fr = frame_of(s, i);
+    const d3 w = world_point(s.poses + 12 * fr, load_point(s, i));
+    const long long k[3] = {quantise(w.x, voxel_size), quantise(w.y, voxel_size), quantise(w.z, voxel_size)};
+    for (int a = 0; a < 3; a++) { mn[a] = min(mn[a], k[a]); mx[a] = max(mx[a], k[a]); }
+  }
+  for (int a = 0; a < 3; a++) {
+    for (int off = 16; off > 0; off >>= 1) { mn[a] = min(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], off)); mx[a] = max(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], off)); }
+    if ((threadIdx.x & 31) == 0) { atomicMin(bbox + a, mn[a]); atomicMax(bbox + 3 + a, mx[a]); }
+  }
+}
+
+// key0 = (linear root id << FB) | frame ; pathbits = octants of the deeper layers
+__global__ void __launch_bounds__(256) k_point_keys(PointSrc s, double voxel_size, int max_layer, long long minx, long long miny, long long minz, long long ey, long long ez,
+                                                    int FB, unsigned long long* __restrict__ keys, unsigned int* __restrict__ idx, unsigned short* __restrict__ pathbits) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= s.n) return;
+  const int fr = frame_of(s, i);
+  const d3 w = world_point(s.poses + 12 * fr, load_point(s, i));
+  const long long kx = quantise(w.x, voxel_size), ky = quantise(w.y, voxel_size), kz = quantise(w.z, voxel_size);
+  const unsigned long long lin = (unsigned long long)(((kx - minx) * ey + (ky - miny)) * ez + (kz - minz));
+  keys[i] = (lin << FB) | (unsigned long long)fr;
+  idx[i] = (unsigned int)i;
+  pathbits[i] = (unsigned short)octant_bits(w, kx, ky, kz, voxel_size, max_layer);
+}
+
+// ------------------------------------------------------------------ exclusive scan (uint32), 3 kernels
+#define SCAN_TILE 1024
+__device__ __forceinline__ unsigned int block_excl_scan_256x4(unsigned int v[4], unsigned int* total) {
+  // 256 threads, 4 consecutive values each; returns the exclusive prefix of this thread's first value
+  __shared__ unsigned int wsum[8];
+  unsigned int t = v[0] + v[1] + v[2] + v[3];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  unsigned int inc = t;
+  for (int off = 1; off < 32; off <<= 1) { unsigned int o = __shfl_up_sync(0xffffffffu, inc, off); if (lane >= off) inc += o; }
+  if (lane == 31) wsum[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    unsigned int x = lane < 8 ? wsum[lane] : 0, xi = x;
+    for (int off = 1; off < 8; off <<= 1) { unsigned int o = __shfl_up_sync(0xffffffffu, xi, off); if (lane >= off) xi += o; }
+    if (lane < 8) wsum[lane] = xi - x;
+    if (lane == 7 && total) *total = xi;
+  }
+  __syncthreads();
+  const unsigned int r = wsum[w] + inc - t;
+  __syncthreads();
+  return r;
+}
+__global__ void __launch_bounds__(256) k_scan_sums(const unsigned int* __restrict__ in, unsigned int* __restrict__ sums, size_t n) {
+  const size_t base = size_t(blockIdx.x) * SCAN_TILE + threadIdx.x * 4;
+  unsigned int v[4];
+  for (int k = 0; k < 4; k++) v[k] = base + k < n ? in[base + k] : 0;
+  __shared__ unsigned int tot;
+  block_excl_scan_256x4(v, &tot);
+  if (threadIdx.x == 0) sums[blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(256) k_scan_single(unsigned int* __restrict__ data, size_t n, unsigned int* __restrict__ total_out) {
+  __shared__ unsigned int carry, tot;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (size_t base0 = 0; base0 < n; base0 += SCAN_TILE) {
+    const size_t base = base0 + threadIdx.x * 4;
+    unsigned int v[4];
+    for (int k = 0; k < 4; k++) v[k] = base + k < n ? data[base + k] : 0;
+    unsigned int ex = block_excl_scan_256x4(v, &tot) + carry;
+    for (int k = 0; k < 4; k++) { if (base + k < n) data[base + k] = ex; ex += v[k]; }
+    __syncthreads();
+    if (threadIdx.x == 0) carry += tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && total_out) *total_out = carry;
+}
+__global__ void __launch_bounds__(256) k_scan_apply(const unsigned int* __restrict__ in, unsigned int* __restrict__ out, const unsigned int* __restrict__ offs, size_t n) {
+  const size_t base = size_t(blockIdx.x) * SCAN_TILE + threadIdx.x * 4;
+  unsigned int v[4];
+  for (int k = 0; k < 4; k++) v[k] = base + k < n ? in[base + k] : 0;
+  unsigned int ex = block_excl_scan_256x4(v, nullptr) + offs[blockIdx.x];
+  for (int k = 0; k < 4; k++) { if (base + k < n) out[base + k] = ex; ex += v[k]; }
+}
+// out = exclusive scan of in (may alias), *total_dev = sum
+static int scan_u32(vxs_ctx* ctx, VoxScratch* s, const unsigned int* in, unsigned int* out, size_t n, unsigned int* total_dev) {
+  if (n == 0) { VXS_CUDA(ctx, cudaMemsetAsync(total_dev, 0, 4, ctx->stream)); return VXS_OK; }
+  const unsigned nb = nblk(n, SCAN_TILE);
+  VXS_CUDA(ctx, s->blocksums.reserve(nb));
+  VXS_LAUNCH(ctx, "k_scan", k_scan_sums, nb, 256, 0, in, s->blocksums.p, n);
+  VXS_LAUNCH(ctx, "k_scan", k_scan_single, 1, 256, 0, s->blocksums.p, size_t(nb), total_dev);
+  VXS_LAUNCH(ctx, "k_scan", k_scan_apply, nb, 256, 0, in, out, s->blocksums.p, n);
+  return VXS_OK;
+}
+
+// ------------------------------------------------------------------ LSD radix sort, 8-bit digits, (uint64 key, uint32 value)
+#define RS_THREADS 256
+#define RS_ITEMS 16
+#define RS_TILE (RS_THREADS * RS_ITEMS)
+__global__ void __launch_bounds__(RS_THREADS) k_radix_hist(const unsigned long long* __restrict__ keys, size_t n, int shift, unsigned int* __restrict__ hist, unsigned int nblocks) {
+  __shared__ unsigned int cnt[256];
+  cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const size_t base = size_t(blockIdx.x) * RS_TILE;
+  for (int r = 0; r < RS_ITEMS; r++) {
+    const size_t i = base + size_t(r) * RS_THREADS + threadIdx.x;
+    if (i < n) atomicAdd(&cnt[(keys[i] >> shift) & 255], 1u);
+  }
+  __syncthreads();
+  hist[size_t(threadIdx.x) * nblocks + blockIdx.x] = cnt[threadIdx.x];
+}
+__global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const unsigned long long* __restrict__ kin, const unsigned int* __restrict__ vin, unsigned long long* __restrict__ kout,
+                                                              unsigned int* __restrict__ vout, size_t n, int shift, const unsigned int* __restrict__ base, unsigned int nblocks) {
+  __shared__ unsigned int wcnt[RS_THREADS / 32][256];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int k = threadIdx.x; k < (RS_THREADS / 32) * 256; k += RS_THREADS) (&wcnt[0][0])[k] = 0;
+  __syncthreads();
+  const size_t wbase = size_t(blockIdx.x) * RS_TILE + size_t(w) * (32 * RS_ITEMS);
+  unsigned long long key[RS_ITEMS];
+  unsigned int rank[RS_ITEMS];
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; r++) {
+    const size_t i = wbase + size_t(r) * 32 + lane;
+    const bool valid = i < n;
+    key[r] = valid ? kin[i] : 0ull;
+    const unsigned int bin = valid ? (unsigned int)((key[r] >> shift) & 255) : 256u;
+    const unsigned int peers = __match_any_sync(0xffffffffu, bin);
+    const int leader = __ffs(peers) - 1;
+    const unsigned int below = __popc(peers & ((1u << lane) - 1u));
+    unsigned int old = 0;
+    if (lane == leader && valid) { old = wcnt[w][bin]; wcnt[w][bin] = old + __popc(peers); }
+    old = __shfl_sync(0xffffffffu, old, leader);
+    rank[r] = old + below;
+    __syncwarp();
+  }
+  __syncthreads();
+  {  // per bin: global base of this block, then exclusive prefix over the warps of the block
+    const int bin = threadIdx.x;
+    unsigned int run = base[size_t(bin) * nblocks + blockIdx.x];
+    for (int ww = 0; ww < RS_THREADS / 32; ww++) { const unsigned int c = wcnt[ww][bin]; wcnt[ww][bin] = run; run += c; }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; r++) {
+    const size_t i = wbase + size_t(r) * 32 + lane;
+    if (i < n) {
+      const unsigned int pos = wcnt[w][(key[r] >> shift) & 255] + rank[r];
+      kout[pos] = key[r];
+      vout[pos] = vin[i];
+    }
+  }
+}
+// sorts by the low `bits` bits; result pointers returned through kres / vres (ping-pong between the A and B buffers)
+static int radix_sort(vxs_ctx* ctx, VoxScratch* s, unsigned long long* kA, unsigned int* vA, unsigned long long* kB, unsigned int* vB, size_t n, int bits,
+                      unsigned long long** kres, unsigned int** vres) {
+  *kres = kA; *vres = vA;
+  if (n == 0) return VXS_OK;
+  const unsigned nb = nblk(n, RS_TILE);
+  VXS_CUDA(ctx, s->hist.reserve(size_t(256) * nb));
+  for (int shift = 0; shift < bits; shift += 8) {
+    VXS_LAUNCH(ctx, "k_radix_hist", k_radix_hist, nb, RS_THREADS, 0, *kres, n, shift, s->hist.p, nb);
+    int rc = scan_u32(ctx, s, s->hist.p, s->hist.p, size_t(256) * nb, s->totals.p + 15);
+    if (rc) return rc;
+    unsigned long long* ko = (*kres == kA) ? kB : kA;
+    unsigned int* vo = (*vres == vA) ? vB : vA;
+    VXS_LAUNCH(ctx, "k_radix_scatter", k_radix_scatter, nb, RS_THREADS, 0, *kres, *vres, ko, vo, n, shift, s->hist.p, nb);
+    *kres = ko; *vres = vo;
+  }
+  return VXS_OK;
+}
+
+// ------------------------------------------------------------------ segments -> records -> nodes
+__global__ void k_flag_heads(const unsigned long long* __restrict__ keys, size_t m, unsigned int* __restrict__ flag) {
+  const size_t j = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (j < m) flag[j] = (j == 0 || keys[j] != keys[j - 1]) ? 1u : 0u;
+}
+__global__ void k_write_records(const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ flag, const unsigned int* __restrict__ ex, size_t m,
+                                unsigned int* __restrict__ rec_start, unsigned long long* __restrict__ rec_key, const unsigned int* __restrict__ total) {
+  const size_t j = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (j < m && flag[j]) { rec_start[ex[j]] = (unsigned int)j; rec_key[ex[j]] = keys[j]; }
+  if (j == 0) rec_start[*total] = (unsigned int)m;
+}
+__global__ void k_flag_nodes(const unsigned long long* __restrict__ rec_key, size_t R, int FB, unsigned int* __restrict__ flag) {
+  const size_t r = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r < R) flag[r] = (r == 0 || (rec_key[r] >> FB) != (rec_key[r - 1] >> FB)) ? 1u : 0u;
+}
+__global__ void k_write_nodes(const unsigned int* __restrict__ flag, const unsigned int* __restrict__ ex, size_t R, unsigned int* __restrict__ node_of_rec,
+                              unsigned int* __restrict__ node_rec_start, const unsigned int* __restrict__ total) {
+  const size_t r = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r < R) { const unsigned int nd = ex[r] + flag[r] - 1u; node_of_rec[r] = nd; if (flag[r]) node_rec_start[nd] = (unsigned int)r; }
+  if (r == 0) node_rec_start[*total] = (unsigned int)R;
+}
+
+// one warp per (node, frame) record: pcrs_local[frame].push(p_body), pcr_add.push(p_world)   (voxel_map.hpp:988-989, loop_refine.hpp:318-320, 383-385)
+__global__ void __launch_bounds__(256) k_rec_clusters(PointSrc s, const unsigned int* __restrict__ idx, const unsigned int* __restrict__ rec_start,
+                                                      const unsigned long long* __restrict__ rec_key, unsigned int R, int FB, double* __restrict__ rec_local,
+                                                      double* __restrict__ rec_world, size_t Rcap) {
+  const int lane = threadIdx.x & 31;
+  const unsigned int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (unsigned int r = warp; r < R; r += nwarps) {
+    const unsigned int beg = rec_start[r], end = rec_start[r + 1];
+    const int fr = int(rec_key[r] & ((1ull << FB) - 1ull));
+    const double* pose = s.poses + 12 * fr;
+    double a[20];
+#pragma unroll
+    for (int k = 0; k < 20; k++) a[k] = 0.0;
+    for (unsigned int j = beg + lane; j < end; j += 32) {
+      const d3 p = load_point(s, idx[j]);
+      const d3 w = world_point(pose, p);
+      a[0] += p.x * p.x; a[1] += p.x * p.y; a[2] += p.x * p.z; a[3] += p.y * p.y; a[4] += p.y * p.z; a[5] += p.z * p.z; a[6] += p.x; a[7] += p.y; a[8] += p.z; a[9] += 1.0;
+      a[10] += w.x * w.x; a[11] += w.x * w.y; a[12] += w.x * w.z; a[13] += w.y * w.y; a[14] += w.y * w.z; a[15] += w.z * w.z; a[16] += w.x; a[17] += w.y; a[18] += w.z; a[19] += 1.0;
+    }
+#pragma unroll
+    for (int k = 0; k < 20; k++)
+      for (int off = 16; off > 0; off >>= 1) a[k] += __shfl_xor_sync(0xffffffffu, a[k], off);
+    if (lane < 20) {
+      double v = a[0];
+#pragma unroll
+      for (int k = 1; k < 20; k++) if (lane == k) v = a[k];
+      if (lane < 10) rec_local[size_t(lane) * Rcap + r] = v; else rec_world[size_t(lane - 10) * Rcap + r] = v;
+    }
+  }
+}
+
+struct DecideParams {
+  double min_eigen_value; double thre; double min_point;   // for THIS layer
+  int layer, max_layer, gba, W, FB;
+};
+enum { NODE_DEAD = 0, NODE_PLANE = 1, NODE_SUBDIVIDE = 2, NODE_LEAF = 3 };
+
+// one thread per node: OctoTree::recut :1150-1172 / OctreeGBA::recut LR:360-399 decision + tras_opt filter :1312-1314 / LR:370-378
+__global__ void __launch_bounds__(128) k_node_decide(DecideParams dp, unsigned int Nn, const unsigned int* __restrict__ node_rec_start, const unsigned long long* __restrict__ rec_key,
+                                                     const double* __restrict__ rec_local, const double* __restrict__ rec_world, size_t Rcap,
+                                                     const long long* __restrict__ parent_root, const int* __restrict__ parent_path, int* __restrict__ state,
+                                                     long long* __restrict__ root, int* __restrict__ path, double* __restrict__ eig, double* __restrict__ sum,
+                                                     double* __restrict__ fix, unsigned int* __restrict__ nent, unsigned int* __restrict__ sel, size_t Ncap) {
+  const unsigned int nd = blockIdx.x * blockDim.x + threadIdx.x;
+  if (nd >= Nn) return;
+  const unsigned int rb = node_rec_start[nd], re = node_rec_start[nd + 1];
+  cluster S; S.P.xx = S.P.xy = S.P.xz = S.P.yy = S.P.yz = S.P.zz = 0.0; S.v = mk3(0, 0, 0); S.n = 0.0;
+  double fx[10];
+#pragma unroll
+  for (int k = 0; k < 10; k++) fx[k] = 0.0;
+  unsigned int nwin = 0;
+  const unsigned long long fmask = (1ull << dp.FB) - 1ull;
+  for (unsigned int r = rb; r < re; r++) {
+    S.P.xx += rec_world[r]; S.P.xy += rec_world[Rcap + r]; S.P.xz += rec_world[2 * Rcap + r]; S.P.yy += rec_world[3 * Rcap + r]; S.P.yz += rec_world[4 * Rcap + r];
+    S.P.zz += rec_world[5 * Rcap + r]; S.v.x += rec_world[6 * Rcap + r]; S.v.y += rec_world[7 * Rcap + r]; S.v.z += rec_world[8 * Rcap + r]; S.n += rec_world[9 * Rcap + r];
+    if (int(rec_key[r] & fmask) >= dp.W) { for (int k = 0; k < 10; k++) fx[k] += rec_local[size_t(k) * Rcap + r]; }
+    else nwin++;
+  }
+  const unsigned long long nodekey = rec_key[rb] >> dp.FB;
+  if (dp.layer == 0) { root[nd] = (long long)nodekey; path[nd] = 0; }
+  else { const unsigned int par = (unsigned int)(nodekey >> 3); root[nd] = parent_root[par]; path[nd] = parent_path[par] * 8 + int(nodekey & 7); }
+  int st = NODE_DEAD; unsigned int take = 0;
+  double w[3] = {0, 0, 0}; d3 u0 = mk3(0, 0, 0), u1 = u0, u2 = u0;
+  const bool alive = dp.gba ? (S.n > 10.0) : (S.n > dp.min_point && nwin > 0);
+  if (alive) {
+    eig3_jacobi(cov_from_sum(S), w, u0, u1, u2);
+    const bool plane = (w[0] < dp.min_eigen_value) && (w[0] / w[2] < dp.thre);
+    if (plane) {
+      st = NODE_PLANE;
+      take = (w[0] / w[1] > 0.12) ? 0u : 1u;
+      if (dp.gba && nwin <= 1) take = 0u;
+    } else st = (dp.layer >= dp.max_layer) ? NODE_LEAF : NODE_SUBDIVIDE;
+  }
+  state[nd] = st; sel[nd] = take; nent[nd] = take ? nwin : 0u;
+  if (take) {
+    eig[nd] = w[0]; eig[Ncap + nd] = w[1]; eig[2 * Ncap + nd] = w[2];
+    eig[3 * Ncap + nd] = u0.x; eig[4 * Ncap + nd] = u1.x; eig[5 * Ncap + nd] = u2.x; eig[6 * Ncap + nd] = u0.y; eig[7 * Ncap + nd] = u1.y; eig[8 * Ncap + nd] = u2.y;
+    eig[9 * Ncap + nd] = u0.z; eig[10 * Ncap + nd] = u1.z; eig[11 * Ncap + nd] = u2.z;
+    sum[nd] = S.P.xx; sum[Ncap + nd] = S.P.xy; sum[2 * Ncap + nd] = S.P.xz; sum[3 * Ncap + nd] = S.P.yy; sum[4 * Ncap + nd] = S.P.yz; sum[5 * Ncap + nd] = S.P.zz;
+    sum[6 * Ncap + nd] = S.v.x; sum[7 * Ncap + nd] = S.v.y; sum[8 * Ncap + nd] = S.v.z; sum[9 * Ncap + nd] = S.n;
+    for (int k = 0; k < 10; k++) fix[size_t(k) * Ncap + nd] = fx[k];
+  }
+}
+
+struct FactorOut {
+  int32_t* ptr; int32_t* frame; int32_t* vox; double* cl; size_t Ecap; double* fix; double* coe; double* eig; double* sum; size_t Vcap;
+  long long V0, E0;
+};
+// LidarFactor::push_voxel for every selected node, straight into the device CSR
+__global__ void __launch_bounds__(128) k_emit_factor(FactorOut fo, unsigned int Nn, int W, int FB, const unsigned int* __restrict__ sel, const unsigned int* __restrict__ voff,
+                                                     const unsigned int* __restrict__ eoff, const unsigned int* __restrict__ node_rec_start,
+                                                     const unsigned long long* __restrict__ rec_key, const double* __restrict__ rec_local, size_t Rcap,
+                                                     const double* __restrict__ eig, const double* __restrict__ sum, const double* __restrict__ fix, size_t Ncap,
+                                                     const long long* __restrict__ root, const int* __restrict__ path, int layer, long long minx, long long miny, long long minz,
+                                                     long long ey, long long ez, vxs_voxel_id* __restrict__ ids) {
+  const unsigned int nd = blockIdx.x * blockDim.x + threadIdx.x;
+  if (nd >= Nn || !sel[nd]) return;
+  const long long v = fo.V0 + voff[nd];
+  long long e = fo.E0 + eoff[nd];
+  fo.ptr[v] = int32_t(e);
+  const unsigned long long fmask = (1ull << FB) - 1ull;
+  for (unsigned int r = node_rec_start[nd]; r < node_rec_start[nd + 1]; r++) {
+    const int fr = int(rec_key[r] & fmask);
+    if (fr >= W) continue;
+    fo.frame[e] = fr; fo.vox[e] = int32_t(v);
+    for (int k = 0; k < 10; k++) fo.cl[size_t(k) * fo.Ecap + e] = rec_local[size_t(k) * Rcap + r];
+    e++;
+  }
+  for (int k = 0; k < 10; k++) { fo.fix[size_t(k) * fo.Vcap + v] = fix[size_t(k) * Ncap + nd]; fo.sum[size_t(k) * fo.Vcap + v] = sum[size_t(k) * Ncap + nd]; }
+  for (int k = 0; k < 12; k++) fo.eig[size_t(k) * fo.Vcap + v] = eig[size_t(k) * Ncap + nd];
+  fo.coe[v] = 1.0;   // voxel_map.hpp:1316, loop_refine.hpp:380
+  if (ids) {
+    const long long lin = root[nd];
+    const long long kz = lin % ez, ky = (lin / ez) % ey, kx = lin / (ez * ey);
+    vxs_voxel_id id; id.x = kx + minx; id.y = ky + miny; id.z = kz + minz; id.layer = layer; id.path = path[nd];
+    ids[v - fo.V0 + 0] = id;
+  }
+}
+__global__ void k_set_last_ptr(int32_t* ptr, long long V, long long E) { ptr[V] = int32_t(E); }
+
+// points of subdivided nodes -> keys of the next layer: ((node*8 + octant) << FB) | frame       (subdivide :1096-1116 / LR:323-356)
+__global__ void k_next_flags(const unsigned int* __restrict__ recflag_ex, const unsigned int* __restrict__ recflag, const unsigned int* __restrict__ node_of_rec,
+                             const int* __restrict__ state, size_t m, unsigned int* __restrict__ flag) {
+  const size_t j = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  const unsigned int rec = recflag_ex[j] + recflag[j] - 1u;
+  flag[j] = state[node_of_rec[rec]] == NODE_SUBDIVIDE ? 1u : 0u;
+}
+__global__ void k_next_keys(const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ idx, const unsigned int* __restrict__ recflag_ex,
+                            const unsigned int* __restrict__ recflag, const unsigned int* __restrict__ node_of_rec, const unsigned int* __restrict__ flag,
+                            const unsigned int* __restrict__ pos, const unsigned short* __restrict__ pathbits, size_t m, int FB, int next_layer,
+                            unsigned long long* __restrict__ keys_out, unsigned int* __restrict__ idx_out) {
+  const size_t j = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (j >= m || !flag[j]) return;
+  const unsigned int rec = recflag_ex[j] + recflag[j] - 1u, nd = node_of_rec[rec], pi = idx[j];
+  const unsigned int oct = (pathbits[pi] >> (3 * (next_layer - 1))) & 7u;
+  keys_out[pos[j]] = ((((unsigned long long)nd << 3) | oct) << FB) | (keys[j] & ((1ull << FB) - 1ull));
+  idx_out[pos[j]] = pi;
+}
+
+static int bits_for(unsigned long long v) { int b = 0; while ((1ull << b) <= v && b < 63) b++; return std::max(b, 1); }
+
+// ------------------------------------------------------------------ driver shared by the local map and the GBA map
+static int build_factor(vxs_ctx* ctx, const vxs_map_params* mp, bool gba, const double* pts_d_host, const float* pts_f_host, int fstride, const int64_t* offsets_host, int nframes,
+                        const double* poses12_host, int W, vxs_factor* out, vxs_voxel_id* ids_out, int64_t ids_cap, int64_t* n_out) {
+  if (!ctx || !mp || !out || !offsets_host || !poses12_host || out->ctx != ctx) return VXS_ERR_ARG;
+  if (mp->max_layer < 0 || mp->max_layer > 3 || !(mp->voxel_size > 0)) return vxs_fail(ctx, VXS_ERR_ARG, "max_layer must be 0..3 and voxel_size > 0");
+  cudaSetDevice(ctx->device);
+  VoxScratch* s = scratch(ctx);
+  cudaStream_t st = ctx->stream;
+  const long long N = offsets_host[nframes];
+  if (N >= (1ll << 32)) return vxs_fail(ctx, VXS_ERR_ARG, "more than 2^32 points in one build");
+  vxs_factor_clear(out);
+  out->W = W;
+  if (n_out) *n_out = 0;
+  VXS_CUDA(ctx, s->totals.reserve(16));
+  if (N == 0) return VXS_OK;
+  const int FB = bits_for((unsigned long long)nframes);
+  // ---- upload
+  PointSrc ps; ps.pd = nullptr; ps.pf = nullptr; ps.fstride = fstride; ps.nframes = nframes; ps.n = N;
+  if (pts_d_host) { VXS_CUDA(ctx, s->pts_d.reserve(size_t(N) * 3)); VXS_CUDA(ctx, cudaMemcpyAsync(s->pts_d.p, pts_d_host, size_t(N) * 24, cudaMemcpyHostToDevice, st)); ps.pd = s->pts_d.p; }
+  else { VXS_CUDA(ctx, s->pts_f.reserve(size_t(N) * fstride)); VXS_CUDA(ctx, cudaMemcpyAsync(s->pts_f.p, pts_f_host, size_t(N) * fstride * 4, cudaMemcpyHostToDevice, st)); ps.pf = s->pts_f.p; }
+  VXS_CUDA(ctx, s->poses.reserve(size_t(nframes) * 12));
+  VXS_CUDA(ctx, cudaMemcpyAsync(s->poses.p, poses12_host, size_t(W) * 96, cudaMemcpyHostToDevice, st));
+  if (nframes > W) { const double ident[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0}; VXS_CUDA(ctx, cudaMemcpyAsync(s->poses.p + size_t(W) * 12, ident, 96, cudaMemcpyHostToDevice, st)); }
+  VXS_CUDA(ctx, s->offsets.reserve(size_t(nframes) + 1));
+  VXS_CUDA(ctx, cudaMemcpyAsync(s->offsets.p, offsets_host, (size_t(nframes) + 1) * 8, cudaMemcpyHostToDevice, st));
+  ps.offsets = s->offsets.p; ps.poses = s->poses.p;
+  // ---- bounding box of the root cells
+  VXS_CUDA(ctx, s->bbox.reserve(6));
+  const long long bb0[6] = {LLONG_MAX, LLONG_MAX, LLONG_MAX, LLONG_MIN, LLONG_MIN, LLONG_MIN};
+  VXS_CUDA(ctx, cudaMemcpyAsync(s->bbox.p, bb0, sizeof bb0, cudaMemcpyHostToDevice, st));
+  VXS_LAUNCH(ctx, "k_bbox", k_bbox, std::min<unsigned>(nblk(size_t(N), 256), unsigned(ctx->sm_count) * 8), 256, 0, ps, mp->voxel_size, s->bbox.p);
+  long long bb[6];
+  VXS_CUDA(ctx, cudaMemcpyAsync(bb, s->bbox.p, sizeof bb, cudaMemcpyDeviceToHost, st));
+  VXS_CUDA(ctx, cudaStreamSynchronize(st));
+  const long double ex = (long double)bb[3] - bb[0] + 1, ey = (long double)bb[4] - bb[1] + 1, ez = (long double)bb[5] - bb[2] + 1;
+  if (ex * ey * ez >= (long double)(1ull << 40)) return vxs_fail(ctx, VXS_ERR_RANGE, "root-cell bounding box exceeds 2^40 cells");
+  const long long eyl = (long long)ey, ezl = (long long)ez;
+  const int root_bits = bits_for((unsigned long long)(ex * ey * ez));
+  // ---- layer-0 keys
+  VXS_CUDA(ctx, s->keysA.reserve(size_t(N))); VXS_CUDA(ctx, s->keysB.reserve(size_t(N)));
+  VXS_CUDA(ctx, s->idxA.reserve(size_t(N))); VXS_CUDA(ctx, s->idxB.reserve(size_t(N)));
+  VXS_CUDA(ctx, s->pathbits.reserve(size_t(N)));
+  VXS_LAUNCH(ctx, "k_point_keys", k_point_keys, nblk(size_t(N), 256), 256, 0, ps, mp->voxel_size, int(mp->max_layer), bb[0], bb[1], bb[2], eyl, ezl, FB, s->keysA.p, s->idxA.p, s->pathbits.p);
+
+  size_t m = size_t(N);
+  int key_bits = root_bits + FB;
+  unsigned long long* kcur = s->keysA.p; unsigned int* vcur = s->idxA.p;
+  long long Vtot = 0, Etot = 0;
+  s->ids_host.clear();
+  for (int layer = 0; layer <= mp->max_layer && m > 0; layer++) {
+    const int g = layer & 1;
+    unsigned long long* kalt = (kcur == s->keysA.p) ? s->keysB.p : s->keysA.p;
+    unsigned int* valt = (vcur == s->idxA.p) ? s->idxB.p : s->idxA.p;
+    unsigned long long* ks; unsigned int* vs;
+    int rc = radix_sort(ctx, s, kcur, vcur, kalt, valt, m, key_bits, &ks, &vs);
+    if (rc) return rc;
+    unsigned long long* kfree = (ks == s->keysA.p) ? s->keysB.p : s->keysA.p;   // the buffer not holding the sorted keys
+    unsigned int* vfree = (vs == s->idxA.p) ? s->idxB.p : s->idxA.p;
+    // records
+    VXS_CUDA(ctx, s->flags.reserve(m)); VXS_CUDA(ctx, s->scanbuf.reserve(m));
+    VXS_LAUNCH(ctx, "k_flag_heads", k_flag_heads, nblk(m, 256), 256, 0, ks, m, s->flags.p);
+    rc = scan_u32(ctx, s, s->flags.p, s->scanbuf.p, m, s->totals.p + 0);
+    if (rc) return rc;
+    unsigned int R = 0;
+    VXS_CUDA(ctx, cudaMemcpyAsync(&R, s->totals.p + 0, 4, cudaMemcpyDeviceToHost, st));
+    VXS_CUDA(ctx, cudaStreamSynchronize(st));
+    VXS_CUDA(ctx, s->rec_start.reserve(size_t(R) + 1)); VXS_CUDA(ctx, s->rec_key.reserve(size_t(R)));
+    VXS_CUDA(ctx, s->node_of_rec.reserve(size_t(R))); VXS_CUDA(ctx, s->rec_node_flag.reserve(size_t(R) * 2));
+    VXS_LAUNCH(ctx, "k_write_records", k_write_records, nblk(m, 256), 256, 0, ks, s->flags.p, s->scanbuf.p, m, s->rec_start.p, s->rec_key.p, s->totals.p + 0);
+    const size_t Rcap = (size_t(R) + 31) & ~size_t(31);
+    VXS_CUDA(ctx, s->rec_local.reserve(Rcap * 10)); VXS_CUDA(ctx, s->rec_world.reserve(Rcap * 10));
+    VXS_LAUNCH(ctx, "k_rec_clusters", k_rec_clusters, std::min<unsigned>(nblk(size_t(R) * 32, 256), unsigned(ctx->sm_count) * 16), 256, 0, ps, vs, s->rec_start.p, s->rec_key.p, R, FB,
+               s->rec_local.p, s->rec_world.p, Rcap);
+    // nodes
+    unsigned int* nflag = s->rec_node_flag.p; unsigned int* nex = s->rec_node_flag.p + R;
+    VXS_LAUNCH(ctx, "k_flag_nodes", k_flag_nodes, nblk(R, 256), 256, 0, s->rec_key.p, size_t(R), FB, nflag);
+    rc = scan_u32(ctx, s, nflag, nex, R, s->totals.p + 1);
+    if (rc) return rc;
+    unsigned int Nn = 0;
+    VXS_CUDA(ctx, cudaMemcpyAsync(&Nn, s->totals.p + 1, 4, cudaMemcpyDeviceToHost, st));
+    VXS_CUDA(ctx, cudaStreamSynchronize(st));
+    VXS_CUDA(ctx, s->node_rec_start.reserve(size_t(Nn) + 1));
+    VXS_LAUNCH(ctx, "k_write_nodes", k_write_nodes, nblk(R, 256), 256, 0, nflag, nex, size_t(R), s->node_of_rec.p, s->node_rec_start.p, s->totals.p + 1);
+    const size_t Ncap = (size_t(Nn) + 31) & ~size_t(31);
+    VXS_CUDA(ctx, s->node_state[g].reserve(Ncap)); VXS_CUDA(ctx, s->node_root[g].reserve(Ncap)); VXS_CUDA(ctx, s->node_path[g].reserve(Ncap));
+    VXS_CUDA(ctx, s->node_eig.reserve(Ncap * 12)); VXS_CUDA(ctx, s->node_sum.reserve(Ncap * 10)); VXS_CUDA(ctx, s->node_fix.reserve(Ncap * 10));
+    VXS_CUDA(ctx, s->node_nent.reserve(Ncap)); VXS_CUDA(ctx, s->node_sel.reserve(Ncap)); VXS_CUDA(ctx, s->node_voff.reserve(Ncap)); VXS_CUDA(ctx, s->node_eoff.reserve(Ncap));
+    DecideParams dp;
+    dp.min_eigen_value = mp->min_eigen_value; dp.thre = mp->plane_thre[std::min(layer, 3)]; dp.min_point = mp->min_point[std::min(layer, 3)];
+    dp.layer = layer; dp.max_layer = mp->max_layer; dp.gba = gba ? 1 : 0; dp.W = W; dp.FB = FB;
+    VXS_LAUNCH(ctx, "k_node_decide", k_node_decide, nblk(Nn, 128), 128, 0, dp, Nn, s->node_rec_start.p, s->rec_key.p, s->rec_local.p, s->rec_world.p, Rcap, s->node_root[g ^ 1].p,
+               s->node_path[g ^ 1].p, s->node_state[g].p, s->node_root[g].p, s->node_path[g].p, s->node_eig.p, s->node_sum.p, s->node_fix.p, s->node_nent.p, s->node_sel.p, Ncap);
+    rc = scan_u32(ctx, s, s->node_sel.p, s->node_voff.p, Nn, s->totals.p + 2);
+    if (rc) return rc;
+    rc = scan_u32(ctx, s, s->node_nent.p, s->node_eoff.p, Nn, s->totals.p + 3);
+    if (rc) return rc;
+    // points that go one layer down
+    unsigned int nextm = 0;
+    unsigned int* nxflag = nullptr; unsigned int* nxpos = nullptr;
+    if (layer < mp->max_layer) {
+      VXS_CUDA(ctx, s->hist.reserve(m * 2));   // reuse the histogram buffer as [flag | pos]
+      nxflag = s->hist.p; nxpos = s->hist.p + m;
+      VXS_LAUNCH(ctx, "k_next_flags", k_next_flags, nblk(m, 256), 256, 0, s->scanbuf.p, s->flags.p, s->node_of_rec.p, s->node_state[g].p, m, nxflag);
+      rc = scan_u32(ctx, s, nxflag, nxpos, m, s->totals.p + 4);
+      if (rc) return rc;
+    }
+    unsigned int tot[5] = {0, 0, 0, 0, 0};
+    VXS_CUDA(ctx, cudaMemcpyAsync(tot, s->totals.p, sizeof tot, cudaMemcpyDeviceToHost, st));
+    VXS_CUDA(ctx, cudaStreamSynchronize(st));
+    const unsigned int selV = tot[2], selE = tot[3];
+    nextm = layer < mp->max_layer ? tot[4] : 0;
+    if (selV > 0) {
+      rc = vxs_factor_reserve(out, size_t(Vtot + selV), size_t(Etot + selE));
+      if (rc) return rc;
+      FactorOut fo; fo.ptr = out->ptr; fo.frame = out->frame; fo.vox = out->vox; fo.cl = out->cl; fo.Ecap = out->Ecap; fo.fix = out->fix; fo.coe = out->coe; fo.eig = out->eig;
+      fo.sum = out->sum; fo.Vcap = out->Vcap; fo.V0 = Vtot; fo.E0 = Etot;
+      vxs_voxel_id* ids_dev = nullptr;
+      if (ids_out) { VXS_CUDA(ctx, s->ids.reserve(selV)); ids_dev = s->ids.p; }
+      VXS_LAUNCH(ctx, "k_emit_factor", k_emit_factor, nblk(Nn, 128), 128, 0, fo, Nn, W, FB, s->node_sel.p, s->node_voff.p, s->node_eoff.p, s->node_rec_start.p, s->rec_key.p,
+                 s->rec_local.p, Rcap, s->node_eig.p, s->node_sum.p, s->node_fix.p, Ncap, s->node_root[g].p, s->node_path[g].p, layer, bb[0], bb[1], bb[2], eyl, ezl, ids_dev);
+      if (ids_out) {
+        const size_t old = s->ids_host.size();
+        s->ids_host.resize(old + selV);
+        VXS_CUDA(ctx, cudaMemcpyAsync(s->ids_host.data() + old, ids_dev, size_t(selV) * sizeof(vxs_voxel_id), cudaMemcpyDeviceToHost, st));
+        VXS_CUDA(ctx, cudaStreamSynchronize(st));
+      }
+      Vtot += selV; Etot += selE;
+      out->V = Vtot; out->E = Etot;   // keeps a later reserve() from dropping what was emitted
+    }
+    if (nextm > 0) {
+      VXS_LAUNCH(ctx, "k_next_keys", k_next_keys, nblk(m, 256), 256, 0, ks, vs, s->scanbuf.p, s->flags.p, s->node_of_rec.p, nxflag, nxpos, s->pathbits.p, m, FB, layer + 1, kfree, vfree);
+      kcur = kfree; vcur = vfree;
+      key_bits = bits_for(((unsigned long long)Nn << 3) | 7ull) + FB;
+    }
+    m = nextm;
+  }
+  if (Vtot > 0) {
+    VXS_LAUNCH(ctx, "k_set_last_ptr", k_set_last_ptr, 1, 1, 0, out->ptr, Vtot, Etot);
+    // fix clusters present?  (only when fixed map points were supplied)
+    out->has_fix = nframes > W;
+  }
+  out->V = Vtot; out->E = Etot;
+  VXS_CUDA(ctx, cudaStreamSynchronize(st));
+  if (n_out) *n_out = Vtot;
+  if (ids_out) { const size_t ncopy = std::min<size_t>(size_t(ids_cap), s->ids_host.size()); if (ncopy) memcpy(ids_out, s->ids_host.data(), ncopy * sizeof(vxs_voxel_id)); }
+  return VXS_OK;
+}
+
+// ------------------------------------------------------------------ public entry points
+extern "C" int vxs_voxel_keys(vxs_ctx* ctx, const double* pw, int64_t n, double voxel_size, int64_t* xyz, uint64_t* hash) {
+  if (!ctx || n < 0 || (n > 0 && (!pw || !xyz || !hash)) || !(voxel_size > 0)) return VXS_ERR_ARG;
+  if (n == 0) return VXS_OK;
+  cudaSetDevice(ctx->device);
+  VoxScratch* s = scratch(ctx);
+  VXS_CUDA(ctx, s->pts_d.reserve(size_t(n) * 3)); VXS_CUDA(ctx, s->keysA.reserve(size_t(n) * 3)); VXS_CUDA(ctx, s->keysB.reserve(size_t(n)));
+  VXS_CUDA(ctx, cudaMemcpyAsync(s->pts_d.p, pw, size_t(n) * 24, cudaMemcpyHostToDevice, ctx->stream));
+  VXS_LAUNCH(ctx, "k_voxel_keys", k_voxel_keys, nblk(size_t(n), 256), 256, 0, s->pts_d.p, (long long)n, voxel_size, (long long*)s->keysA.p, s->keysB.p);
+  VXS_CUDA(ctx, cudaMemcpyAsync(xyz, s->keysA.p, size_t(n) * 24, cudaMemcpyDeviceToHost, ctx->stream));
+  VXS_CUDA(ctx, cudaMemcpyAsync(hash, s->keysB.p, size_t(n) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  VXS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return VXS_OK;
+}
+
+extern "C" int vxs_build_window_factor(vxs_ctx* ctx, const vxs_map_params* mp, const double* pts_body, const int64_t* scan_offsets, const double* poses12, int W,
+                                       const double* fix_pts, int64_t n_fix, vxs_factor* out, vxs_voxel_id* ids_out, int64_t ids_cap, int64_t* n_out) {
+  if (!ctx || !scan_offsets || W <= 0 || (scan_offsets[W] > 0 && !pts_body)) return VXS_ERR_ARG;
+  if (!fix_pts || n_fix <= 0) return build_factor(ctx, mp, false, pts_body, nullptr, 3, scan_offsets, W, poses12, W, out, ids_out, ids_cap, n_out);
+  // fixed map points ride along as pseudo-frame W (already in world coordinates)
+  const int64_t nw = scan_offsets[W];
+  std::vector<double> all(size_t(nw + n_fix) * 3);
+  if (nw) memcpy(all.data(), pts_body, size_t(nw) * 24);
+  memcpy(all.data() + size_t(nw) * 3, fix_pts, size_t(n_fix) * 24);
+  std::vector<int64_t> off(scan_offsets, scan_offsets + W + 1);
+  off.push_back(nw + n_fix);
+  return build_factor(ctx, mp, false, all.data(), nullptr, 3, off.data(), W + 1, poses12, W, out, ids_out, ids_cap, n_out);
+}
+
+extern "C" int vxs_build_gba_factor(vxs_ctx* ctx, const vxs_map_params* mp, const float* xyz, int stride_floats, const int64_t* kf_offsets, const double* poses12, int W,
+                                    vxs_factor* out, vxs_voxel_id* ids_out, int64_t ids_cap, int64_t* n_out) {
+  if (!ctx || !kf_offsets || W <= 0 || stride_floats < 3 || (kf_offsets[W] > 0 && !xyz)) return VXS_ERR_ARG;
+  return build_factor(ctx, mp, true, nullptr, xyz, stride_floats, kf_offsets, W, poses12, W, out, ids_out, ids_cap, n_out);
+}
+
+// HBA_add_edge BA loop, voxelslam.cpp:2360-2399
+extern "C" int vxs_hba_window(vxs_ctx* ctx, const vxs_map_params* coarse, const vxs_map_params* fine, const float* xyz, int stride_floats, const int64_t* kf_offsets,
+                              double* poses12, int W, int max_iter, int thread_num, double* hess_out, double* resis_log, int* outer_iters) {
+  if (!ctx || !coarse || !fine || !poses12 || W <= 0) return VXS_ERR_ARG;
+  vxs_map_params gp = *coarse;
+  const int up = 4;
+  int converge_flag = 0, iters = 0, warn = 0;
+  double converge_thre = 0.05;
+  vxs_factor* f = nullptr;
+  int rc = vxs_factor_create(ctx, W, &f);
+  if (rc) return rc;
+  for (int iterCnt = 0; iterCnt < max_iter; iterCnt++) {
+    if (converge_flag == 1 || iterCnt == max_iter - 1) { const int ml = gp.max_layer; gp = *fine; gp.max_layer = ml; }   // :2362-2372 (max_layer is the shared global)
+    int64_t nv = 0;
+    rc = vxs_build_gba_factor(ctx, &gp, xyz, stride_floats, kf_offsets, poses12, W, f, nullptr, 0, &nv);
+    if (rc < 0) break;
+    double resis[2] = {0, 0};
+    int is_converge = 0;
+    rc = vxs_lidar_ba(ctx, f, poses12, up, thread_num, hess_out, resis, &is_converge, nullptr, 0, nullptr);
+    if (rc < 0) break;
+    if (rc > 0) warn = rc;
+    if (resis_log) { resis_log[2 * iters] = resis[0]; resis_log[2 * iters + 1] = resis[1]; }
+    iters++;
+    if ((fabs(resis[0] - resis[1]) / resis[0] < converge_thre && is_converge) || (iterCnt == max_iter - 2 && converge_flag == 0)) {
+      converge_thre = 0.01;
+      if (converge_flag == 0) converge_flag = 1;
+      else if (converge_flag == 1) break;
+    }
+  }
+  vxs_factor_destroy(f);
+  if (outer_iters) *outer_iters = iters;
+  return rc < 0 ? rc : warn;
+}

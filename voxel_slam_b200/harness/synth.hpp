@@ -70,8 +70,8 @@ inline void jr3_inv(const double* R, double* J) {
 }
 
 // generic small dense (row-major) helpers
-inline bool inv_nxn(const double* A, double* Ainv, int n) {  // Gauss–Jordan, partial pivoting
-  std::vector<double> M(size_t(n) * 2 * n);
+inline bool inv_nxn(const double* A, double* Ainv, int n) {  // Gauss–Jordan, partial pivoting (n <= 16)
+  double M[16 * 32];
   for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) { M[size_t(i) * 2 * n + j] = A[i * n + j]; M[size_t(i) * 2 * n + n + j] = (i == j); }
   for (int c = 0; c < n; c++) {
     int p = c; double big = std::fabs(M[size_t(c) * 2 * n + c]);
@@ -217,7 +217,8 @@ struct ImuPre {
     inv_nxn(cov, cov_inv, 15);
     if (jac_enable) {
       const int bs = with_g ? 33 : 30;
-      std::vector<double> joc(size_t(15) * bs, 0.0);  // row-major 15 x bs : [joca | jocb | jocg]
+      double joc[15 * 33];  // row-major 15 x bs : [joca | jocb | jocg]
+      for (int i = 0; i < 15 * bs; i++) joc[i] = 0.0;
       auto J = [&](int r, int c) -> double& { return joc[size_t(r) * bs + c]; };
       double JR_inv[9], R2T[9], M[9], M2[9], resT[9], Jr[9];
       jr3_inv(res_r, JR_inv); mat3_t(R2, R2T); mat3_t(res_r, resT);
@@ -236,10 +237,12 @@ struct ImuPre {
         J(9 + r, 9 + c) = -(r == c); J(12 + r, 12 + c) = -(r == c); J(9 + r, 15 + 9 + c) = (r == c); J(12 + r, 15 + 12 + c) = (r == c);
         if (with_g) { J(3 + r, 30 + c) = R1T[3 * r + c] * (-0.5 * dtime * dtime); J(6 + r, 30 + c) = R1T[3 * r + c] * (-dtime); }
       }
-      std::vector<double> CJ(size_t(15) * bs);
+      double CJ[15 * 33];
       for (int r = 0; r < 15; r++) for (int c = 0; c < bs; c++) { double s = 0; for (int k = 0; k < 15; k++) s += cov_inv[r * 15 + k] * J(k, c); CJ[size_t(r) * bs + c] = s; }
       for (int a = 0; a < bs; a++) for (int b = 0; b < bs; b++) { double s = 0; for (int k = 0; k < 15; k++) s += J(k, a) * CJ[size_t(k) * bs + b]; jtj[size_t(b) * bs + a] = s; }
-      for (int a = 0; a < bs; a++) { double s = 0; for (int k = 0; k < 15; k++) { double cr = 0; for (int m = 0; m < 15; m++) cr += cov_inv[k * 15 + m] * rr[m]; s += J(k, a) * cr; } gg[a] = s; }
+      double cr[15];
+      for (int k = 0; k < 15; k++) { double t = 0; for (int m = 0; m < 15; m++) t += cov_inv[k * 15 + m] * rr[m]; cr[k] = t; }
+      for (int a = 0; a < bs; a++) { double s = 0; for (int k = 0; k < 15; k++) s += J(k, a) * cr[k]; gg[a] = s; }
     }
     double cost = 0;
     for (int r = 0; r < 15; r++) { double s = 0; for (int k = 0; k < 15; k++) s += cov_inv[r * 15 + k] * rr[k]; cost += rr[r] * s; }
