@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""bench.py — local-BA iterations/sec at 1 M pts/scan, 50-frame window (BASELINE.json metric), on N GPUs of one node.
+
+A "step" is ONE Levenberg–Marquardt iteration of the sliding-window LiDAR-inertial BA (LI_BA_Optimizer::damping_iter body,
+voxel_map.hpp:581-649): Hessian build over the voxel factor (+ the CPU-side IMU blocks through the callback), gauge fix,
+damped LDL^T solve of the 15W system, state retraction, residual-only evaluation — i.e. one vxs_li_ba(max_iter=1) call.
+
+  value : K steps with the voxel factor already resident in HBM (built on the GPU from the synthetic scans before timing).
+  e2e   : the reference-facing call with HOST buffers: push the host LidarFactor (pinned CSR arrays, H2D), run the
+          reference's 3-iteration damping_iter, read back poses + Hessian + the factor side effects (eig / pcr_adds) —
+          iterations actually executed / time.
+  N > 1 : one process per GPU (torchrun); the window does not need a collective (SURVEY §8e / north_star restrict the
+          all-reduce to global BA), so every rank solves its own independent window: "replicas", weak scaling.
+  --impl reference : the CPU restatement of the reference (oracle/, 5 threads as the reference hard-codes) on the same window
+          geometry, rank 0 only.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "local-BA LM iterations/sec (W=50 window, 1M pts/scan)"
+UNIT = "iterations/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi samples DURING the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, device):
+        self.rows, self.proc, self.device = [], None, device
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.device)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def scene_points(vx, W, pts, L, seed):
+    tr = np.stack([vx.true_pose(L, i) for i in range(W)])
+    est = tr.copy()
+    for i in range(1, W):
+        est[i] = vx.perturb_pose(tr[i], seed * 1000 + i, 2e-3, 1e-2)
+    p = np.empty((W * pts, 3), dtype=np.float64)
+    for i in range(W):
+        vx.gen_scan(L, i, pts, tr[i], seed=0x5EED0000 + seed, out=p[i * pts:(i + 1) * pts])
+    off = np.arange(W + 1, dtype=np.int64) * pts
+    return tr, est, p, off
+
+
+def states_from(poses):
+    s = np.zeros((poses.shape[0], 24))
+    s[:, :12] = poses
+    s[:, 12:15] = (0.5, 0.3, 0.0)
+    s[:, 21:24] = (0.0, 0.0, -9.8)
+    return s
+
+
+def dist_setup(args):
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_
+        torch.cuda.set_device(local)
+        dist_.init_process_group(backend="nccl" if args.impl != "reference" else "gloo")
+        dist = dist_
+    return rank, world, local, dist
+
+
+def barrier_max(dist, local, value):
+    if dist is None:
+        return value
+    import torch
+    t = torch.tensor([value], dtype=torch.float64, device=f"cuda:{local}" if dist.get_backend() == "nccl" else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier(dist, local):
+    if dist is not None:
+        import torch
+        if dist.get_backend() == "nccl":
+            torch.cuda.synchronize(local)
+        dist.barrier()
+
+
+# ---------------------------------------------------------------------------------------------------------------- ours
+def run_ours(args):
+    import voxel_slam_b200 as vx
+    from voxel_slam_b200 import api
+    rank, world, local, dist = dist_setup(args)
+    W, pts, L, K, Wu = args.win, args.pts_per_scan, args.L, args.steps, args.warmup
+    ctx = vx.Context(local)
+    t0 = time.time()
+    tr, est, p, off = scene_points(vx, W, pts, L, seed=1 + rank)
+    t_gen = time.time() - t0
+    mp = vx.MapParams.make(voxel_size=1.0, min_eigen_value=0.0025, max_layer=2)
+    f = vx.Factor(ctx, W)
+    ctx.timing(True); ctx.timing_reset()
+    t0 = time.time()
+    nvox = ctx.build_window_factor(mp, p, off, est, f)
+    t_vox = time.time() - t0
+    vox_stages = ctx.timing_read(); ctx.timing(False)
+    V, E, _ = f.counts()
+    log(f"[rank {rank}] scene W={W} pts/scan={pts} L={L}: generated in {t_gen:.1f}s; GPU map build {t_vox * 1e3:.1f} ms -> V={V} voxels, E={E} entries (k={E / max(V, 1):.1f})")
+    del p
+    st0 = states_from(est)
+    imu = vx.ImuWindow(tr)
+    n = 15 * W
+
+    def step():
+        imu.reset()
+        return ctx.li_ba(f, st0, imu, with_gravity=False, max_iter=1, want_hess=False, trace_cap=4)
+
+    # ---- value: K steps, factor resident in HBM
+    for _ in range(max(Wu, 3)):
+        step()
+    launches0 = ctx.launches
+    sampler = ClockSampler(local); sampler.start()
+    barrier(dist, local)
+    ctx.timer_start()
+    for _ in range(K):
+        step()
+    ms = ctx.timer_stop()
+    ms = barrier_max(dist, local, ms)
+    clocks = sampler.stop()
+    launches = ctx.launches - launches0
+    value = world * K / (ms * 1e-3)
+
+    # ---- per-kernel durations (CUDA events around every launch on the ctx stream), same steps
+    ctx.timing(True); ctx.timing_reset()
+    reps = min(K, 10)
+    for _ in range(reps):
+        step()
+    stages = ctx.timing_read(); ctx.timing(False)
+    kern = {k: {"ms_per_step": v[0] / reps, "launches_per_step": v[1] / reps, "us_per_launch": v[0] / max(v[1], 1) * 1e3} for k, v in stages.items() if v[1] > 0}
+
+    # ---- e2e: host LidarFactor in, 3-iteration damping_iter, results out
+    ptr, fr, cl, fx, co = f.read_structure()
+    eig0, sum0 = f.read_back()
+    f.clear()
+    f.push_voxels(ptr, fr, cl, eig0, sum0)        # back to the state the map build left (cached eig at the cut poses)
+    hp = dict(ptr=api.pinned_array(ptr.shape, np.int64), fr=api.pinned_array(fr.shape, np.int32), cl=api.pinned_array(cl.shape, np.float64),
+              eig=api.pinned_array(eig0.shape, np.float64), s=api.pinned_array(sum0.shape, np.float64))
+    hp["ptr"][:] = ptr; hp["fr"][:] = fr; hp["cl"][:] = cl; hp["eig"][:] = eig0; hp["s"][:] = sum0
+    out_eig, out_sum = api.pinned_array(eig0.shape, np.float64), api.pinned_array(sum0.shape, np.float64)
+    del cl
+
+    def e2e_call():
+        imu.reset()
+        f.clear()
+        f.push_voxels(hp["ptr"], hp["fr"], hp["cl"], hp["eig"], hp["s"])
+        o = ctx.li_ba(f, st0, imu, with_gravity=False, max_iter=3, want_hess=True, trace_cap=8)
+        api.lib().vxs_factor_read_back(f._p, out_eig.ctypes.data_as(C.POINTER(C.c_double)), out_sum.ctypes.data_as(C.POINTER(C.c_double)))
+        return o
+
+    o = e2e_call()
+    Ke = max(3, min(K, 10))
+    barrier(dist, local)
+    t0 = time.perf_counter(); ctx.timer_start()
+    iters = 0
+    for _ in range(Ke):
+        iters += len(e2e_call()["trace"])
+    ms_e = ctx.timer_stop()
+    wall_e = (time.perf_counter() - t0) * 1e3
+    ms_e = barrier_max(dist, local, max(ms_e, wall_e))
+    e2e_value = world * iters / (ms_e * 1e-3)
+    it_call = iters / Ke
+    h2d = (ptr.nbytes + fr.nbytes + E * 80 + V * (96 + 80)) / it_call + W * 24 * 8 * 2 + (W - 1) * (900 + 30) * 8
+    d2h = (V * 176 + n * n * 8) / it_call + (3 * n + 2) * 8
+
+    # ---- sanity of what was timed: the 3-iteration solve moves the poses towards the truth
+    err0, err1 = float(np.abs(est - tr).max()), float(np.abs(o["states"][:, :12] - tr).max())
+
+    # ---- roofline (HBM) for the kernels of the hot path; algorithmic bytes per SURVEY.md §8(d)
+    peaks, src = measured_peaks()
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    fp64_peak = ctx.fp64_tflops()
+    kv = E / max(V, 1)
+
+    def roof(names, bytes_per_launch, flops=None):
+        t = sum(kern[k]["ms_per_step"] for k in names if k in kern)
+        if t <= 0:
+            return None
+        r = {"kernel": "+".join(names), "bound": "hbm", "achieved": bytes_per_launch / (t * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s", "frac": bytes_per_launch / (t * 1e-3) / 1e9 / hbm,
+             "traffic": None, "ms": t, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({src})", "algorithmic_bytes": bytes_per_launch}
+        if flops:
+            r["fp64"] = {"achieved_tflops": flops / (t * 1e-3) / 1e12, "peak_tflops": fp64_peak, "frac": flops / (t * 1e-3) / 1e12 / fp64_peak, "peak_source": "vxs_diag_fp64_tflops (measured here)"}
+        return r
+
+    nl = 6 * W
+    bytes_resid = E * 80 + V * 176 + 96 * W
+    bytes_hess = E * 80 + V * 176 + 8 * (nl * nl + nl + 1)
+    flops_hess = V * (700.0 * kv + 110.0 * kv * kv)
+    roof_hess = roof(["k_jac", "k_syrk"], bytes_hess, flops_hess)
+    roof_resid = roof(["k_cluster_sum", "k_eig_residual"], bytes_resid)
+    roof_jac = roof(["k_jac"], E * 80 + V * 176 + E * 144)
+    dom = max(kern.items(), key=lambda kv_: kv_[1]["ms_per_step"])[0] if kern else None
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline_from_structure(vx, W, ptr, fr, hp["cl"], eig0, sum0, st0, tr, reps=2)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(Wu, 3), "ms_per_step": ms / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic (seeded 3-plane room, SURVEY.md §8d; random-free IMU stand-in on the CPU callback)",
+            "config": {"workload": f"metric shape M: W={W} window, {pts} pts/scan, L={L} m room, voxel 1 m, max_layer 2 -> V={V} plane voxels, E={E} (voxel,frame) clusters; n=15W={n} LI-BA system",
+                       "step": "one LM iteration = vxs_li_ba(max_iter=1): Hessian build + IMU blocks (CPU callback) + damped LDLT + retraction + residual evaluation",
+                       "l2": "working set (clusters 80 B x E + rank-3 rows 144 B x V x W) is larger than the 126 MB L2; no extra flush",
+                       "parallelism": "replicas: one independent window per GPU, no collective" if world > 1 else "1 GPU"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "iterations_per_call": it_call,
+                    "call": "push host LidarFactor (pinned CSR) + LI_BA damping_iter (3 iterations) + read back poses, Hessian, eig/pcr_adds"},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roof_hess, "roofline_residual": roof_resid, "roofline_jac": roof_jac, "dominant_kernel": dom,
+            "kernels": kern, "cpu_baseline": cpu,
+            "voxelize": {"ms_total": t_vox * 1e3, "points": int(W * pts), "stages_ms": {k: v[0] for k, v in vox_stages.items() if v[1] > 0}},
+            "check": {"pose_err_before": err0, "pose_err_after_3_iters": err1, "trace": [[float(t["r1"]), float(t["r2"]), int(t["accepted"])] for t in o["trace"]]},
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier(); dist.destroy_process_group()
+
+
+def oracle_factor_from_csr(W, ptr, fr, cl, eig, s):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_api as oa
+    V = ptr.shape[0] - 1
+    dense = np.zeros((V, W, 10))
+    vox = np.repeat(np.arange(V), np.diff(ptr))
+    dense[vox, fr] = cl
+    return oa.OracleFactor.from_dense(W, dense, None, None, eig, s)
+
+
+def cpu_baseline_from_structure(vx, W, ptr, fr, cl, eig, s, st0, tr, reps=2):
+    """The oracle (CPU restatement of the reference, reference thread structure: 5 threads) on the SAME factor, timed on this host."""
+    of = oracle_factor_from_csr(W, ptr, fr, cl, eig, s)
+    imu = vx.ImuWindow(tr)
+    ts = []
+    for _ in range(reps):
+        imu.reset()
+        t0 = time.perf_counter()
+        of.li_ba(st0, imu, with_gravity=False, max_iter=1)
+        ts.append(time.perf_counter() - t0)
+    t = min(ts)
+    return {"value": 1.0 / t, "unit": UNIT, "cores": 5, "kind": "port", "host_cores": os.cpu_count(),
+            "sample": f"{reps} full-size LM iterations (all {ptr.shape[0] - 1} voxels) of the oracle LI_BA_Optimizer, best of {reps}; 5 threads as voxel_map.hpp:467,531 hard-code"}
+
+
+# ---------------------------------------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    rank, world, local, dist = dist_setup(args)
+    if rank != 0:
+        if dist is not None:
+            dist.barrier(); dist.destroy_process_group()
+        return
+    import __graft_entry__ as ge
+    ge.build(quiet=True)
+    import voxel_slam_b200 as vx
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_api as oa
+    W, L, K, Wu = args.win, args.L, args.steps, args.warmup
+    pts_map = min(args.pts_per_scan, 200000)   # LM cost depends on voxels x frames, not on points per scan: build the map from a bounded cloud
+    tr, est, p, off = scene_points(vx, W, pts_map, L, seed=1)
+    mp = vx.MapParams.make(voxel_size=1.0, min_eigen_value=0.0025, max_layer=2)
+    t0 = time.time()
+    of = oa.build_window_factor(mp, p, off, est, threads=5)
+    t_map = time.time() - t0
+    V = of.size()
+    log(f"[reference] oracle map build from {W}x{pts_map} points: {t_map:.1f}s, V={V}")
+    st0 = states_from(est)
+    imu = vx.ImuWindow(tr)
+    ex = of.export()
+    cl, eig, s = ex["clusters10"], ex["eig12"], ex["sum10"]
+    # probe one iteration, then bound the sample so the whole run stays within a few minutes
+    t0 = time.perf_counter(); imu.reset(); of.li_ba(st0, imu, max_iter=1); t_full = time.perf_counter() - t0
+    budget = 150.0
+    phi = min(1.0, budget / ((K + Wu) * t_full))
+    if phi < 1.0:
+        keep = max(64, int(V * phi))
+        sel = np.linspace(0, V - 1, keep).astype(np.int64)
+        fsub = oa.OracleFactor.from_dense(W, cl[sel], None, None, eig[sel], s[sel])
+        phi = keep / V
+    else:
+        fsub = oa.OracleFactor.from_dense(W, cl, None, None, eig, s)
+    # fixed (voxel-independent) part of an iteration: the dense LDLT of the 15W system
+    n = 15 * W
+    A = np.eye(n) * 2 + 0.01 * np.ones((n, n)); t0 = time.perf_counter(); oa.ldlt_solve(A, np.ones(n)); t_fix = time.perf_counter() - t0
+
+    def step():
+        imu.reset()
+        t0 = time.perf_counter()
+        fsub.li_ba(st0, imu, max_iter=1)
+        return time.perf_counter() - t0
+
+    for _ in range(Wu):
+        step()
+    t_steps = [step() for _ in range(K)]
+    t_step = float(np.mean(t_steps))
+    t_iter_full = (max(t_step - t_fix, 0.0)) / phi + t_fix      # voxel-proportional part scaled back to the full window
+    value = 1.0 / t_iter_full
+    sample = (f"window geometry of the metric shape (W={W}, L={L}, V={V} voxels) built from {pts_map} pts/scan; each step = one full LM iteration of the oracle LI_BA_Optimizer "
+              f"(5 threads) over a {phi:.3f} fraction of the voxels, voxel-proportional time scaled to the full window (LDLT {t_fix * 1e3:.0f} ms not scaled)")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wu, "ms_per_step": t_iter_full * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic (same seeded scene as the GPU arm)",
+            "config": {"workload": f"metric shape M: W={W} window, L={L} m room, V={V} plane voxels; n=15W={n} LI-BA system", "parallelism": "CPU, 5 threads (reference thread structure)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 5, "kind": "port", "host_cores": os.cpu_count(), "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier(); dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--win", type=int, default=50)
+    ap.add_argument("--pts-per-scan", type=int, default=1000000)
+    ap.add_argument("--L", type=float, default=130.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -52,6 +52,13 @@ int64_t vxs_ctx_launch_count(const vxs_ctx* ctx);
 int vxs_ctx_timing_enable(vxs_ctx* ctx, int on);
 int vxs_ctx_timing_read(vxs_ctx* ctx, int cap, const char** names, double* ms_total, int64_t* calls, int* n_out);
 int vxs_ctx_timing_reset(vxs_ctx* ctx);
+/* one CUDA-event stopwatch on the ctx stream (bench.py times its K steps with it): start records an event, stop records a
+ * second one, synchronises and returns the elapsed device time in milliseconds */
+int vxs_ctx_timer_start(vxs_ctx* ctx);
+int vxs_ctx_timer_stop(vxs_ctx* ctx, double* ms);
+/* diagnostics: measured fp64 FMA throughput of this device (TFLOP/s, 2 flop per FMA) — the roofline denominator of the
+ * SYRK part of the Hessian, which MEASURED_PEAKS.json does not carry */
+int vxs_diag_fp64_tflops(vxs_ctx* ctx, double* tflops);
 
 /* ---------------------------------------------------------------- multi-GPU (one process per GPU; NCCL over NVLink)
  * Voxel-sharded BA: every rank holds the factor voxels it owns and the replicated poses; [H_lidar, g, r] are

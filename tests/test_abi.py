@@ -42,3 +42,14 @@ def test_product_never_touches_the_oracle():
                 if "oracle/" in txt or "liboracle" in txt or "oracle_api" in txt or "vxo_" in txt:
                     bad.append(os.path.join(d, fn))
     assert not bad, bad
+
+
+def test_cpp_shim_plain_layer_compiles():
+    """The header-only C++ shim with the reference's class names compiles (plain layer; the Eigen-typed layer needs the reference headers)."""
+    import subprocess
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with tempfile.NamedTemporaryFile("w", suffix=".cpp", delete=False) as f:
+        f.write('#include "voxel_slam_b200/csrc/shim/voxel_ba_shim.hpp"\nint main() { vxs_shim::Lidar_BA_Optimizer o; return o.thd_num == 2 ? 0 : 1; }\n')
+    r = subprocess.run(["g++", "-std=c++14", "-fsyntax-only", "-I", root, f.name], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr

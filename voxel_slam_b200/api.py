@@ -203,6 +203,19 @@ class Context:
         self._check(lib().vxs_ctx_timing_read(self._p, C.c_int(cap), names, ms, calls, C.byref(n)))
         return {names[i].decode(): (ms[i], calls[i]) for i in range(n.value)}
 
+    def timer_start(self):
+        self._check(lib().vxs_ctx_timer_start(self._p))
+
+    def timer_stop(self):
+        ms = C.c_double(0)
+        self._check(lib().vxs_ctx_timer_stop(self._p, C.byref(ms)))
+        return ms.value
+
+    def fp64_tflops(self):
+        t = C.c_double(0)
+        self._check(lib().vxs_diag_fp64_tflops(self._p, C.byref(t)))
+        return t.value
+
     # --- multi-GPU
     @staticmethod
     def comm_unique_id():

@@ -1,0 +1,213 @@
+// voxel_ba_shim.hpp — header-only C++ shim that re-creates the reference's call surface on top of the C-ABI (include/vxs.h),
+// so voxelslam.cpp keeps compiling against the same names:
+//
+//   LidarFactor                (voxel_map.hpp:109-290)   -> vxs_shim::LidarFactor          (host staging + device factor)
+//   Lidar_BA_Optimizer         (voxel_map.hpp:293-444)   -> vxs_shim::Lidar_BA_Optimizer
+//   LI_BA_Optimizer            (voxel_map.hpp:450-655)   -> vxs_shim::LI_BA_Optimizer
+//   LI_BA_OptimizerGravity     (voxel_map.hpp:658-864)   -> vxs_shim::LI_BA_OptimizerGravity
+//
+// Two layers:
+//   * a plain layer (no Eigen): flat arrays in, flat arrays out — compile-tested in this repository (tests/test_abi.py);
+//   * an Eigen/reference-typed layer behind VXS_SHIM_WITH_REFERENCE_TYPES: include it AFTER the reference's tools.hpp and
+//     preintegration.hpp (it uses their IMUST, PointCluster, IMU_PRE, DIM).  Eigen is not installed in the build container, so this
+//     layer is written against the reference headers but could not be compiled here (INTEGRATION.md says how to enable it).
+#pragma once
+#include <cstring>
+#include <deque>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "../../../include/vxs.h"
+
+namespace vxs_shim {
+
+inline void check(vxs_ctx* ctx, int rc, const char* what) {
+  if (rc < 0) throw std::runtime_error(std::string(what) + ": " + (ctx ? vxs_ctx_last_error(ctx) : "libvxs error"));
+}
+
+// One context per calling thread (local mapping thread, global mapping thread).
+class Context {
+ public:
+  explicit Context(int device = 0) { int rc = vxs_ctx_create(device, &ctx_); if (rc) throw std::runtime_error("vxs_ctx_create failed: no CUDA device, and libvxs has no CPU fallback"); }
+  ~Context() { vxs_ctx_destroy(ctx_); }
+  Context(const Context&) = delete;
+  Context& operator=(const Context&) = delete;
+  vxs_ctx* get() const { return ctx_; }
+ private:
+  vxs_ctx* ctx_ = nullptr;
+};
+
+// LidarFactor: push_voxel() stages on the host exactly like the reference's vectors; the first solver call uploads the batch.
+class LidarFactor {
+ public:
+  int win_size;
+  // read-back mirrors of the reference members the callers touch after a solve (voxel_map.hpp:1217-1222, voxelslam.cpp:651-655)
+  std::vector<double> eig12;   // [V][12]  eig_values | eig_vectors (row-major, eigenvectors in columns)
+  std::vector<double> sum10;   // [V][10]  pcr_adds
+
+  LidarFactor(Context& c, int w) : win_size(w), ctx_(c.get()) { check(ctx_, vxs_factor_create(ctx_, w, &dev_), "vxs_factor_create"); }
+  ~LidarFactor() { vxs_factor_destroy(dev_); }
+  LidarFactor(const LidarFactor&) = delete;
+  LidarFactor& operator=(const LidarFactor&) = delete;
+
+  // voxel_map.hpp:122-130.  clusters10: win_size x 10 (N==0 => frame absent); fix10/eig12/sum10 as in vxs.h
+  void push_voxel(const double* clusters10, const double* fix10, double coe, const double* eig, const double* sum) {
+    for (int i = 0; i < win_size; i++) {
+      const double* c = clusters10 + 10 * i;
+      if (c[9] != 0.0) { frame_.push_back(i); cl_.insert(cl_.end(), c, c + 10); }
+    }
+    ptr_.push_back(int64_t(frame_.size()));
+    fix_.insert(fix_.end(), fix10, fix10 + 10); coe_.push_back(coe);
+    eig12.insert(eig12.end(), eig, eig + 12); sum10.insert(sum10.end(), sum, sum + 10);
+    dirty_ = true;
+  }
+  void clear() {  // voxel_map.hpp:281-286
+    ptr_.assign(1, 0); frame_.clear(); cl_.clear(); fix_.clear(); coe_.clear(); eig12.clear(); sum10.clear();
+    check(ctx_, vxs_factor_clear(dev_), "vxs_factor_clear");
+    dirty_ = false;
+  }
+  size_t size() const { return ptr_.size() - 1; }
+
+  vxs_factor* device() {  // flush staged voxels
+    if (dirty_) {
+      check(ctx_, vxs_factor_clear(dev_), "vxs_factor_clear");
+      check(ctx_, vxs_factor_set_win_size(dev_, win_size), "vxs_factor_set_win_size");
+      check(ctx_, vxs_factor_push_voxels(dev_, int64_t(size()), ptr_.data(), frame_.data(), cl_.data(), fix_.data(), coe_.data(), eig12.data(), sum10.data()), "vxs_factor_push_voxels");
+      dirty_ = false;
+    }
+    return dev_;
+  }
+  void sync_back() { if (size()) check(ctx_, vxs_factor_read_back(dev_, eig12.data(), sum10.data()), "vxs_factor_read_back"); }
+  vxs_ctx* ctx() const { return ctx_; }
+
+ private:
+  vxs_ctx* ctx_;
+  vxs_factor* dev_ = nullptr;
+  std::vector<int64_t> ptr_{0};
+  std::vector<int32_t> frame_;
+  std::vector<double> cl_, fix_, coe_;
+  bool dirty_ = false;
+};
+
+// Lidar_BA_Optimizer (flat layer): poses12 = W x 12 in/out, hess = (6W)^2 column-major out (may be null), resis gets 2 entries appended
+class Lidar_BA_Optimizer {
+ public:
+  int thd_num = 2;
+  bool damping_iter(double* poses12, LidarFactor& voxhess, double* hess, std::vector<double>& resis, int max_iter = 3) {
+    double r[2] = {0, 0}; int conv = 0;
+    int rc = vxs_lidar_ba(voxhess.ctx(), voxhess.device(), poses12, max_iter, thd_num, hess, r, &conv, nullptr, 0, nullptr);
+    check(voxhess.ctx(), rc, "vxs_lidar_ba");
+    resis.push_back(r[0]); resis.push_back(r[1]);
+    voxhess.sync_back();
+    return conv != 0;
+  }
+};
+
+// LI_BA_Optimizer / LI_BA_OptimizerGravity (flat layer): states24 = W x 24, hooks wrap the caller's IMU_PRE objects
+class LI_BA_Optimizer {
+ public:
+  double imu_coef = 1e-4;   // voxel_map.hpp:446
+  void damping_iter(double* states24, LidarFactor& voxhess, const vxs_imu_hooks& imu, double* hess) {
+    double r[2];
+    check(voxhess.ctx(), vxs_li_ba(voxhess.ctx(), voxhess.device(), states24, 0, 3, imu_coef, &imu, hess, r, nullptr, 0, nullptr), "vxs_li_ba");
+    voxhess.sync_back();
+  }
+};
+class LI_BA_OptimizerGravity {
+ public:
+  double imu_coef = 1e-4;
+  void damping_iter(double* states24, LidarFactor& voxhess, const vxs_imu_hooks& imu, std::vector<double>& resis, double* hess, int max_iter = 2) {
+    double r[2] = {0, 0};
+    check(voxhess.ctx(), vxs_li_ba(voxhess.ctx(), voxhess.device(), states24, 1, max_iter, imu_coef, &imu, hess, r, nullptr, 0, nullptr), "vxs_li_ba");
+    resis.push_back(r[0]); resis.push_back(r[1]);
+    voxhess.sync_back();
+  }
+};
+
+}  // namespace vxs_shim
+
+// ------------------------------------------------------------------------------------------------------------------------------
+#if defined(VXS_SHIM_WITH_REFERENCE_TYPES)
+// Requires the reference's tools.hpp (IMUST, PointCluster, DIM) and preintegration.hpp (IMU_PRE) to be included first.
+namespace vxs_shim {
+
+inline void pack_cluster(const PointCluster& c, double* o) {
+  o[0] = c.P(0, 0); o[1] = c.P(0, 1); o[2] = c.P(0, 2); o[3] = c.P(1, 1); o[4] = c.P(1, 2); o[5] = c.P(2, 2);
+  o[6] = c.v[0]; o[7] = c.v[1]; o[8] = c.v[2]; o[9] = double(c.N);
+}
+inline void pack_state(const IMUST& x, double* s) {
+  for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) s[3 * r + c] = x.R(r, c);
+  for (int k = 0; k < 3; k++) { s[9 + k] = x.p[k]; s[12 + k] = x.v[k]; s[15 + k] = x.bg[k]; s[18 + k] = x.ba[k]; s[21 + k] = x.g[k]; }
+}
+inline void unpack_state(const double* s, IMUST& x) {
+  for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) x.R(r, c) = s[3 * r + c];
+  for (int k = 0; k < 3; k++) { x.p[k] = s[9 + k]; x.v[k] = s[12 + k]; x.bg[k] = s[15 + k]; x.ba[k] = s[18 + k]; x.g[k] = s[21 + k]; }
+}
+
+// LidarFactor::push_voxel with the reference's argument list (voxel_map.hpp:122)
+inline void push_voxel(LidarFactor& f, std::vector<PointCluster>& vec_orig, PointCluster& fix, double coe, Eigen::Vector3d& eig_value, Eigen::Matrix3d& eig_vector, PointCluster& pcr_add) {
+  std::vector<double> cl(size_t(f.win_size) * 10);
+  for (int i = 0; i < f.win_size; i++) pack_cluster(vec_orig[i], &cl[10 * i]);
+  double fx[10], e[12], s[10];
+  pack_cluster(fix, fx); pack_cluster(pcr_add, s);
+  for (int k = 0; k < 3; k++) e[k] = eig_value[k];
+  for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) e[3 + 3 * r + c] = eig_vector(r, c);
+  f.push_voxel(cl.data(), fx, coe, e, s);
+}
+
+// the IMU factor stays the reference's own code: these hooks call IMU_PRE::give_evaluate(_g) / update_state on the caller's deque
+struct ImuAdapter {
+  std::deque<IMU_PRE*>* imus;
+  static int eval(void* u, const double* states24, int W, int with_g, int want_jac, double* blocks, double* gvec, double* cost) {
+    auto* self = static_cast<ImuAdapter*>(u);
+    const int bs = with_g ? 33 : 30;
+    Eigen::MatrixXd jtj(bs, bs); Eigen::VectorXd gg(bs);
+    std::vector<IMUST> xs(W);
+    for (int i = 0; i < W; i++) unpack_state(states24 + 24 * i, xs[i]);
+    double c = 0;
+    for (int i = 0; i + 1 < W; i++) {
+      jtj.setZero(); gg.setZero();
+      c += with_g ? (*self->imus)[i]->give_evaluate_g(xs[i], xs[i + 1], jtj, gg, want_jac != 0) : (*self->imus)[i]->give_evaluate(xs[i], xs[i + 1], jtj, gg, want_jac != 0);
+      if (want_jac) { std::memcpy(blocks + size_t(i) * bs * bs, jtj.data(), sizeof(double) * bs * bs); std::memcpy(gvec + size_t(i) * bs, gg.data(), sizeof(double) * bs); }
+    }
+    *cost = c;
+    return 0;
+  }
+  static int update(void* u, const double* dxi, int W) {
+    auto* self = static_cast<ImuAdapter*>(u);
+    for (int j = 0; j + 1 < W; j++) (*self->imus)[j]->update_state(Eigen::Map<const Eigen::Matrix<double, DIM, 1>>(dxi + DIM * j));
+    return 0;
+  }
+  static int rollback(void* u) {
+    auto* self = static_cast<ImuAdapter*>(u);
+    for (IMU_PRE* p : *self->imus) { p->dbg = p->dbg_buf; p->dba = p->dba_buf; }
+    return 0;
+  }
+  vxs_imu_hooks hooks() { vxs_imu_hooks h; h.user = this; h.eval = &eval; h.update = &update; h.rollback = &rollback; return h; }
+};
+
+// LI_BA_Optimizer::damping_iter(x_stats, voxhess, imus_factor, hess)  — voxelslam.cpp:1652-1653 call site
+inline void li_ba_damping_iter(std::vector<IMUST>& x_stats, LidarFactor& voxhess, std::deque<IMU_PRE*>& imus_factor, Eigen::MatrixXd* hess, double imu_coef) {
+  const int W = voxhess.win_size;
+  std::vector<double> st(size_t(W) * 24);
+  for (int i = 0; i < W; i++) pack_state(x_stats[i], &st[24 * i]);
+  hess->resize(W * DIM, W * DIM);
+  ImuAdapter ad{&imus_factor};
+  LI_BA_Optimizer opt; opt.imu_coef = imu_coef;
+  opt.damping_iter(st.data(), voxhess, ad.hooks(), hess->data());
+  for (int i = 0; i < W; i++) unpack_state(&st[24 * i], x_stats[i]);
+}
+// Lidar_BA_Optimizer::damping_iter(xs, voxhess, &hess, resis, up, is_display) — voxelslam.cpp:2381-2384 call site
+inline bool lidar_ba_damping_iter(std::vector<IMUST>& x_stats, LidarFactor& voxhess, Eigen::MatrixXd* hess, std::vector<double>& resis, int max_iter, int thd_num) {
+  const int W = voxhess.win_size;
+  std::vector<double> p(size_t(W) * 12), st(24);
+  for (int i = 0; i < W; i++) { pack_state(x_stats[i], st.data()); std::memcpy(&p[12 * i], st.data(), 96); }
+  hess->resize(6 * W, 6 * W);
+  Lidar_BA_Optimizer opt; opt.thd_num = thd_num;
+  bool conv = opt.damping_iter(p.data(), voxhess, hess->data(), resis, max_iter);
+  for (int i = 0; i < W; i++) { for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) x_stats[i].R(r, c) = p[12 * i + 3 * r + c]; for (int k = 0; k < 3; k++) x_stats[i].p[k] = p[12 * i + 9 + k]; }
+  return conv;
+}
+
+}  // namespace vxs_shim
+#endif  // VXS_SHIM_WITH_REFERENCE_TYPES

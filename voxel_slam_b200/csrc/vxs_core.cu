@@ -25,6 +25,7 @@ extern "C" int vxs_ctx_create(int device, vxs_ctx** out) {
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return VXS_ERR_CUDA; }
   cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming);
+  cudaEventCreate(&c->ev_t0); cudaEventCreate(&c->ev_t1);
   c->scal.reserve(64);
   c->flags.reserve(16);
   *out = c;
@@ -49,6 +50,8 @@ extern "C" int vxs_ctx_destroy(vxs_ctx* c) {
   c->scal.release(); c->flags.release(); c->stage.release(); c->stage_i64.release();
   if (c->h_pin) cudaFreeHost(c->h_pin);
   if (c->ev_copy) cudaEventDestroy(c->ev_copy);
+  if (c->ev_t0) cudaEventDestroy(c->ev_t0);
+  if (c->ev_t1) cudaEventDestroy(c->ev_t1);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -92,6 +95,53 @@ extern "C" int vxs_ctx_timing_read(vxs_ctx* c, int cap, const char** names, doub
   int n = std::min<int>(cap, int(c->stages.size()));
   for (int i = 0; i < n; i++) { names[i] = c->stages[i].name; ms_total[i] = c->stages[i].ms_total; calls[i] = c->stages[i].calls; }
   if (n_out) *n_out = n;
+  return VXS_OK;
+}
+
+extern "C" int vxs_ctx_timer_start(vxs_ctx* c) {
+  if (!c) return VXS_ERR_ARG;
+  cudaSetDevice(c->device);
+  VXS_CUDA(c, cudaStreamSynchronize(c->stream));
+  VXS_CUDA(c, cudaEventRecord(c->ev_t0, c->stream));
+  return VXS_OK;
+}
+extern "C" int vxs_ctx_timer_stop(vxs_ctx* c, double* ms) {
+  if (!c || !ms) return VXS_ERR_ARG;
+  VXS_CUDA(c, cudaEventRecord(c->ev_t1, c->stream));
+  VXS_CUDA(c, cudaEventSynchronize(c->ev_t1));
+  float f = 0;
+  VXS_CUDA(c, cudaEventElapsedTime(&f, c->ev_t0, c->ev_t1));
+  *ms = f;
+  return VXS_OK;
+}
+
+// fp64 FMA peak: 8 independent chains per thread, enough warps to fill every SM
+__global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double b = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; i++) {
+    a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+    a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+extern "C" int vxs_diag_fp64_tflops(vxs_ctx* c, double* tflops) {
+  if (!c || !tflops) return VXS_ERR_ARG;
+  cudaSetDevice(c->device);
+  const int blocks = c->sm_count * 8, iters = 20000;
+  VXS_CUDA(c, c->stage.reserve(size_t(blocks) * 256));
+  double best = 0;
+  for (int rep = 0; rep < 4; rep++) {
+    VXS_CUDA(c, cudaEventRecord(c->ev_t0, c->stream));
+    VXS_LAUNCH(c, "k_dfma_peak", k_dfma_peak, blocks, 256, 0, c->stage.p, iters);
+    VXS_CUDA(c, cudaEventRecord(c->ev_t1, c->stream));
+    VXS_CUDA(c, cudaEventSynchronize(c->ev_t1));
+    float ms = 0;
+    VXS_CUDA(c, cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1));
+    const double tf = double(blocks) * 256 * iters * 8 * 2 / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  *tflops = best;
   return VXS_OK;
 }
 

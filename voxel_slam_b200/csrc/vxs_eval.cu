@@ -150,6 +150,10 @@ __device__ __forceinline__ void store_zero_rows(double* dst, int nframes) {
   for (int i = 0; i < nframes * 9; i++) p[i] = make_double2(0.0, 0.0);
 }
 
+// Gradient / block-diagonal accumulation without per-entry atomics: a thread keeps the 30 sums of the frame it is currently
+// looking at in registers and only flushes them (fp64 RED) when its frame changes.  In a sliding window the entry a lane
+// handles has the same frame for (almost) every voxel, so the flush happens a handful of times per thread instead of once per
+// entry; in sparse global-BA windows it degenerates gracefully to the per-entry scatter (where contention is low anyway).
 template <int G, bool DENSE>
 __global__ void __launch_bounds__(128) k_jac(FactorView f, const double* __restrict__ poses, int pstride, double* __restrict__ X, double* __restrict__ gD) {
   const int lane = threadIdx.x & (G - 1);
@@ -158,6 +162,12 @@ __global__ void __launch_bounds__(128) k_jac(FactorView f, const double* __restr
   const int W = f.W;
   double* gbuf = gD;
   double* Dbuf = gD + size_t(W) * 6;
+  int cur_fr = -1;
+  rot3 R; d3 t;
+  R.r00 = R.r01 = R.r02 = R.r10 = R.r11 = R.r12 = R.r20 = R.r21 = R.r22 = 0.0; t = mk3(0, 0, 0);
+  double acc[30];
+#pragma unroll
+  for (int i = 0; i < 30; i++) acc[i] = 0.0;
   for (int v = group; v < f.V; v += ngroups) {
     const int beg = f.ptr[v], end = f.ptr[v + 1];
     if (DENSE && beg == end && lane == 0) store_zero_rows(X + size_t(v) * W * 18, W);
@@ -175,8 +185,19 @@ __global__ void __launch_bounds__(128) k_jac(FactorView f, const double* __restr
     for (int en = beg + lane; en < end; en += G) {
       cluster c = load_cluster_soa(f.cl, f.Ecap, size_t(en));
       const int fr = __ldg(f.frame + en);
-      rot3 R; d3 t;
-      load_pose(poses, pstride, fr, R, t);
+      if (fr != cur_fr) {
+        if (cur_fr >= 0) {
+          double* g = gbuf + cur_fr * 6; double* D = Dbuf + cur_fr * 24;
+#pragma unroll
+          for (int i = 0; i < 6; i++) atomicAdd(g + i, acc[i]);
+#pragma unroll
+          for (int i = 0; i < 24; i++) atomicAdd(D + i, acc[6 + i]);
+#pragma unroll
+          for (int i = 0; i < 30; i++) acc[i] = 0.0;
+        }
+        cur_fr = fr;
+        load_pose(poses, pstride, fr, R, t);
+      }
       entry_out o;
       entry_jacobian(kc, c, R, t, o);
       double* xd = DENSE ? X + (size_t(v) * W + fr) * 18 : X + size_t(en) * 18;
@@ -188,17 +209,20 @@ __global__ void __launch_bounds__(128) k_jac(FactorView f, const double* __restr
         if (fr - prev > 1) store_zero_rows(X + (size_t(v) * W + prev + 1) * 18, fr - prev - 1);
         if (en == end - 1 && fr < W - 1) store_zero_rows(X + (size_t(v) * W + fr + 1) * 18, W - 1 - fr);
       }
-      double* g = gbuf + fr * 6;
 #pragma unroll
-      for (int i = 0; i < 6; i++) atomicAdd(g + i, kc.coe * o.g[i]);
-      double* D = Dbuf + fr * 24;
+      for (int i = 0; i < 6; i++) acc[i] += kc.coe * o.g[i];
 #pragma unroll
-      for (int i = 0; i < 9; i++) atomicAdd(D + i, o.Drr[i]);
+      for (int i = 0; i < 9; i++) { acc[6 + i] += o.Drr[i]; acc[15 + i] += o.Drt[i]; }
 #pragma unroll
-      for (int i = 0; i < 9; i++) atomicAdd(D + 9 + i, o.Drt[i]);
-#pragma unroll
-      for (int i = 0; i < 6; i++) atomicAdd(D + 18 + i, o.Dtt[i]);
+      for (int i = 0; i < 6; i++) acc[24 + i] += o.Dtt[i];
     }
+  }
+  if (cur_fr >= 0) {
+    double* g = gbuf + cur_fr * 6; double* D = Dbuf + cur_fr * 24;
+#pragma unroll
+    for (int i = 0; i < 6; i++) atomicAdd(g + i, acc[i]);
+#pragma unroll
+    for (int i = 0; i < 24; i++) atomicAdd(D + i, acc[6 + i]);
   }
 }
 
@@ -409,6 +433,11 @@ static int pick_group(const vxs_factor* f) {
   const double avg = f->V > 0 ? double(f->E) / double(f->V) : 1.0;
   return avg > 16.0 ? 32 : (avg > 8.0 ? 16 : 8);
 }
+static int pick_group_jac(const vxs_factor* f) {   // one lane per frame slot of the window when it fits (W <= 64)
+  const double avg = f->V > 0 ? double(f->E) / double(f->V) : 1.0;
+  if (avg > 24.0 && f->W > 32) return 64;
+  return avg > 16.0 ? 32 : (avg > 8.0 ? 16 : 8);
+}
 
 // layout of the all-reducible accumulator block: [ C (6W)^2 | g 6W | D 24W | r1 ]
 static size_t hess_block_doubles(int W) { return size_t(6 * W) * size_t(6 * W) + size_t(30) * W + 1; }
@@ -449,10 +478,12 @@ int vxs_eval_hessian_dev(vxs_ctx* ctx, vxs_factor* f, const double* poses_dev, i
     const unsigned blocks_v = nblk(size_t(f->V), 256);
     VXS_CUDA(ctx, f->partial.reserve(blocks_v));
     if (!f->counter.p) { VXS_CUDA(ctx, f->counter.reserve(4)); VXS_CUDA(ctx, cudaMemsetAsync(f->counter.p, 0, 16, ctx->stream)); }
+    const int GJ = pick_group_jac(f);
+    unsigned gridj = unsigned(std::min<size_t>((size_t(f->V) * GJ + 127) / 128, size_t(ctx->sm_count) * 8));
     unsigned grid = unsigned(std::min<size_t>((size_t(f->V) * G + 127) / 128, size_t(ctx->sm_count) * 16));
-#define LAUNCH_JAC(GG, DD) { auto kp = k_jac<GG, DD>; VXS_LAUNCH(ctx, "k_jac", kp, grid, 128, 0, fv, poses_dev, pstride, f->X.p, gD); }
-    if (dense) { if (G == 32) LAUNCH_JAC(32, true) else if (G == 16) LAUNCH_JAC(16, true) else LAUNCH_JAC(8, true) }
-    else { if (G == 32) LAUNCH_JAC(32, false) else if (G == 16) LAUNCH_JAC(16, false) else LAUNCH_JAC(8, false) }
+#define LAUNCH_JAC(GG, DD) { auto kp = k_jac<GG, DD>; VXS_LAUNCH(ctx, "k_jac", kp, gridj, 128, 0, fv, poses_dev, pstride, f->X.p, gD); }
+    if (dense) { if (GJ == 64) LAUNCH_JAC(64, true) else if (GJ == 32) LAUNCH_JAC(32, true) else if (GJ == 16) LAUNCH_JAC(16, true) else LAUNCH_JAC(8, true) }
+    else { if (GJ == 64) LAUNCH_JAC(64, false) else if (GJ == 32) LAUNCH_JAC(32, false) else if (GJ == 16) LAUNCH_JAC(16, false) else LAUNCH_JAC(8, false) }
 #undef LAUNCH_JAC
     if (dense) {
       const int NG = (W + SYRK_FT - 1) / SYRK_FT, ntiles = NG * (NG + 1) / 2;

@@ -40,6 +40,7 @@ struct vxs_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_copy = nullptr;
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
   std::string err;
   int64_t launches = 0;
   // timing
