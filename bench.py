@@ -165,12 +165,19 @@ def run_ours(args):
     V, E, _ = f.counts()
     log(f"[rank {rank}] scene W={W} pts/scan={pts} L={L}: generated in {t_gen:.1f}s; GPU map build {t_vox * 1e3:.1f} ms -> V={V} voxels, E={E} entries (k={E / max(V, 1):.1f})")
     del p
+    # host copy of the factor exactly as the map build left it (cached eig / pcr_adds at the cut poses) — the e2e leg pushes this
+    ptr, fr, cl, fx, co = f.read_structure()
+    eig0, sum0 = f.read_back()
+    f.cache_save()
     st0 = states_from(est)
     imu = vx.ImuWindow(tr)
     n = 15 * W
 
     def step():
+        # every step is the FIRST LM iteration from the same map state: the factor's cached eig / pcr_adds are restored on the
+        # device (9 MB D2D copy inside the timed region) so the step is accepted for the same reason each time
         imu.reset()
+        f.cache_restore()
         return ctx.li_ba(f, st0, imu, with_gravity=False, max_iter=1, want_hess=False, trace_cap=4)
 
     # ---- value: K steps, factor resident in HBM
@@ -197,10 +204,6 @@ def run_ours(args):
     kern = {k: {"ms_per_step": v[0] / reps, "launches_per_step": v[1] / reps, "us_per_launch": v[0] / max(v[1], 1) * 1e3} for k, v in stages.items() if v[1] > 0}
 
     # ---- e2e: host LidarFactor in, 3-iteration damping_iter, results out
-    ptr, fr, cl, fx, co = f.read_structure()
-    eig0, sum0 = f.read_back()
-    f.clear()
-    f.push_voxels(ptr, fr, cl, eig0, sum0)        # back to the state the map build left (cached eig at the cut poses)
     hp = dict(ptr=api.pinned_array(ptr.shape, np.int64), fr=api.pinned_array(fr.shape, np.int32), cl=api.pinned_array(cl.shape, np.float64),
               eig=api.pinned_array(eig0.shape, np.float64), s=api.pinned_array(sum0.shape, np.float64))
     hp["ptr"][:] = ptr; hp["fr"][:] = fr; hp["cl"][:] = cl; hp["eig"][:] = eig0; hp["s"][:] = sum0

@@ -366,6 +366,12 @@ class Factor:
         co = _f64(coe) if coe is not None else None
         self.ctx._check(lib().vxs_factor_push_voxels_dense(self._p, C.c_int64(n), _dp(cl), _dp(fx), _dp(co), _dp(e), _dp(s)))
 
+    def cache_save(self):
+        self.ctx._check(lib().vxs_factor_cache_save(self._p))
+
+    def cache_restore(self):
+        self.ctx._check(lib().vxs_factor_cache_restore(self._p))
+
     def read_back(self):
         v = self.counts()[0]
         eig, s = np.zeros((v, 12)), np.zeros((v, 10))

@@ -161,8 +161,8 @@ static void factor_free_arrays(vxs_factor* f) {
 }
 static void vxs_factor_release_device(vxs_factor* f) {
   factor_free_arrays(f);
-  f->X.release(); f->C.release(); f->gD.release(); f->partial.release(); f->counter.release();
-  f->V = f->E = 0;
+  f->X.release(); f->C.release(); f->gD.release(); f->partial.release(); f->counter.release(); f->cache_copy.release();
+  f->V = f->E = 0; f->cache_copy_V = 0;
 }
 extern "C" int vxs_factor_destroy(vxs_factor* f) {
   if (!f) return VXS_OK;
@@ -317,6 +317,30 @@ extern "C" int vxs_factor_push_voxels_dense(vxs_factor* f, int64_t n_vox, const 
     ptr[size_t(v) + 1] = int64_t(frame.size());
   }
   return vxs_factor_push_voxels(f, n_vox, ptr.data(), frame.data(), cl.data(), fix10, coe, eig12, sum10);
+}
+
+extern "C" int vxs_factor_cache_save(vxs_factor* f) {
+  if (!f || !f->ctx) return VXS_ERR_ARG;
+  vxs_ctx* ctx = f->ctx;
+  cudaSetDevice(ctx->device);
+  const size_t V = size_t(f->V);
+  if (V == 0) { f->cache_copy_V = 0; return VXS_OK; }
+  VXS_CUDA(ctx, f->cache_copy.reserve(V * 22));
+  VXS_CUDA(ctx, cudaMemcpy2DAsync(f->cache_copy.p, V * 8, f->eig, f->Vcap * 8, V * 8, 12, cudaMemcpyDeviceToDevice, ctx->stream));
+  VXS_CUDA(ctx, cudaMemcpy2DAsync(f->cache_copy.p + V * 12, V * 8, f->sum, f->Vcap * 8, V * 8, 10, cudaMemcpyDeviceToDevice, ctx->stream));
+  f->cache_copy_V = V;
+  return VXS_OK;
+}
+extern "C" int vxs_factor_cache_restore(vxs_factor* f) {
+  if (!f || !f->ctx) return VXS_ERR_ARG;
+  vxs_ctx* ctx = f->ctx;
+  const size_t V = size_t(f->V);
+  if (V == 0) return VXS_OK;
+  if (f->cache_copy_V != V) return vxs_fail(ctx, VXS_ERR_ARG, "vxs_factor_cache_restore: no snapshot of this factor");
+  cudaSetDevice(ctx->device);
+  VXS_CUDA(ctx, cudaMemcpy2DAsync(f->eig, f->Vcap * 8, f->cache_copy.p, V * 8, V * 8, 12, cudaMemcpyDeviceToDevice, ctx->stream));
+  VXS_CUDA(ctx, cudaMemcpy2DAsync(f->sum, f->Vcap * 8, f->cache_copy.p + V * 12, V * 8, V * 8, 10, cudaMemcpyDeviceToDevice, ctx->stream));
+  return VXS_OK;
 }
 
 extern "C" int vxs_factor_read_back(vxs_factor* f, double* eig12, double* sum10) {

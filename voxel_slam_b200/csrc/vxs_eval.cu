@@ -155,19 +155,18 @@ __device__ __forceinline__ void store_zero_rows(double* dst, int nframes) {
 // handles has the same frame for (almost) every voxel, so the flush happens a handful of times per thread instead of once per
 // entry; in sparse global-BA windows it degenerates gracefully to the per-entry scatter (where contention is low anyway).
 template <int G, bool DENSE>
-__global__ void __launch_bounds__(128) k_jac(FactorView f, const double* __restrict__ poses, int pstride, double* __restrict__ X, double* __restrict__ gD) {
-  const int lane = threadIdx.x & (G - 1);
-  const int group = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+__global__ void __launch_bounds__(128, 3) k_jac(FactorView f, const double* __restrict__ poses, int pstride, double* __restrict__ X, double* __restrict__ gD) {
+  __shared__ double acc[30][128];   // per-thread running sums for the thread's current frame (column = thread: conflict-free)
+  const int tid = threadIdx.x;
+  const int lane = tid & (G - 1);
+  const int group = (blockIdx.x * blockDim.x + tid) / G;
   const int ngroups = (gridDim.x * blockDim.x) / G;
   const int W = f.W;
   double* gbuf = gD;
   double* Dbuf = gD + size_t(W) * 6;
   int cur_fr = -1;
-  rot3 R; d3 t;
-  R.r00 = R.r01 = R.r02 = R.r10 = R.r11 = R.r12 = R.r20 = R.r21 = R.r22 = 0.0; t = mk3(0, 0, 0);
-  double acc[30];
 #pragma unroll
-  for (int i = 0; i < 30; i++) acc[i] = 0.0;
+  for (int i = 0; i < 30; i++) acc[i][tid] = 0.0;
   for (int v = group; v < f.V; v += ngroups) {
     const int beg = f.ptr[v], end = f.ptr[v + 1];
     if (DENSE && beg == end && lane == 0) store_zero_rows(X + size_t(v) * W * 18, W);
@@ -189,15 +188,14 @@ __global__ void __launch_bounds__(128) k_jac(FactorView f, const double* __restr
         if (cur_fr >= 0) {
           double* g = gbuf + cur_fr * 6; double* D = Dbuf + cur_fr * 24;
 #pragma unroll
-          for (int i = 0; i < 6; i++) atomicAdd(g + i, acc[i]);
+          for (int i = 0; i < 6; i++) { atomicAdd(g + i, acc[i][tid]); acc[i][tid] = 0.0; }
 #pragma unroll
-          for (int i = 0; i < 24; i++) atomicAdd(D + i, acc[6 + i]);
-#pragma unroll
-          for (int i = 0; i < 30; i++) acc[i] = 0.0;
+          for (int i = 0; i < 24; i++) { atomicAdd(D + i, acc[6 + i][tid]); acc[6 + i][tid] = 0.0; }
         }
         cur_fr = fr;
-        load_pose(poses, pstride, fr, R, t);
       }
+      rot3 R; d3 t;
+      load_pose(poses, pstride, fr, R, t);
       entry_out o;
       entry_jacobian(kc, c, R, t, o);
       double* xd = DENSE ? X + (size_t(v) * W + fr) * 18 : X + size_t(en) * 18;
@@ -210,19 +208,19 @@ __global__ void __launch_bounds__(128) k_jac(FactorView f, const double* __restr
         if (en == end - 1 && fr < W - 1) store_zero_rows(X + (size_t(v) * W + fr + 1) * 18, W - 1 - fr);
       }
 #pragma unroll
-      for (int i = 0; i < 6; i++) acc[i] += kc.coe * o.g[i];
+      for (int i = 0; i < 6; i++) acc[i][tid] += kc.coe * o.g[i];
 #pragma unroll
-      for (int i = 0; i < 9; i++) { acc[6 + i] += o.Drr[i]; acc[15 + i] += o.Drt[i]; }
+      for (int i = 0; i < 9; i++) { acc[6 + i][tid] += o.Drr[i]; acc[15 + i][tid] += o.Drt[i]; }
 #pragma unroll
-      for (int i = 0; i < 6; i++) acc[24 + i] += o.Dtt[i];
+      for (int i = 0; i < 6; i++) acc[24 + i][tid] += o.Dtt[i];
     }
   }
   if (cur_fr >= 0) {
     double* g = gbuf + cur_fr * 6; double* D = Dbuf + cur_fr * 24;
 #pragma unroll
-    for (int i = 0; i < 6; i++) atomicAdd(g + i, acc[i]);
+    for (int i = 0; i < 6; i++) atomicAdd(g + i, acc[i][tid]);
 #pragma unroll
-    for (int i = 0; i < 24; i++) atomicAdd(D + i, acc[6 + i]);
+    for (int i = 0; i < 24; i++) atomicAdd(D + i, acc[6 + i][tid]);
   }
 }
 

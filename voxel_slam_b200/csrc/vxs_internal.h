@@ -86,6 +86,8 @@ struct vxs_factor {
   DevBuf<double> gD;             // [W][6] gradient + [W][24] block-diagonal remainder
   DevBuf<double> partial;        // block partial sums for the residual
   DevBuf<unsigned int> counter;
+  DevBuf<double> cache_copy;     // [22][Vcap] snapshot of eig | sum
+  size_t cache_copy_V = 0;
 };
 
 inline int vxs_fail(vxs_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) {

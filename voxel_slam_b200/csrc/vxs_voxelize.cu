@@ -305,33 +305,40 @@ __global__ void k_write_nodes(const unsigned int* __restrict__ flag, const unsig
   if (r == 0) node_rec_start[*total] = (unsigned int)R;
 }
 
-// one warp per (node, frame) record: pcrs_local[frame].push(p_body), pcr_add.push(p_world)   (voxel_map.hpp:988-989, loop_refine.hpp:318-320, 383-385)
+// G lanes per (node, frame) record: pcrs_local[frame].push(p_body), pcr_add.push(p_world)   (voxel_map.hpp:988-989, loop_refine.hpp:318-320, 383-385).
+// The point loads are gathers through the sort permutation either way, so short records (deep octree layers, sparse scans)
+// are handled by narrow groups — down to one thread per record — instead of wasting a warp on two points.
+template <int G>
 __global__ void __launch_bounds__(256) k_rec_clusters(PointSrc s, const unsigned int* __restrict__ idx, const unsigned int* __restrict__ rec_start,
                                                       const unsigned long long* __restrict__ rec_key, unsigned int R, int FB, double* __restrict__ rec_local,
                                                       double* __restrict__ rec_world, size_t Rcap) {
-  const int lane = threadIdx.x & 31;
-  const unsigned int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (unsigned int r = warp; r < R; r += nwarps) {
-    const unsigned int beg = rec_start[r], end = rec_start[r + 1];
-    const int fr = int(rec_key[r] & ((1ull << FB) - 1ull));
+  const int lane = threadIdx.x & (G - 1);
+  const unsigned int group = (blockIdx.x * blockDim.x + threadIdx.x) / G, ngroups = (gridDim.x * blockDim.x) / G;
+  const unsigned int iters = (R + ngroups - 1) / ngroups;
+  for (unsigned int it = 0; it < iters; it++) {
+    const unsigned int r = group + it * ngroups;
+    const bool valid = r < R;
+    unsigned int beg = 0, end = 0; int fr = 0;
+    if (valid) { beg = rec_start[r]; end = rec_start[r + 1]; fr = int(rec_key[r] & ((1ull << FB) - 1ull)); }
     const double* pose = s.poses + 12 * fr;
     double a[20];
 #pragma unroll
     for (int k = 0; k < 20; k++) a[k] = 0.0;
-    for (unsigned int j = beg + lane; j < end; j += 32) {
+    for (unsigned int j = beg + lane; j < end; j += G) {
       const d3 p = load_point(s, idx[j]);
       const d3 w = world_point(pose, p);
       a[0] += p.x * p.x; a[1] += p.x * p.y; a[2] += p.x * p.z; a[3] += p.y * p.y; a[4] += p.y * p.z; a[5] += p.z * p.z; a[6] += p.x; a[7] += p.y; a[8] += p.z; a[9] += 1.0;
       a[10] += w.x * w.x; a[11] += w.x * w.y; a[12] += w.x * w.z; a[13] += w.y * w.y; a[14] += w.y * w.z; a[15] += w.z * w.z; a[16] += w.x; a[17] += w.y; a[18] += w.z; a[19] += 1.0;
     }
+    if (G > 1) {
 #pragma unroll
-    for (int k = 0; k < 20; k++)
-      for (int off = 16; off > 0; off >>= 1) a[k] += __shfl_xor_sync(0xffffffffu, a[k], off);
-    if (lane < 20) {
-      double v = a[0];
+      for (int k = 0; k < 20; k++)
 #pragma unroll
-      for (int k = 1; k < 20; k++) if (lane == k) v = a[k];
-      if (lane < 10) rec_local[size_t(lane) * Rcap + r] = v; else rec_world[size_t(lane - 10) * Rcap + r] = v;
+        for (int off = G / 2; off > 0; off >>= 1) a[k] += __shfl_xor_sync(0xffffffffu, a[k], off);
+    }
+    if (valid && lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 10; k++) { rec_local[size_t(k) * Rcap + r] = a[k]; rec_world[size_t(k) * Rcap + r] = a[10 + k]; }
     }
   }
 }
@@ -518,8 +525,15 @@ static int build_factor(vxs_ctx* ctx, const vxs_map_params* mp, bool gba, const 
     VXS_LAUNCH(ctx, "k_write_records", k_write_records, nblk(m, 256), 256, 0, ks, s->flags.p, s->scanbuf.p, m, s->rec_start.p, s->rec_key.p, s->totals.p + 0);
     const size_t Rcap = (size_t(R) + 31) & ~size_t(31);
     VXS_CUDA(ctx, s->rec_local.reserve(Rcap * 10)); VXS_CUDA(ctx, s->rec_world.reserve(Rcap * 10));
-    VXS_LAUNCH(ctx, "k_rec_clusters", k_rec_clusters, std::min<unsigned>(nblk(size_t(R) * 32, 256), unsigned(ctx->sm_count) * 16), 256, 0, ps, vs, s->rec_start.p, s->rec_key.p, R, FB,
-               s->rec_local.p, s->rec_world.p, Rcap);
+    {
+      const double avg = double(m) / double(std::max(R, 1u));
+      const int G = avg > 48.0 ? 32 : (avg > 12.0 ? 8 : (avg > 3.0 ? 4 : 1));
+      const unsigned grid = std::min<unsigned>(nblk(size_t(R) * G, 256), unsigned(ctx->sm_count) * 16);
+      if (G == 32) { auto kp = k_rec_clusters<32>; VXS_LAUNCH(ctx, "k_rec_clusters", kp, grid, 256, 0, ps, vs, s->rec_start.p, s->rec_key.p, R, FB, s->rec_local.p, s->rec_world.p, Rcap); }
+      else if (G == 8) { auto kp = k_rec_clusters<8>; VXS_LAUNCH(ctx, "k_rec_clusters", kp, grid, 256, 0, ps, vs, s->rec_start.p, s->rec_key.p, R, FB, s->rec_local.p, s->rec_world.p, Rcap); }
+      else if (G == 4) { auto kp = k_rec_clusters<4>; VXS_LAUNCH(ctx, "k_rec_clusters", kp, grid, 256, 0, ps, vs, s->rec_start.p, s->rec_key.p, R, FB, s->rec_local.p, s->rec_world.p, Rcap); }
+      else { auto kp = k_rec_clusters<1>; VXS_LAUNCH(ctx, "k_rec_clusters", kp, grid, 256, 0, ps, vs, s->rec_start.p, s->rec_key.p, R, FB, s->rec_local.p, s->rec_world.p, Rcap); }
+    }
     // nodes
     unsigned int* nflag = s->rec_node_flag.p; unsigned int* nex = s->rec_node_flag.p + R;
     VXS_LAUNCH(ctx, "k_flag_nodes", k_flag_nodes, nblk(R, 256), 256, 0, s->rec_key.p, size_t(R), FB, nflag);
