@@ -274,7 +274,10 @@ __global__ void __launch_bounds__(SYRK_THREADS, 2) k_syrk(const double* __restri
   const int v_begin = chunk * vox_per_chunk, v_end = min(V, v_begin + vox_per_chunk);
   if (v_begin >= v_end) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int wy = warp >> 1, wx = warp & 1;
+  // Warps are pinned to SM sub-partitions by their index.  Diagonal and sliver tiles have idle units; rotating the
+  // warp -> unit assignment with the block index spreads that idleness over the four FP64 pipes instead of starving one.
+  const int unit = (warp + blockIdx.x) & 3;
+  const int wy = unit >> 1, wx = unit & 1;
   const int li0 = wy * 8 + (lane >> 3), li1 = li0 + 4, lj = wx * 8 + (lane & 7);   // local frame indices within the tile
   const int fi0 = I * SYRK_FT + li0, fi1 = I * SYRK_FT + li1, fj = J * SYRK_FT + lj;
   // warp-uniform skip: unit entirely below the diagonal of a diagonal tile, or entirely in the padding
