@@ -8,10 +8,9 @@
 //                   two-level reduction of sum coe*lambda0 ("last block" pattern).         176 B / voxel
 //   k_jac           group per voxel, lane per entry: g_i, D_i and the three scaled rank-1 rows x^m_i,
 //                   rows stored for the SYRK, g/D accumulated with fp64 RED.                 k*80+176 B read, k*144 B written / voxel
-//   k_syrk          H -= X^T X over frame pairs: CTA tile 16x16 frames, each thread two 6x6 blocks (72 fp64 accumulators),
-//                   warp tile 8x8 frames so every shared-memory read is a broadcast/128-B wavefront; rows staged with
-//                   cp.async (zero-fill beyond W), 3-stage pipeline; split over voxel chunks, fp64 RED epilogue.
-//                   fp64-FMA bound for k >~ 4.
+//   k_syrk          H -= X^T X over frame pairs: warp unit = 4x8 frame pairs, one 6x6 block (36 fp64 accumulators) per lane,
+//                   CTA = 8 warps (16 row frames x 2 column groups), 2 CTAs/SM; rows staged with cp.async (zero-fill),
+//                   3-stage pipeline; split over voxel chunks, fp64 RED epilogue.  fp64-FMA bound for k >~ 4.
 //   k_pairs         sparse windows (k << W, top-level global BA): group per voxel, block pairs straight to RED.
 //   k_assemble      dense n x n system from the block accumulators (+ the CPU-evaluated IMU 30x30 blocks), mirror of the lower triangle.
 #include <algorithm>
@@ -248,12 +247,18 @@ __global__ void __launch_bounds__(128) k_pairs(FactorView f, const double* __res
 }
 
 // ------------------------------------------------------------------ Hessian part 2b: dense windows, SYRK over frame pairs
-#define SYRK_FT 16      // frames per CTA tile side
-#define SYRK_VB 4       // voxels per pipeline stage
-#define SYRK_STAGES 3
-#define SYRK_THREADS 128
-#define SYRK_PART (SYRK_FT * 18)                 // doubles per (voxel, part)
-#define SYRK_STAGE_DOUBLES (SYRK_VB * 2 * SYRK_PART)
+// Unit of work = one warp x (4 row frames x 8 column frames): lane (ty,tx) owns the 6x6 block of frame pair (i = row0+ty,
+// j = col0+tx), 36 fp64 accumulators.  Every shared-memory read is a quarter-warp broadcast (a) or 8 distinct 16-B chunks (b).
+// Measured on B200: a warp alone cannot keep the FP64 pipe busy (fixed issue latency between its DFMAs), so the kernel
+// is built for occupancy — 36 accumulators/thread => ~120 registers => 2 CTAs x 8 warps per SM — instead of bigger
+// register tiles.  Column groups are 8 frames wide with the remainder group (W mod 8 frames) placed FIRST: a remainder
+// group at the end would pair with every row group, at the front it pairs only with itself (pairs need i <= j).
+// CTA tile = 4 row units (16 frames) x 2 column groups; X rows are staged with cp.async (16 B, zero-fill), 3 stages.
+#define SY_THREADS 256
+#define SY_VB 4
+#define SY_STAGES 3
+#define SY_PART (16 * 18)                      // doubles per (voxel, part): 16 frames x 18
+#define SY_STAGE_DOUBLES (SY_VB * 2 * SY_PART)
 
 __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, bool pred) {
   unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -264,74 +269,92 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-__global__ void __launch_bounds__(SYRK_THREADS, 2) k_syrk(const double* __restrict__ X, double* __restrict__ C, int V, int W, int ntiles, int NG, int vox_per_chunk) {
+struct SyrkGeom { int r0, ngc, nbp, nq, ntiles; };
+__host__ __device__ inline int sy_gstart(const SyrkGeom& g, int grp) { return grp <= 0 ? 0 : g.r0 + 8 * (grp - 1); }
+__host__ __device__ inline int sy_glen(const SyrkGeom& g, int grp) { return grp < 0 || grp >= g.ngc ? 0 : (grp == 0 ? g.r0 : 8); }
+__host__ __device__ inline bool sy_tile_needed(const SyrkGeom& g, int W, int Q, int B) {
+  const int last_grp = min(2 * B + 1, g.ngc - 1);
+  const int colmax = sy_gstart(g, last_grp) + sy_glen(g, last_grp) - 1;
+  return colmax >= 16 * Q && 16 * Q < W;
+}
+static SyrkGeom sy_geom(int W) {
+  SyrkGeom g;
+  g.r0 = (W % 8 == 0) ? 8 : (W % 8);
+  g.ngc = (W - g.r0) / 8 + 1;
+  g.nbp = (g.ngc + 1) / 2;
+  g.nq = (W + 15) / 16;
+  g.ntiles = 0;
+  for (int Q = 0; Q < g.nq; Q++) for (int B = 0; B < g.nbp; B++) if (sy_tile_needed(g, W, Q, B)) g.ntiles++;
+  return g;
+}
+
+__global__ void __launch_bounds__(SY_THREADS, 2) k_syrk(const double* __restrict__ X, double* __restrict__ C, int V, int W, SyrkGeom g, int vox_per_chunk) {
   extern __shared__ __align__(16) double smem[];
-  const int tile = blockIdx.x % ntiles, chunk = blockIdx.x / ntiles;
-  // decode tile -> (I,J), I <= J
-  int I = 0, rem = tile;
-  while (rem >= NG - I) { rem -= NG - I; I++; }
-  const int J = I + rem;
+  const int tile = blockIdx.x % g.ntiles, chunk = blockIdx.x / g.ntiles;
+  int Q = 0, B = 0;
+  {
+    int cnt = 0; bool found = false;
+    for (int q = 0; q < g.nq && !found; q++)
+      for (int b = 0; b < g.nbp; b++)
+        if (sy_tile_needed(g, W, q, b)) { if (cnt == tile) { Q = q; B = b; found = true; break; } cnt++; }
+  }
   const int v_begin = chunk * vox_per_chunk, v_end = min(V, v_begin + vox_per_chunk);
   if (v_begin >= v_end) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // Warps are pinned to SM sub-partitions by their index.  Diagonal and sliver tiles have idle units; rotating the
-  // warp -> unit assignment with the block index spreads that idleness over the four FP64 pipes instead of starving one.
-  const int unit = (warp + blockIdx.x) & 3;
-  const int wy = unit >> 1, wx = unit & 1;
-  const int li0 = wy * 8 + (lane >> 3), li1 = li0 + 4, lj = wx * 8 + (lane & 7);   // local frame indices within the tile
-  const int fi0 = I * SYRK_FT + li0, fi1 = I * SYRK_FT + li1, fj = J * SYRK_FT + lj;
-  // warp-uniform skip: unit entirely below the diagonal of a diagonal tile, or entirely in the padding
-  const bool warp_active = !((I == J) && (wy > wx)) && (I * SYRK_FT + wy * 8 < W) && (J * SYRK_FT + wx * 8 < W);
+  const int wy = warp >> 1, wx = warp & 1, ty = lane >> 3, tx = lane & 7;
+  const int row0 = 16 * Q, col0 = sy_gstart(g, 2 * B);
+  const int ncol = sy_glen(g, 2 * B) + sy_glen(g, 2 * B + 1);          // frames in the column part (<= 16)
+  const int gb = 2 * B + wx;
+  const int li = 4 * wy + ty, fi = row0 + li;                           // row frame of this lane
+  const int lj = (wx ? sy_glen(g, 2 * B) : 0) + tx, fj = col0 + lj;     // column frame of this lane
+  const bool validj = tx < sy_glen(g, gb);
+  const int unit_row0 = row0 + 4 * wy, unit_colmax = sy_gstart(g, gb) + sy_glen(g, gb) - 1;
+  const bool warp_active = (gb < g.ngc) && (unit_row0 < W) && (unit_colmax >= unit_row0);
 
-  double acc0[36], acc1[36];
+  double acc[36];
 #pragma unroll
-  for (int i = 0; i < 36; i++) { acc0[i] = 0.0; acc1[i] = 0.0; }
+  for (int i = 0; i < 36; i++) acc[i] = 0.0;
 
-  const int nsteps = (v_end - v_begin + SYRK_VB - 1) / SYRK_VB;
+  const int nsteps = (v_end - v_begin + SY_VB - 1) / SY_VB;
   const size_t rowW = size_t(W) * 18;
-  // chunks of 16 B per stage: VB voxels x 2 parts x (FT*18/2) double2
-  constexpr int CH_PER_PART = SYRK_PART / 2;            // 144
-  constexpr int CH_PER_STAGE = SYRK_VB * 2 * CH_PER_PART;
+  constexpr int CH_PER_PART = SY_PART / 2;             // 144 double2 chunks
+  constexpr int CH_PER_STAGE = SY_VB * 2 * CH_PER_PART;
   auto issue = [&](int step) {
-    double* sbase = smem + size_t(step % SYRK_STAGES) * SYRK_STAGE_DOUBLES;
-    const int v0 = v_begin + step * SYRK_VB;
-    for (int ch = tid; ch < CH_PER_STAGE; ch += SYRK_THREADS) {
+    double* sbase = smem + size_t(step % SY_STAGES) * SY_STAGE_DOUBLES;
+    const int v0 = v_begin + step * SY_VB;
+    for (int ch = tid; ch < CH_PER_STAGE; ch += SY_THREADS) {
       const int vb = ch / (2 * CH_PER_PART), r2 = ch - vb * 2 * CH_PER_PART, part = r2 / CH_PER_PART, off2 = r2 - part * CH_PER_PART;
-      const int fr_local = off2 / 9;                     // 9 double2 per frame
-      const int gframe = (part == 0 ? I : J) * SYRK_FT + fr_local;
+      const int fl = off2 / 9;                           // local frame slot, 9 double2 per frame
+      const int gframe = (part == 0) ? row0 + fl : col0 + fl;
       const int v = v0 + vb;
-      const bool ok = (v < v_end) && (gframe < W);
-      const double* src = X + size_t(ok ? v : v_begin) * rowW + size_t(ok ? gframe : 0) * 18 + size_t(off2 - fr_local * 9) * 2;
-      cp_async16_zfill(sbase + (size_t(vb) * 2 + part) * SYRK_PART + size_t(off2) * 2, src, ok);
+      const bool ok = (v < v_end) && (gframe < W) && (part == 0 || fl < ncol);
+      const double* src = X + size_t(ok ? v : v_begin) * rowW + size_t(ok ? gframe : 0) * 18 + size_t(off2 - fl * 9) * 2;
+      cp_async16_zfill(sbase + (size_t(vb) * 2 + part) * SY_PART + size_t(off2) * 2, src, ok);
     }
   };
-  for (int s = 0; s < SYRK_STAGES - 1; s++) { if (s < nsteps) issue(s); cp_async_commit(); }
+  for (int s = 0; s < SY_STAGES - 1; s++) { if (s < nsteps) issue(s); cp_async_commit(); }
   for (int step = 0; step < nsteps; step++) {
-    cp_async_wait<SYRK_STAGES - 2>();
+    cp_async_wait<SY_STAGES - 2>();
     __syncthreads();
-    if (step + SYRK_STAGES - 1 < nsteps) issue(step + SYRK_STAGES - 1);
+    if (step + SY_STAGES - 1 < nsteps) issue(step + SY_STAGES - 1);
     cp_async_commit();
     if (warp_active) {
-      const double* sbase = smem + size_t(step % SYRK_STAGES) * SYRK_STAGE_DOUBLES;
+      const double* sbase = smem + size_t(step % SY_STAGES) * SY_STAGE_DOUBLES;
 #pragma unroll
-      for (int vb = 0; vb < SYRK_VB; vb++) {
-        const double* A = sbase + size_t(vb) * 2 * SYRK_PART;
-        const double* B = A + SYRK_PART;
+      for (int vb = 0; vb < SY_VB; vb++) {
+        const double* A = sbase + size_t(vb) * 2 * SY_PART;
+        const double* Bp = A + SY_PART;
 #pragma unroll
         for (int m = 0; m < 3; m++) {
-          const double2* pa0 = reinterpret_cast<const double2*>(A + li0 * 18 + m * 6);
-          const double2* pa1 = reinterpret_cast<const double2*>(A + li1 * 18 + m * 6);
-          const double2* pb = reinterpret_cast<const double2*>(B + lj * 18 + m * 6);
-          double a0[6], a1[6], b[6];
+          const double2* pa = reinterpret_cast<const double2*>(A + li * 18 + m * 6);
+          const double2* pb = reinterpret_cast<const double2*>(Bp + lj * 18 + m * 6);
+          double a[6], b[6];
 #pragma unroll
-          for (int q = 0; q < 3; q++) {
-            double2 t0 = pa0[q], t1 = pa1[q], tb = pb[q];
-            a0[2 * q] = t0.x; a0[2 * q + 1] = t0.y; a1[2 * q] = t1.x; a1[2 * q + 1] = t1.y; b[2 * q] = tb.x; b[2 * q + 1] = tb.y;
-          }
+          for (int q = 0; q < 3; q++) { double2 t0 = pa[q], tb = pb[q]; a[2 * q] = t0.x; a[2 * q + 1] = t0.y; b[2 * q] = tb.x; b[2 * q + 1] = tb.y; }
 #pragma unroll
           for (int r = 0; r < 6; r++)
 #pragma unroll
-            for (int c = 0; c < 6; c++) { acc0[r * 6 + c] = fma(a0[r], b[c], acc0[r * 6 + c]); acc1[r * 6 + c] = fma(a1[r], b[c], acc1[r * 6 + c]); }
+            for (int c = 0; c < 6; c++) acc[r * 6 + c] = fma(a[r], b[c], acc[r * 6 + c]);
         }
       }
     }
@@ -339,19 +362,11 @@ __global__ void __launch_bounds__(SYRK_THREADS, 2) k_syrk(const double* __restri
   cp_async_wait<0>();
   // epilogue: H_ij -= sum x_i x_j^T for i <= j
   const int nl = W * 6;
-  if (warp_active && fj < W) {
-    if (fi0 < W && fi0 <= fj) {
+  if (warp_active && validj && fi < W && fi <= fj) {
 #pragma unroll
-      for (int r = 0; r < 6; r++)
+    for (int r = 0; r < 6; r++)
 #pragma unroll
-        for (int c = 0; c < 6; c++) atomicAdd(C + size_t(6 * fj + c) * nl + 6 * fi0 + r, -acc0[r * 6 + c]);
-    }
-    if (fi1 < W && fi1 <= fj) {
-#pragma unroll
-      for (int r = 0; r < 6; r++)
-#pragma unroll
-        for (int c = 0; c < 6; c++) atomicAdd(C + size_t(6 * fj + c) * nl + 6 * fi1 + r, -acc1[r * 6 + c]);
-    }
+      for (int c = 0; c < 6; c++) atomicAdd(C + size_t(6 * fj + c) * nl + 6 * fi + r, -acc[r * 6 + c]);
   }
 }
 
@@ -487,16 +502,16 @@ int vxs_eval_hessian_dev(vxs_ctx* ctx, vxs_factor* f, const double* poses_dev, i
     else { if (GJ == 64) LAUNCH_JAC(64, false) else if (GJ == 32) LAUNCH_JAC(32, false) else if (GJ == 16) LAUNCH_JAC(16, false) else LAUNCH_JAC(8, false) }
 #undef LAUNCH_JAC
     if (dense) {
-      const int NG = (W + SYRK_FT - 1) / SYRK_FT, ntiles = NG * (NG + 1) / 2;
+      const SyrkGeom g = sy_geom(W);
       // enough chunks to fill the machine a few times over; tiles of one chunk are adjacent in launch order (L2 reuse of X)
       int target_ctas = ctx->sm_count * 2 * 4;
-      int nchunks = std::max(1, std::min<int>((target_ctas + ntiles - 1) / ntiles, int((f->V + SYRK_VB * 8 - 1) / (SYRK_VB * 8))));
+      int nchunks = std::max(1, std::min<int>((target_ctas + g.ntiles - 1) / g.ntiles, int((f->V + SY_VB * 8 - 1) / (SY_VB * 8))));
       int vpc = int((f->V + nchunks - 1) / nchunks);
-      vpc = ((vpc + SYRK_VB - 1) / SYRK_VB) * SYRK_VB;
+      vpc = ((vpc + SY_VB - 1) / SY_VB) * SY_VB;
       nchunks = int((f->V + vpc - 1) / vpc);
-      const size_t smem = size_t(SYRK_STAGES) * SYRK_STAGE_DOUBLES * 8;
+      const size_t smem = size_t(SY_STAGES) * SY_STAGE_DOUBLES * 8;
       VXS_CUDA(ctx, cudaFuncSetAttribute(k_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-      VXS_LAUNCH(ctx, "k_syrk", k_syrk, unsigned(nchunks * ntiles), SYRK_THREADS, smem, f->X.p, C, int(f->V), W, ntiles, NG, vpc);
+      VXS_LAUNCH(ctx, "k_syrk", k_syrk, unsigned(nchunks * g.ntiles), SY_THREADS, smem, f->X.p, C, int(f->V), W, g, vpc);
     } else {
       if (G == 32) { auto kp = k_pairs<32>; VXS_LAUNCH(ctx, "k_pairs", kp, grid, 128, 0, fv, f->X.p, C); }
       else if (G == 16) { auto kp = k_pairs<16>; VXS_LAUNCH(ctx, "k_pairs", kp, grid, 128, 0, fv, f->X.p, C); }
