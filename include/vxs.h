@@ -59,6 +59,8 @@ int vxs_ctx_timer_stop(vxs_ctx* ctx, double* ms);
 /* diagnostics: measured fp64 FMA throughput of this device (TFLOP/s, 2 flop per FMA) — the roofline denominator of the
  * SYRK part of the Hessian, which MEASURED_PEAKS.json does not carry */
 int vxs_diag_fp64_tflops(vxs_ctx* ctx, double* tflops);
+/* same for the fp64 tensor-core path (mma.sync.m8n8k4.f64, SASS DMMA) */
+int vxs_diag_dmma_tflops(vxs_ctx* ctx, double* tflops);
 
 /* ---------------------------------------------------------------- multi-GPU (one process per GPU; NCCL over NVLink)
  * Voxel-sharded BA: every rank holds the factor voxels it owns and the replicated poses; [H_lidar, g, r] are

@@ -216,6 +216,11 @@ class Context:
         self._check(lib().vxs_diag_fp64_tflops(self._p, C.byref(t)))
         return t.value
 
+    def dmma_tflops(self):
+        t = C.c_double(0)
+        self._check(lib().vxs_diag_dmma_tflops(self._p, C.byref(t)))
+        return t.value
+
     # --- multi-GPU
     @staticmethod
     def comm_unique_id():

@@ -145,6 +145,42 @@ extern "C" int vxs_diag_fp64_tflops(vxs_ctx* c, double* tflops) {
   return VXS_OK;
 }
 
+// fp64 tensor-core (DMMA, mma.sync.m8n8k4.f64) peak: 8 independent accumulator tiles per warp
+__global__ void __launch_bounds__(256) k_dmma_peak(double* out, int iters) {
+  double c[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) c[i] = 0.0;
+  double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int t = 0; t < 8; t++)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c[2 * t]), "+d"(c[2 * t + 1]) : "d"(a), "d"(b));
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) s += c[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+extern "C" int vxs_diag_dmma_tflops(vxs_ctx* c, double* tflops) {
+  if (!c || !tflops) return VXS_ERR_ARG;
+  cudaSetDevice(c->device);
+  const int blocks = c->sm_count * 4, iters = 4000;
+  VXS_CUDA(c, c->stage.reserve(size_t(blocks) * 256));
+  double best = 0;
+  for (int rep = 0; rep < 4; rep++) {
+    VXS_CUDA(c, cudaEventRecord(c->ev_t0, c->stream));
+    VXS_LAUNCH(c, "k_dmma_peak", k_dmma_peak, blocks, 256, 0, c->stage.p, iters);
+    VXS_CUDA(c, cudaEventRecord(c->ev_t1, c->stream));
+    VXS_CUDA(c, cudaEventSynchronize(c->ev_t1));
+    float ms = 0;
+    VXS_CUDA(c, cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1));
+    const double tf = double(blocks) * 8 /*warps*/ * iters * 8 /*mma*/ * 256 /*fma*/ * 2 / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  *tflops = best;
+  return VXS_OK;
+}
+
 // ------------------------------------------------------------------ factor container
 extern "C" int vxs_factor_create(vxs_ctx* ctx, int win_size, vxs_factor** out) {
   if (!ctx || !out || win_size <= 0) return VXS_ERR_ARG;

@@ -8,9 +8,9 @@
 //                   two-level reduction of sum coe*lambda0 ("last block" pattern).         176 B / voxel
 //   k_jac           group per voxel, lane per entry: g_i, D_i and the three scaled rank-1 rows x^m_i,
 //                   rows stored for the SYRK, g/D accumulated with fp64 RED.                 k*80+176 B read, k*144 B written / voxel
-//   k_syrk          H -= X^T X over frame pairs: warp unit = 4x8 frame pairs, one 6x6 block (36 fp64 accumulators) per lane,
-//                   CTA = 8 warps (16 row frames x 2 column groups), 2 CTAs/SM; rows staged with cp.async (zero-fill),
-//                   3-stage pipeline; split over voxel chunks, fp64 RED epilogue.  fp64-FMA bound for k >~ 4.
+//   k_syrk          H -= X^T X on the fp64 tensor cores (mma.sync.m8n8k4.f64 / DMMA): warp unit = 48x48 output (8x8 frames,
+//                   6x6 mma tiles, 72 accumulators/lane), CTA = 2x2 units, X staged with cp.async (zero-fill), 3 stages;
+//                   split over voxel chunks, fp64 RED epilogue.  fp64-bound for k >~ 4.
 //   k_pairs         sparse windows (k << W, top-level global BA): group per voxel, block pairs straight to RED.
 //   k_assemble      dense n x n system from the block accumulators (+ the CPU-evaluated IMU 30x30 blocks), mirror of the lower triangle.
 #include <algorithm>
@@ -144,9 +144,22 @@ __global__ void __launch_bounds__(256) k_eig_residual(FactorView f, double* part
 }
 
 // ------------------------------------------------------------------ Hessian part 1: per-entry Jacobian rows
-__device__ __forceinline__ void store_zero_rows(double* dst, int nframes) {
-  double2* p = reinterpret_cast<double2*>(dst);
-  for (int i = 0; i < nframes * 9; i++) p[i] = make_double2(0.0, 0.0);
+// Dense-window layout of the scaled rank-3 rows, shaped for the fp64 tensor-core SYRK (k_syrk):
+//   rows of X = (voxel, m) flattened, 3 per voxel; four voxels = 12 rows = three k-chunks of 4 rows;
+//   XT[voxel_group][chunk 0..2][column 0..6W-1][kr 0..3]   (column = 6*frame + c)
+// so that (a) one k-chunk of a range of frames is one contiguous run (bulk cp.async staging) and (b) a warp's mma fragment
+// (lane l -> row l&3, column c0 + l>>2) is 32 consecutive doubles in shared memory.
+__device__ __forceinline__ size_t xt_index(int v, int frame, int m, int c, int n) {
+  const int r = 3 * (v & 3) + m;
+  return ((size_t(v >> 2) * 3 + (r >> 2)) * n + 6 * frame + c) * 4 + (r & 3);
+}
+__device__ __forceinline__ void xt_store_zero(double* X, int v, int f0, int nframes, int n) {
+  for (int f = f0; f < f0 + nframes; f++)
+    for (int m = 0; m < 3; m++) {
+      const size_t b = xt_index(v, f, m, 0, n);
+#pragma unroll
+      for (int c = 0; c < 6; c++) X[b + 4 * c] = 0.0;
+    }
 }
 
 // Gradient / block-diagonal accumulation without per-entry atomics: a thread keeps the 30 sums of the frame it is currently
@@ -168,7 +181,7 @@ __global__ void __launch_bounds__(128, 3) k_jac(FactorView f, const double* __re
   for (int i = 0; i < 30; i++) acc[i][tid] = 0.0;
   for (int v = group; v < f.V; v += ngroups) {
     const int beg = f.ptr[v], end = f.ptr[v + 1];
-    if (DENSE && beg == end && lane == 0) store_zero_rows(X + size_t(v) * W * 18, W);
+    if (DENSE && beg == end && lane == 0) xt_store_zero(X, v, 0, W, 6 * W);
     if (beg + lane >= end) continue;
     const size_t st = f.Vcap;
     const double* e = f.eig + v;
@@ -197,14 +210,21 @@ __global__ void __launch_bounds__(128, 3) k_jac(FactorView f, const double* __re
       load_pose(poses, pstride, fr, R, t);
       entry_out o;
       entry_jacobian(kc, c, R, t, o);
-      double* xd = DENSE ? X + (size_t(v) * W + fr) * 18 : X + size_t(en) * 18;
-      double2* x2 = reinterpret_cast<double2*>(xd);
+      if (DENSE) {
 #pragma unroll
-      for (int i = 0; i < 9; i++) x2[i] = make_double2(o.x[2 * i], o.x[2 * i + 1]);
-      if (DENSE) {  // zero the slots of frames that do not observe this voxel
+        for (int m = 0; m < 3; m++) {
+          const size_t b = xt_index(v, fr, m, 0, 6 * W);
+#pragma unroll
+          for (int cc = 0; cc < 6; cc++) X[b + 4 * cc] = o.x[6 * m + cc];
+        }
+        // zero the slots of frames that do not observe this voxel
         const int prev = (en > beg) ? __ldg(f.frame + en - 1) : -1;
-        if (fr - prev > 1) store_zero_rows(X + (size_t(v) * W + prev + 1) * 18, fr - prev - 1);
-        if (en == end - 1 && fr < W - 1) store_zero_rows(X + (size_t(v) * W + fr + 1) * 18, W - 1 - fr);
+        if (fr - prev > 1) xt_store_zero(X, v, prev + 1, fr - prev - 1, 6 * W);
+        if (en == end - 1 && fr < W - 1) xt_store_zero(X, v, fr + 1, W - 1 - fr, 6 * W);
+      } else {
+        double2* x2 = reinterpret_cast<double2*>(X + size_t(en) * 18);
+#pragma unroll
+        for (int i = 0; i < 9; i++) x2[i] = make_double2(o.x[2 * i], o.x[2 * i + 1]);
       }
 #pragma unroll
       for (int i = 0; i < 6; i++) acc[i][tid] += kc.coe * o.g[i];
@@ -246,19 +266,20 @@ __global__ void __launch_bounds__(128) k_pairs(FactorView f, const double* __res
   }
 }
 
-// ------------------------------------------------------------------ Hessian part 2b: dense windows, SYRK over frame pairs
-// Unit of work = one warp x (4 row frames x 8 column frames): lane (ty,tx) owns the 6x6 block of frame pair (i = row0+ty,
-// j = col0+tx), 36 fp64 accumulators.  Every shared-memory read is a quarter-warp broadcast (a) or 8 distinct 16-B chunks (b).
-// Measured on B200: a warp alone cannot keep the FP64 pipe busy (fixed issue latency between its DFMAs), so the kernel
-// is built for occupancy — 36 accumulators/thread => ~120 registers => 2 CTAs x 8 warps per SM — instead of bigger
-// register tiles.  Column groups are 8 frames wide with the remainder group (W mod 8 frames) placed FIRST: a remainder
-// group at the end would pair with every row group, at the front it pairs only with itself (pairs need i <= j).
-// CTA tile = 4 row units (16 frames) x 2 column groups; X rows are staged with cp.async (16 B, zero-fill), 3 stages.
-#define SY_THREADS 256
-#define SY_VB 4
+// ------------------------------------------------------------------ Hessian part 2b: dense windows, SYRK on the fp64 tensor cores
+// H -= X^T X with X = (3V) x (6W).  Measured on B200 (profiles/): with scalar DFMA the kernel is limited by the
+// shared-memory -> register delivery (2 B per FMA at 72 accumulators/thread equals the 128 B/clk LSU limit at full FP64 rate),
+// not by the FP64 pipe.  mma.sync.m8n8k4.f64 (SASS DMMA, same 36.9 TFLOP/s peak as the FMA pipe on B200) shares each operand
+// across 8 lanes inside the tensor core: 0.33 B per FMA.
+//   * column blocks of 8 frames (48 columns), the remainder block (W mod 8 frames) FIRST so it only pairs with itself;
+//   * warp unit = (row block a, column block b), a <= b: 6x6 mma tiles of 8x8, 72 fp64 accumulators per lane;
+//   * CTA = 2x2 units; k runs over (voxel, m) rows in chunks of 4; XT (see xt_index) is staged with 16-B cp.async,
+//     3 stages of 4 voxels (12 rows); split over voxel chunks; fp64 RED epilogue into the upper block triangle.
+#define SY_THREADS 128
 #define SY_STAGES 3
-#define SY_PART (16 * 18)                      // doubles per (voxel, part): 16 frames x 18
-#define SY_STAGE_DOUBLES (SY_VB * 2 * SY_PART)
+#define SY_PCOLS 96                             // columns per part (2 blocks x 48)
+#define SY_PART (3 * SY_PCOLS * 4)              // doubles per part per stage: 3 chunks x 96 cols x 4 rows
+#define SY_STAGE_DOUBLES (2 * SY_PART)
 
 __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, bool pred) {
   unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -268,68 +289,61 @@ __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsr
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
 
-struct SyrkGeom { int r0, ngc, nbp, nq, ntiles; };
+struct SyrkGeom { int r0, ngc, nbp, ntiles; };
 __host__ __device__ inline int sy_gstart(const SyrkGeom& g, int grp) { return grp <= 0 ? 0 : g.r0 + 8 * (grp - 1); }
 __host__ __device__ inline int sy_glen(const SyrkGeom& g, int grp) { return grp < 0 || grp >= g.ngc ? 0 : (grp == 0 ? g.r0 : 8); }
-__host__ __device__ inline bool sy_tile_needed(const SyrkGeom& g, int W, int Q, int B) {
-  const int last_grp = min(2 * B + 1, g.ngc - 1);
-  const int colmax = sy_gstart(g, last_grp) + sy_glen(g, last_grp) - 1;
-  return colmax >= 16 * Q && 16 * Q < W;
-}
 static SyrkGeom sy_geom(int W) {
   SyrkGeom g;
   g.r0 = (W % 8 == 0) ? 8 : (W % 8);
   g.ngc = (W - g.r0) / 8 + 1;
   g.nbp = (g.ngc + 1) / 2;
-  g.nq = (W + 15) / 16;
-  g.ntiles = 0;
-  for (int Q = 0; Q < g.nq; Q++) for (int B = 0; B < g.nbp; B++) if (sy_tile_needed(g, W, Q, B)) g.ntiles++;
+  g.ntiles = g.nbp * (g.nbp + 1) / 2;
   return g;
 }
 
-__global__ void __launch_bounds__(SY_THREADS, 2) k_syrk(const double* __restrict__ X, double* __restrict__ C, int V, int W, SyrkGeom g, int vox_per_chunk) {
+__global__ void __launch_bounds__(SY_THREADS, 2) k_syrk(const double* __restrict__ XT, double* __restrict__ C, int ngroups_vox, int W, SyrkGeom g, int groups_per_chunk) {
   extern __shared__ __align__(16) double smem[];
   const int tile = blockIdx.x % g.ntiles, chunk = blockIdx.x / g.ntiles;
-  int Q = 0, B = 0;
-  {
-    int cnt = 0; bool found = false;
-    for (int q = 0; q < g.nq && !found; q++)
-      for (int b = 0; b < g.nbp; b++)
-        if (sy_tile_needed(g, W, q, b)) { if (cnt == tile) { Q = q; B = b; found = true; break; } cnt++; }
-  }
-  const int v_begin = chunk * vox_per_chunk, v_end = min(V, v_begin + vox_per_chunk);
-  if (v_begin >= v_end) return;
+  int A = 0, rem = tile;
+  while (rem >= g.nbp - A) { rem -= g.nbp - A; A++; }
+  const int B = A + rem;
+  const int g_begin = chunk * groups_per_chunk, g_end = min(ngroups_vox, g_begin + groups_per_chunk);
+  if (g_begin >= g_end) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int wy = warp >> 1, wx = warp & 1, ty = lane >> 3, tx = lane & 7;
-  const int row0 = 16 * Q, col0 = sy_gstart(g, 2 * B);
-  const int ncol = sy_glen(g, 2 * B) + sy_glen(g, 2 * B + 1);          // frames in the column part (<= 16)
-  const int gb = 2 * B + wx;
-  const int li = 4 * wy + ty, fi = row0 + li;                           // row frame of this lane
-  const int lj = (wx ? sy_glen(g, 2 * B) : 0) + tx, fj = col0 + lj;     // column frame of this lane
-  const bool validj = tx < sy_glen(g, gb);
-  const int unit_row0 = row0 + 4 * wy, unit_colmax = sy_gstart(g, gb) + sy_glen(g, gb) - 1;
-  const bool warp_active = (gb < g.ngc) && (unit_row0 < W) && (unit_colmax >= unit_row0);
+  const int wy = warp >> 1, wx = warp & 1;
+  const int n = 6 * W;
+  const int ga = 2 * A + wy, gb = 2 * B + wx;
+  const bool warp_active = (ga < g.ngc) && (gb < g.ngc) && (ga <= gb);
+  // part geometry: part I = blocks 2A, 2A+1 (contiguous frames), part J = blocks 2B, 2B+1
+  const int colI0 = 6 * sy_gstart(g, 2 * A), ncolI = 6 * (sy_glen(g, 2 * A) + sy_glen(g, 2 * A + 1));
+  const int colJ0 = 6 * sy_gstart(g, 2 * B), ncolJ = 6 * (sy_glen(g, 2 * B) + sy_glen(g, 2 * B + 1));
+  const int offI = wy ? 6 * sy_glen(g, 2 * A) : 0, offJ = wx ? 6 * sy_glen(g, 2 * B) : 0;   // unit's first column inside its part
+  const int nvalI = 6 * sy_glen(g, ga), nvalJ = 6 * sy_glen(g, gb);                          // valid columns of the unit's block
+  const int ntI = (nvalI + 7) >> 3, ntJ = (nvalJ + 7) >> 3;                                  // 8-column mma tiles actually needed (<= 6)
+  const int rowbase = 6 * sy_gstart(g, ga), colbase = 6 * sy_gstart(g, gb);                  // global scalar offsets of the unit
+  const bool full_unit = (ntI == 6) && (ntJ == 6);
 
-  double acc[36];
+  double acc[72];
 #pragma unroll
-  for (int i = 0; i < 36; i++) acc[i] = 0.0;
+  for (int i = 0; i < 72; i++) acc[i] = 0.0;
 
-  const int nsteps = (v_end - v_begin + SY_VB - 1) / SY_VB;
-  const size_t rowW = size_t(W) * 18;
-  constexpr int CH_PER_PART = SY_PART / 2;             // 144 double2 chunks
-  constexpr int CH_PER_STAGE = SY_VB * 2 * CH_PER_PART;
+  const int nsteps = g_end - g_begin;                  // one voxel group (4 voxels, 3 k-chunks) per step
+  constexpr int CH_PER_RUN = SY_PCOLS * 2;             // 16-B chunks per (k-chunk, part) run: 96 cols x 32 B
+  constexpr int CH_PER_STAGE = 3 * 2 * CH_PER_RUN;     // 1152
   auto issue = [&](int step) {
     double* sbase = smem + size_t(step % SY_STAGES) * SY_STAGE_DOUBLES;
-    const int v0 = v_begin + step * SY_VB;
+    const size_t gsrc = size_t(g_begin + step) * 3 * n * 4;
     for (int ch = tid; ch < CH_PER_STAGE; ch += SY_THREADS) {
-      const int vb = ch / (2 * CH_PER_PART), r2 = ch - vb * 2 * CH_PER_PART, part = r2 / CH_PER_PART, off2 = r2 - part * CH_PER_PART;
-      const int fl = off2 / 9;                           // local frame slot, 9 double2 per frame
-      const int gframe = (part == 0) ? row0 + fl : col0 + fl;
-      const int v = v0 + vb;
-      const bool ok = (v < v_end) && (gframe < W) && (part == 0 || fl < ncol);
-      const double* src = X + size_t(ok ? v : v_begin) * rowW + size_t(ok ? gframe : 0) * 18 + size_t(off2 - fl * 9) * 2;
-      cp_async16_zfill(sbase + (size_t(vb) * 2 + part) * SY_PART + size_t(off2) * 2, src, ok);
+      const int run = ch / CH_PER_RUN, off = ch - run * CH_PER_RUN;      // run = part*3 + kchunk
+      const int part = run / 3, kc = run - part * 3;
+      const int col = off >> 1;                                            // column inside the part
+      const bool ok = col < (part ? ncolJ : ncolI);
+      const double* src = XT + gsrc + (size_t(kc) * n + (part ? colJ0 : colI0) + (ok ? col : 0)) * 4 + (off & 1) * 2;
+      cp_async16_zfill(sbase + size_t(part) * SY_PART + (size_t(kc) * SY_PCOLS + col) * 4 + (off & 1) * 2, src, ok);
     }
   };
   for (int s = 0; s < SY_STAGES - 1; s++) { if (s < nsteps) issue(s); cp_async_commit(); }
@@ -339,34 +353,50 @@ __global__ void __launch_bounds__(SY_THREADS, 2) k_syrk(const double* __restrict
     if (step + SY_STAGES - 1 < nsteps) issue(step + SY_STAGES - 1);
     cp_async_commit();
     if (warp_active) {
-      const double* sbase = smem + size_t(step % SY_STAGES) * SY_STAGE_DOUBLES;
+      const double* pI = smem + size_t(step % SY_STAGES) * SY_STAGE_DOUBLES + size_t(offI) * 4 + lane;
+      const double* pJ = smem + size_t(step % SY_STAGES) * SY_STAGE_DOUBLES + SY_PART + size_t(offJ) * 4 + lane;
 #pragma unroll
-      for (int vb = 0; vb < SY_VB; vb++) {
-        const double* A = sbase + size_t(vb) * 2 * SY_PART;
-        const double* Bp = A + SY_PART;
+      for (int kc = 0; kc < 3; kc++) {
+        double fa[6], fb[6];
 #pragma unroll
-        for (int m = 0; m < 3; m++) {
-          const double2* pa = reinterpret_cast<const double2*>(A + li * 18 + m * 6);
-          const double2* pb = reinterpret_cast<const double2*>(Bp + lj * 18 + m * 6);
-          double a[6], b[6];
+        for (int t = 0; t < 6; t++) { fa[t] = pI[(kc * SY_PCOLS + 8 * t) * 4]; fb[t] = pJ[(kc * SY_PCOLS + 8 * t) * 4]; }
+        if (full_unit) {   // common case: both blocks have 8 frames -> 36 unconditional tensor-core tiles
 #pragma unroll
-          for (int q = 0; q < 3; q++) { double2 t0 = pa[q], tb = pb[q]; a[2 * q] = t0.x; a[2 * q + 1] = t0.y; b[2 * q] = tb.x; b[2 * q + 1] = tb.y; }
+          for (int ti = 0; ti < 6; ti++)
 #pragma unroll
-          for (int r = 0; r < 6; r++)
+            for (int tj = 0; tj < 6; tj++) dmma884(acc[2 * (ti * 6 + tj)], acc[2 * (ti * 6 + tj) + 1], fa[ti], fb[tj]);
+        } else {           // remainder block: only the tiles that hold valid columns
 #pragma unroll
-            for (int c = 0; c < 6; c++) acc[r * 6 + c] = fma(a[r], b[c], acc[r * 6 + c]);
+          for (int ti = 0; ti < 6; ti++) {
+            if (ti < ntI) {
+#pragma unroll
+              for (int tj = 0; tj < 6; tj++)
+                if (tj < ntJ) dmma884(acc[2 * (ti * 6 + tj)], acc[2 * (ti * 6 + tj) + 1], fa[ti], fb[tj]);
+            }
+          }
         }
       }
     }
   }
   cp_async_wait<0>();
-  // epilogue: H_ij -= sum x_i x_j^T for i <= j
-  const int nl = W * 6;
-  if (warp_active && validj && fi < W && fi <= fj) {
+  // epilogue: lane holds C[8ti + lane/4][8tj + 2(lane%4) + {0,1}] of every tile; H_ij -= x_i x_j^T for frame(i) <= frame(j)
+  if (warp_active) {
+    const int rl = lane >> 2, cl = 2 * (lane & 3);
 #pragma unroll
-    for (int r = 0; r < 6; r++)
+    for (int ti = 0; ti < 6; ti++)
 #pragma unroll
-      for (int c = 0; c < 6; c++) atomicAdd(C + size_t(6 * fj + c) * nl + 6 * fi + r, -acc[r * 6 + c]);
+      for (int tj = 0; tj < 6; tj++) {
+        const int r = 8 * ti + rl;
+        if (ti < ntI && tj < ntJ && r < nvalI) {
+          const int R = rowbase + r;
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            const int c = 8 * tj + cl + e;
+            const int Cc = colbase + c;
+            if (c < nvalJ && (R / 6) <= (Cc / 6)) atomicAdd(C + size_t(Cc) * n + R, -acc[2 * (ti * 6 + tj) + e]);
+          }
+        }
+      }
   }
 }
 
@@ -489,8 +519,11 @@ int vxs_eval_hessian_dev(vxs_ctx* ctx, vxs_factor* f, const double* poses_dev, i
     const int G = pick_group(f);
     // dense-slot rows when the window is reasonably covered (SURVEY §5 "long-context" row): V*W*144 B vs E*144 B
     const bool dense = (double(f->V) * W <= 4.0 * double(f->E)) && (double(f->V) * W * 144.0 <= 24e9);
-    const size_t xdoubles = dense ? size_t(f->V) * W * 18 : size_t(f->E) * 18;
+    const size_t vpad = (size_t(f->V) + 3) & ~size_t(3);
+    const size_t xdoubles = dense ? vpad * W * 18 : size_t(f->E) * 18;
     VXS_CUDA(ctx, f->X.reserve(xdoubles));
+    if (dense && (f->V & 3))   // rows of the padding voxels of the last group of 4 must be zero
+      VXS_CUDA(ctx, cudaMemsetAsync(f->X.p + (vpad - 4) * W * 18, 0, size_t(4) * W * 18 * 8, ctx->stream));
     const unsigned blocks_v = nblk(size_t(f->V), 256);
     VXS_CUDA(ctx, f->partial.reserve(blocks_v));
     if (!f->counter.p) { VXS_CUDA(ctx, f->counter.reserve(4)); VXS_CUDA(ctx, cudaMemsetAsync(f->counter.p, 0, 16, ctx->stream)); }
@@ -503,15 +536,15 @@ int vxs_eval_hessian_dev(vxs_ctx* ctx, vxs_factor* f, const double* poses_dev, i
 #undef LAUNCH_JAC
     if (dense) {
       const SyrkGeom g = sy_geom(W);
+      const int ngv = int((f->V + 3) / 4);                 // voxel groups of 4 (12 rows of X each)
       // enough chunks to fill the machine a few times over; tiles of one chunk are adjacent in launch order (L2 reuse of X)
       int target_ctas = ctx->sm_count * 2 * 4;
-      int nchunks = std::max(1, std::min<int>((target_ctas + g.ntiles - 1) / g.ntiles, int((f->V + SY_VB * 8 - 1) / (SY_VB * 8))));
-      int vpc = int((f->V + nchunks - 1) / nchunks);
-      vpc = ((vpc + SY_VB - 1) / SY_VB) * SY_VB;
-      nchunks = int((f->V + vpc - 1) / vpc);
+      int nchunks = std::max(1, std::min<int>((target_ctas + g.ntiles - 1) / g.ntiles, (ngv + 7) / 8));
+      int gpc = (ngv + nchunks - 1) / nchunks;
+      nchunks = (ngv + gpc - 1) / gpc;
       const size_t smem = size_t(SY_STAGES) * SY_STAGE_DOUBLES * 8;
       VXS_CUDA(ctx, cudaFuncSetAttribute(k_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-      VXS_LAUNCH(ctx, "k_syrk", k_syrk, unsigned(nchunks * g.ntiles), SY_THREADS, smem, f->X.p, C, int(f->V), W, g, vpc);
+      VXS_LAUNCH(ctx, "k_syrk", k_syrk, unsigned(nchunks * g.ntiles), SY_THREADS, smem, f->X.p, C, ngv, W, g, gpc);
     } else {
       if (G == 32) { auto kp = k_pairs<32>; VXS_LAUNCH(ctx, "k_pairs", kp, grid, 128, 0, fv, f->X.p, C); }
       else if (G == 16) { auto kp = k_pairs<16>; VXS_LAUNCH(ctx, "k_pairs", kp, grid, 128, 0, fv, f->X.p, C); }
