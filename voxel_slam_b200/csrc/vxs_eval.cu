@@ -305,6 +305,11 @@ static SyrkGeom sy_geom(int W) {
   return g;
 }
 
+// A warp's share of a CTA tile: up to three "pieces", each = two 8-row mma tile rows x six 8-column tile columns (12 tiles)
+// of one unit.  Splitting units into pieces and dealing the pieces round-robin keeps all four warps (= all four tensor pipes of
+// the SM) busy on diagonal / remainder tiles, where a unit-per-warp mapping leaves one to three warps idle.
+struct SyPiece { int offI, offJ, ntI, ntJ, rowbase, colbase, nvalI, nvalJ; };
+
 __global__ void __launch_bounds__(SY_THREADS, 2) k_syrk(const double* __restrict__ XT, double* __restrict__ C, int ngroups_vox, int W, SyrkGeom g, int groups_per_chunk) {
   extern __shared__ __align__(16) double smem[];
   const int tile = blockIdx.x % g.ntiles, chunk = blockIdx.x / g.ntiles;
@@ -314,18 +319,34 @@ __global__ void __launch_bounds__(SY_THREADS, 2) k_syrk(const double* __restrict
   const int g_begin = chunk * groups_per_chunk, g_end = min(ngroups_vox, g_begin + groups_per_chunk);
   if (g_begin >= g_end) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int wy = warp >> 1, wx = warp & 1;
   const int n = 6 * W;
-  const int ga = 2 * A + wy, gb = 2 * B + wx;
-  const bool warp_active = (ga < g.ngc) && (gb < g.ngc) && (ga <= gb);
   // part geometry: part I = blocks 2A, 2A+1 (contiguous frames), part J = blocks 2B, 2B+1
   const int colI0 = 6 * sy_gstart(g, 2 * A), ncolI = 6 * (sy_glen(g, 2 * A) + sy_glen(g, 2 * A + 1));
   const int colJ0 = 6 * sy_gstart(g, 2 * B), ncolJ = 6 * (sy_glen(g, 2 * B) + sy_glen(g, 2 * B + 1));
-  const int offI = wy ? 6 * sy_glen(g, 2 * A) : 0, offJ = wx ? 6 * sy_glen(g, 2 * B) : 0;   // unit's first column inside its part
-  const int nvalI = 6 * sy_glen(g, ga), nvalJ = 6 * sy_glen(g, gb);                          // valid columns of the unit's block
-  const int ntI = (nvalI + 7) >> 3, ntJ = (nvalJ + 7) >> 3;                                  // 8-column mma tiles actually needed (<= 6)
-  const int rowbase = 6 * sy_gstart(g, ga), colbase = 6 * sy_gstart(g, gb);                  // global scalar offsets of the unit
-  const bool full_unit = (ntI == 6) && (ntJ == 6);
+
+  // enumerate the pieces of this tile in a fixed order and keep those with index % 4 == warp (warp-uniform, <= 3)
+  SyPiece pc[3];
+  int npc = 0;
+  {
+    int q = 0;
+    for (int u = 0; u < 4; u++) {
+      const int wy = u >> 1, wx = u & 1, ga = 2 * A + wy, gb = 2 * B + wx;
+      if (!(ga < g.ngc && gb < g.ngc && ga <= gb)) continue;
+      const int nvalI = 6 * sy_glen(g, ga), nvalJ = 6 * sy_glen(g, gb);
+      const int ntI = (nvalI + 7) >> 3, ntJ = (nvalJ + 7) >> 3;
+      for (int t0 = 0; t0 < ntI; t0 += 2, q++) {
+        if ((q & 3) != warp || npc >= 3) continue;
+        SyPiece P;
+        P.offI = (wy ? 6 * sy_glen(g, 2 * A) : 0) + 8 * t0;
+        P.offJ = wx ? 6 * sy_glen(g, 2 * B) : 0;
+        P.ntI = min(2, ntI - t0); P.ntJ = ntJ;
+        P.rowbase = 6 * sy_gstart(g, ga) + 8 * t0; P.colbase = 6 * sy_gstart(g, gb);
+        P.nvalI = nvalI - 8 * t0; P.nvalJ = nvalJ;
+        if (npc == 0) pc[0] = P; else if (npc == 1) pc[1] = P; else pc[2] = P;
+        npc++;
+      }
+    }
+  }
 
   double acc[72];
 #pragma unroll
@@ -352,27 +373,32 @@ __global__ void __launch_bounds__(SY_THREADS, 2) k_syrk(const double* __restrict
     __syncthreads();
     if (step + SY_STAGES - 1 < nsteps) issue(step + SY_STAGES - 1);
     cp_async_commit();
-    if (warp_active) {
-      const double* pI = smem + size_t(step % SY_STAGES) * SY_STAGE_DOUBLES + size_t(offI) * 4 + lane;
-      const double* pJ = smem + size_t(step % SY_STAGES) * SY_STAGE_DOUBLES + SY_PART + size_t(offJ) * 4 + lane;
+    const double* sI = smem + size_t(step % SY_STAGES) * SY_STAGE_DOUBLES + lane;
+    const double* sJ = sI + SY_PART;
 #pragma unroll
-      for (int kc = 0; kc < 3; kc++) {
-        double fa[6], fb[6];
+    for (int p = 0; p < 3; p++) {
+      if (p < npc) {
+        const double* pI = sI + size_t(pc[p].offI) * 4;
+        const double* pJ = sJ + size_t(pc[p].offJ) * 4;
+        const bool full = (pc[p].ntI == 2) && (pc[p].ntJ == 6);
 #pragma unroll
-        for (int t = 0; t < 6; t++) { fa[t] = pI[(kc * SY_PCOLS + 8 * t) * 4]; fb[t] = pJ[(kc * SY_PCOLS + 8 * t) * 4]; }
-        if (full_unit) {   // common case: both blocks have 8 frames -> 36 unconditional tensor-core tiles
+        for (int kc = 0; kc < 3; kc++) {
+          double fa[2], fb[6];
 #pragma unroll
-          for (int ti = 0; ti < 6; ti++)
+          for (int t = 0; t < 2; t++) fa[t] = pI[(kc * SY_PCOLS + 8 * t) * 4];
 #pragma unroll
-            for (int tj = 0; tj < 6; tj++) dmma884(acc[2 * (ti * 6 + tj)], acc[2 * (ti * 6 + tj) + 1], fa[ti], fb[tj]);
-        } else {           // remainder block: only the tiles that hold valid columns
+          for (int t = 0; t < 6; t++) fb[t] = pJ[(kc * SY_PCOLS + 8 * t) * 4];
+          if (full) {
 #pragma unroll
-          for (int ti = 0; ti < 6; ti++) {
-            if (ti < ntI) {
+            for (int ti = 0; ti < 2; ti++)
+#pragma unroll
+              for (int tj = 0; tj < 6; tj++) dmma884(acc[p * 24 + 2 * (ti * 6 + tj)], acc[p * 24 + 2 * (ti * 6 + tj) + 1], fa[ti], fb[tj]);
+          } else {
+#pragma unroll
+            for (int ti = 0; ti < 2; ti++)
 #pragma unroll
               for (int tj = 0; tj < 6; tj++)
-                if (tj < ntJ) dmma884(acc[2 * (ti * 6 + tj)], acc[2 * (ti * 6 + tj) + 1], fa[ti], fb[tj]);
-            }
+                if (ti < pc[p].ntI && tj < pc[p].ntJ) dmma884(acc[p * 24 + 2 * (ti * 6 + tj)], acc[p * 24 + 2 * (ti * 6 + tj) + 1], fa[ti], fb[tj]);
           }
         }
       }
@@ -380,23 +406,26 @@ __global__ void __launch_bounds__(SY_THREADS, 2) k_syrk(const double* __restrict
   }
   cp_async_wait<0>();
   // epilogue: lane holds C[8ti + lane/4][8tj + 2(lane%4) + {0,1}] of every tile; H_ij -= x_i x_j^T for frame(i) <= frame(j)
-  if (warp_active) {
-    const int rl = lane >> 2, cl = 2 * (lane & 3);
+  const int rl = lane >> 2, cl = 2 * (lane & 3);
 #pragma unroll
-    for (int ti = 0; ti < 6; ti++)
+  for (int p = 0; p < 3; p++) {
+    if (p < npc) {
 #pragma unroll
-      for (int tj = 0; tj < 6; tj++) {
-        const int r = 8 * ti + rl;
-        if (ti < ntI && tj < ntJ && r < nvalI) {
-          const int R = rowbase + r;
+      for (int ti = 0; ti < 2; ti++)
 #pragma unroll
-          for (int e = 0; e < 2; e++) {
-            const int c = 8 * tj + cl + e;
-            const int Cc = colbase + c;
-            if (c < nvalJ && (R / 6) <= (Cc / 6)) atomicAdd(C + size_t(Cc) * n + R, -acc[2 * (ti * 6 + tj) + e]);
+        for (int tj = 0; tj < 6; tj++) {
+          const int r = 8 * ti + rl;
+          if (ti < pc[p].ntI && tj < pc[p].ntJ && r < pc[p].nvalI) {
+            const int R = pc[p].rowbase + r;
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+              const int c = 8 * tj + cl + e;
+              const int Cc = pc[p].colbase + c;
+              if (c < pc[p].nvalJ && (R / 6) <= (Cc / 6)) atomicAdd(C + size_t(Cc) * n + R, -acc[p * 24 + 2 * (ti * 6 + tj) + e]);
+            }
           }
         }
-      }
+    }
   }
 }
 
