@@ -243,6 +243,86 @@ __global__ void __launch_bounds__(128, 3) k_jac(FactorView f, const double* __re
   }
 }
 
+// Dense windows, W <= 128: same math as k_jac<.,true>, but a CTA owns whole voxel groups (4 voxels = one 12-row slab of XT),
+// builds the slab in shared memory and writes it out with coalesced 16-B stores — XT sectors interleave rows of different
+// voxels, so per-entry stores would be partial-sector writes from different warps.  Threads are 64-lane groups (lane = frame slot
+// in a sliding window), two voxels per round, two rounds per group; gradient / D sums as in k_jac.
+__global__ void __launch_bounds__(128, 3) k_jac_slab(FactorView f, const double* __restrict__ poses, int pstride, double* __restrict__ XT, double* __restrict__ gD, int ngroups_vox) {
+  extern __shared__ __align__(16) double sm[];
+  const int tid = threadIdx.x, half = tid >> 6, lane = tid & 63;
+  const int W = f.W, n = 6 * W;
+  const int slab = 3 * n * 4;                        // doubles per voxel group
+  double* acc = sm;                                  // [30][128]
+  double* T = sm + 30 * 128;                         // [3][n][4]
+  double* gbuf = gD;
+  double* Dbuf = gD + size_t(W) * 6;
+  int cur_fr = -1;
+#pragma unroll
+  for (int i = 0; i < 30; i++) acc[i * 128 + tid] = 0.0;
+  for (int G = blockIdx.x; G < ngroups_vox; G += gridDim.x) {
+    for (int i = tid; i < slab / 2; i += 128) reinterpret_cast<double2*>(T)[i] = make_double2(0.0, 0.0);
+    __syncthreads();
+    for (int round = 0; round < 2; round++) {
+      const int v = 4 * G + 2 * round + half;
+      if (v >= f.V) continue;
+      const int beg = f.ptr[v], end = f.ptr[v + 1];
+      if (beg + lane >= end) continue;
+      const size_t st = f.Vcap;
+      const double* e = f.eig + v;
+      double lam[3] = {__ldg(e), __ldg(e + st), __ldg(e + 2 * st)};
+      d3 u0 = mk3(__ldg(e + 3 * st), __ldg(e + 6 * st), __ldg(e + 9 * st));
+      d3 u1 = mk3(__ldg(e + 4 * st), __ldg(e + 7 * st), __ldg(e + 10 * st));
+      d3 u2 = mk3(__ldg(e + 5 * st), __ldg(e + 8 * st), __ldg(e + 11 * st));
+      const double* s = f.sum + v;
+      d3 sv = mk3(__ldg(s + 6 * st), __ldg(s + 7 * st), __ldg(s + 8 * st));
+      const double NN = __ldg(s + 9 * st);
+      const voxel_consts kc = make_voxel_consts(lam, u0, u1, u2, sv, NN, __ldg(f.coe + v));
+      for (int en = beg + lane; en < end; en += 64) {
+        cluster c = load_cluster_soa(f.cl, f.Ecap, size_t(en));
+        const int fr = __ldg(f.frame + en);
+        if (fr != cur_fr) {
+          if (cur_fr >= 0) {
+            double* g = gbuf + cur_fr * 6; double* D = Dbuf + cur_fr * 24;
+#pragma unroll
+            for (int i = 0; i < 6; i++) { atomicAdd(g + i, acc[i * 128 + tid]); acc[i * 128 + tid] = 0.0; }
+#pragma unroll
+            for (int i = 0; i < 24; i++) { atomicAdd(D + i, acc[(6 + i) * 128 + tid]); acc[(6 + i) * 128 + tid] = 0.0; }
+          }
+          cur_fr = fr;
+        }
+        rot3 R; d3 t;
+        load_pose(poses, pstride, fr, R, t);
+        entry_out o;
+        entry_jacobian(kc, c, R, t, o);
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+          const int r = 3 * (v & 3) + m;
+          double* dst = T + (size_t(r >> 2) * n + 6 * fr) * 4 + (r & 3);
+#pragma unroll
+          for (int cc = 0; cc < 6; cc++) dst[4 * cc] = o.x[6 * m + cc];
+        }
+#pragma unroll
+        for (int i = 0; i < 6; i++) acc[i * 128 + tid] += kc.coe * o.g[i];
+#pragma unroll
+        for (int i = 0; i < 9; i++) { acc[(6 + i) * 128 + tid] += o.Drr[i]; acc[(15 + i) * 128 + tid] += o.Drt[i]; }
+#pragma unroll
+        for (int i = 0; i < 6; i++) acc[(24 + i) * 128 + tid] += o.Dtt[i];
+      }
+    }
+    __syncthreads();
+    double2* dst = reinterpret_cast<double2*>(XT + size_t(G) * slab);
+    for (int i = tid; i < slab / 2; i += 128) dst[i] = reinterpret_cast<const double2*>(T)[i];
+    __syncthreads();
+  }
+  if (cur_fr >= 0) {
+    double* g = gbuf + cur_fr * 6; double* D = Dbuf + cur_fr * 24;
+#pragma unroll
+    for (int i = 0; i < 6; i++) atomicAdd(g + i, acc[i * 128 + tid]);
+#pragma unroll
+    for (int i = 0; i < 24; i++) atomicAdd(D + i, acc[(6 + i) * 128 + tid]);
+  }
+}
+
 // ------------------------------------------------------------------ Hessian part 2a: sparse windows, block pairs -> RED
 template <int G>
 __global__ void __launch_bounds__(128) k_pairs(FactorView f, const double* __restrict__ X, double* __restrict__ C) {
@@ -551,7 +631,7 @@ int vxs_eval_hessian_dev(vxs_ctx* ctx, vxs_factor* f, const double* poses_dev, i
     const size_t vpad = (size_t(f->V) + 3) & ~size_t(3);
     const size_t xdoubles = dense ? vpad * W * 18 : size_t(f->E) * 18;
     VXS_CUDA(ctx, f->X.reserve(xdoubles));
-    if (dense && (f->V & 3))   // rows of the padding voxels of the last group of 4 must be zero
+    if (dense && W > 128 && (f->V & 3))   // rows of the padding voxels of the last group of 4 must be zero (k_jac_slab zero-fills itself)
       VXS_CUDA(ctx, cudaMemsetAsync(f->X.p + (vpad - 4) * W * 18, 0, size_t(4) * W * 18 * 8, ctx->stream));
     const unsigned blocks_v = nblk(size_t(f->V), 256);
     VXS_CUDA(ctx, f->partial.reserve(blocks_v));
@@ -560,7 +640,13 @@ int vxs_eval_hessian_dev(vxs_ctx* ctx, vxs_factor* f, const double* poses_dev, i
     unsigned gridj = unsigned(std::min<size_t>((size_t(f->V) * GJ + 127) / 128, size_t(ctx->sm_count) * 8));
     unsigned grid = unsigned(std::min<size_t>((size_t(f->V) * G + 127) / 128, size_t(ctx->sm_count) * 16));
 #define LAUNCH_JAC(GG, DD) { auto kp = k_jac<GG, DD>; VXS_LAUNCH(ctx, "k_jac", kp, gridj, 128, 0, fv, poses_dev, pstride, f->X.p, gD); }
-    if (dense) { if (GJ == 64) LAUNCH_JAC(64, true) else if (GJ == 32) LAUNCH_JAC(32, true) else if (GJ == 16) LAUNCH_JAC(16, true) else LAUNCH_JAC(8, true) }
+    if (dense && W <= 128) {
+      const int ngv = int((f->V + 3) / 4);
+      const size_t smem = (size_t(30) * 128 + size_t(3) * 6 * W * 4) * 8;
+      VXS_CUDA(ctx, cudaFuncSetAttribute(k_jac_slab, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+      const unsigned grids = unsigned(std::min<int>(ngv, ctx->sm_count * 3 * 2));
+      VXS_LAUNCH(ctx, "k_jac", k_jac_slab, grids, 128, smem, fv, poses_dev, pstride, f->X.p, gD, ngv);
+    } else if (dense) { if (GJ == 64) LAUNCH_JAC(64, true) else if (GJ == 32) LAUNCH_JAC(32, true) else if (GJ == 16) LAUNCH_JAC(16, true) else LAUNCH_JAC(8, true) }
     else { if (GJ == 64) LAUNCH_JAC(64, false) else if (GJ == 32) LAUNCH_JAC(32, false) else if (GJ == 16) LAUNCH_JAC(16, false) else LAUNCH_JAC(8, false) }
 #undef LAUNCH_JAC
     if (dense) {
