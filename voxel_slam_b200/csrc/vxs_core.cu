@@ -197,7 +197,7 @@ static void factor_free_arrays(vxs_factor* f) {
 }
 static void vxs_factor_release_device(vxs_factor* f) {
   factor_free_arrays(f);
-  f->X.release(); f->C.release(); f->gD.release(); f->partial.release(); f->counter.release(); f->cache_copy.release();
+  f->X.release(); f->C.release(); f->gD.release(); f->partial.release(); f->counter.release(); f->cache_copy.release(); f->vc.release();
   f->V = f->E = 0; f->cache_copy_V = 0;
 }
 extern "C" int vxs_factor_destroy(vxs_factor* f) {

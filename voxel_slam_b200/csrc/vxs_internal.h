@@ -86,6 +86,7 @@ struct vxs_factor {
   DevBuf<double> gD;             // [W][6] gradient + [W][24] block-diagonal remainder
   DevBuf<double> partial;        // block partial sums for the residual
   DevBuf<unsigned int> counter;
+  DevBuf<double> vc;             // [8][Vcap] per-voxel constants for k_jac
   DevBuf<double> cache_copy;     // [22][Vcap] snapshot of eig | sum
   size_t cache_copy_V = 0;
 };

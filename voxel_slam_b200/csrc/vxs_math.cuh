@@ -137,12 +137,13 @@ struct voxel_consts {
   d3 u0, u1, u2;     // eigenvectors, u0 = plane normal (kk = 0)
   d3 vbar;           // pcr_add.v / NN
   double NN;         // pcr_add.N
+  double invN;       // 1 / NN
   double s1, s2, s3; // sqrt(-coe*alpha_m): alpha1 = 2/(l0-l1), alpha2 = 2/(l0-l2), alpha3 = -2/NN^2  (all <= 0)
   double coe;
 };
 VXS_HD voxel_consts make_voxel_consts(const double lam[3], d3 u0, d3 u1, d3 u2, d3 sumv, double NN, double coe) {
   voxel_consts k;
-  k.u0 = u0; k.u1 = u1; k.u2 = u2; k.NN = NN; k.coe = coe;
+  k.u0 = u0; k.u1 = u1; k.u2 = u2; k.NN = NN; k.invN = 1.0 / NN; k.coe = coe;
   k.vbar = mk3(sumv.x / NN, sumv.y / NN, sumv.z / NN);
   k.s1 = sqrt(coe * (2.0 / (lam[1] - lam[0])));
   k.s2 = sqrt(coe * (2.0 / (lam[2] - lam[0])));
@@ -171,7 +172,7 @@ VXS_HD void auk_t_times(d3 y, const cluster& c, const rot3& R, d3 r, d3 Pr, d3 t
 
 VXS_HD void entry_jacobian(const voxel_consts& k, const cluster& c, const rot3& R, d3 t, entry_out& o) {
   const d3 u = k.u0;
-  const double NN = k.NN, invN = 1.0 / NN, ni = c.n;
+  const double invN = k.invN, ni = c.n;
   d3 r = mulT(R, u);                 // RiTuk
   d3 w = cross(c.v, r);              // viRiTuk = hat(vi) * RiTuk
   d3 Pr = mul(c.P, r);               // PiRiTuk

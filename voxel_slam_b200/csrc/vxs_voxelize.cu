@@ -131,7 +131,8 @@ __global__ void __launch_bounds__(256) k_bbox(PointSrc s, double voxel_size, lon
 
 // key0 = (linear root id << FB) | frame ; pathbits = octants of the deeper layers
 __global__ void __launch_bounds__(256) k_point_keys(PointSrc s, double voxel_size, int max_layer, long long minx, long long miny, long long minz, long long ey, long long ez,
-                                                    int FB, unsigned long long* __restrict__ keys, unsigned int* __restrict__ idx, unsigned short* __restrict__ pathbits) {
+                                                    int FB, unsigned long long* __restrict__ keys, unsigned int* __restrict__ idx, unsigned short* __restrict__ pathbits,
+                                                    int shard_rank, int shard_n, unsigned int* __restrict__ owned) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= s.n) return;
   const int fr = frame_of(s, i);
@@ -141,6 +142,13 @@ __global__ void __launch_bounds__(256) k_point_keys(PointSrc s, double voxel_siz
   keys[i] = (lin << FB) | (unsigned long long)fr;
   idx[i] = (unsigned int)i;
   pathbits[i] = (unsigned short)octant_bits(w, kx, ky, kz, voxel_size, max_layer);
+  // multi-GPU: a root cell (and its whole octree) belongs to rank hash(VOXEL_LOC) mod n  
+  if (owned) owned[i] = (voxel_hash(kx, ky, kz) % (unsigned long long)shard_n) == (unsigned long long)shard_rank ? 1u : 0u;
+}
+__global__ void k_compact_owned(const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ idx, const unsigned int* __restrict__ owned,
+                                const unsigned int* __restrict__ pos, size_t n, unsigned long long* __restrict__ keys_out, unsigned int* __restrict__ idx_out) {
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n && owned[i]) { keys_out[pos[i]] = keys[i]; idx_out[pos[i]] = idx[i]; }
 }
 
 // ------------------------------------------------------------------ exclusive scan (uint32), 3 kernels
@@ -496,11 +504,24 @@ static int build_factor(vxs_ctx* ctx, const vxs_map_params* mp, bool gba, const 
   VXS_CUDA(ctx, s->keysA.reserve(size_t(N))); VXS_CUDA(ctx, s->keysB.reserve(size_t(N)));
   VXS_CUDA(ctx, s->idxA.reserve(size_t(N))); VXS_CUDA(ctx, s->idxB.reserve(size_t(N)));
   VXS_CUDA(ctx, s->pathbits.reserve(size_t(N)));
-  VXS_LAUNCH(ctx, "k_point_keys", k_point_keys, nblk(size_t(N), 256), 256, 0, ps, mp->voxel_size, int(mp->max_layer), bb[0], bb[1], bb[2], eyl, ezl, FB, s->keysA.p, s->idxA.p, s->pathbits.p);
+  const bool sharded = ctx->nranks > 1;
+  unsigned int* owned = nullptr;
+  if (sharded) { VXS_CUDA(ctx, s->flags.reserve(size_t(N))); VXS_CUDA(ctx, s->scanbuf.reserve(size_t(N))); owned = s->flags.p; }
+  VXS_LAUNCH(ctx, "k_point_keys", k_point_keys, nblk(size_t(N), 256), 256, 0, ps, mp->voxel_size, int(mp->max_layer), bb[0], bb[1], bb[2], eyl, ezl, FB, s->keysA.p, s->idxA.p, s->pathbits.p,
+             ctx->rank, ctx->nranks, owned);
 
   size_t m = size_t(N);
   int key_bits = root_bits + FB;
   unsigned long long* kcur = s->keysA.p; unsigned int* vcur = s->idxA.p;
+  if (sharded) {  // keep only the points whose root cell this rank owns
+    int rc0 = scan_u32(ctx, s, owned, s->scanbuf.p, size_t(N), s->totals.p + 5);
+    if (rc0) return rc0;
+    VXS_LAUNCH(ctx, "k_compact_owned", k_compact_owned, nblk(size_t(N), 256), 256, 0, s->keysA.p, s->idxA.p, owned, s->scanbuf.p, size_t(N), s->keysB.p, s->idxB.p);
+    unsigned int mo = 0;
+    VXS_CUDA(ctx, cudaMemcpyAsync(&mo, s->totals.p + 5, 4, cudaMemcpyDeviceToHost, st));
+    VXS_CUDA(ctx, cudaStreamSynchronize(st));
+    m = mo; kcur = s->keysB.p; vcur = s->idxB.p;
+  }
   long long Vtot = 0, Etot = 0;
   s->ids_host.clear();
   for (int layer = 0; layer <= mp->max_layer && m > 0; layer++) {
