@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(128) k_pairs(FactorView f, const double* __res
 //   * warp unit = (row block a, column block b), a <= b: 6x6 mma tiles of 8x8, 72 fp64 accumulators per lane;
 //   * CTA = 2x2 units; k runs over (voxel, m) rows in chunks of 4; XT (see xt_index) is staged with 16-B cp.async,
 //     3 stages of 4 voxels (12 rows); split over voxel chunks; fp64 RED epilogue into the upper block triangle.
-#define SY_THREADS 256
+#define SY_THREADS 128
 #define SY_STAGES 3
 #define SY_PCOLS 96                             // columns per part (2 blocks x 48)
 #define SY_PART (3 * SY_PCOLS * 4)              // doubles per part per stage: 3 chunks x 96 cols x 4 rows
@@ -393,11 +393,10 @@ static SyrkGeom sy_geom(int W) {
   return g;
 }
 
-// A warp's share of a CTA tile: up to three "pieces", each = one 8-row mma tile row x six 8-column tile columns (6 tiles) of one
-// unit.  Measured (profiles/): one warp cannot issue DMMA back to back fast enough to fill its tensor pipe, so the CTA runs 8
-// warps with 36 accumulators each (<= 128 registers, 2 CTAs = 16 warps per SM) rather than 4 warps with 72; pieces are dealt in
-// contiguous ranges so that all warps stay busy on diagonal / remainder tiles and a warp's pieces usually share their B fragments.
-struct SyPiece { int offI, offJ, ntJ, rowbase, colbase, nvalI, nvalJ, unit; };
+// A warp's share of a CTA tile: up to three "pieces", each = two 8-row mma tile rows x six 8-column tile columns (12 tiles)
+// of one unit.  Splitting units into pieces and dealing the pieces round-robin keeps all four warps (= all four tensor pipes of
+// the SM) busy on diagonal / remainder tiles, where a unit-per-warp mapping leaves one to three warps idle.
+struct SyPiece { int offI, offJ, ntI, ntJ, rowbase, colbase, nvalI, nvalJ; };
 
 __global__ void __launch_bounds__(SY_THREADS, 2) k_syrk(const double* __restrict__ XT, double* __restrict__ C, int ngroups_vox, int W, SyrkGeom g, int groups_per_chunk) {
   extern __shared__ __align__(16) double smem[];
@@ -413,13 +412,7 @@ __global__ void __launch_bounds__(SY_THREADS, 2) k_syrk(const double* __restrict
   const int colI0 = 6 * sy_gstart(g, 2 * A), ncolI = 6 * (sy_glen(g, 2 * A) + sy_glen(g, 2 * A + 1));
   const int colJ0 = 6 * sy_gstart(g, 2 * B), ncolJ = 6 * (sy_glen(g, 2 * B) + sy_glen(g, 2 * B + 1));
 
-  // count the pieces of the tile, then take the contiguous range [warp*quota, (warp+1)*quota)
-  int P = 0;
-  for (int u = 0; u < 4; u++) {
-    const int ga = 2 * A + (u >> 1), gb = 2 * B + (u & 1);
-    if (ga < g.ngc && gb < g.ngc && ga <= gb) P += (6 * sy_glen(g, ga) + 7) >> 3;
-  }
-  const int quota = (P + (SY_THREADS / 32) - 1) / (SY_THREADS / 32);
+  // enumerate the pieces of this tile in a fixed order and keep those with index % 4 == warp (warp-uniform, <= 3)
   SyPiece pc[3];
   int npc = 0;
   {
@@ -429,23 +422,23 @@ __global__ void __launch_bounds__(SY_THREADS, 2) k_syrk(const double* __restrict
       if (!(ga < g.ngc && gb < g.ngc && ga <= gb)) continue;
       const int nvalI = 6 * sy_glen(g, ga), nvalJ = 6 * sy_glen(g, gb);
       const int ntI = (nvalI + 7) >> 3, ntJ = (nvalJ + 7) >> 3;
-      for (int t0 = 0; t0 < ntI; t0++, q++) {
-        if (q < warp * quota || q >= (warp + 1) * quota || npc >= 3) continue;
-        SyPiece Pp;
-        Pp.offI = (wy ? 6 * sy_glen(g, 2 * A) : 0) + 8 * t0;
-        Pp.offJ = wx ? 6 * sy_glen(g, 2 * B) : 0;
-        Pp.ntJ = ntJ;
-        Pp.rowbase = 6 * sy_gstart(g, ga) + 8 * t0; Pp.colbase = 6 * sy_gstart(g, gb);
-        Pp.nvalI = nvalI - 8 * t0; Pp.nvalJ = nvalJ; Pp.unit = u;
-        if (npc == 0) pc[0] = Pp; else if (npc == 1) pc[1] = Pp; else pc[2] = Pp;
+      for (int t0 = 0; t0 < ntI; t0 += 2, q++) {
+        if ((q & 3) != warp || npc >= 3) continue;
+        SyPiece P;
+        P.offI = (wy ? 6 * sy_glen(g, 2 * A) : 0) + 8 * t0;
+        P.offJ = wx ? 6 * sy_glen(g, 2 * B) : 0;
+        P.ntI = min(2, ntI - t0); P.ntJ = ntJ;
+        P.rowbase = 6 * sy_gstart(g, ga) + 8 * t0; P.colbase = 6 * sy_gstart(g, gb);
+        P.nvalI = nvalI - 8 * t0; P.nvalJ = nvalJ;
+        if (npc == 0) pc[0] = P; else if (npc == 1) pc[1] = P; else pc[2] = P;
         npc++;
       }
     }
   }
 
-  double acc[36];
+  double acc[72];
 #pragma unroll
-  for (int i = 0; i < 36; i++) acc[i] = 0.0;
+  for (int i = 0; i < 72; i++) acc[i] = 0.0;
 
   const int nsteps = g_end - g_begin;                  // one voxel group (4 voxels, 3 k-chunks) per step
   constexpr int CH_PER_RUN = SY_PCOLS * 2;             // 16-B chunks per (k-chunk, part) run: 96 cols x 32 B
@@ -471,47 +464,55 @@ __global__ void __launch_bounds__(SY_THREADS, 2) k_syrk(const double* __restrict
     const double* sI = smem + size_t(step % SY_STAGES) * SY_STAGE_DOUBLES + lane;
     const double* sJ = sI + SY_PART;
 #pragma unroll
-    for (int kc = 0; kc < 3; kc++) {
-      double fb[6];
+    for (int p = 0; p < 3; p++) {
+      if (p < npc) {
+        const double* pI = sI + size_t(pc[p].offI) * 4;
+        const double* pJ = sJ + size_t(pc[p].offJ) * 4;
+        const bool full = (pc[p].ntI == 2) && (pc[p].ntJ == 6);
 #pragma unroll
-      for (int p = 0; p < 3; p++) {
-        if (p < npc) {
-          if (p == 0 || pc[p].unit != pc[p - 1].unit) {     // B fragments are shared by the pieces of one unit
-            const double* pJ = sJ + size_t(pc[p].offJ) * 4;
+        for (int kc = 0; kc < 3; kc++) {
+          double fa[2], fb[6];
 #pragma unroll
-            for (int t = 0; t < 6; t++) fb[t] = pJ[(kc * SY_PCOLS + 8 * t) * 4];
-          }
-          const double fa = sI[size_t(pc[p].offI) * 4 + (kc * SY_PCOLS) * 4];
-          if (pc[p].ntJ == 6) {
+          for (int t = 0; t < 2; t++) fa[t] = pI[(kc * SY_PCOLS + 8 * t) * 4];
 #pragma unroll
-            for (int tj = 0; tj < 6; tj++) dmma884(acc[p * 12 + 2 * tj], acc[p * 12 + 2 * tj + 1], fa, fb[tj]);
+          for (int t = 0; t < 6; t++) fb[t] = pJ[(kc * SY_PCOLS + 8 * t) * 4];
+          if (full) {
+#pragma unroll
+            for (int ti = 0; ti < 2; ti++)
+#pragma unroll
+              for (int tj = 0; tj < 6; tj++) dmma884(acc[p * 24 + 2 * (ti * 6 + tj)], acc[p * 24 + 2 * (ti * 6 + tj) + 1], fa[ti], fb[tj]);
           } else {
 #pragma unroll
-            for (int tj = 0; tj < 6; tj++)
-              if (tj < pc[p].ntJ) dmma884(acc[p * 12 + 2 * tj], acc[p * 12 + 2 * tj + 1], fa, fb[tj]);
+            for (int ti = 0; ti < 2; ti++)
+#pragma unroll
+              for (int tj = 0; tj < 6; tj++)
+                if (ti < pc[p].ntI && tj < pc[p].ntJ) dmma884(acc[p * 24 + 2 * (ti * 6 + tj)], acc[p * 24 + 2 * (ti * 6 + tj) + 1], fa[ti], fb[tj]);
           }
         }
       }
     }
   }
   cp_async_wait<0>();
-  // epilogue: lane holds C[lane/4][8tj + 2(lane%4) + {0,1}] of every tile; H_ij -= x_i x_j^T for frame(i) <= frame(j)
+  // epilogue: lane holds C[8ti + lane/4][8tj + 2(lane%4) + {0,1}] of every tile; H_ij -= x_i x_j^T for frame(i) <= frame(j)
   const int rl = lane >> 2, cl = 2 * (lane & 3);
 #pragma unroll
   for (int p = 0; p < 3; p++) {
-    if (p < npc && rl < pc[p].nvalI) {
-      const int R = pc[p].rowbase + rl;
+    if (p < npc) {
 #pragma unroll
-      for (int tj = 0; tj < 6; tj++) {
-        if (tj < pc[p].ntJ) {
+      for (int ti = 0; ti < 2; ti++)
 #pragma unroll
-          for (int e = 0; e < 2; e++) {
-            const int c = 8 * tj + cl + e;
-            const int Cc = pc[p].colbase + c;
-            if (c < pc[p].nvalJ && (R / 6) <= (Cc / 6)) atomicAdd(C + size_t(Cc) * n + R, -acc[p * 12 + 2 * tj + e]);
+        for (int tj = 0; tj < 6; tj++) {
+          const int r = 8 * ti + rl;
+          if (ti < pc[p].ntI && tj < pc[p].ntJ && r < pc[p].nvalI) {
+            const int R = pc[p].rowbase + r;
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+              const int c = 8 * tj + cl + e;
+              const int Cc = pc[p].colbase + c;
+              if (c < pc[p].nvalJ && (R / 6) <= (Cc / 6)) atomicAdd(C + size_t(Cc) * n + R, -acc[p * 24 + 2 * (ti * 6 + tj) + e]);
+            }
           }
         }
-      }
     }
   }
 }
@@ -664,7 +665,7 @@ int vxs_eval_hessian_dev(vxs_ctx* ctx, vxs_factor* f, const double* poses_dev, i
       const int ngv = int((f->V + 3) / 4);                 // voxel groups of 4 (12 rows of X each)
       // enough chunks to fill the machine a few times over; tiles of one chunk are adjacent in launch order (L2 reuse of X)
       int target_ctas = ctx->sm_count * 2 * 4;
-      int nchunks = std::max(1, std::min<int>((target_ctas + g.ntiles - 1) / g.ntiles, (ngv + 7) / 8));
+      int nchunks = std::max(1, std::min<int>(target_ctas / g.ntiles, (ngv + 7) / 8));   // floor: CTAs fit whole waves of 2 per SM
       int gpc = (ngv + nchunks - 1) / nchunks;
       nchunks = (ngv + gpc - 1) / gpc;
       const size_t smem = size_t(SY_STAGES) * SY_STAGE_DOUBLES * 8;
