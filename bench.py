@@ -261,6 +261,9 @@ def run_ours(args):
     roof_jac = roof(["k_jac"], E * 80 + V * 176 + E * 144)
     dom = max(kern.items(), key=lambda kv_: kv_[1]["ms_per_step"])[0] if kern else None
 
+    c2 = None
+    if rank == 0 and world == 1:
+        c2 = c2_leg(vx, ctx, hbm)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline_from_structure(vx, W, ptr, fr, hp["cl"], eig0, sum0, st0, tr, reps=2)
@@ -277,13 +280,37 @@ def run_ours(args):
                     "call": "push host LidarFactor (pinned CSR) + LI_BA damping_iter (3 iterations) + read back poses, Hessian, eig/pcr_adds"},
             "gpu_launches": int(launches), "clocks": clocks,
             "roofline": roof_hess, "roofline_residual": roof_resid, "roofline_jac": roof_jac, "dominant_kernel": dom,
-            "kernels": kern, "cpu_baseline": cpu,
+            "kernels": kern, "cpu_baseline": cpu, "c2_plane_fit": c2,
             "voxelize": {"ms_total": t_vox * 1e3, "points": int(W * pts), "stages_ms": {k: v[0] for k, v in vox_stages.items() if v[1] > 0}},
             "check": {"pose_err_before": err0, "pose_err_after_3_iters": err1, "trace": [[float(t["r1"]), float(t["r2"]), int(t["accepted"])] for t in o["trace"]]},
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier(); dist.destroy_process_group()
+
+
+def c2_leg(vx, ctx, hbm):
+    """BASELINE.json configs[1]: per-voxel covariance + 3x3 eigensolve over 1 M points / ~100 k voxels (L=183, max_layer 0):
+    the GPU voxel-map build on device-resident-after-upload points; kernel times from CUDA events."""
+    L, n = 183.0, 1000000
+    pose = vx.true_pose(L, 0)
+    pts = vx.gen_scan(L, 0, n, pose, seed=0x5EED0000 + 2000)
+    off = np.array([0, n], dtype=np.int64)
+    mp = vx.MapParams.make(voxel_size=1.0, min_eigen_value=0.0025, max_layer=0)
+    f = vx.Factor(ctx, 1)
+    ctx.build_window_factor(mp, pts, off, pose[None, :], f)          # warm-up (allocations)
+    ctx.timing(True); ctx.timing_reset()
+    reps = 5
+    for _ in range(reps):
+        nv = ctx.build_window_factor(mp, pts, off, pose[None, :], f)
+    st = ctx.timing_read(); ctx.timing(False)
+    ms = {k: v[0] / reps for k, v in st.items() if v[1] > 0}
+    t_all = sum(ms.values())
+    t_acc = ms.get("k_rec_clusters", 0.0) + ms.get("k_point_keys", 0.0) + ms.get("k_bbox", 0.0)
+    f.close()
+    return {"workload": f"C2: {n} pts, L={L}, max_layer=0 -> {nv} plane voxels", "kernel_ms_total": t_all, "points_per_s": n / (t_all * 1e-3), "voxels": int(nv),
+            "kernels_ms": ms, "hbm_frac_transform_accumulate": (24.0 * n * 3 / (t_acc * 1e-3) / 1e9 / hbm) if t_acc > 0 else None,
+            "note": "kernel time only (CUDA events); the H2D copy of the 24 MB scan is outside. transform+accumulate reads each 24-B point three times (bbox, keys, clusters)"}
 
 
 def oracle_factor_from_csr(W, ptr, fr, cl, eig, s):

@@ -69,23 +69,48 @@ __global__ void __launch_bounds__(256) k_cluster_sum(FactorView f, const double*
       load_pose(poses, pstride, __ldg(f.frame + e), R, t);
       cluster_transform_acc(c, R, t, acc);
     }
+    if (G == 32) {
+      // reduce-scatter over the warp: 12 64-bit shuffles instead of 50 (the kernel was LSU-bound on shuffles, profiles/):
+      // after the five steps the lanes with even index hold one fully reduced component each.
+      double a[10] = {acc.P.xx, acc.P.xy, acc.P.xz, acc.P.yy, acc.P.yz, acc.P.zz, acc.v.x, acc.v.y, acc.v.z, acc.n};
+      const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4, b2 = lane & 2;
+      double b[6], c[4], d[2];
 #pragma unroll
-    for (int off = G / 2; off > 0; off >>= 1) {
-      acc.P.xx += __shfl_xor_sync(0xffffffffu, acc.P.xx, off); acc.P.xy += __shfl_xor_sync(0xffffffffu, acc.P.xy, off);
-      acc.P.xz += __shfl_xor_sync(0xffffffffu, acc.P.xz, off); acc.P.yy += __shfl_xor_sync(0xffffffffu, acc.P.yy, off);
-      acc.P.yz += __shfl_xor_sync(0xffffffffu, acc.P.yz, off); acc.P.zz += __shfl_xor_sync(0xffffffffu, acc.P.zz, off);
-      acc.v.x += __shfl_xor_sync(0xffffffffu, acc.v.x, off); acc.v.y += __shfl_xor_sync(0xffffffffu, acc.v.y, off);
-      acc.v.z += __shfl_xor_sync(0xffffffffu, acc.v.z, off); acc.n += __shfl_xor_sync(0xffffffffu, acc.n, off);
-    }
-    if (valid && lane == 0) {
-      if (f.has_fix) {  // PointCluster sig = sig_vecs[a]  (voxel_map.hpp:255)
-        cluster fx = load_cluster_soa(f.fix, f.Vcap, size_t(v));
-        acc.P.xx += fx.P.xx; acc.P.xy += fx.P.xy; acc.P.xz += fx.P.xz; acc.P.yy += fx.P.yy; acc.P.yz += fx.P.yz; acc.P.zz += fx.P.zz;
-        acc.v = acc.v + fx.v; acc.n += fx.n;
+      for (int i = 0; i < 5; i++) { const double keep = b16 ? a[5 + i] : a[i], send = b16 ? a[i] : a[5 + i]; b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16); }
+      b[5] = 0.0;
+#pragma unroll
+      for (int i = 0; i < 3; i++) { const double keep = b8 ? b[3 + i] : b[i], send = b8 ? b[i] : b[3 + i]; c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8); }
+      c[3] = 0.0;
+#pragma unroll
+      for (int i = 0; i < 2; i++) { const double keep = b4 ? c[2 + i] : c[i], send = b4 ? c[i] : c[2 + i]; d[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4); }
+      double e = (b2 ? d[1] : d[0]) + __shfl_xor_sync(0xffffffffu, b2 ? d[0] : d[1], 2);
+      e += __shfl_xor_sync(0xffffffffu, e, 1);
+      const int s3 = (b4 ? 2 : 0) + (b2 ? 1 : 0), s2 = b2 ? 1 : 0;
+      const int comp = (b16 ? 5 : 0) + (b8 ? 3 : 0) + s3;
+      const bool holder = !(lane & 1) && s3 < (b8 ? 2 : 3) && s2 < (b4 ? 1 : 2);
+      if (valid && holder) {
+        if (f.has_fix) e += __ldg(f.fix + size_t(comp) * f.Vcap + v);   // PointCluster sig = sig_vecs[a]  (voxel_map.hpp:255)
+        f.sum[size_t(comp) * f.Vcap + v] = e;
       }
-      double* s = f.sum + v; const size_t st = f.Vcap;
-      s[0] = acc.P.xx; s[st] = acc.P.xy; s[2 * st] = acc.P.xz; s[3 * st] = acc.P.yy; s[4 * st] = acc.P.yz; s[5 * st] = acc.P.zz;
-      s[6 * st] = acc.v.x; s[7 * st] = acc.v.y; s[8 * st] = acc.v.z; s[9 * st] = acc.n;
+    } else {
+#pragma unroll
+      for (int off = G / 2; off > 0; off >>= 1) {
+        acc.P.xx += __shfl_xor_sync(0xffffffffu, acc.P.xx, off); acc.P.xy += __shfl_xor_sync(0xffffffffu, acc.P.xy, off);
+        acc.P.xz += __shfl_xor_sync(0xffffffffu, acc.P.xz, off); acc.P.yy += __shfl_xor_sync(0xffffffffu, acc.P.yy, off);
+        acc.P.yz += __shfl_xor_sync(0xffffffffu, acc.P.yz, off); acc.P.zz += __shfl_xor_sync(0xffffffffu, acc.P.zz, off);
+        acc.v.x += __shfl_xor_sync(0xffffffffu, acc.v.x, off); acc.v.y += __shfl_xor_sync(0xffffffffu, acc.v.y, off);
+        acc.v.z += __shfl_xor_sync(0xffffffffu, acc.v.z, off); acc.n += __shfl_xor_sync(0xffffffffu, acc.n, off);
+      }
+      if (valid && lane == 0) {
+        if (f.has_fix) {  // PointCluster sig = sig_vecs[a]  (voxel_map.hpp:255)
+          cluster fx = load_cluster_soa(f.fix, f.Vcap, size_t(v));
+          acc.P.xx += fx.P.xx; acc.P.xy += fx.P.xy; acc.P.xz += fx.P.xz; acc.P.yy += fx.P.yy; acc.P.yz += fx.P.yz; acc.P.zz += fx.P.zz;
+          acc.v = acc.v + fx.v; acc.n += fx.n;
+        }
+        double* s = f.sum + v; const size_t st = f.Vcap;
+        s[0] = acc.P.xx; s[st] = acc.P.xy; s[2 * st] = acc.P.xz; s[3 * st] = acc.P.yy; s[4 * st] = acc.P.yz; s[5 * st] = acc.P.zz;
+        s[6 * st] = acc.v.x; s[7 * st] = acc.v.y; s[8 * st] = acc.v.z; s[9 * st] = acc.n;
+      }
     }
   }
 }
@@ -268,16 +293,18 @@ __global__ void __launch_bounds__(128, 3) k_jac_slab(FactorView f, const double*
   extern __shared__ __align__(16) double sm[];
   const int tid = threadIdx.x, half = tid >> 6, lane = tid & 63;
   const int W = f.W, n = 6 * W;
-  const int slab = 3 * n * 4;                        // doubles per voxel group
+  const int slab = 3 * n * 4;                        // doubles per voxel group (global layout [chunk][col][kr])
+  const int TW = 7 * W;                              // padded row length of the shared slab: [chunk][kr][7*frame + c] — a lane (frame)
+  const int tslab = 12 * TW;                         // advances 7 doubles, so 16 lanes hit 32 distinct banks (6 would 4-way conflict)
   double* acc = sm;                                  // [30][128]
-  double* T = sm + 30 * 128;                         // [3][n][4]
+  double* T = sm + 30 * 128;
   double* gbuf = gD;
   double* Dbuf = gD + size_t(W) * 6;
   int cur_fr = -1;
 #pragma unroll
   for (int i = 0; i < 30; i++) acc[i * 128 + tid] = 0.0;
   for (int G = blockIdx.x; G < ngroups_vox; G += gridDim.x) {
-    for (int i = tid; i < slab / 2; i += 128) reinterpret_cast<double2*>(T)[i] = make_double2(0.0, 0.0);
+    for (int i = tid; i < tslab / 2; i += 128) reinterpret_cast<double2*>(T)[i] = make_double2(0.0, 0.0);
     __syncthreads();
     for (int round = 0; round < 2; round++) {
       const int v = 4 * G + 2 * round + half;
@@ -304,10 +331,10 @@ __global__ void __launch_bounds__(128, 3) k_jac_slab(FactorView f, const double*
         entry_jacobian(kc, c, R, t, o);
 #pragma unroll
         for (int m = 0; m < 3; m++) {
-          const int r = 3 * (v & 3) + m;
-          double* dst = T + (size_t(r >> 2) * n + 6 * fr) * 4 + (r & 3);
+          const int r = 3 * (v & 3) + m;     // row of the slab = (chunk r>>2, kr r&3)
+          double* dst = T + size_t(r) * TW + 7 * fr;
 #pragma unroll
-          for (int cc = 0; cc < 6; cc++) dst[4 * cc] = o.x[6 * m + cc];
+          for (int cc = 0; cc < 6; cc++) dst[cc] = o.x[6 * m + cc];
         }
 #pragma unroll
         for (int i = 0; i < 6; i++) acc[i * 128 + tid] += kc.coe * o.g[i];
@@ -319,7 +346,12 @@ __global__ void __launch_bounds__(128, 3) k_jac_slab(FactorView f, const double*
     }
     __syncthreads();
     double2* dst = reinterpret_cast<double2*>(XT + size_t(G) * slab);
-    for (int i = tid; i < slab / 2; i += 128) dst[i] = reinterpret_cast<const double2*>(T)[i];
+    for (int i = tid; i < 3 * n; i += 128) {        // i = chunk*n + col : gather the four kr values, write one 32-B sector
+      const int ch = i / n, col = i - ch * n, fq = col / 6, cc = col - fq * 6;
+      const double* src = T + size_t(4 * ch) * TW + 7 * fq + cc;
+      dst[2 * i] = make_double2(src[0], src[TW]);
+      dst[2 * i + 1] = make_double2(src[2 * TW], src[3 * TW]);
+    }
     __syncthreads();
   }
   if (cur_fr >= 0) {
@@ -443,17 +475,27 @@ __global__ void __launch_bounds__(SY_THREADS, 2) k_syrk(const double* __restrict
   const int nsteps = g_end - g_begin;                  // one voxel group (4 voxels, 3 k-chunks) per step
   constexpr int CH_PER_RUN = SY_PCOLS * 2;             // 16-B chunks per (k-chunk, part) run: 96 cols x 32 B
   constexpr int CH_PER_STAGE = 3 * 2 * CH_PER_RUN;     // 1152
+  constexpr int CH_PER_THREAD = CH_PER_STAGE / SY_THREADS;   // 9
+  // the loader's address arithmetic does not depend on the step: do it once (source offset inside a voxel group, smem offset, predicate)
+  int ld_src[CH_PER_THREAD], ld_dst[CH_PER_THREAD];
+  unsigned ld_ok = 0;
+#pragma unroll
+  for (int j = 0; j < CH_PER_THREAD; j++) {
+    const int ch = tid + j * SY_THREADS;
+    const int run = ch / CH_PER_RUN, off = ch - run * CH_PER_RUN;      // run = part*3 + kchunk
+    const int part = run / 3, kc = run - part * 3;
+    const int col = off >> 1;                                            // column inside the part
+    const bool ok = col < (part ? ncolJ : ncolI);
+    ld_src[j] = (kc * n + (part ? colJ0 : colI0) + (ok ? col : 0)) * 4 + (off & 1) * 2;
+    ld_dst[j] = part * SY_PART + (kc * SY_PCOLS + col) * 4 + (off & 1) * 2;
+    ld_ok |= (ok ? 1u : 0u) << j;
+  }
+  const size_t group_stride = size_t(3) * n * 4;
   auto issue = [&](int step) {
     double* sbase = smem + size_t(step % SY_STAGES) * SY_STAGE_DOUBLES;
-    const size_t gsrc = size_t(g_begin + step) * 3 * n * 4;
-    for (int ch = tid; ch < CH_PER_STAGE; ch += SY_THREADS) {
-      const int run = ch / CH_PER_RUN, off = ch - run * CH_PER_RUN;      // run = part*3 + kchunk
-      const int part = run / 3, kc = run - part * 3;
-      const int col = off >> 1;                                            // column inside the part
-      const bool ok = col < (part ? ncolJ : ncolI);
-      const double* src = XT + gsrc + (size_t(kc) * n + (part ? colJ0 : colI0) + (ok ? col : 0)) * 4 + (off & 1) * 2;
-      cp_async16_zfill(sbase + size_t(part) * SY_PART + (size_t(kc) * SY_PCOLS + col) * 4 + (off & 1) * 2, src, ok);
-    }
+    const double* gbase = XT + size_t(g_begin + step) * group_stride;
+#pragma unroll
+    for (int j = 0; j < CH_PER_THREAD; j++) cp_async16_zfill(sbase + ld_dst[j], gbase + ld_src[j], (ld_ok >> j) & 1u);
   };
   for (int s = 0; s < SY_STAGES - 1; s++) { if (s < nsteps) issue(s); cp_async_commit(); }
   for (int step = 0; step < nsteps; step++) {
@@ -653,7 +695,7 @@ int vxs_eval_hessian_dev(vxs_ctx* ctx, vxs_factor* f, const double* poses_dev, i
 #define LAUNCH_JAC(GG, DD) { auto kp = k_jac<GG, DD>; VXS_LAUNCH(ctx, "k_jac", kp, gridj, 128, 0, fv, poses_dev, pstride, f->X.p, gD); }
     if (dense && W <= 128) {
       const int ngv = int((f->V + 3) / 4);
-      const size_t smem = (size_t(30) * 128 + size_t(3) * 6 * W * 4) * 8;
+      const size_t smem = (size_t(30) * 128 + size_t(12) * 7 * W) * 8;
       VXS_CUDA(ctx, cudaFuncSetAttribute(k_jac_slab, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
       const unsigned grids = unsigned(std::min<int>(ngv, ctx->sm_count * 3 * 2));
       VXS_LAUNCH(ctx, "k_jac", k_jac_slab, grids, 128, smem, fv, poses_dev, pstride, f->X.p, gD, ngv);
