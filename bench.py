@@ -120,6 +120,7 @@ def dist_setup(args):
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line (NCCL prints its version banner there otherwise)
         import torch
         import torch.distributed as dist_
         torch.cuda.set_device(local)
