@@ -6,7 +6,7 @@ CPU-only checks can verify the ABI), but every compute entry point needs a CUDA 
 """
 from .api import (  # noqa: F401
     VxsError, lib, harness, Context, Factor, ImuWindow, MapParams, LmTrace, VoxelId,
-    gen_scan, true_pose, perturb_pose, declared_symbols, LIB_PATH, HARNESS_PATH,
+    gen_scan, true_pose, perturb_pose, declared_symbols, LIB_PATH, HARNESS_PATH, lawnmower_pose, gen_scan_city,
 )
 
 __all__ = [

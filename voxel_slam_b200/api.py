@@ -128,6 +128,20 @@ def gen_scan(L, frame, n, pose12_true, seed=0x5EED0000, off=0.37, sigma=0.01, ma
     return xyz
 
 
+def lawnmower_pose(i, per_row, step=4.0, row_gap=8.0, off=0.37):
+    out = np.zeros(12)
+    harness().vxh_lawnmower_pose(C.c_int(i), C.c_int(per_row), C.c_double(step), C.c_double(row_gap), C.c_double(off), _dp(out))
+    return out
+
+
+def gen_scan_city(frame, n, pose12_true, seed=0xC17E, G=10.0, rng_m=20.0, off=0.37, sigma=0.01, out=None):
+    p = _f64(pose12_true)
+    xyz = np.empty((n, 3), dtype=np.float32) if out is None else out
+    harness().vxh_gen_scan_city_f32(C.c_uint64(seed), C.c_int(frame), C.c_int64(n), _dp(p), C.c_double(G), C.c_double(rng_m), C.c_double(off), C.c_double(sigma),
+                                    xyz.ctypes.data_as(C.POINTER(C.c_float)))
+    return xyz
+
+
 class ImuWindow:
     """W-1 synthetic IMU preintegration factors (stand-in for the reference's unchanged IMU_PRE objects)."""
 

@@ -20,6 +20,13 @@ void vxh_gen_scan_f32(double L, double off, double sigma, double max_range, uint
   for (size_t i = 0; i < tmp.size(); i++) xyz_body[i] = float(tmp[i]);
 }
 
+void vxh_lawnmower_pose(int i, int per_row, double step, double row_gap, double off, double* pose12) { lawnmower_pose(i, per_row, step, row_gap, off, pose12); }
+void vxh_gen_scan_city_f32(uint64_t seed, int frame, int64_t n, const double* pose12_true, double G, double range, double off, double sigma, float* xyz_body) {
+  std::vector<double> tmp(size_t(n) * 3);
+  gen_scan_city(seed, frame, n, pose12_true, G, range, off, sigma, tmp.data());
+  for (size_t i = 0; i < tmp.size(); i++) xyz_body[i] = float(tmp[i]);
+}
+
 struct ImuHandle { ImuWindow win, initial; };
 
 void* vxh_imu_create(const double* poses12_true, int W, double T, int samples, double gyr_noise, double acc_noise, uint64_t seed) {

@@ -133,6 +133,39 @@ inline void gen_scan(const Scene& sc, int frame, int64_t n, const double* pose12
   }
 }
 
+// ------------------------------------------------------------------ large "city grid" scene for the global-BA workloads (C4-like)
+// floor z = off, walls x = off + G*i and y = off + G*j (height 0..4 m above the floor).  A keyframe at (cx, cy) sees points within
+// `range` on the floor and on the two nearest wall lines of each direction, so every keyframe is constrained in all six dofs and
+// co-visibility stays local (k ~ 5-15 keyframes per voxel).
+inline void lawnmower_pose(int i, int per_row, double step, double row_gap, double off, double* pose12) {
+  const int row = i / per_row, col = i % per_row;
+  const double x = off + 3.0 + step * ((row & 1) ? (per_row - 1 - col) : col), y = off + 3.0 + row_gap * row;
+  double w[3] = {0, 0, 0.3 * std::sin(0.37 * i)};
+  exp3(w, pose12);
+  pose12[9] = x; pose12[10] = y; pose12[11] = off + 1.5;
+}
+inline void gen_scan_city(uint64_t seed, int frame, int64_t n, const double* pose12_true, double G, double range, double off, double sigma, double* xyz_body) {
+  SplitMix64 g(seed + 7000003ull * uint64_t(frame + 1));
+  double Rt[9]; mat3_t(pose12_true, Rt);
+  const double* t = pose12_true + 9;
+  for (int64_t k = 0; k < n; k++) {
+    double pw[3];
+    const int kind = int(g.next() % 3);
+    if (kind == 0) {  // floor
+      pw[0] = t[0] + range * (2 * g.uni() - 1); pw[1] = t[1] + range * (2 * g.uni() - 1); pw[2] = off + sigma * g.gauss();
+    } else {          // wall line x = const (kind 1) or y = const (kind 2): one of the two nearest lines
+      const int a = kind - 1, b = 1 - a;
+      const double cell = std::floor((t[a] - off) / G);
+      const double line = off + G * (cell + double(g.next() & 1));
+      pw[a] = line + sigma * g.gauss();
+      pw[b] = t[b] + range * (2 * g.uni() - 1);
+      pw[2] = off + 4.0 * g.uni();
+    }
+    double d[3] = {pw[0] - t[0], pw[1] - t[1], pw[2] - t[2]};
+    mat3_vec(Rt, d, xyz_body + 3 * k);
+  }
+}
+
 // ------------------------------------------------------------------ IMU factor stand-in (mirrors preintegration.hpp:11-331)
 struct ImuPre {
   double R_delta[9], p_delta[3], v_delta[3], bg[3], ba[3];
