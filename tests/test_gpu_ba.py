@@ -58,7 +58,7 @@ def test_residual_and_cache_parity(ctx, W, pts, L):
     check_eig(eig, ex["eig12"], 1e-7)   # lambda0 carries the cancellation of cov = P/N - c c^T (cond ~1e8): 1e-7 of lambda_max
 
 
-@pytest.mark.parametrize("W,pts,L", [(5, 4000, 6.0), (10, 20000, 12.0), (20, 6000, 8.0), (37, 3000, 6.0)])
+@pytest.mark.parametrize("W,pts,L", [(5, 4000, 6.0), (10, 20000, 12.0), (20, 6000, 8.0), (37, 3000, 6.0), (50, 2500, 6.0), (70, 2000, 5.0), (130, 1200, 4.0)])
 def test_hessian_parity(ctx, W, pts, L):
     sc = scenes.make_window(W=W, pts_per_scan=pts, L=L, seed=5)
     f = gpu_factor(ctx, sc)

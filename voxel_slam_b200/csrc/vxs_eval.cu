@@ -289,9 +289,11 @@ __global__ void __launch_bounds__(128, 3) k_jac(FactorView f, const double* __re
 // builds the slab in shared memory and writes it out with coalesced 16-B stores — XT sectors interleave rows of different
 // voxels, so per-entry stores would be partial-sector writes from different warps.  Threads are 64-lane groups (lane = frame slot
 // in a sliding window), two voxels per round, two rounds per group; gradient / D sums as in k_jac.
+template <int LPV>   // lanes per voxel: 64 (W <= 64, two voxels per round) or 128 (W <= 128, one voxel per round) so that a lane keeps one frame slot
 __global__ void __launch_bounds__(128, 3) k_jac_slab(FactorView f, const double* __restrict__ poses, int pstride, double* __restrict__ XT, double* __restrict__ gD, int ngroups_vox) {
   extern __shared__ __align__(16) double sm[];
-  const int tid = threadIdx.x, half = tid >> 6, lane = tid & 63;
+  constexpr int VPR = 128 / LPV;                     // voxels per round
+  const int tid = threadIdx.x, half = tid / LPV, lane = tid % LPV;
   const int W = f.W, n = 6 * W;
   const int slab = 3 * n * 4;                        // doubles per voxel group (global layout [chunk][col][kr])
   const int TW = 7 * W;                              // padded row length of the shared slab: [chunk][kr][7*frame + c] — a lane (frame)
@@ -306,13 +308,13 @@ __global__ void __launch_bounds__(128, 3) k_jac_slab(FactorView f, const double*
   for (int G = blockIdx.x; G < ngroups_vox; G += gridDim.x) {
     for (int i = tid; i < tslab / 2; i += 128) reinterpret_cast<double2*>(T)[i] = make_double2(0.0, 0.0);
     __syncthreads();
-    for (int round = 0; round < 2; round++) {
-      const int v = 4 * G + 2 * round + half;
+    for (int round = 0; round < 4 / VPR; round++) {
+      const int v = 4 * G + VPR * round + half;
       if (v >= f.V) continue;
       const int beg = f.ptr[v], end = f.ptr[v + 1];
       if (beg + lane >= end) continue;
       const voxel_consts kc = load_voxel_consts(f, v);
-      for (int en = beg + lane; en < end; en += 64) {
+      for (int en = beg + lane; en < end; en += LPV) {
         cluster c = load_cluster_soa(f.cl, f.Ecap, size_t(en));
         const int fr = __ldg(f.frame + en);
         if (fr != cur_fr) {
@@ -696,9 +698,16 @@ int vxs_eval_hessian_dev(vxs_ctx* ctx, vxs_factor* f, const double* poses_dev, i
     if (dense && W <= 128) {
       const int ngv = int((f->V + 3) / 4);
       const size_t smem = (size_t(30) * 128 + size_t(12) * 7 * W) * 8;
-      VXS_CUDA(ctx, cudaFuncSetAttribute(k_jac_slab, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
       const unsigned grids = unsigned(std::min<int>(ngv, ctx->sm_count * 3 * 2));
-      VXS_LAUNCH(ctx, "k_jac", k_jac_slab, grids, 128, smem, fv, poses_dev, pstride, f->X.p, gD, ngv);
+      if (W <= 64) {
+        auto kp = k_jac_slab<64>;
+        VXS_CUDA(ctx, cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        VXS_LAUNCH(ctx, "k_jac", kp, grids, 128, smem, fv, poses_dev, pstride, f->X.p, gD, ngv);
+      } else {
+        auto kp = k_jac_slab<128>;
+        VXS_CUDA(ctx, cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        VXS_LAUNCH(ctx, "k_jac", kp, grids, 128, smem, fv, poses_dev, pstride, f->X.p, gD, ngv);
+      }
     } else if (dense) { if (GJ == 64) LAUNCH_JAC(64, true) else if (GJ == 32) LAUNCH_JAC(32, true) else if (GJ == 16) LAUNCH_JAC(16, true) else LAUNCH_JAC(8, true) }
     else { if (GJ == 64) LAUNCH_JAC(64, false) else if (GJ == 32) LAUNCH_JAC(32, false) else if (GJ == 16) LAUNCH_JAC(16, false) else LAUNCH_JAC(8, false) }
 #undef LAUNCH_JAC
