@@ -503,8 +503,13 @@ def run_gba_window(args):
         step()
     stages = ctx.timing_read(); ctx.timing(False)
     tot = np.array([float(V), float(E)])
+    mine = [float(V), float(E)] + [stages.get(k, (0.0, 0))[0] / 3 for k in ("k_syrk", "k_jac", "k_cluster_sum", "nccl_allreduce", "k_ldlt_all")]
+    per_rank = [mine]
     if dist is not None:
         t = torch.tensor(tot, device=f"cuda:{local}"); dist.all_reduce(t); tot = t.cpu().numpy()
+        g = [torch.zeros(len(mine), dtype=torch.float64, device=f"cuda:{local}") for _ in range(world)]
+        dist.all_gather(g, torch.tensor(mine, dtype=torch.float64, device=f"cuda:{local}"))
+        per_rank = [x.cpu().tolist() for x in g]
     if rank == 0:
         line = {"metric": "global-BA LM iterations/sec (one voxel-sharded pose-only BA)", "value": K / (ms * 1e-3), "unit": "iterations/s", "n_gpus": world, "steps": K,
                 "warmup": max(Wu, 3), "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic (seeded 3-plane room)",
@@ -513,6 +518,7 @@ def run_gba_window(args):
                            "allreduce_bytes_per_step": 8 * ((6 * W) ** 2 + 30 * W + 2)},
                 "rank0_stage_ms_per_step": {k: v[0] / 3 for k, v in sorted(stages.items(), key=lambda kv: -kv[1][0]) if v[1] > 0},
                 "map_build_ms_rank0": t_vox * 1e3,
+                "per_rank_[V,E,syrk,jac,cluster_sum,nccl,ldlt]_ms": [[round(x, 3) for x in r] for r in per_rank],
                 "check": {"trace": [[float(t["r1"]), float(t["r2"]), int(t["accepted"])] for t in o["trace"]]}}
         print(json.dumps(line), flush=True)
     if dist is not None:

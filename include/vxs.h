@@ -173,6 +173,13 @@ int vxs_hba_window(vxs_ctx* ctx, const vxs_map_params* coarse, const vxs_map_par
                    int stride_floats, const int64_t* kf_offsets, double* poses12, int W, int max_iter, int thread_num,
                    double* hess_out, double* resis_log, int* outer_iters);
 
+/* PGO edge extraction of HBA_add_edge (voxelslam.cpp:2405-2427) from the raw Hessian of the LAST vxs_lidar_ba / vxs_hba_window
+ * on this ctx, without downloading the Hessian: for every pair i<j whose six diagonal entries of block (i,j) are all >= 1e-6 in
+ * magnitude, one edge with variance v6[k] = 1/|H(6i+k, 6j+k)|, rot = R_i^T R_j (row-major), tra = R_i^T (p_j - p_i).
+ * edge_ij: [cap][2] int32, v6: [cap][6], rot: [cap][9], tra: [cap][3]; *n_edges = number found (may exceed cap: truncated). */
+int vxs_hba_edges(vxs_ctx* ctx, int W, const double* poses12, int64_t cap, int32_t* edge_ij, double* v6, double* rot, double* tra,
+                  int64_t* n_edges);
+
 #ifdef __cplusplus
 }
 #endif

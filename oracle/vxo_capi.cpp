@@ -226,6 +226,25 @@ void* vxo_build_gba_factor(const vxs_map_params* mp, const float* xyz, int strid
   if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   return of;
 }
+// PGO edges from a raw Hessian (voxelslam.cpp:2405-2427)
+int64_t vxo_hba_edges(const double* hess, int W, const double* poses12, int64_t cap, int32_t* eij, double* v6, double* rot, double* tra) {
+  const int n = 6 * W;
+  auto xs = states_from_poses12(poses12, W);
+  int64_t m = 0;
+  for (int i = 0; i < W - 1; i++) for (int j = i + 1; j < W; j++) {
+    bool add = true; double v[6];
+    for (int k = 0; k < 6; k++) { double hc = std::fabs(hess[size_t(6 * j + k) * n + 6 * i + k]); if (hc < 1e-6) { add = false; break; } v[k] = 1.0 / hc; }
+    if (!add) continue;
+    if (m < cap) {
+      eij[2 * m] = i; eij[2 * m + 1] = j;
+      for (int k = 0; k < 6; k++) v6[6 * m + k] = v[k];
+      V3 t = tr(xs[i].R) * (xs[j].p - xs[i].p); M3 r = tr(xs[i].R) * xs[j].R;
+      for (int a = 0; a < 3; a++) { tra[3 * m + a] = t[a]; for (int b = 0; b < 3; b++) rot[9 * m + 3 * a + b] = r(a, b); }
+    }
+    m++;
+  }
+  return m;
+}
 int vxo_hba_window(const vxs_map_params* coarse, const vxs_map_params* fine, const float* xyz, int stride_floats, const int64_t* kf_offsets, double* poses12, int W, int max_iter,
                    int thread_num, double* hess_out, double* resis_log, int* outer_iters) {
   auto xs = states_from_poses12(poses12, W);

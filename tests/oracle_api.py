@@ -181,6 +181,15 @@ def build_gba_factor(mp, xyz_f32, kf_offsets, poses12, threads=2, stride_floats=
     return f
 
 
+def hba_edges(hess, W, poses12):
+    cap = W * (W - 1) // 2
+    H = np.asfortranarray(hess, dtype=np.float64); p = _f64(poses12)
+    eij = np.zeros((cap, 2), dtype=np.int32); v6 = np.zeros((cap, 6)); rot = np.zeros((cap, 9)); tra = np.zeros((cap, 3))
+    lib().vxo_hba_edges.restype = C.c_int64
+    m = lib().vxo_hba_edges(_dp(H), C.c_int(W), _dp(p), C.c_int64(cap), eij.ctypes.data_as(C.POINTER(C.c_int32)), _dp(v6), _dp(rot), _dp(tra))
+    return dict(n=m, ij=eij[:m], v6=v6[:m], rot=rot[:m], tra=tra[:m])
+
+
 def hba_window(coarse, fine, xyz_f32, kf_offsets, poses12, max_iter, thread_num=2, stride_floats=3):
     x = np.ascontiguousarray(xyz_f32, dtype=np.float32)
     off = np.ascontiguousarray(kf_offsets, dtype=np.int64)

@@ -143,6 +143,36 @@ def test_hba_window_parity(ctx):
     assert np.abs(g["poses"] - tr).max() < 0.5 * np.abs(est - tr).max()
 
 
+def test_hba_edges_on_device(ctx):
+    """PGO edge extraction (voxelslam.cpp:2405-2427) from the device-resident raw Hessian vs the oracle on the oracle's Hessian."""
+    W = 10
+    tr, est, xyz, off = make_gba(W, 4000, 8.0, 57)
+    coarse = vx.MapParams.make(voxel_size=2.0, min_eigen_value=0.1, max_layer=2)
+    fine = vx.MapParams.make(voxel_size=1.0, min_eigen_value=0.0025, max_layer=2)
+    g = ctx.hba_window(coarse, fine, xyz, off, est, max_iter=3, thread_num=2)
+    e = ctx.hba_edges(W, g["poses"])
+    r = oa.hba_window(coarse, fine, xyz, off, est, max_iter=3, thread_num=2)
+    eo = oa.hba_edges(r["hess"], W, r["poses"])
+    assert e["n"] == eo["n"] > 0 and np.array_equal(e["ij"], eo["ij"])
+    assert np.max(np.abs(e["v6"] - eo["v6"]) / eo["v6"]) < 1e-6
+    assert np.max(np.abs(e["rot"] - eo["rot"])) < 1e-9 and np.max(np.abs(e["tra"] - eo["tra"])) < 1e-8
+
+
+def test_factor_cache_save_restore(ctx):
+    sc = scenes.make_window(W=5, pts_per_scan=3000, L=6.0, seed=2)
+    f = vx.Factor(ctx, 5)
+    f.push_voxels_dense(sc["clusters10"], sc["eig12"], sc["sum10"], fix10=sc["fix10"])
+    f.cache_save()
+    a = ctx.lidar_ba(f, sc["poses_est"], max_iter=2)
+    e1, _ = f.read_back()
+    assert not np.array_equal(e1, sc["eig12"])              # the solve overwrote the cache
+    f.cache_restore()
+    e2, s2 = f.read_back()
+    assert np.array_equal(e2, sc["eig12"]) and np.array_equal(s2, sc["sum10"])
+    b = ctx.lidar_ba(f, sc["poses_est"], max_iter=2)
+    assert np.array_equal(a["poses"], b["poses"])             # identical re-run from the restored map state
+
+
 def test_radix_sort_and_scan_at_scale(ctx):
     """1.5 M points, multiple sort tiles and scan blocks: per-voxel counts must still match the oracle exactly."""
     W, pts, L = 3, 500000, 30.0

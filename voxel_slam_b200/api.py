@@ -334,6 +334,20 @@ class Context:
         return dict(poses=p, hess=H, resis_log=log[: 2 * it.value], outer_iters=it.value)
 
 
+def _hba_edges(self, W, poses12, cap=None):
+    cap = cap if cap is not None else W * (W - 1) // 2
+    p = _f64(poses12)
+    eij = np.zeros((max(cap, 1), 2), dtype=np.int32); v6 = np.zeros((max(cap, 1), 6)); rot = np.zeros((max(cap, 1), 9)); tra = np.zeros((max(cap, 1), 3))
+    n = C.c_int64(0)
+    self._check(lib().vxs_hba_edges(self._p, C.c_int(W), _dp(p), C.c_int64(cap), eij.ctypes.data_as(C.POINTER(C.c_int32)), _dp(v6), _dp(rot), _dp(tra), C.byref(n)))
+    m = min(n.value, cap)
+    order = np.lexsort((eij[:m, 1], eij[:m, 0]))
+    return dict(n=n.value, ij=eij[:m][order], v6=v6[:m][order], rot=rot[:m][order], tra=tra[:m][order])
+
+
+Context.hba_edges = _hba_edges
+
+
 class Factor:
     """Device-resident LidarFactor."""
 

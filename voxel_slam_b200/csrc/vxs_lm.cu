@@ -10,6 +10,7 @@
 #include <dlfcn.h>
 #include <math.h>
 #include <string.h>
+#include <algorithm>
 #include <vector>
 #include "vxs_internal.h"
 #include "vxs_math.cuh"
@@ -130,13 +131,27 @@ static int solve_and_fetch(LmCommon& c, double u, const double* extra_dev, doubl
   VXS_CUDA(ctx, ctx->dx.reserve(size_t(n)));
   VXS_CUDA(ctx, ctx->dvec.reserve(size_t(n)));
   VXS_CUDA(ctx, ctx->rhs.reserve(size_t(n)));
-  int rc = vxs_solve_damped(ctx, ctx->Hraw.p, ctx->jact.p, n, c.gauge, u, ctx->dx.p, ctx->dvec.p, ctx->rhs.p, singular);
+  // results come back through pinned staging: a D2H copy into pageable memory is a synchronous staged copy per call
+  const size_t need = size_t(3) * n + 8;
+  if (ctx->h_pin_cap < need) {
+    if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+    ctx->h_pin = nullptr; ctx->h_pin_cap = 0;
+    VXS_CUDA(ctx, cudaHostAlloc((void**)&ctx->h_pin, need * 8, cudaHostAllocDefault));
+    ctx->h_pin_cap = need;
+  }
+  int* sing_pin = reinterpret_cast<int*>(ctx->h_pin + 3 * size_t(n) + 1);
+  int rc = vxs_solve_damped(ctx, ctx->Hraw.p, ctx->jact.p, n, c.gauge, u, ctx->dx.p, ctx->dvec.p, ctx->rhs.p, singular ? sing_pin : nullptr);
   if (rc) return rc;
-  VXS_CUDA(ctx, cudaMemcpyAsync(c.dx.data(), ctx->dx.p, size_t(n) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  VXS_CUDA(ctx, cudaMemcpyAsync(c.D.data(), ctx->dvec.p, size_t(n) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  VXS_CUDA(ctx, cudaMemcpyAsync(c.rhs.data(), ctx->rhs.p, size_t(n) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  if (extra_dev) VXS_CUDA(ctx, cudaMemcpyAsync(extra_host, extra_dev, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  VXS_CUDA(ctx, cudaMemcpyAsync(ctx->h_pin, ctx->dx.p, size_t(n) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  VXS_CUDA(ctx, cudaMemcpyAsync(ctx->h_pin + n, ctx->dvec.p, size_t(n) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  VXS_CUDA(ctx, cudaMemcpyAsync(ctx->h_pin + 2 * size_t(n), ctx->rhs.p, size_t(n) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (extra_dev) VXS_CUDA(ctx, cudaMemcpyAsync(ctx->h_pin + 3 * size_t(n), extra_dev, 8, cudaMemcpyDeviceToHost, ctx->stream));
   VXS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(c.dx.data(), ctx->h_pin, size_t(n) * 8);
+  memcpy(c.D.data(), ctx->h_pin + n, size_t(n) * 8);
+  memcpy(c.rhs.data(), ctx->h_pin + 2 * size_t(n), size_t(n) * 8);
+  if (extra_dev) *extra_host = ctx->h_pin[3 * size_t(n)];
+  if (singular) *singular = *sing_pin;
   return VXS_OK;
 }
 
@@ -278,4 +293,60 @@ extern "C" int vxs_li_ba(vxs_ctx* ctx, vxs_factor* f, double* states24, int with
     VXS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
   return warn;
+}
+
+// ------------------------------------------------------------------ PGO edges from the raw Hessian (voxelslam.cpp:2405-2427)
+__global__ void k_hba_edges(const double* __restrict__ H, int n, int W, const double* __restrict__ poses, unsigned int* __restrict__ count, long long cap,
+                            int* __restrict__ eij, double* __restrict__ v6, double* __restrict__ rot, double* __restrict__ tra) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)W * W) return;
+  const int i = int(idx / W), j = int(idx % W);
+  if (j <= i) return;
+  double v[6];
+  for (int k = 0; k < 6; k++) {
+    const double hc = fabs(H[size_t(6 * j + k) * n + 6 * i + k]);
+    if (hc < 1e-6) return;
+    v[k] = 1.0 / hc;
+  }
+  const unsigned int slot = atomicAdd(count, 1u);
+  if ((long long)slot >= cap) return;
+  eij[2 * slot] = i; eij[2 * slot + 1] = j;
+  for (int k = 0; k < 6; k++) v6[6 * slot + k] = v[k];
+  const rot3 Ri = load_rot(poses + 12 * i), Rj = load_rot(poses + 12 * j);
+  const d3 dp = mk3(poses[12 * j + 9] - poses[12 * i + 9], poses[12 * j + 10] - poses[12 * i + 10], poses[12 * j + 11] - poses[12 * i + 11]);
+  const d3 t = mulT(Ri, dp);
+  tra[3 * slot] = t.x; tra[3 * slot + 1] = t.y; tra[3 * slot + 2] = t.z;
+  // R_i^T R_j
+  const double a[9] = {Ri.r00, Ri.r01, Ri.r02, Ri.r10, Ri.r11, Ri.r12, Ri.r20, Ri.r21, Ri.r22}, b[9] = {Rj.r00, Rj.r01, Rj.r02, Rj.r10, Rj.r11, Rj.r12, Rj.r20, Rj.r21, Rj.r22};
+  for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) rot[9 * slot + 3 * r + c] = a[r] * b[c] + a[3 + r] * b[3 + c] + a[6 + r] * b[6 + c];
+}
+
+extern "C" int vxs_hba_edges(vxs_ctx* ctx, int W, const double* poses12, int64_t cap, int32_t* edge_ij, double* v6, double* rot, double* tra, int64_t* n_edges) {
+  if (!ctx || W <= 0 || !poses12 || cap < 0 || !n_edges) return VXS_ERR_ARG;
+  const int n = 6 * W;
+  if (ctx->Hraw.cap < size_t(n) * n) return vxs_fail(ctx, VXS_ERR_ARG, "vxs_hba_edges: no Hessian of this size on the ctx (run vxs_lidar_ba / vxs_hba_window first)");
+  cudaSetDevice(ctx->device);
+  const size_t c = size_t(std::max<int64_t>(cap, 1));
+  VXS_CUDA(ctx, ctx->stage.reserve(c * 18 + size_t(W) * 12));
+  VXS_CUDA(ctx, ctx->stage_i64.reserve(c + 2));
+  double* d_v6 = ctx->stage.p; double* d_rot = d_v6 + c * 6; double* d_tra = d_rot + c * 9; double* d_pose = d_tra + c * 3;
+  int* d_eij = reinterpret_cast<int*>(ctx->stage_i64.p);
+  unsigned int* d_cnt = reinterpret_cast<unsigned int*>(ctx->flags.p + 8);
+  VXS_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, sizeof(unsigned int), ctx->stream));
+  VXS_CUDA(ctx, cudaMemcpyAsync(d_pose, poses12, size_t(W) * 96, cudaMemcpyHostToDevice, ctx->stream));
+  const unsigned blocks = unsigned((size_t(W) * W + 255) / 256);
+  VXS_LAUNCH(ctx, "k_hba_edges", k_hba_edges, blocks, 256, 0, ctx->Hraw.p, n, W, d_pose, d_cnt, (long long)cap, d_eij, d_v6, d_rot, d_tra);
+  unsigned int cnt = 0;
+  VXS_CUDA(ctx, cudaMemcpyAsync(&cnt, d_cnt, sizeof cnt, cudaMemcpyDeviceToHost, ctx->stream));
+  VXS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *n_edges = cnt;
+  const size_t m = size_t(std::min<int64_t>(cnt, cap));
+  if (m) {
+    VXS_CUDA(ctx, cudaMemcpyAsync(edge_ij, d_eij, m * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    VXS_CUDA(ctx, cudaMemcpyAsync(v6, d_v6, m * 48, cudaMemcpyDeviceToHost, ctx->stream));
+    VXS_CUDA(ctx, cudaMemcpyAsync(rot, d_rot, m * 72, cudaMemcpyDeviceToHost, ctx->stream));
+    VXS_CUDA(ctx, cudaMemcpyAsync(tra, d_tra, m * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    VXS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return VXS_OK;
 }
