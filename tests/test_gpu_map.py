@@ -170,7 +170,7 @@ def test_factor_cache_save_restore(ctx):
     e2, s2 = f.read_back()
     assert np.array_equal(e2, sc["eig12"]) and np.array_equal(s2, sc["sum10"])
     b = ctx.lidar_ba(f, sc["poses_est"], max_iter=2)
-    assert np.array_equal(a["poses"], b["poses"])             # identical re-run from the restored map state
+    assert np.max(np.abs(a["poses"] - b["poses"])) < 1e-12    # same re-run from the restored map state (fp64 RED order is the only difference)
 
 
 def test_radix_sort_and_scan_at_scale(ctx):
