@@ -49,9 +49,24 @@ __device__ __forceinline__ void load_pose(const double* __restrict__ poses, int 
   t = mk3(__ldg(p + 9), __ldg(p + 10), __ldg(p + 11));
 }
 
+// Poses staged once per CTA in shared memory, component-major [12][W]: lanes of a group read consecutive frames, so each of the 12
+// reads is one conflict-free wavefront instead of a 96-byte-strided global gather (the LSU, not DRAM, bounds these kernels).
+#define POSE_SMEM_MAX_W 512
+__device__ __forceinline__ void stage_poses(double* sp, const double* __restrict__ poses, int pstride, int W) {
+  for (int i = threadIdx.x; i < 12 * W; i += blockDim.x) { const int fr = i / 12, c = i - fr * 12; sp[c * W + fr] = __ldg(poses + size_t(fr) * pstride + c); }
+  __syncthreads();
+}
+__device__ __forceinline__ void load_pose_s(const double* sp, int W, int fr, rot3& R, d3& t) {
+  R.r00 = sp[fr]; R.r01 = sp[W + fr]; R.r02 = sp[2 * W + fr]; R.r10 = sp[3 * W + fr]; R.r11 = sp[4 * W + fr]; R.r12 = sp[5 * W + fr];
+  R.r20 = sp[6 * W + fr]; R.r21 = sp[7 * W + fr]; R.r22 = sp[8 * W + fr];
+  t = mk3(sp[9 * W + fr], sp[10 * W + fr], sp[11 * W + fr]);
+}
+
 // ------------------------------------------------------------------ residual: transform + sum
-template <int G>
+template <int G, bool SP>
 __global__ void __launch_bounds__(256) k_cluster_sum(FactorView f, const double* __restrict__ poses, int pstride) {
+  extern __shared__ __align__(16) double sp[];
+  if (SP) stage_poses(sp, poses, pstride, f.W);
   const int lane = threadIdx.x & (G - 1);
   const int group = (blockIdx.x * blockDim.x + threadIdx.x) / G;
   const int ngroups = (gridDim.x * blockDim.x) / G;
@@ -66,7 +81,7 @@ __global__ void __launch_bounds__(256) k_cluster_sum(FactorView f, const double*
     for (int e = beg + lane; e < end; e += G) {
       cluster c = load_cluster_soa(f.cl, f.Ecap, size_t(e));
       rot3 R; d3 t;
-      load_pose(poses, pstride, __ldg(f.frame + e), R, t);
+      if (SP) load_pose_s(sp, f.W, __ldg(f.frame + e), R, t); else load_pose(poses, pstride, __ldg(f.frame + e), R, t);
       cluster_transform_acc(c, R, t, acc);
     }
     if (G == 32) {
@@ -300,11 +315,13 @@ __global__ void __launch_bounds__(128, 3) k_jac_slab(FactorView f, const double*
   const int tslab = 12 * TW;                         // advances 7 doubles, so 16 lanes hit 32 distinct banks (6 would 4-way conflict)
   double* acc = sm;                                  // [30][128]
   double* T = sm + 30 * 128;
+  double* sp = T + tslab;                            // [12][W] poses
   double* gbuf = gD;
   double* Dbuf = gD + size_t(W) * 6;
   int cur_fr = -1;
 #pragma unroll
   for (int i = 0; i < 30; i++) acc[i * 128 + tid] = 0.0;
+  stage_poses(sp, poses, pstride, W);
   for (int G = blockIdx.x; G < ngroups_vox; G += gridDim.x) {
     for (int i = tid; i < tslab / 2; i += 128) reinterpret_cast<double2*>(T)[i] = make_double2(0.0, 0.0);
     __syncthreads();
@@ -328,7 +345,7 @@ __global__ void __launch_bounds__(128, 3) k_jac_slab(FactorView f, const double*
           cur_fr = fr;
         }
         rot3 R; d3 t;
-        load_pose(poses, pstride, fr, R, t);
+        load_pose_s(sp, W, fr, R, t);
         entry_out o;
         entry_jacobian(kc, c, R, t, o);
 #pragma unroll
@@ -430,7 +447,7 @@ static SyrkGeom sy_geom(int W) {
 // A warp's share of a CTA tile: up to three "pieces", each = two 8-row mma tile rows x six 8-column tile columns (12 tiles)
 // of one unit.  Splitting units into pieces and dealing the pieces round-robin keeps all four warps (= all four tensor pipes of
 // the SM) busy on diagonal / remainder tiles, where a unit-per-warp mapping leaves one to three warps idle.
-struct SyPiece { int offI, offJ, ntI, ntJ, rowbase, colbase, nvalI, nvalJ; };
+struct SyPiece { int offI, offJ, ntI, ntJ, rowbase, colbase, nvalI, nvalJ; unsigned mask; };   // mask: bit ti*6+tj = tile needed
 
 __global__ void __launch_bounds__(SY_THREADS, 2) k_syrk(const double* __restrict__ XT, double* __restrict__ C, int ngroups_vox, int W, SyrkGeom g, int groups_per_chunk) {
   extern __shared__ __align__(16) double smem[];
@@ -464,6 +481,12 @@ __global__ void __launch_bounds__(SY_THREADS, 2) k_syrk(const double* __restrict
         P.ntI = min(2, ntI - t0); P.ntJ = ntJ;
         P.rowbase = 6 * sy_gstart(g, ga) + 8 * t0; P.colbase = 6 * sy_gstart(g, gb);
         P.nvalI = nvalI - 8 * t0; P.nvalJ = nvalJ;
+        // tiles of a diagonal unit whose rows all belong to later frames than all of their columns hold only pairs with
+        // frame(i) > frame(j): never stored, so never computed (11 of the 36 tiles of a full diagonal unit)
+        P.mask = 0u;
+        for (int ti = 0; ti < P.ntI; ti++)
+          for (int tj = 0; tj < P.ntJ; tj++)
+            if (!(ga == gb && (8 * (t0 + ti)) / 6 > (8 * tj + 7) / 6)) P.mask |= 1u << (ti * 6 + tj);
         if (npc == 0) pc[0] = P; else if (npc == 1) pc[1] = P; else pc[2] = P;
         npc++;
       }
@@ -512,7 +535,7 @@ __global__ void __launch_bounds__(SY_THREADS, 2) k_syrk(const double* __restrict
       if (p < npc) {
         const double* pI = sI + size_t(pc[p].offI) * 4;
         const double* pJ = sJ + size_t(pc[p].offJ) * 4;
-        const bool full = (pc[p].ntI == 2) && (pc[p].ntJ == 6);
+        const bool full = pc[p].mask == 0xFFFu;
 #pragma unroll
         for (int kc = 0; kc < 3; kc++) {
           double fa[2], fb[6];
@@ -530,7 +553,7 @@ __global__ void __launch_bounds__(SY_THREADS, 2) k_syrk(const double* __restrict
             for (int ti = 0; ti < 2; ti++)
 #pragma unroll
               for (int tj = 0; tj < 6; tj++)
-                if (ti < pc[p].ntI && tj < pc[p].ntJ) dmma884(acc[p * 24 + 2 * (ti * 6 + tj)], acc[p * 24 + 2 * (ti * 6 + tj) + 1], fa[ti], fb[tj]);
+                if ((pc[p].mask >> (ti * 6 + tj)) & 1u) dmma884(acc[p * 24 + 2 * (ti * 6 + tj)], acc[p * 24 + 2 * (ti * 6 + tj) + 1], fa[ti], fb[tj]);
           }
         }
       }
@@ -547,7 +570,7 @@ __global__ void __launch_bounds__(SY_THREADS, 2) k_syrk(const double* __restrict
 #pragma unroll
         for (int tj = 0; tj < 6; tj++) {
           const int r = 8 * ti + rl;
-          if (ti < pc[p].ntI && tj < pc[p].ntJ && r < pc[p].nvalI) {
+          if (((pc[p].mask >> (ti * 6 + tj)) & 1u) && r < pc[p].nvalI) {
             const int R = pc[p].rowbase + r;
 #pragma unroll
             for (int e = 0; e < 2; e++) {
@@ -659,9 +682,12 @@ int vxs_eval_residual_dev(vxs_ctx* ctx, vxs_factor* f, const double* poses_dev, 
   {
     const size_t groups_needed = size_t(f->V);
     unsigned grid = unsigned(std::min<size_t>((groups_needed * G + 255) / 256, size_t(ctx->sm_count) * 8));
-    if (G == 32) { auto kp = k_cluster_sum<32>; VXS_LAUNCH(ctx, "k_cluster_sum", kp, grid, 256, 0, fv, poses_dev, pstride); }
-    else if (G == 16) { auto kp = k_cluster_sum<16>; VXS_LAUNCH(ctx, "k_cluster_sum", kp, grid, 256, 0, fv, poses_dev, pstride); }
-    else { auto kp = k_cluster_sum<8>; VXS_LAUNCH(ctx, "k_cluster_sum", kp, grid, 256, 0, fv, poses_dev, pstride); }
+    const bool spm = f->W <= POSE_SMEM_MAX_W;
+    const size_t psm = spm ? size_t(12) * f->W * 8 : 0;
+#define LAUNCH_CS(GG) { if (spm) { auto kp = k_cluster_sum<GG, true>; VXS_LAUNCH(ctx, "k_cluster_sum", kp, grid, 256, psm, fv, poses_dev, pstride); } \
+                        else { auto kp = k_cluster_sum<GG, false>; VXS_LAUNCH(ctx, "k_cluster_sum", kp, grid, 256, 0, fv, poses_dev, pstride); } }
+    if (G == 32) LAUNCH_CS(32) else if (G == 16) LAUNCH_CS(16) else LAUNCH_CS(8)
+#undef LAUNCH_CS
   }
   { auto kp = k_eig_residual<true>; VXS_LAUNCH(ctx, "k_eig_residual", kp, blocks_v, 256, 0, fv, f->partial.p, f->counter.p, residual_dev); }
   if (ctx->nranks > 1) return vxs_comm_allreduce(ctx, residual_dev, 1);
@@ -697,7 +723,7 @@ int vxs_eval_hessian_dev(vxs_ctx* ctx, vxs_factor* f, const double* poses_dev, i
 #define LAUNCH_JAC(GG, DD) { auto kp = k_jac<GG, DD>; VXS_LAUNCH(ctx, "k_jac", kp, gridj, 128, 0, fv, poses_dev, pstride, f->X.p, gD); }
     if (dense && W <= 128) {
       const int ngv = int((f->V + 3) / 4);
-      const size_t smem = (size_t(30) * 128 + size_t(12) * 7 * W) * 8;
+      const size_t smem = (size_t(30) * 128 + size_t(12) * 7 * W + size_t(12) * W) * 8;
       const unsigned grids = unsigned(std::min<int>(ngv, ctx->sm_count * 3 * 2));
       if (W <= 64) {
         auto kp = k_jac_slab<64>;
