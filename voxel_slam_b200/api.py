@@ -235,6 +235,11 @@ class Context:
         self._check(lib().vxs_diag_dmma_tflops(self._p, C.byref(t)))
         return t.value
 
+    def ldlt_phases(self, n):
+        out = (C.c_double * 8)()
+        self._check(lib().vxs_diag_ldlt_phases(self._p, int(n), out))
+        return list(out)
+
     # --- multi-GPU
     @staticmethod
     def comm_unique_id():

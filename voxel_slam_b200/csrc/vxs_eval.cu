@@ -62,6 +62,16 @@ __device__ __forceinline__ void load_pose_s(const double* sp, int W, int fr, rot
   t = mk3(sp[9 * W + fr], sp[10 * W + fr], sp[11 * W + fr]);
 }
 
+// L2 prefetch of the cluster columns (and frame index) of entry e: the evaluation kernels are latency-bound at their register-limited
+// occupancy (ncu: long-scoreboard stalls dominate), so each group pulls the entries of its NEXT voxel towards L2 one iteration ahead.
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_entry(const FactorView& f, int e) {
+  if (size_t(e) >= f.Ecap) return;
+#pragma unroll
+  for (int c = 0; c < 10; c++) prefetch_l2(f.cl + size_t(c) * f.Ecap + e);
+  prefetch_l2(f.frame + e);
+}
+
 // ------------------------------------------------------------------ residual: transform + sum
 template <int G, bool SP>
 __global__ void __launch_bounds__(256) k_cluster_sum(FactorView f, const double* __restrict__ poses, int pstride) {
@@ -71,11 +81,19 @@ __global__ void __launch_bounds__(256) k_cluster_sum(FactorView f, const double*
   const int group = (blockIdx.x * blockDim.x + threadIdx.x) / G;
   const int ngroups = (gridDim.x * blockDim.x) / G;
   const int iters = (f.V + ngroups - 1) / ngroups;
+  int nbeg = (group + ngroups < f.V) ? __ldg(f.ptr + group + ngroups) : -1;   // first entry of the voxel of the next iteration
   for (int it = 0; it < iters; it++) {
     const int v = group + it * ngroups;
     const bool valid = v < f.V;
     int beg = 0, end = 0;
     if (valid) { beg = f.ptr[v]; end = f.ptr[v + 1]; }
+    const int v2 = v + 2 * ngroups;
+    const int n2beg = (v2 < f.V) ? __ldg(f.ptr + v2) : -1;
+    if (nbeg >= 0) {
+#pragma unroll
+      for (int q = 0; q < (G == 32 ? 2 : 1); q++) prefetch_entry(f, nbeg + lane + q * G);   // a sliding-window voxel has ~W entries
+    }
+    nbeg = n2beg;
     cluster acc;
     acc.P.xx = acc.P.xy = acc.P.xz = acc.P.yy = acc.P.yz = acc.P.zz = 0.0; acc.v = mk3(0, 0, 0); acc.n = 0.0;
     for (int e = beg + lane; e < end; e += G) {
@@ -323,6 +341,17 @@ __global__ void __launch_bounds__(128, 3) k_jac_slab(FactorView f, const double*
   for (int i = 0; i < 30; i++) acc[i * 128 + tid] = 0.0;
   stage_poses(sp, poses, pstride, W);
   for (int G = blockIdx.x; G < ngroups_vox; G += gridDim.x) {
+    {   // pull the next group's entries and voxel constants towards L2 while this one is computed
+      const int Gn = G + gridDim.x;
+#pragma unroll
+      for (int round = 0; round < 4 / VPR; round++) {
+        const int vn = 4 * Gn + VPR * round + half;
+        if (Gn < ngroups_vox && vn < f.V) {
+          prefetch_entry(f, __ldg(f.ptr + vn) + lane);
+          if (lane < 9) prefetch_l2(f.eig + size_t(3 + lane) * f.Vcap + vn); else if (lane < 17) prefetch_l2(f.vc + size_t(lane - 9) * f.Vcap + vn);
+        }
+      }
+    }
     for (int i = tid; i < tslab / 2; i += 128) reinterpret_cast<double2*>(T)[i] = make_double2(0.0, 0.0);
     __syncthreads();
     for (int round = 0; round < 4 / VPR; round++) {

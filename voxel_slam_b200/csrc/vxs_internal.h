@@ -35,6 +35,7 @@ struct DevBuf {  // grow-only device buffer
 };
 
 struct vxs_ctx {
+  long long* ldlt_prof = nullptr;   // vxs_diag_ldlt_phases: device stamp buffer, otherwise null
   int device = 0;
   int sm_count = VXS_SM_COUNT_FALLBACK;
   cudaStream_t stream = nullptr;
