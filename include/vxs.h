@@ -63,8 +63,9 @@ int vxs_diag_fp64_tflops(vxs_ctx* ctx, double* tflops);
 int vxs_diag_dmma_tflops(vxs_ctx* ctx, double* tflops);
 /* damped solve of a synthetic n x n system: out[0] = ms per solve (events), out[1..4] = us per 32-column panel that CTA 0 spends in
  * {panel load, strip solve, Schur update, grid barrier}, out[5] = panels, out[6] = SM clock (kHz) used for the conversion,
- * out[7] = us per panel of the look-ahead diagonal factor */
-int vxs_diag_ldlt_phases(vxs_ctx* ctx, int n, double out[8]);
+ * out[7] = us per panel of the look-ahead diagonal factor, out[8] = residual |(H + u diag H) dx + g|_inf / |g|_inf of the solve
+ * checked on the host.  VXS_LDLT_LOOKAHEAD_CTA=0 in the environment keeps the look-ahead on CTA 0 (A/B switch). */
+int vxs_diag_ldlt_phases(vxs_ctx* ctx, int n, double out[10]);
 
 /* ---------------------------------------------------------------- multi-GPU (one process per GPU; NCCL over NVLink)
  * Voxel-sharded BA: every rank holds the factor voxels it owns and the replicated poses; [H_lidar, g, r] are

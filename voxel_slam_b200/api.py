@@ -236,7 +236,7 @@ class Context:
         return t.value
 
     def ldlt_phases(self, n):
-        out = (C.c_double * 8)()
+        out = (C.c_double * 10)()
         self._check(lib().vxs_diag_ldlt_phases(self._p, int(n), out))
         return list(out)
 
