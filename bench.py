@@ -262,9 +262,10 @@ def run_ours(args):
     roof_jac = roof(["k_jac"], E * 80 + V * 176 + E * 144)
     dom = max(kern.items(), key=lambda kv_: kv_[1]["ms_per_step"])[0] if kern else None
 
-    c2 = None
+    c2 = ds = None
     if rank == 0 and world == 1:
         c2 = c2_leg(vx, ctx, hbm)
+        ds = ds_leg(ctx)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline_from_structure(vx, W, ptr, fr, hp["cl"], eig0, sum0, st0, tr, reps=2)
@@ -281,13 +282,28 @@ def run_ours(args):
                     "call": "push host LidarFactor (pinned CSR) + LI_BA damping_iter (3 iterations) + read back poses, Hessian, eig/pcr_adds"},
             "gpu_launches": int(launches), "clocks": clocks,
             "roofline": roof_hess, "roofline_residual": roof_resid, "roofline_jac": roof_jac, "dominant_kernel": dom,
-            "kernels": kern, "cpu_baseline": cpu, "c2_plane_fit": c2,
+            "kernels": kern, "cpu_baseline": cpu, "c2_plane_fit": c2, "down_sampling": ds,
             "voxelize": {"ms_total": t_vox * 1e3, "points": int(W * pts), "stages_ms": {k: v[0] for k, v in vox_stages.items() if v[1] > 0}},
             "check": {"pose_err_before": err0, "pose_err_after_3_iters": err1, "trace": [[float(t["r1"]), float(t["r2"]), int(t["accepted"])] for t in o["trace"]]},
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier(); dist.destroy_process_group()
+
+
+def ds_leg(ctx):
+    """down_sampling_voxel (tools.hpp:201) of 4 M float points at 0.25 m through the host-buffer C-ABI call."""
+    n = 4_000_000
+    pts = np.random.default_rng(3).uniform(-100.0, 100.0, (n, 3)).astype(np.float32)
+    ctx.down_sampling(pts, 0.25)
+    ctx.timing(True); ctx.timing_reset()
+    t0 = time.perf_counter()
+    g = ctx.down_sampling(pts, 0.25)
+    wall = (time.perf_counter() - t0) * 1e3
+    st = ctx.timing_read(); ctx.timing(False)
+    kms = sum(v[0] for v in st.values())
+    return {"points": n, "cells": int(len(g["index"])), "ms_call_pageable_host_buffers": wall, "ms_kernels": kms, "gpoints_per_s_kernels": n / max(kms, 1e-9) / 1e6,
+            "algorithmic_bytes": n * 12, "stages_ms": {k: v[0] for k, v in st.items() if v[1] > 0}}
 
 
 def c2_leg(vx, ctx, hbm):

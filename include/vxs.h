@@ -64,8 +64,9 @@ int vxs_diag_dmma_tflops(vxs_ctx* ctx, double* tflops);
 /* damped solve of a synthetic n x n system: out[0] = ms per solve (events), out[1..4] = us per 32-column panel that CTA 0 spends in
  * {panel load, strip solve, Schur update, grid barrier}, out[5] = panels, out[6] = SM clock (kHz) used for the conversion,
  * out[7] = us per panel of the look-ahead diagonal factor, out[8] = residual |(H + u diag H) dx + g|_inf / |g|_inf of the solve
- * checked on the host.  VXS_LDLT_LOOKAHEAD_CTA=0 in the environment keeps the look-ahead on CTA 0 (A/B switch). */
-int vxs_diag_ldlt_phases(vxs_ctx* ctx, int n, double out[10]);
+ * checked on the host, out[9..11] reserved (0).
+ * VXS_LDLT_LOOKAHEAD_CTA=0 in the environment keeps the look-ahead on CTA 0 (A/B switch). */
+int vxs_diag_ldlt_phases(vxs_ctx* ctx, int n, double out[12]);
 
 /* ---------------------------------------------------------------- multi-GPU (one process per GPU; NCCL over NVLink)
  * Voxel-sharded BA: every rank holds the factor voxels it owns and the replicated poses; [H_lidar, g, r] are
@@ -184,6 +185,20 @@ int vxs_hba_window(vxs_ctx* ctx, const vxs_map_params* coarse, const vxs_map_par
  * edge_ij: [cap][2] int32, v6: [cap][6], rot: [cap][9], tra: [cap][3]; *n_edges = number found (may exceed cap: truncated). */
 int vxs_hba_edges(vxs_ctx* ctx, int W, const double* poses12, int64_t cap, int32_t* edge_ij, double* v6, double* rot, double* tra,
                   int64_t* n_edges);
+
+/* ---------------------------------------------------------------- voxel-grid down-sampling
+ * down_sampling_voxel (tools.hpp:201-238; callers voxelslam.cpp:2440 submap merge, :1146 / :2118 scan pre-processing): one point per
+ * occupied cell of size voxel_size, the running FLOAT mean of the cell's points taken in input order (bit-exact, order dependent).
+ * down_sampling_close (tools.hpp:240-302): one INPUT point per cell, the one nearest to the cell's float centroid.
+ * pts: n points, x,y,z float at the start of each point, stride_floats between points (3 packed, 12 for pcl::PointXYZINormal).
+ * Outputs (each may be NULL, capacity cap): xyz_out[.][3]; count_out = points in the cell (the reference stores it in `curvature`);
+ * index_out = input index of the cell's FIRST point (voxel: the point whose other fields the reference keeps) / of the PICKED point
+ * (close).  Cells come out in ascending (x, y, z) cell order (the reference's unordered_map order is unspecified).
+ * *n_out = number of cells, or -1 when voxel_size < 0.001 (the reference returns with the cloud untouched). */
+int vxs_down_sampling_voxel(vxs_ctx* ctx, const float* pts, int stride_floats, int64_t n, double voxel_size, float* xyz_out, float* count_out,
+                            int64_t* first_index_out, int64_t cap, int64_t* n_out);
+int vxs_down_sampling_close(vxs_ctx* ctx, const float* pts, int stride_floats, int64_t n, double voxel_size, float* xyz_out, float* count_out,
+                            int64_t* picked_index_out, int64_t cap, int64_t* n_out);
 
 #ifdef __cplusplus
 }

@@ -318,4 +318,16 @@ void vxo_hostmath_transform(const double* c10, const double* pose12, double* out
   out10[0] = acc.P.xx; out10[1] = acc.P.xy; out10[2] = acc.P.xz; out10[3] = acc.P.yy; out10[4] = acc.P.yz; out10[5] = acc.P.zz; out10[6] = acc.v.x; out10[7] = acc.v.y; out10[8] = acc.v.z; out10[9] = acc.n;
 }
 
+
+// tools.hpp:201-302; mode 0 = down_sampling_voxel, 1 = down_sampling_close.  Returns the number of cells (-1: untouched); out arrays hold min(cap, cells).
+int64_t vxo_down_sampling(int mode, const float* pts, int stride, int64_t n, double voxel_size, float* xyz_out, float* cnt_out, int64_t* idx_out, int64_t cap) {
+  std::vector<DsPoint> out;
+  const bool done = mode == 0 ? down_sampling_voxel(pts, stride, n, voxel_size, out) : down_sampling_close(pts, stride, n, voxel_size, out);
+  if (!done) return -1;
+  for (int64_t i = 0; i < int64_t(out.size()) && i < cap; i++) {
+    xyz_out[3 * i] = out[i].x; xyz_out[3 * i + 1] = out[i].y; xyz_out[3 * i + 2] = out[i].z; cnt_out[i] = out[i].cnt; idx_out[i] = out[i].idx;
+  }
+  return int64_t(out.size());
+}
+
 }  // extern "C"

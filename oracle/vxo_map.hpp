@@ -10,6 +10,7 @@
 //   voxelslam.cpp:600-628    build-from-scratch sequence (cut all scans, then recut + tras_opt)
 //   loop_refine.hpp:273-537  OctreeGBA, OctreeGBA_multi_recut
 //   voxelslam.cpp:2360-2427  HBA_add_edge BA loop + PGO edge extraction
+//   tools.hpp:201-302        down_sampling_voxel / down_sampling_close
 #pragma once
 #include <unordered_map>
 #include "vxo_core.hpp"
@@ -391,6 +392,68 @@ inline int hba_window(std::vector<State>& xs, const Keyframes& kf, GbaParams gp,
       }
   }
   return iters_run;
+}
+
+
+// ---------------------------------------------------------------- tools.hpp:201-302 voxel-grid down-sampling (float point clouds)
+struct DsPoint { float x, y, z, cnt; int64_t idx; };
+// float quantisation of a FLOAT coordinate (tools.hpp:210-215): loc = p / voxel_size (double division, stored as float); loc < 0: loc -= 1.0
+inline VoxelLoc voxel_key_f(const float* p, double voxel_size) {
+  int64_t k[3];
+  for (int j = 0; j < 3; j++) {
+    float loc = float(double(p[j]) / voxel_size);
+    if (loc < 0) loc = float(double(loc) - 1.0);
+    k[j] = int64_t(loc);
+  }
+  return VoxelLoc{k[0], k[1], k[2]};
+}
+// tools.hpp:201-238.  Returns false when voxel_size < 0.001 (cloud untouched).  out order = the map's iteration order (unspecified in
+// the reference as well); idx = input index of the first point of the cell (the reference keeps that point's other fields), cnt = curvature.
+inline bool down_sampling_voxel(const float* pts, int stride, int64_t n, double voxel_size, std::vector<DsPoint>& out) {
+  out.clear();
+  if (voxel_size < 0.001) return false;
+  std::unordered_map<VoxelLoc, DsPoint, VoxelLocHash> feat_map;
+  for (int64_t i = 0; i < n; i++) {
+    const float* p = pts + size_t(i) * stride;
+    const VoxelLoc position = voxel_key_f(p, voxel_size);
+    auto it = feat_map.find(position);
+    if (it == feat_map.end()) feat_map[position] = DsPoint{p[0], p[1], p[2], 1.0f, i};
+    else {
+      DsPoint& pp = it->second;                       // float arithmetic throughout (PointType fields are float)
+      pp.x = (pp.x * pp.cnt + p[0]) / (pp.cnt + 1);
+      pp.y = (pp.y * pp.cnt + p[1]) / (pp.cnt + 1);
+      pp.z = (pp.z * pp.cnt + p[2]) / (pp.cnt + 1);
+      pp.cnt += 1;
+    }
+  }
+  for (auto& kv : feat_map) out.push_back(kv.second);
+  return true;
+}
+// tools.hpp:240-302: the input point nearest to the cell's float centroid; idx = its input index
+inline bool down_sampling_close(const float* pts, int stride, int64_t n, double voxel_size, std::vector<DsPoint>& out) {
+  out.clear();
+  if (voxel_size < 0.001) return false;
+  std::unordered_map<VoxelLoc, std::vector<int64_t>, VoxelLocHash> feat_map;
+  for (int64_t i = 0; i < n; i++) feat_map[voxel_key_f(pts + size_t(i) * stride, voxel_size)].push_back(i);
+  for (auto& kv : feat_map) {
+    const std::vector<int64_t>& pl = kv.second;
+    const int plsize = int(pl.size());
+    const float* p0 = pts + size_t(pl[0]) * stride;
+    float bx = p0[0], by = p0[1], bz = p0[2];
+    for (int i = 1; i < plsize; i++) { const float* pp = pts + size_t(pl[i]) * stride; bx += pp[0]; by += pp[1]; bz += pp[2]; }
+    bx /= plsize; by /= plsize; bz /= plsize;
+    double ndis = 100;
+    int mnum = 0;
+    for (int i = 0; i < plsize; i++) {
+      const float* pp = pts + size_t(pl[i]) * stride;
+      const double xx = bx - pp[0], yy = by - pp[1], zz = bz - pp[2];   // float differences, widened afterwards (tools.hpp:285-287)
+      const double dis = xx * xx + yy * yy + zz * zz;
+      if (dis < ndis) { mnum = i; ndis = dis; }
+    }
+    const float* pb = pts + size_t(pl[mnum]) * stride;
+    out.push_back(DsPoint{pb[0], pb[1], pb[2], float(plsize), pl[mnum]});
+  }
+  return true;
 }
 
 }  // namespace vxo

@@ -190,6 +190,19 @@ def hba_edges(hess, W, poses12):
     return dict(n=m, ij=eij[:m], v6=v6[:m], rot=rot[:m], tra=tra[:m])
 
 
+def down_sampling(pts_f32, voxel_size, close=False, stride_floats=None):
+    x = np.ascontiguousarray(pts_f32, dtype=np.float32)
+    stride = int(stride_floats) if stride_floats else (x.shape[1] if x.ndim == 2 else 3)
+    n = x.size // stride
+    xyz = np.zeros((max(n, 1), 3), dtype=np.float32); cnt = np.zeros(max(n, 1), dtype=np.float32); idx = np.zeros(max(n, 1), dtype=np.int64)
+    lib().vxo_down_sampling.restype = C.c_int64
+    m = lib().vxo_down_sampling(C.c_int(1 if close else 0), x.ctypes.data_as(C.POINTER(C.c_float)), C.c_int(stride), C.c_int64(n), C.c_double(voxel_size),
+                                xyz.ctypes.data_as(C.POINTER(C.c_float)), cnt.ctypes.data_as(C.POINTER(C.c_float)), idx.ctypes.data_as(C.POINTER(C.c_int64)), C.c_int64(n))
+    if m < 0:
+        return None
+    return dict(xyz=xyz[:m], count=cnt[:m], index=idx[:m])
+
+
 def hba_window(coarse, fine, xyz_f32, kf_offsets, poses12, max_iter, thread_num=2, stride_floats=3):
     x = np.ascontiguousarray(xyz_f32, dtype=np.float32)
     off = np.ascontiguousarray(kf_offsets, dtype=np.int64)

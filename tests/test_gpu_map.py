@@ -180,3 +180,50 @@ def test_radix_sort_and_scan_at_scale(ctx):
     f = vx.Factor(ctx, W)
     n, ids = ctx.build_window_factor(sc["mp"], sc["pts"], sc["offsets"], sc["poses_est"], f, want_ids=True, ids_cap=sc["oracle_factor"].size() + 1000)
     compare_factors(f, ids, sc["oracle_factor"], W)
+
+
+def _ds_cloud(n, seed, stride=3, span=40.0):
+    rng = np.random.default_rng(seed)
+    pts = np.zeros((n, stride), dtype=np.float32)
+    pts[:, :3] = rng.uniform(-span, span, size=(n, 3)).astype(np.float32)
+    pts[: n // 10, :3] = np.round(pts[: n // 10, :3] * 2) / 2      # on cell faces, incl. 0 and negatives (the loc < 0 branch)
+    pts[n // 10: n // 5, :3] = pts[: n // 5 - n // 10, :3]           # exact duplicates
+    if stride > 3:
+        pts[:, 3:] = rng.uniform(size=(n, stride - 3)).astype(np.float32)
+    return pts
+
+
+@pytest.mark.parametrize("close", [False, True])
+@pytest.mark.parametrize("stride,vs,span", [(3, 0.5, 40.0), (12, 0.125, 6.0), (3, 2.0, 6.0)])
+def test_down_sampling_parity(ctx, close, stride, vs, span):
+    """tools.hpp:201-302 — bit-exact against the oracle: same cells, same float means / picked points, same counts."""
+    pts = _ds_cloud(200000, 5 + stride, stride, span)
+    g = ctx.down_sampling(pts, vs, close=close, stride_floats=stride)
+    o = oa.down_sampling(pts, vs, close=close, stride_floats=stride)
+    assert len(g["index"]) == len(o["index"])
+    go, oo = np.argsort(g["index"]), np.argsort(o["index"])
+    assert np.array_equal(g["index"][go], o["index"][oo])
+    assert np.array_equal(g["xyz"][go].view(np.uint32), o["xyz"][oo].view(np.uint32))
+    assert np.array_equal(g["count"][go], o["count"][oo])
+    assert int(g["count"].sum()) == pts.shape[0]
+    # cells come out in ascending cell order
+    k = oa.voxel_keys(pts[g["index"], :3].astype(np.float64), vs)[0]
+    lin = (k[:, 0] - k[:, 0].min()) * (1 << 40) + (k[:, 1] - k[:, 1].min()) * (1 << 20) + (k[:, 2] - k[:, 2].min())
+    assert np.all(np.diff(lin) > 0)
+
+
+def test_down_sampling_edges_and_scale(ctx):
+    pts = _ds_cloud(1000, 3)
+    assert ctx.down_sampling(pts, 0.0005) is None and ctx.down_sampling(pts, 0.0005, close=True) is None
+    assert len(ctx.down_sampling(pts[:0], 0.5)["index"]) == 0
+    one = ctx.down_sampling(pts[:1], 0.5)
+    assert one["index"].tolist() == [0] and np.array_equal(one["xyz"][0], pts[0, :3]) and one["count"][0] == 1
+    # 5 M points: every point lands in exactly one cell, the first-point indices are unique, a second pass at the same size keeps
+    # the number of cells or merges means that crossed a face (never grows)
+    big = _ds_cloud(5_000_000, 9, 3, 120.0)
+    g = ctx.down_sampling(big, 0.25)
+    assert int(g["count"].sum()) == big.shape[0] and len(np.unique(g["index"])) == len(g["index"])
+    g2 = ctx.down_sampling(g["xyz"], 0.25)
+    assert len(g2["index"]) <= len(g["index"])
+    c = ctx.down_sampling(big, 0.25, close=True)
+    assert len(c["index"]) == len(g["index"]) and np.array_equal(c["xyz"], big[c["index"], :3])

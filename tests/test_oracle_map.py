@@ -1,6 +1,7 @@
 """Voxel-map side of the oracle: point-to-voxel assignment and cluster sums against an independent numpy recomputation,
 plane logic invariants, global-BA map and the HBA window loop."""
 import numpy as np
+import pytest
 
 import oracle_api as oa
 import scenes
@@ -107,3 +108,63 @@ def test_hba_window_improves_poses():
     assert out["status"] == 0 and 1 <= out["outer_iters"] <= 4
     assert np.abs(out["poses"] - tr).max() < 0.5 * np.abs(est - tr).max()
     assert np.isfinite(out["hess"]).all() and np.abs(out["hess"]).max() > 0
+
+
+def _ds_cloud(n, seed, stride=3):
+    rng = np.random.default_rng(seed)
+    pts = np.zeros((n, stride), dtype=np.float32)
+    pts[:, :3] = (rng.uniform(-6.0, 6.0, size=(n, 3))).astype(np.float32)
+    pts[: n // 10, :3] = np.round(pts[: n // 10, :3] * 2) / 2          # points exactly on cell faces, including 0 and negatives
+    pts[n // 10: n // 5, :3] = pts[: n // 5 - n // 10, :3]               # exact duplicates
+    if stride > 3:
+        pts[:, 3:] = rng.uniform(size=(n, stride - 3)).astype(np.float32)
+    return pts
+
+
+def _ds_reference_python(pts, voxel_size, close):
+    """tools.hpp:201-302 written out with numpy float32 scalars (every operation rounds to float, like PointType fields)."""
+    f32 = np.float32
+    cells = {}
+    for i in range(pts.shape[0]):
+        key = []
+        for j in range(3):
+            loc = f32(np.float64(pts[i, j]) / np.float64(voxel_size))
+            if loc < 0:
+                loc = f32(np.float64(loc) - 1.0)
+            key.append(int(np.trunc(loc)))
+        cells.setdefault(tuple(key), []).append(i)
+    out = {}
+    for key, ids in cells.items():
+        if not close:
+            x = [f32(v) for v in pts[ids[0], :3]]; cnt = f32(1)
+            for i in ids[1:]:
+                x = [f32(f32(f32(x[j] * cnt) + pts[i, j]) / f32(cnt + f32(1))) for j in range(3)]
+                cnt = f32(cnt + f32(1))
+            out[ids[0]] = (np.array(x, dtype=np.float32), float(cnt))
+        else:
+            c = [f32(v) for v in pts[ids[0], :3]]
+            for i in ids[1:]:
+                c = [f32(c[j] + pts[i, j]) for j in range(3)]
+            c = [f32(c[j] / f32(len(ids))) for j in range(3)]
+            nd, best = 100.0, 0
+            for t, i in enumerate(ids):
+                d = [np.float64(f32(c[j] - pts[i, j])) for j in range(3)]
+                dis = d[0] * d[0] + d[1] * d[1] + d[2] * d[2]
+                if dis < nd:
+                    best, nd = t, dis
+            out[ids[best]] = (pts[ids[best], :3].copy(), float(len(ids)))
+    return out
+
+
+@pytest.mark.parametrize("close", [False, True])
+@pytest.mark.parametrize("stride", [3, 12])
+def test_down_sampling_oracle_matches_float32_restatement(close, stride):
+    pts = _ds_cloud(3000, 11 + stride, stride)
+    for vs in (0.5, 0.125):
+        o = oa.down_sampling(pts, vs, close=close, stride_floats=stride)
+        ref = _ds_reference_python(pts, vs, close)
+        assert len(o["index"]) == len(ref) and set(o["index"].tolist()) == set(ref.keys())
+        for k, i in enumerate(o["index"].tolist()):
+            assert np.array_equal(o["xyz"][k], ref[i][0]) and o["count"][k] == ref[i][1]
+    assert oa.down_sampling(pts, 0.0005, close=close, stride_floats=stride) is None       # tools.hpp:203: cloud left untouched
+    assert len(oa.down_sampling(pts[:0], 0.5, close=close, stride_floats=stride)["index"]) == 0

@@ -236,7 +236,7 @@ class Context:
         return t.value
 
     def ldlt_phases(self, n):
-        out = (C.c_double * 10)()
+        out = (C.c_double * 12)()
         self._check(lib().vxs_diag_ldlt_phases(self._p, int(n), out))
         return list(out)
 
@@ -351,6 +351,25 @@ def _hba_edges(self, W, poses12, cap=None):
 
 
 Context.hba_edges = _hba_edges
+
+
+def _down_sampling(self, pts_f32, voxel_size, close=False, stride_floats=None):
+    """down_sampling_voxel / down_sampling_close (tools.hpp:201-302) on the device.  Returns None when the reference would leave the
+    cloud untouched, else dict(xyz, count, index) in ascending cell order."""
+    x = np.ascontiguousarray(pts_f32, dtype=np.float32)
+    stride = int(stride_floats) if stride_floats else (x.shape[1] if x.ndim == 2 else 3)
+    n = x.size // stride
+    xyz = np.zeros((max(n, 1), 3), dtype=np.float32); cnt = np.zeros(max(n, 1), dtype=np.float32); idx = np.zeros(max(n, 1), dtype=np.int64)
+    m = C.c_int64(0)
+    fn = lib().vxs_down_sampling_close if close else lib().vxs_down_sampling_voxel
+    self._check(fn(self._p, x.ctypes.data_as(C.POINTER(C.c_float)), C.c_int(stride), C.c_int64(n), C.c_double(voxel_size), xyz.ctypes.data_as(C.POINTER(C.c_float)),
+                   cnt.ctypes.data_as(C.POINTER(C.c_float)), idx.ctypes.data_as(C.POINTER(C.c_int64)), C.c_int64(n), C.byref(m)))
+    if m.value < 0:
+        return None
+    return dict(xyz=xyz[: m.value], count=cnt[: m.value], index=idx[: m.value])
+
+
+Context.down_sampling = _down_sampling
 
 
 class Factor:

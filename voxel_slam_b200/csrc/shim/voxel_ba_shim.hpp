@@ -209,5 +209,40 @@ inline bool lidar_ba_damping_iter(std::vector<IMUST>& x_stats, LidarFactor& voxh
   return conv;
 }
 
+// down_sampling_voxel(pl_feat, voxel_size) — tools.hpp:201 (call sites voxelslam.cpp:1146, 2118, 2440).  PointType is
+// pcl::PointXYZINormal (48 bytes, x,y,z first): the cloud goes up as it is, the surviving points keep the fields of the first point of
+// their cell and get curvature = points in the cell, exactly like the reference; only the ORDER of the output differs (cell order
+// instead of unordered_map order).
+inline void down_sampling_voxel(Context& ctx, pcl::PointCloud<PointType>& pl_feat, double voxel_size) {
+  const int64_t n = int64_t(pl_feat.size());
+  std::vector<float> xyz(size_t(n) * 3), cnt(n);
+  std::vector<int64_t> first(n);
+  int64_t m = 0;
+  check(ctx.get(), vxs_down_sampling_voxel(ctx.get(), reinterpret_cast<const float*>(pl_feat.points.data()), int(sizeof(PointType) / sizeof(float)), n, voxel_size,
+                                           xyz.data(), cnt.data(), first.data(), n, &m), "vxs_down_sampling_voxel");
+  if (m < 0) return;
+  pcl::PointCloud<PointType> out;
+  out.reserve(size_t(m));
+  for (int64_t i = 0; i < m; i++) {
+    PointType pp = pl_feat.points[size_t(first[i])];
+    pp.x = xyz[3 * i]; pp.y = xyz[3 * i + 1]; pp.z = xyz[3 * i + 2]; pp.curvature = cnt[i];
+    out.push_back(pp);
+  }
+  pl_feat.swap(out);
+}
+// down_sampling_close(pl_feat, voxel_size) — tools.hpp:240
+inline void down_sampling_close(Context& ctx, pcl::PointCloud<PointType>& pl_feat, double voxel_size) {
+  const int64_t n = int64_t(pl_feat.size());
+  std::vector<int64_t> pick(n);
+  int64_t m = 0;
+  check(ctx.get(), vxs_down_sampling_close(ctx.get(), reinterpret_cast<const float*>(pl_feat.points.data()), int(sizeof(PointType) / sizeof(float)), n, voxel_size,
+                                           nullptr, nullptr, pick.data(), n, &m), "vxs_down_sampling_close");
+  if (m < 0) return;
+  pcl::PointCloud<PointType> out;
+  out.reserve(size_t(m));
+  for (int64_t i = 0; i < m; i++) out.push_back(pl_feat.points[size_t(pick[i])]);
+  pl_feat.swap(out);
+}
+
 }  // namespace vxs_shim
 #endif  // VXS_SHIM_WITH_REFERENCE_TYPES

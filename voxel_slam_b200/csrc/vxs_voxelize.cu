@@ -631,6 +631,139 @@ static int build_factor(vxs_ctx* ctx, const vxs_map_params* mp, bool gba, const 
 }
 
 // ------------------------------------------------------------------ public entry points
+// ------------------------------------------------------------------ voxel-grid down-sampling (tools.hpp:201-302)
+// down_sampling_voxel keeps one point per occupied cell: the running float mean of the cell's points in input order,
+//   pp = (pp*cnt + p) / (cnt + 1)  per coordinate, cnt = 1, 2, ...   (tools.hpp:226-232) — float arithmetic, order dependent, so the
+// cell's points are reduced sequentially by one thread in their original order (the LSD radix sort is stable);
+// down_sampling_close keeps the input point nearest to the cell's float centroid (first minimum, distances in fp64, start value 100).
+// The reference iterates an unordered_map, so its output ORDER is unspecified; here cells come out in ascending (x, y, z) cell order and
+// every output carries the index of the first input point of its cell (the reference copies that point's other fields).
+__global__ void __launch_bounds__(256) k_ds_bbox(const float* __restrict__ pts, int stride, long long n, double voxel_size, long long* __restrict__ bbox) {
+  long long mn[3] = {LLONG_MAX, LLONG_MAX, LLONG_MAX}, mx[3] = {LLONG_MIN, LLONG_MIN, LLONG_MIN};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float* p = pts + size_t(i) * stride;
+    for (int a = 0; a < 3; a++) { const long long k = quantise((double)p[a], voxel_size); mn[a] = min(mn[a], k); mx[a] = max(mx[a], k); }
+  }
+  for (int a = 0; a < 3; a++) {
+    for (int off = 16; off > 0; off >>= 1) { mn[a] = min(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], off)); mx[a] = max(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], off)); }
+    if ((threadIdx.x & 31) == 0) { atomicMin(bbox + a, mn[a]); atomicMax(bbox + 3 + a, mx[a]); }
+  }
+}
+__global__ void __launch_bounds__(256) k_ds_keys(const float* __restrict__ pts, int stride, long long n, double voxel_size, long long minx, long long miny, long long minz,
+                                                 unsigned long long ey, unsigned long long ez, unsigned long long* __restrict__ keys, unsigned int* __restrict__ idx) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = pts + size_t(i) * stride;
+  const unsigned long long x = (unsigned long long)(quantise((double)p[0], voxel_size) - minx), y = (unsigned long long)(quantise((double)p[1], voxel_size) - miny),
+                           z = (unsigned long long)(quantise((double)p[2], voxel_size) - minz);
+  keys[i] = (x * ey + y) * ez + z;
+  idx[i] = (unsigned int)i;
+}
+// mode 0: running mean (down_sampling_voxel); mode 1: nearest to centroid (down_sampling_close)
+__global__ void __launch_bounds__(128) k_ds_reduce(const float* __restrict__ pts, int stride, const unsigned int* __restrict__ idx, const unsigned int* __restrict__ seg_start,
+                                                   unsigned int nseg, int mode, float* __restrict__ xyz_out, float* __restrict__ cnt_out, long long* __restrict__ pick_out) {
+  const unsigned int sgi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sgi >= nseg) return;
+  const unsigned int b = seg_start[sgi], e = seg_start[sgi + 1];
+  const float* p0 = pts + size_t(idx[b]) * stride;
+  float x = p0[0], y = p0[1], z = p0[2];
+  if (mode == 0) {
+    float cnt = 1.0f;
+    for (unsigned int j = b + 1; j < e; j++) {
+      const float* p = pts + size_t(idx[j]) * stride;
+      const float c1 = __fadd_rn(cnt, 1.0f);
+      x = __fdiv_rn(__fadd_rn(__fmul_rn(x, cnt), p[0]), c1);
+      y = __fdiv_rn(__fadd_rn(__fmul_rn(y, cnt), p[1]), c1);
+      z = __fdiv_rn(__fadd_rn(__fmul_rn(z, cnt), p[2]), c1);
+      cnt = c1;
+    }
+    xyz_out[3 * size_t(sgi)] = x; xyz_out[3 * size_t(sgi) + 1] = y; xyz_out[3 * size_t(sgi) + 2] = z;
+    cnt_out[sgi] = cnt;
+    pick_out[sgi] = (long long)idx[b];
+  } else {
+    for (unsigned int j = b + 1; j < e; j++) {
+      const float* p = pts + size_t(idx[j]) * stride;
+      x = __fadd_rn(x, p[0]); y = __fadd_rn(y, p[1]); z = __fadd_rn(z, p[2]);
+    }
+    const float fn = (float)(int)(e - b);
+    x = __fdiv_rn(x, fn); y = __fdiv_rn(y, fn); z = __fdiv_rn(z, fn);
+    double ndis = 100.0;
+    unsigned int best = b;
+    for (unsigned int j = b; j < e; j++) {
+      const float* p = pts + size_t(idx[j]) * stride;
+      const double xx = (double)__fsub_rn(x, p[0]), yy = (double)__fsub_rn(y, p[1]), zz = (double)__fsub_rn(z, p[2]);
+      const double dis = __dadd_rn(__dadd_rn(__dmul_rn(xx, xx), __dmul_rn(yy, yy)), __dmul_rn(zz, zz));
+      if (dis < ndis) { best = j; ndis = dis; }
+    }
+    const float* pb = pts + size_t(idx[best]) * stride;
+    xyz_out[3 * size_t(sgi)] = pb[0]; xyz_out[3 * size_t(sgi) + 1] = pb[1]; xyz_out[3 * size_t(sgi) + 2] = pb[2];
+    cnt_out[sgi] = fn;
+    pick_out[sgi] = (long long)idx[best];
+  }
+}
+
+static int down_sample(vxs_ctx* ctx, int mode, const float* pts_host, int stride, int64_t n, double voxel_size, float* xyz_out, float* count_out, int64_t* index_out,
+                       int64_t cap, int64_t* n_out) {
+  if (!ctx || !n_out || n < 0 || stride < 3 || (n > 0 && !pts_host)) return VXS_ERR_ARG;
+  *n_out = -1;
+  if (voxel_size < 0.001) return VXS_OK;                 // tools.hpp:203 / 247: the cloud is left untouched
+  *n_out = 0;
+  if (n == 0) return VXS_OK;
+  if (n >= (1ll << 32)) return vxs_fail(ctx, VXS_ERR_ARG, "more than 2^32 points in one down-sampling call");
+  cudaSetDevice(ctx->device);
+  VoxScratch* s = scratch(ctx);
+  cudaStream_t st = ctx->stream;
+  VXS_CUDA(ctx, s->totals.reserve(16));
+  VXS_CUDA(ctx, s->pts_f.reserve(size_t(n) * stride));
+  VXS_CUDA(ctx, cudaMemcpyAsync(s->pts_f.p, pts_host, size_t(n) * stride * 4, cudaMemcpyHostToDevice, st));
+  VXS_CUDA(ctx, s->bbox.reserve(6));
+  const long long bb0[6] = {LLONG_MAX, LLONG_MAX, LLONG_MAX, LLONG_MIN, LLONG_MIN, LLONG_MIN};
+  VXS_CUDA(ctx, cudaMemcpyAsync(s->bbox.p, bb0, sizeof bb0, cudaMemcpyHostToDevice, st));
+  VXS_LAUNCH(ctx, "k_ds_bbox", k_ds_bbox, std::min<unsigned>(nblk(size_t(n), 256), unsigned(ctx->sm_count) * 8), 256, 0, s->pts_f.p, stride, (long long)n, voxel_size, s->bbox.p);
+  long long bb[6];
+  VXS_CUDA(ctx, cudaMemcpyAsync(bb, s->bbox.p, sizeof bb, cudaMemcpyDeviceToHost, st));
+  VXS_CUDA(ctx, cudaStreamSynchronize(st));
+  const long double ex = (long double)bb[3] - bb[0] + 1, ey = (long double)bb[4] - bb[1] + 1, ez = (long double)bb[5] - bb[2] + 1;
+  if (ex * ey * ez >= (long double)(1ull << 62)) return vxs_fail(ctx, VXS_ERR_RANGE, "down-sampling grid exceeds 2^62 cells");
+  const int key_bits = bits_for((unsigned long long)(ex * ey * ez));
+  VXS_CUDA(ctx, s->keysA.reserve(size_t(n))); VXS_CUDA(ctx, s->keysB.reserve(size_t(n)));
+  VXS_CUDA(ctx, s->idxA.reserve(size_t(n))); VXS_CUDA(ctx, s->idxB.reserve(size_t(n)));
+  VXS_LAUNCH(ctx, "k_ds_keys", k_ds_keys, nblk(size_t(n), 256), 256, 0, s->pts_f.p, stride, (long long)n, voxel_size, bb[0], bb[1], bb[2], (unsigned long long)ey, (unsigned long long)ez,
+             s->keysA.p, s->idxA.p);
+  unsigned long long* ks; unsigned int* vs;
+  int rc = radix_sort(ctx, s, s->keysA.p, s->idxA.p, s->keysB.p, s->idxB.p, size_t(n), key_bits, &ks, &vs);
+  if (rc) return rc;
+  VXS_CUDA(ctx, s->flags.reserve(size_t(n))); VXS_CUDA(ctx, s->scanbuf.reserve(size_t(n)));
+  VXS_LAUNCH(ctx, "k_flag_heads", k_flag_heads, nblk(size_t(n), 256), 256, 0, ks, size_t(n), s->flags.p);
+  rc = scan_u32(ctx, s, s->flags.p, s->scanbuf.p, size_t(n), s->totals.p + 0);
+  if (rc) return rc;
+  unsigned int R = 0;
+  VXS_CUDA(ctx, cudaMemcpyAsync(&R, s->totals.p + 0, 4, cudaMemcpyDeviceToHost, st));
+  VXS_CUDA(ctx, cudaStreamSynchronize(st));
+  VXS_CUDA(ctx, s->rec_start.reserve(size_t(R) + 1)); VXS_CUDA(ctx, s->rec_key.reserve(size_t(R)));
+  VXS_LAUNCH(ctx, "k_write_records", k_write_records, nblk(size_t(n), 256), 256, 0, ks, s->flags.p, s->scanbuf.p, size_t(n), s->rec_start.p, s->rec_key.p, s->totals.p + 0);
+  // outputs: reuse the cluster scratch (4 floats + 1 int64 per cell)
+  VXS_CUDA(ctx, s->rec_local.reserve(size_t(R) * 2 + 2)); VXS_CUDA(ctx, s->rec_world.reserve(size_t(R) + 1));
+  float* d_xyz = reinterpret_cast<float*>(s->rec_local.p); float* d_cnt = d_xyz + 3 * size_t(R);
+  long long* d_pick = reinterpret_cast<long long*>(s->rec_world.p);
+  VXS_LAUNCH(ctx, "k_ds_reduce", k_ds_reduce, nblk(size_t(R), 128), 128, 0, s->pts_f.p, stride, vs, s->rec_start.p, R, mode, d_xyz, d_cnt, d_pick);
+  *n_out = int64_t(R);
+  const size_t ncopy = size_t(std::min<int64_t>(cap, int64_t(R)));
+  if (xyz_out && ncopy) VXS_CUDA(ctx, cudaMemcpyAsync(xyz_out, d_xyz, ncopy * 12, cudaMemcpyDeviceToHost, st));
+  if (count_out && ncopy) VXS_CUDA(ctx, cudaMemcpyAsync(count_out, d_cnt, ncopy * 4, cudaMemcpyDeviceToHost, st));
+  if (index_out && ncopy) VXS_CUDA(ctx, cudaMemcpyAsync(index_out, d_pick, ncopy * 8, cudaMemcpyDeviceToHost, st));
+  VXS_CUDA(ctx, cudaStreamSynchronize(st));
+  return VXS_OK;
+}
+extern "C" int vxs_down_sampling_voxel(vxs_ctx* ctx, const float* pts, int stride_floats, int64_t n, double voxel_size, float* xyz_out, float* count_out, int64_t* first_index_out,
+                                       int64_t cap, int64_t* n_out) {
+  return down_sample(ctx, 0, pts, stride_floats, n, voxel_size, xyz_out, count_out, first_index_out, cap, n_out);
+}
+extern "C" int vxs_down_sampling_close(vxs_ctx* ctx, const float* pts, int stride_floats, int64_t n, double voxel_size, float* xyz_out, float* count_out, int64_t* picked_index_out,
+                                       int64_t cap, int64_t* n_out) {
+  return down_sample(ctx, 1, pts, stride_floats, n, voxel_size, xyz_out, count_out, picked_index_out, cap, n_out);
+}
+
 extern "C" int vxs_voxel_keys(vxs_ctx* ctx, const double* pw, int64_t n, double voxel_size, int64_t* xyz, uint64_t* hash) {
   if (!ctx || n < 0 || (n > 0 && (!pw || !xyz || !hash)) || !(voxel_size > 0)) return VXS_ERR_ARG;
   if (n == 0) return VXS_OK;
