@@ -200,6 +200,14 @@ int vxs_down_sampling_voxel(vxs_ctx* ctx, const float* pts, int stride_floats, i
 int vxs_down_sampling_close(vxs_ctx* ctx, const float* pts, int stride_floats, int64_t n, double voxel_size, float* xyz_out, float* count_out,
                             int64_t* picked_index_out, int64_t cap, int64_t* n_out);
 
+/* Submap merge of HBA_add_edge (voxelslam.cpp:2428-2447): the clouds of the W keyframes of a window are moved into the frame of
+ * keyframe 0 (v' = dR v + dp in fp64, dR = R_0^T R_i, dp = R_0^T (p_i - p_0), stored as float) and passed through
+ * down_sampling_voxel(voxel_size) — the caller passes the reference's voxel_size / 8.  Outputs as vxs_down_sampling_voxel;
+ * first_index_out indexes the concatenated input, so the keyframe of a surviving point (the reference stores its map id in
+ * `intensity`) follows from kf_offsets.  voxel_size < 0.001: the merged cloud is returned as it is (count 0). */
+int vxs_submap_merge(vxs_ctx* ctx, const float* xyz, int stride_floats, const int64_t* kf_offsets, const double* poses12, int W,
+                     double voxel_size, float* xyz_out, float* count_out, int64_t* first_index_out, int64_t cap, int64_t* n_out);
+
 #ifdef __cplusplus
 }
 #endif

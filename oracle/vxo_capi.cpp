@@ -330,4 +330,20 @@ int64_t vxo_down_sampling(int mode, const float* pts, int stride, int64_t n, dou
   return int64_t(out.size());
 }
 
+// voxelslam.cpp:2428-2447 submap merge; returns the number of cells (or n when voxel_size < 0.001: the merged cloud, untouched)
+int64_t vxo_submap_merge(const float* pts, int stride, const int64_t* kf_offsets, const double* poses12, int W, double voxel_size, float* xyz_out, float* cnt_out, int64_t* idx_out,
+                         int64_t cap) {
+  std::vector<float> merged; std::vector<DsPoint> out;
+  const bool done = submap_merge(pts, stride, kf_offsets, poses12, W, voxel_size, merged, out);
+  if (!done) {
+    const int64_t n = kf_offsets[W];
+    for (int64_t i = 0; i < n && i < cap; i++) { xyz_out[3 * i] = merged[3 * i]; xyz_out[3 * i + 1] = merged[3 * i + 1]; xyz_out[3 * i + 2] = merged[3 * i + 2]; cnt_out[i] = 0; idx_out[i] = i; }
+    return n;
+  }
+  for (int64_t i = 0; i < int64_t(out.size()) && i < cap; i++) {
+    xyz_out[3 * i] = out[i].x; xyz_out[3 * i + 1] = out[i].y; xyz_out[3 * i + 2] = out[i].z; cnt_out[i] = out[i].cnt; idx_out[i] = out[i].idx;
+  }
+  return int64_t(out.size());
+}
+
 }  // extern "C"

@@ -456,4 +456,28 @@ inline bool down_sampling_close(const float* pts, int stride, int64_t n, double 
   return true;
 }
 
+// voxelslam.cpp:2428-2447: submap merge of HBA_add_edge.  xs: W poses (R row-major, p); clouds concatenated with kf_offsets.
+// merged (n x 3 float) receives the transformed points; then down_sampling_voxel(voxel_size) (the caller passes voxel_size / 8).
+inline bool submap_merge(const float* pts, int stride, const int64_t* kf_offsets, const double* poses12, int W, double voxel_size, std::vector<float>& merged,
+                         std::vector<DsPoint>& out) {
+  const int64_t n = kf_offsets[W];
+  merged.assign(size_t(n) * 3, 0.0f);
+  const double* P0 = poses12;
+  for (int i = 0; i < W; i++) {
+    const double* Pi = poses12 + 12 * size_t(i);
+    double dR[9], dp[3];
+    const double d[3] = {Pi[9] - P0[9], Pi[10] - P0[10], Pi[11] - P0[11]};
+    for (int r = 0; r < 3; r++) {
+      for (int c = 0; c < 3; c++) dR[3 * r + c] = (P0[r] * Pi[c] + P0[3 + r] * Pi[3 + c]) + P0[6 + r] * Pi[6 + c];   // xc.R.transpose() * xs[i].R
+      dp[r] = (P0[r] * d[0] + P0[3 + r] * d[1]) + P0[6 + r] * d[2];                                                  // xc.R.transpose() * (xs[i].p - xc.p)
+    }
+    for (int64_t k = kf_offsets[i]; k < kf_offsets[i + 1]; k++) {
+      const float* p = pts + size_t(k) * stride;
+      const double x = p[0], y = p[1], z = p[2];
+      for (int r = 0; r < 3; r++) merged[3 * size_t(k) + r] = float(((dR[3 * r] * x + dR[3 * r + 1] * y) + dR[3 * r + 2] * z) + dp[r]);    // v3 = dR * v3 + dp; ap.x = v3[0]
+    }
+  }
+  return down_sampling_voxel(merged.data(), 3, n, voxel_size, out);
+}
+
 }  // namespace vxo

@@ -203,6 +203,20 @@ def down_sampling(pts_f32, voxel_size, close=False, stride_floats=None):
     return dict(xyz=xyz[:m], count=cnt[:m], index=idx[:m])
 
 
+def submap_merge(xyz_f32, kf_offsets, poses12, voxel_size, stride_floats=None):
+    x = np.ascontiguousarray(xyz_f32, dtype=np.float32)
+    stride = int(stride_floats) if stride_floats else (x.shape[1] if x.ndim == 2 else 3)
+    off = np.ascontiguousarray(kf_offsets, dtype=np.int64)
+    W = off.shape[0] - 1
+    n = int(off[-1])
+    p = _f64(poses12)
+    xyz = np.zeros((max(n, 1), 3), dtype=np.float32); cnt = np.zeros(max(n, 1), dtype=np.float32); idx = np.zeros(max(n, 1), dtype=np.int64)
+    lib().vxo_submap_merge.restype = C.c_int64
+    m = lib().vxo_submap_merge(x.ctypes.data_as(C.POINTER(C.c_float)), C.c_int(stride), off.ctypes.data_as(C.POINTER(C.c_int64)), _dp(p), C.c_int(W), C.c_double(voxel_size),
+                               xyz.ctypes.data_as(C.POINTER(C.c_float)), cnt.ctypes.data_as(C.POINTER(C.c_float)), idx.ctypes.data_as(C.POINTER(C.c_int64)), C.c_int64(n))
+    return dict(xyz=xyz[:m], count=cnt[:m], index=idx[:m])
+
+
 def hba_window(coarse, fine, xyz_f32, kf_offsets, poses12, max_iter, thread_num=2, stride_floats=3):
     x = np.ascontiguousarray(xyz_f32, dtype=np.float32)
     off = np.ascontiguousarray(kf_offsets, dtype=np.int64)

@@ -227,3 +227,26 @@ def test_down_sampling_edges_and_scale(ctx):
     assert len(g2["index"]) <= len(g["index"])
     c = ctx.down_sampling(big, 0.25, close=True)
     assert len(c["index"]) == len(g["index"]) and np.array_equal(c["xyz"], big[c["index"], :3])
+
+
+@pytest.mark.parametrize("stride", [3, 12])
+def test_submap_merge_parity(ctx, stride):
+    """voxelslam.cpp:2428-2447 — merged cloud and its down-sampling bit-exact against the oracle."""
+    rng = np.random.default_rng(31 + stride)
+    W, per = 10, 30000
+    poses = np.stack([vx.true_pose(20.0, i) for i in range(W)])
+    pts = np.zeros((W * per, stride), dtype=np.float32)
+    pts[:, :3] = rng.uniform(-25, 25, (W * per, 3)).astype(np.float32)
+    off = np.arange(W + 1, dtype=np.int64) * per
+    off[3] -= 1000                                           # ragged keyframes
+    for vs in (0.0, 0.125, 1.0):
+        g = ctx.submap_merge(pts, off, poses, vs, stride_floats=stride)
+        o = oa.submap_merge(pts, off, poses, vs, stride_floats=stride)
+        assert len(g["index"]) == len(o["index"])
+        go, oo = np.argsort(g["index"]), np.argsort(o["index"])
+        assert np.array_equal(g["index"][go], o["index"][oo])
+        assert np.array_equal(g["xyz"][go].view(np.uint32), o["xyz"][oo].view(np.uint32))
+        assert np.array_equal(g["count"][go], o["count"][oo])
+    # empty window and empty keyframes
+    e = ctx.submap_merge(pts[:0], np.zeros(W + 1, dtype=np.int64), poses, 0.125, stride_floats=stride)
+    assert len(e["index"]) == 0

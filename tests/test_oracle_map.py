@@ -168,3 +168,23 @@ def test_down_sampling_oracle_matches_float32_restatement(close, stride):
             assert np.array_equal(o["xyz"][k], ref[i][0]) and o["count"][k] == ref[i][1]
     assert oa.down_sampling(pts, 0.0005, close=close, stride_floats=stride) is None       # tools.hpp:203: cloud left untouched
     assert len(oa.down_sampling(pts[:0], 0.5, close=close, stride_floats=stride)["index"]) == 0
+
+
+def test_submap_merge_oracle_consistency():
+    """voxelslam.cpp:2428-2447: merged cloud = float(dR v + dp) in the frame of keyframe 0, then down_sampling_voxel."""
+    rng = np.random.default_rng(21)
+    W, per = 4, 800
+    poses = np.stack([scenes.true_pose(12.0, i) for i in range(W)]) if hasattr(scenes, "true_pose") else None
+    if poses is None:
+        poses = np.stack([vx.true_pose(12.0, i) for i in range(W)])
+    pts = rng.uniform(-8, 8, (W * per, 3)).astype(np.float32)
+    off = np.arange(W + 1, dtype=np.int64) * per
+    raw = oa.submap_merge(pts, off, poses, 0.0)          # < 0.001: merged cloud returned as it is
+    R0, p0 = poses[0, :9].reshape(3, 3), poses[0, 9:]
+    for i in range(W):
+        Ri, pi = poses[i, :9].reshape(3, 3), poses[i, 9:]
+        ref = (pts[off[i]:off[i + 1]].astype(np.float64) @ (R0.T @ Ri).T + R0.T @ (pi - p0))
+        assert np.max(np.abs(raw["xyz"][off[i]:off[i + 1]] - ref)) < 2e-6
+    o = oa.submap_merge(pts, off, poses, 0.25)
+    d = oa.down_sampling(raw["xyz"], 0.25)
+    assert np.array_equal(np.sort(o["index"]), np.sort(d["index"])) and int(o["count"].sum()) == W * per

@@ -372,6 +372,25 @@ def _down_sampling(self, pts_f32, voxel_size, close=False, stride_floats=None):
 Context.down_sampling = _down_sampling
 
 
+def _submap_merge(self, xyz_f32, kf_offsets, poses12, voxel_size, stride_floats=None):
+    """Submap merge of HBA_add_edge (voxelslam.cpp:2428-2447): clouds into the frame of keyframe 0 + down_sampling_voxel."""
+    x = np.ascontiguousarray(xyz_f32, dtype=np.float32)
+    stride = int(stride_floats) if stride_floats else (x.shape[1] if x.ndim == 2 else 3)
+    off = np.ascontiguousarray(kf_offsets, dtype=np.int64)
+    W = off.shape[0] - 1
+    n = int(off[-1])
+    p = _f64(poses12)
+    xyz = np.zeros((max(n, 1), 3), dtype=np.float32); cnt = np.zeros(max(n, 1), dtype=np.float32); idx = np.zeros(max(n, 1), dtype=np.int64)
+    m = C.c_int64(0)
+    self._check(lib().vxs_submap_merge(self._p, x.ctypes.data_as(C.POINTER(C.c_float)), C.c_int(stride), off.ctypes.data_as(C.POINTER(C.c_int64)), _dp(p), C.c_int(W),
+                                       C.c_double(voxel_size), xyz.ctypes.data_as(C.POINTER(C.c_float)), cnt.ctypes.data_as(C.POINTER(C.c_float)),
+                                       idx.ctypes.data_as(C.POINTER(C.c_int64)), C.c_int64(n), C.byref(m)))
+    return dict(xyz=xyz[: m.value], count=cnt[: m.value], index=idx[: m.value])
+
+
+Context.submap_merge = _submap_merge
+
+
 class Factor:
     """Device-resident LidarFactor."""
 

@@ -16,6 +16,7 @@
 #include <deque>
 #include <stdexcept>
 #include <string>
+#include <algorithm>
 #include <vector>
 #include "../../../include/vxs.h"
 
@@ -242,6 +243,32 @@ inline void down_sampling_close(Context& ctx, pcl::PointCloud<PointType>& pl_fea
   out.reserve(size_t(m));
   for (int64_t i = 0; i < m; i++) out.push_back(pl_feat.points[size_t(pick[i])]);
   pl_feat.swap(out);
+}
+
+// Submap merge at the end of HBA_add_edge (voxelslam.cpp:2428-2447): smps[i]->plptr clouds -> *plptr in the frame of xs[0], down-sampled
+// at voxel_size / 8, intensity = map id of the keyframe the surviving point came from.
+template <class KeyframePtrVec>
+inline void submap_merge(Context& ctx, const std::vector<IMUST>& xs, const KeyframePtrVec& smps, double voxel_size, pcl::PointCloud<PointType>& out) {
+  const int W = int(xs.size());
+  std::vector<int64_t> off(size_t(W) + 1, 0);
+  for (int i = 0; i < W; i++) off[i + 1] = off[i] + int64_t(smps[i]->plptr->size());
+  std::vector<PointType> all; all.reserve(size_t(off[W]));
+  for (int i = 0; i < W; i++) all.insert(all.end(), smps[i]->plptr->points.begin(), smps[i]->plptr->points.end());
+  std::vector<double> p(size_t(W) * 12), st(24);
+  for (int i = 0; i < W; i++) { pack_state(xs[i], st.data()); std::memcpy(&p[12 * size_t(i)], st.data(), 96); }
+  const int64_t n = off[W];
+  std::vector<float> xyz(size_t(n) * 3), cnt(n);
+  std::vector<int64_t> first(n);
+  int64_t m = 0;
+  check(ctx.get(), vxs_submap_merge(ctx.get(), reinterpret_cast<const float*>(all.data()), int(sizeof(PointType) / sizeof(float)), off.data(), p.data(), W, voxel_size / 8,
+                                    xyz.data(), cnt.data(), first.data(), n, &m), "vxs_submap_merge");
+  out.clear(); out.reserve(size_t(m));
+  for (int64_t k = 0; k < m; k++) {
+    PointType pp = all[size_t(first[k])];
+    const int kf = int(std::upper_bound(off.begin(), off.end(), first[k]) - off.begin()) - 1;
+    pp.x = xyz[3 * k]; pp.y = xyz[3 * k + 1]; pp.z = xyz[3 * k + 2]; pp.curvature = cnt[k]; pp.intensity = smps[kf]->mp;
+    out.push_back(pp);
+  }
 }
 
 }  // namespace vxs_shim

@@ -25,7 +25,7 @@ using namespace vxs;
 
 // ------------------------------------------------------------------ scratch
 struct VoxScratch {
-  DevBuf<double> pts_d; DevBuf<float> pts_f; DevBuf<double> poses; DevBuf<long long> offsets; DevBuf<long long> bbox;
+  DevBuf<double> pts_d; DevBuf<float> pts_f, pts_f2; DevBuf<double> poses; DevBuf<long long> offsets; DevBuf<long long> bbox;
   DevBuf<unsigned long long> keysA, keysB; DevBuf<unsigned int> idxA, idxB; DevBuf<unsigned short> pathbits;
   DevBuf<unsigned int> hist, flags, scanbuf, blocksums, totals;
   DevBuf<unsigned int> rec_start, node_of_rec, node_rec_start, rec_node_flag;
@@ -41,7 +41,7 @@ static VoxScratch* scratch(vxs_ctx* c) { if (!c->vox_scratch) c->vox_scratch = n
 void vxs_voxelize_release(vxs_ctx* c) {
   if (!c->vox_scratch) return;
   VoxScratch* s = static_cast<VoxScratch*>(c->vox_scratch);
-  s->pts_d.release(); s->pts_f.release(); s->poses.release(); s->offsets.release(); s->bbox.release(); s->keysA.release(); s->keysB.release();
+  s->pts_d.release(); s->pts_f.release(); s->pts_f2.release(); s->poses.release(); s->offsets.release(); s->bbox.release(); s->keysA.release(); s->keysB.release();
   s->idxA.release(); s->idxB.release(); s->pathbits.release(); s->hist.release(); s->flags.release(); s->scanbuf.release(); s->blocksums.release();
   s->totals.release(); s->rec_start.release(); s->node_of_rec.release(); s->node_rec_start.release(); s->rec_node_flag.release(); s->rec_key.release();
   s->rec_local.release(); s->rec_world.release();
@@ -702,24 +702,16 @@ __global__ void __launch_bounds__(128) k_ds_reduce(const float* __restrict__ pts
   }
 }
 
-static int down_sample(vxs_ctx* ctx, int mode, const float* pts_host, int stride, int64_t n, double voxel_size, float* xyz_out, float* count_out, int64_t* index_out,
-                       int64_t cap, int64_t* n_out) {
-  if (!ctx || !n_out || n < 0 || stride < 3 || (n > 0 && !pts_host)) return VXS_ERR_ARG;
-  *n_out = -1;
-  if (voxel_size < 0.001) return VXS_OK;                 // tools.hpp:203 / 247: the cloud is left untouched
-  *n_out = 0;
-  if (n == 0) return VXS_OK;
-  if (n >= (1ll << 32)) return vxs_fail(ctx, VXS_ERR_ARG, "more than 2^32 points in one down-sampling call");
-  cudaSetDevice(ctx->device);
+// pts_dev: device-resident cloud (n points, stride floats)
+static int down_sample_dev(vxs_ctx* ctx, int mode, const float* pts_dev, int stride, int64_t n, double voxel_size, float* xyz_out, float* count_out, int64_t* index_out,
+                           int64_t cap, int64_t* n_out) {
   VoxScratch* s = scratch(ctx);
   cudaStream_t st = ctx->stream;
   VXS_CUDA(ctx, s->totals.reserve(16));
-  VXS_CUDA(ctx, s->pts_f.reserve(size_t(n) * stride));
-  VXS_CUDA(ctx, cudaMemcpyAsync(s->pts_f.p, pts_host, size_t(n) * stride * 4, cudaMemcpyHostToDevice, st));
   VXS_CUDA(ctx, s->bbox.reserve(6));
   const long long bb0[6] = {LLONG_MAX, LLONG_MAX, LLONG_MAX, LLONG_MIN, LLONG_MIN, LLONG_MIN};
   VXS_CUDA(ctx, cudaMemcpyAsync(s->bbox.p, bb0, sizeof bb0, cudaMemcpyHostToDevice, st));
-  VXS_LAUNCH(ctx, "k_ds_bbox", k_ds_bbox, std::min<unsigned>(nblk(size_t(n), 256), unsigned(ctx->sm_count) * 8), 256, 0, s->pts_f.p, stride, (long long)n, voxel_size, s->bbox.p);
+  VXS_LAUNCH(ctx, "k_ds_bbox", k_ds_bbox, std::min<unsigned>(nblk(size_t(n), 256), unsigned(ctx->sm_count) * 8), 256, 0, pts_dev, stride, (long long)n, voxel_size, s->bbox.p);
   long long bb[6];
   VXS_CUDA(ctx, cudaMemcpyAsync(bb, s->bbox.p, sizeof bb, cudaMemcpyDeviceToHost, st));
   VXS_CUDA(ctx, cudaStreamSynchronize(st));
@@ -728,7 +720,7 @@ static int down_sample(vxs_ctx* ctx, int mode, const float* pts_host, int stride
   const int key_bits = bits_for((unsigned long long)(ex * ey * ez));
   VXS_CUDA(ctx, s->keysA.reserve(size_t(n))); VXS_CUDA(ctx, s->keysB.reserve(size_t(n)));
   VXS_CUDA(ctx, s->idxA.reserve(size_t(n))); VXS_CUDA(ctx, s->idxB.reserve(size_t(n)));
-  VXS_LAUNCH(ctx, "k_ds_keys", k_ds_keys, nblk(size_t(n), 256), 256, 0, s->pts_f.p, stride, (long long)n, voxel_size, bb[0], bb[1], bb[2], (unsigned long long)ey, (unsigned long long)ez,
+  VXS_LAUNCH(ctx, "k_ds_keys", k_ds_keys, nblk(size_t(n), 256), 256, 0, pts_dev, stride, (long long)n, voxel_size, bb[0], bb[1], bb[2], (unsigned long long)ey, (unsigned long long)ez,
              s->keysA.p, s->idxA.p);
   unsigned long long* ks; unsigned int* vs;
   int rc = radix_sort(ctx, s, s->keysA.p, s->idxA.p, s->keysB.p, s->idxB.p, size_t(n), key_bits, &ks, &vs);
@@ -746,7 +738,7 @@ static int down_sample(vxs_ctx* ctx, int mode, const float* pts_host, int stride
   VXS_CUDA(ctx, s->rec_local.reserve(size_t(R) * 2 + 2)); VXS_CUDA(ctx, s->rec_world.reserve(size_t(R) + 1));
   float* d_xyz = reinterpret_cast<float*>(s->rec_local.p); float* d_cnt = d_xyz + 3 * size_t(R);
   long long* d_pick = reinterpret_cast<long long*>(s->rec_world.p);
-  VXS_LAUNCH(ctx, "k_ds_reduce", k_ds_reduce, nblk(size_t(R), 128), 128, 0, s->pts_f.p, stride, vs, s->rec_start.p, R, mode, d_xyz, d_cnt, d_pick);
+  VXS_LAUNCH(ctx, "k_ds_reduce", k_ds_reduce, nblk(size_t(R), 128), 128, 0, pts_dev, stride, vs, s->rec_start.p, R, mode, d_xyz, d_cnt, d_pick);
   *n_out = int64_t(R);
   const size_t ncopy = size_t(std::min<int64_t>(cap, int64_t(R)));
   if (xyz_out && ncopy) VXS_CUDA(ctx, cudaMemcpyAsync(xyz_out, d_xyz, ncopy * 12, cudaMemcpyDeviceToHost, st));
@@ -755,6 +747,79 @@ static int down_sample(vxs_ctx* ctx, int mode, const float* pts_host, int stride
   VXS_CUDA(ctx, cudaStreamSynchronize(st));
   return VXS_OK;
 }
+static int down_sample(vxs_ctx* ctx, int mode, const float* pts_host, int stride, int64_t n, double voxel_size, float* xyz_out, float* count_out, int64_t* index_out,
+                       int64_t cap, int64_t* n_out) {
+  if (!ctx || !n_out || n < 0 || stride < 3 || (n > 0 && !pts_host)) return VXS_ERR_ARG;
+  *n_out = -1;
+  if (voxel_size < 0.001) return VXS_OK;                 // tools.hpp:203 / 247: the cloud is left untouched
+  *n_out = 0;
+  if (n == 0) return VXS_OK;
+  if (n >= (1ll << 32)) return vxs_fail(ctx, VXS_ERR_ARG, "more than 2^32 points in one down-sampling call");
+  cudaSetDevice(ctx->device);
+  VoxScratch* s = scratch(ctx);
+  VXS_CUDA(ctx, s->pts_f.reserve(size_t(n) * stride));
+  VXS_CUDA(ctx, cudaMemcpyAsync(s->pts_f.p, pts_host, size_t(n) * stride * 4, cudaMemcpyHostToDevice, ctx->stream));
+  return down_sample_dev(ctx, mode, s->pts_f.p, stride, n, voxel_size, xyz_out, count_out, index_out, cap, n_out);
+}
+
+// ------------------------------------------------------------------ submap merge of HBA_add_edge (voxelslam.cpp:2428-2447)
+// every keyframe cloud is moved into the frame of keyframe 0: v' = dR v + dp in fp64, stored as float, dR = R_0^T R_i, dp = R_0^T (p_i - p_0)
+__global__ void __launch_bounds__(256) k_merge_transform(const float* __restrict__ pts, int stride, const long long* __restrict__ offsets, int W, const double* __restrict__ rel12,
+                                                         long long n, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int lo = 0, hi = W;
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (offsets[mid] <= i) lo = mid; else hi = mid; }
+  const double* T = rel12 + 12 * lo;
+  const float* p = pts + size_t(i) * stride;
+  const double x = (double)p[0], y = (double)p[1], z = (double)p[2];
+  out[3 * i] = __double2float_rn(dot3_rn(T[0], T[1], T[2], x, y, z, T[9]));
+  out[3 * i + 1] = __double2float_rn(dot3_rn(T[3], T[4], T[5], x, y, z, T[10]));
+  out[3 * i + 2] = __double2float_rn(dot3_rn(T[6], T[7], T[8], x, y, z, T[11]));
+}
+extern "C" int vxs_submap_merge(vxs_ctx* ctx, const float* xyz, int stride_floats, const int64_t* kf_offsets, const double* poses12, int W, double voxel_size,
+                                float* xyz_out, float* count_out, int64_t* first_index_out, int64_t cap, int64_t* n_out) {
+  if (!ctx || !n_out || !kf_offsets || !poses12 || W <= 0 || stride_floats < 3) return VXS_ERR_ARG;
+  const int64_t n = kf_offsets[W];
+  if (n < 0 || (n > 0 && !xyz)) return VXS_ERR_ARG;
+  *n_out = 0;
+  if (n == 0) return VXS_OK;
+  if (n >= (1ll << 32)) return vxs_fail(ctx, VXS_ERR_ARG, "more than 2^32 points in one submap merge");
+  cudaSetDevice(ctx->device);
+  VoxScratch* s = scratch(ctx);
+  cudaStream_t st = ctx->stream;
+  // relative poses on the host (W x 12, a few hundred flops): dR = R_0^T R_i, dp = R_0^T (p_i - p_0), sums in index order
+  std::vector<double> rel(size_t(W) * 12);
+  const double* P0 = poses12;
+  for (int i = 0; i < W; i++) {
+    const double* Pi = poses12 + 12 * size_t(i);
+    const double d[3] = {Pi[9] - P0[9], Pi[10] - P0[10], Pi[11] - P0[11]};
+    for (int r = 0; r < 3; r++) {
+      for (int c = 0; c < 3; c++) rel[12 * size_t(i) + 3 * r + c] = (P0[r] * Pi[c] + P0[3 + r] * Pi[3 + c]) + P0[6 + r] * Pi[6 + c];
+      rel[12 * size_t(i) + 9 + r] = (P0[r] * d[0] + P0[3 + r] * d[1]) + P0[6 + r] * d[2];
+    }
+  }
+  VXS_CUDA(ctx, s->pts_f.reserve(size_t(n) * stride_floats));
+  VXS_CUDA(ctx, cudaMemcpyAsync(s->pts_f.p, xyz, size_t(n) * stride_floats * 4, cudaMemcpyHostToDevice, st));
+  VXS_CUDA(ctx, s->poses.reserve(size_t(W) * 12));
+  VXS_CUDA(ctx, cudaMemcpyAsync(s->poses.p, rel.data(), rel.size() * 8, cudaMemcpyHostToDevice, st));
+  VXS_CUDA(ctx, s->offsets.reserve(size_t(W) + 1));
+  VXS_CUDA(ctx, cudaMemcpyAsync(s->offsets.p, kf_offsets, (size_t(W) + 1) * 8, cudaMemcpyHostToDevice, st));
+  VXS_CUDA(ctx, s->pts_f2.reserve(size_t(n) * 3));
+  VXS_LAUNCH(ctx, "k_merge_transform", k_merge_transform, nblk(size_t(n), 256), 256, 0, s->pts_f.p, stride_floats, s->offsets.p, W, s->poses.p, (long long)n, s->pts_f2.p);
+  VXS_CUDA(ctx, cudaStreamSynchronize(st));   // rel goes out of scope
+  if (voxel_size < 0.001) {                   // down_sampling_voxel would return at once: the merged cloud itself is the result
+    *n_out = n;
+    const size_t ncopy = size_t(std::min<int64_t>(cap, n));
+    if (xyz_out && ncopy) VXS_CUDA(ctx, cudaMemcpyAsync(xyz_out, s->pts_f2.p, ncopy * 12, cudaMemcpyDeviceToHost, st));
+    if (count_out) for (size_t i = 0; i < ncopy; i++) count_out[i] = 0.0f;
+    if (first_index_out) for (size_t i = 0; i < ncopy; i++) first_index_out[i] = int64_t(i);
+    VXS_CUDA(ctx, cudaStreamSynchronize(st));
+    return VXS_OK;
+  }
+  return down_sample_dev(ctx, 0, s->pts_f2.p, 3, n, voxel_size, xyz_out, count_out, first_index_out, cap, n_out);
+}
+
 extern "C" int vxs_down_sampling_voxel(vxs_ctx* ctx, const float* pts, int stride_floats, int64_t n, double voxel_size, float* xyz_out, float* count_out, int64_t* first_index_out,
                                        int64_t cap, int64_t* n_out) {
   return down_sample(ctx, 0, pts, stride_floats, n, voxel_size, xyz_out, count_out, first_index_out, cap, n_out);
