@@ -260,6 +260,10 @@ def run_ours(args):
     roof_hess = roof(["k_jac", "k_syrk"], bytes_hess, flops_hess)
     roof_resid = roof(["k_cluster_sum", "k_eig_residual"], bytes_resid)
     roof_jac = roof(["k_jac"], E * 80 + V * 176 + E * 144)
+    for r_, names_ in ((roof_hess, ["k_jac_slab", "k_syrk"]), (roof_resid, ["k_cluster_sum", "k_eig_residual"]), (roof_jac, ["k_jac_slab"])):
+        if r_ is not None:
+            r_["traffic"] = ncu_traffic(names_)
+            r_["traffic_source"] = "profiles/r01_ncu_full_ba_kernels.txt (ncu --set full of this command, DRAM read + write per launch)"
     dom = max(kern.items(), key=lambda kv_: kv_[1]["ms_per_step"])[0] if kern else None
 
     c2 = ds = None
@@ -289,6 +293,28 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier(); dist.destroy_process_group()
+
+
+def ncu_traffic(kernels):
+    """DRAM bytes per launch (read + write) of the named kernels from the committed `ncu --set full` summary of this same command
+    (profiles/r01_ncu_full_ba_kernels.txt); None when the summary is absent."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_ncu_full_ba_kernels.txt")
+    try:
+        txt = open(path).read()
+    except OSError:
+        return None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    total, seen = 0.0, set()
+    for blk in txt.split("== ")[1:]:
+        name = blk.split()[0]
+        if name not in kernels or name in seen:
+            continue
+        seen.add(name)
+        for line in blk.splitlines():
+            f = line.split()
+            if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                total += float(f[1]) * unit.get(f[2], 1.0)
+    return total if len(seen) == len(set(kernels)) else None
 
 
 def ds_leg(ctx):

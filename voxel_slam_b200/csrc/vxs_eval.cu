@@ -14,6 +14,7 @@
 //   k_pairs         sparse windows (k << W, top-level global BA): group per voxel, block pairs straight to RED.
 //   k_assemble      dense n x n system from the block accumulators (+ the CPU-evaluated IMU 30x30 blocks), mirror of the lower triangle.
 #include <algorithm>
+#include <cstdlib>
 #include "vxs_internal.h"
 #include "vxs_math.cuh"
 
@@ -770,7 +771,13 @@ int vxs_eval_hessian_dev(vxs_ctx* ctx, vxs_factor* f, const double* poses_dev, i
       const SyrkGeom g = sy_geom(W);
       const int ngv = int((f->V + 3) / 4);                 // voxel groups of 4 (12 rows of X each)
       // enough chunks to fill the machine a few times over; tiles of one chunk are adjacent in launch order (L2 reuse of X)
-      int target_ctas = ctx->sm_count * 2 * 4;
+      // Waves: CTA durations differ by 3x between tile kinds (full off-diagonal / diagonal / remainder) and the CTAs are dispatched in order,
+      // so the last wave leaves SMs idle for up to one CTA duration; ncu showed 68.6 % DMMA-pipe activity on average against 85.5 % on
+      // the busiest SM at 4 waves.  More, shorter CTAs shrink that tail (each pays one pipeline fill and one 96x96 RED epilogue); measured at the
+      // metric shape: 4 waves 0.781 ms, 8: 0.737, 12: 0.736, 16: 0.742, 24: 0.762.
+      static int waves = -1;
+      if (waves < 0) { const char* e = getenv("VXS_SYRK_WAVES"); waves = e ? std::max(1, atoi(e)) : 12; }
+      int target_ctas = ctx->sm_count * 2 * waves;
       int nchunks = std::max(1, std::min<int>(target_ctas / g.ntiles, (ngv + 7) / 8));   // floor: CTAs fit whole waves of 2 per SM
       int gpc = (ngv + nchunks - 1) / nchunks;
       nchunks = (ngv + gpc - 1) / gpc;
