@@ -85,6 +85,15 @@ int vxs_factor_set_win_size(vxs_factor* f, int win_size);                       
 int vxs_factor_push_voxels(vxs_factor* f, int64_t n_vox, const int64_t* entry_ptr, const int32_t* entry_frame,
                            const double* entry_cluster10, const double* fix10, const double* coe, const double* eig12,
                            const double* sum10);
+/* Asynchronous variant for an EMPTY factor (the per-solve upload of the shim): returns as soon as the copies are queued.  The bulk
+ * (clusters, 80 B per entry) travels on a copy stream in chunks of whole voxel groups and the first Hessian build of the next
+ * vxs_lidar_ba / vxs_li_ba runs chunk by chunk behind it, so the PCIe transfer overlaps the Jacobian and SYRK kernels.  The host
+ * buffers must stay valid — and should be pinned (vxs_host_alloc) — until that solve (or vxs_factor_sync_uploads) has returned.
+ * Falls back to the synchronous vxs_factor_push_voxels when the factor is not empty or the push is tiny. */
+int vxs_factor_push_voxels_async(vxs_factor* f, int64_t n_vox, const int64_t* entry_ptr, const int32_t* entry_frame,
+                                 const double* entry_cluster10, const double* fix10, const double* coe, const double* eig12,
+                                 const double* sum10);
+int vxs_factor_sync_uploads(vxs_factor* f);   /* host-side wait for everything queued by the async push */
 /* Same, in the reference's dense layout vector<vector<PointCluster>>: clusters10 is [n_vox][win_size][10], N==0 = absent. */
 int vxs_factor_push_voxels_dense(vxs_factor* f, int64_t n_vox, const double* clusters10, const double* fix10,
                                  const double* coe, const double* eig12, const double* sum10);

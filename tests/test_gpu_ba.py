@@ -194,3 +194,38 @@ def test_two_concurrent_callers(ctx):
     [t.join() for t in th]
     for o in outs:
         assert np.max(np.abs(o["poses"] - ref["poses"])) < 1e-8
+
+
+def test_async_push_matches_sync_push(ctx):
+    """vxs_factor_push_voxels_async: the chunked first Hessian build behind the upload events gives the same solve as the synchronous
+    push (accumulation order differs: RED of four voxel chunks instead of one launch)."""
+    W = 12
+    sc = scenes.make_window(W=W, pts_per_scan=40000, L=14.0, seed=23)
+    fs = gpu_factor(ctx, sc)
+    ptr, fr, cl, fix, coe = fs.read_structure()
+    eig, s = fs.read_back()
+    assert ptr.shape[0] - 1 >= 256          # large enough for the chunked path
+    ref = ctx.lidar_ba(fs, sc["poses_est"], max_iter=3, thd_num=2)
+    hp = dict(ptr=vx.api.pinned_array(ptr.shape, np.int64), fr=vx.api.pinned_array(fr.shape, np.int32), cl=vx.api.pinned_array(cl.shape, np.float64),
+              eig=vx.api.pinned_array(eig.shape, np.float64), s=vx.api.pinned_array(s.shape, np.float64), fix=vx.api.pinned_array(fix.shape, np.float64))
+    hp["ptr"][:] = ptr; hp["fr"][:] = fr; hp["cl"][:] = cl; hp["eig"][:] = eig; hp["s"][:] = s; hp["fix"][:] = fix
+    fa = vx.Factor(ctx, W)
+    for rep in range(2):                     # second round: clear() while nothing is pending, then reuse of the staging buffers
+        fa.clear()
+        fa.push_voxels_async(hp["ptr"], hp["fr"], hp["cl"], hp["eig"], hp["s"], fix10=hp["fix"])
+        got = ctx.lidar_ba(fa, sc["poses_est"], max_iter=3, thd_num=2)
+        assert len(got["trace"]) == len(ref["trace"])
+        for a, b in zip(got["trace"], ref["trace"]):
+            assert a["accepted"] == b["accepted"] and abs(a["r1"] - b["r1"]) / b["r1"] < 1e-10 and abs(a["r2"] - b["r2"]) / b["r2"] < 1e-10
+        assert got["trace"][0]["r1"] == ref["trace"][0]["r1"]      # same cached eigenvalues, same deterministic reduction
+        assert np.max(np.abs(got["poses"] - ref["poses"])) < 1e-9 * np.max(np.abs(ref["poses"] - sc["poses_est"]))
+        assert relinf(got["hess"], ref["hess"]) < 1e-12
+    # consumers other than the Hessian build wait for the upload too
+    fa.clear()
+    fa.push_voxels_async(hp["ptr"], hp["fr"], hp["cl"], hp["eig"], hp["s"], fix10=hp["fix"])
+    p2, f2, c2, _, _ = fa.read_structure()
+    assert np.array_equal(p2, ptr) and np.array_equal(f2, fr) and np.array_equal(c2, cl)
+    fa.clear()
+    fa.push_voxels_async(hp["ptr"], hp["fr"], hp["cl"], hp["eig"], hp["s"], fix10=hp["fix"])
+    assert abs(ctx.evaluate_residual(fa, sc["poses_est"]) - ctx.evaluate_residual(fs, sc["poses_est"])) <= 1e-12 * abs(ctx.evaluate_residual(fs, sc["poses_est"]))
+    fa.sync_uploads()

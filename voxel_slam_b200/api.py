@@ -431,6 +431,22 @@ class Factor:
         self.ctx._check(lib().vxs_factor_push_voxels(self._p, C.c_int64(ptr.shape[0] - 1), ptr.ctypes.data_as(C.POINTER(C.c_int64)), fr.ctypes.data_as(C.POINTER(C.c_int32)),
                                                      _dp(cl), _dp(fx), _dp(co), _dp(e), _dp(s)))
 
+    def push_voxels_async(self, entry_ptr, entry_frame, entry_cluster10, eig12, sum10, fix10=None, coe=None):
+        """vxs_factor_push_voxels_async: returns with the copies queued; the arrays are kept alive on this object until the next push /
+        sync (pass pinned arrays from api.pinned_array for a real overlap)."""
+        ptr = np.ascontiguousarray(entry_ptr, dtype=np.int64)
+        fr = np.ascontiguousarray(entry_frame, dtype=np.int32)
+        cl, e, s = _f64(entry_cluster10), _f64(eig12), _f64(sum10)
+        fx = _f64(fix10) if fix10 is not None else None
+        co = _f64(coe) if coe is not None else None
+        self._async_keep = (ptr, fr, cl, e, s, fx, co)
+        self.ctx._check(lib().vxs_factor_push_voxels_async(self._p, C.c_int64(ptr.shape[0] - 1), ptr.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                           fr.ctypes.data_as(C.POINTER(C.c_int32)), _dp(cl), _dp(fx), _dp(co), _dp(e), _dp(s)))
+
+    def sync_uploads(self):
+        self.ctx._check(lib().vxs_factor_sync_uploads(self._p))
+        self._async_keep = None
+
     def push_voxels_raw(self, n_vox, ptr_p, frame_p, cl_p, fix_p, coe_p, eig_p, sum_p):
         """Raw-pointer variant (pinned buffers from vxs_host_alloc) used by bench.py's end-to-end leg."""
         self.ctx._check(lib().vxs_factor_push_voxels(self._p, C.c_int64(n_vox), ptr_p, frame_p, cl_p, fix_p, coe_p, eig_p, sum_p))

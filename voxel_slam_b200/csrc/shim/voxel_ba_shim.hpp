@@ -14,6 +14,7 @@
 #pragma once
 #include <cstring>
 #include <deque>
+#include <new>
 #include <stdexcept>
 #include <string>
 #include <algorithm>
@@ -36,6 +37,18 @@ class Context {
   vxs_ctx* get() const { return ctx_; }
  private:
   vxs_ctx* ctx_ = nullptr;
+};
+
+// page-locked std::vector storage for the bulk of the staged factor, so that vxs_factor_push_voxels_async really overlaps PCIe and compute
+template <class T>
+struct PinnedAllocator {
+  using value_type = T;
+  PinnedAllocator() = default;
+  template <class U> PinnedAllocator(const PinnedAllocator<U>&) {}
+  T* allocate(size_t n) { void* p = nullptr; if (vxs_host_alloc(&p, uint64_t(n) * sizeof(T)) != 0 || !p) throw std::bad_alloc(); return static_cast<T*>(p); }
+  void deallocate(T* p, size_t) { vxs_host_free(p); }
+  template <class U> bool operator==(const PinnedAllocator<U>&) const { return true; }
+  template <class U> bool operator!=(const PinnedAllocator<U>&) const { return false; }
 };
 
 // LidarFactor: push_voxel() stages on the host exactly like the reference's vectors; the first solver call uploads the batch.
@@ -73,7 +86,9 @@ class LidarFactor {
     if (dirty_) {
       check(ctx_, vxs_factor_clear(dev_), "vxs_factor_clear");
       check(ctx_, vxs_factor_set_win_size(dev_, win_size), "vxs_factor_set_win_size");
-      check(ctx_, vxs_factor_push_voxels(dev_, int64_t(size()), ptr_.data(), frame_.data(), cl_.data(), fix_.data(), coe_.data(), eig12.data(), sum10.data()), "vxs_factor_push_voxels");
+      // asynchronous: the solver's first Hessian build runs behind the upload chunks; the staged vectors stay untouched until it returns
+      check(ctx_, vxs_factor_push_voxels_async(dev_, int64_t(size()), ptr_.data(), frame_.data(), cl_.data(), fix_.data(), coe_.data(), eig12.data(), sum10.data()),
+            "vxs_factor_push_voxels_async");
       dirty_ = false;
     }
     return dev_;
@@ -85,8 +100,9 @@ class LidarFactor {
   vxs_ctx* ctx_;
   vxs_factor* dev_ = nullptr;
   std::vector<int64_t> ptr_{0};
-  std::vector<int32_t> frame_;
-  std::vector<double> cl_, fix_, coe_;
+  std::vector<int32_t, PinnedAllocator<int32_t>> frame_;
+  std::vector<double, PinnedAllocator<double>> cl_;
+  std::vector<double> fix_, coe_;
   bool dirty_ = false;
 };
 

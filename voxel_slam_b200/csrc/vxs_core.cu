@@ -47,7 +47,7 @@ extern "C" int vxs_ctx_destroy(vxs_ctx* c) {
   for (auto ev : c->event_pool) cudaEventDestroy(ev);
   c->Hraw.release(); c->Mp.release(); c->Lm.release(); c->himu.release(); c->gimu.release(); c->jact.release(); c->dvec.release();
   c->rhs.release(); c->dx.release(); c->dtmp.release(); c->states_a.release(); c->states_b.release(); c->perm.release();
-  c->scal.release(); c->flags.release(); c->stage.release(); c->stage_i64.release();
+  c->scal.release(); c->flags.release(); c->stage.release(); c->stage2.release(); c->stage_i64.release();
   if (c->h_pin) cudaFreeHost(c->h_pin);
   if (c->ev_copy) cudaEventDestroy(c->ev_copy);
   if (c->ev_t0) cudaEventDestroy(c->ev_t0);
@@ -198,6 +198,9 @@ static void factor_free_arrays(vxs_factor* f) {
 static void vxs_factor_release_device(vxs_factor* f) {
   factor_free_arrays(f);
   f->X.release(); f->C.release(); f->gD.release(); f->partial.release(); f->counter.release(); f->cache_copy.release(); f->vc.release();
+  for (int c = 0; c < vxs_factor::UP_MAX; c++) if (f->up_ev[c]) { cudaEventDestroy(f->up_ev[c]); f->up_ev[c] = nullptr; }
+  if (f->up_fence) { cudaEventDestroy(f->up_fence); f->up_fence = nullptr; }
+  f->up_pending = f->up_n = 0;
   f->V = f->E = 0; f->cache_copy_V = 0;
 }
 extern "C" int vxs_factor_destroy(vxs_factor* f) {
@@ -206,13 +209,19 @@ extern "C" int vxs_factor_destroy(vxs_factor* f) {
     vxs_ctx* c = f->ctx;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     vxs_factor_release_device(f);
     for (size_t i = 0; i < c->factors.size(); i++) if (c->factors[i] == f) { c->factors.erase(c->factors.begin() + i); break; }
   }
   delete f;
   return VXS_OK;
 }
-extern "C" int vxs_factor_clear(vxs_factor* f) { if (!f || !f->ctx) return VXS_ERR_ARG; f->V = 0; f->E = 0; f->has_fix = false; return VXS_OK; }
+extern "C" int vxs_factor_clear(vxs_factor* f) {
+  if (!f || !f->ctx) return VXS_ERR_ARG;
+  int rc = vxs_factor_wait_uploads(f);   // an upload still in flight targets the arrays the next push will write
+  f->V = 0; f->E = 0; f->has_fix = false;
+  return rc;
+}
 extern "C" int vxs_factor_set_win_size(vxs_factor* f, int w) { if (!f || w <= 0 || f->V != 0) return VXS_ERR_ARG; f->W = w; return VXS_OK; }
 extern "C" int vxs_factor_counts(const vxs_factor* f, int64_t* n_vox, int64_t* n_entries, int* win_size) {
   if (!f) return VXS_ERR_ARG;
@@ -298,6 +307,7 @@ extern "C" int vxs_factor_push_voxels(vxs_factor* f, int64_t n_vox, const int64_
   if (n_vox == 0) return VXS_OK;
   vxs_ctx* ctx = f->ctx;
   cudaSetDevice(ctx->device);
+  { int rcw = vxs_factor_wait_uploads(f); if (rcw) return rcw; }
   const int64_t n_ent = entry_ptr[n_vox] - entry_ptr[0];
   if (entry_ptr[0] != 0 || n_ent < 0) return vxs_fail(ctx, VXS_ERR_ARG, "entry_ptr must start at 0 and be non-decreasing");
   int rc = vxs_factor_reserve(f, size_t(f->V + n_vox), size_t(f->E + n_ent));
@@ -337,6 +347,86 @@ extern "C" int vxs_factor_push_voxels(vxs_factor* f, int64_t n_vox, const int64_
   return VXS_OK;
 }
 
+int vxs_factor_wait_uploads(vxs_factor* f) {
+  if (!f || !f->ctx || f->up_pending == 0) return VXS_OK;
+  vxs_ctx* ctx = f->ctx;
+  for (int c = 0; c < f->up_n; c++) VXS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, f->up_ev[c], 0));
+  f->up_pending = 0;
+  return VXS_OK;
+}
+extern "C" int vxs_factor_sync_uploads(vxs_factor* f) {
+  if (!f || !f->ctx) return VXS_ERR_ARG;
+  if (f->up_n > 0 && f->up_ev[f->up_n - 1]) VXS_CUDA(f->ctx, cudaEventSynchronize(f->up_ev[f->up_n - 1]));   // chunks complete in order on one stream
+  VXS_CUDA(f->ctx, cudaStreamSynchronize(f->ctx->stream));
+  return VXS_OK;
+}
+
+// Same contract as vxs_factor_push_voxels for an EMPTY factor, but nothing is waited for: the per-voxel records go up on the ctx stream,
+// the clusters (the bulk: 80 B per entry) on the copy stream in chunks of whole voxel groups, each followed by its AoS -> SoA conversion
+// and an event.  The first Hessian build then runs chunk by chunk behind those events, so the PCIe transfer of chunk c+1 overlaps the
+// Jacobian / SYRK work on chunk c.  The host buffers must stay valid (and should be pinned) until a consuming call has returned.
+extern "C" int vxs_factor_push_voxels_async(vxs_factor* f, int64_t n_vox, const int64_t* entry_ptr, const int32_t* entry_frame, const double* entry_cluster10,
+                                            const double* fix10, const double* coe, const double* eig12, const double* sum10) {
+  if (!f || !f->ctx || n_vox < 0 || (n_vox > 0 && (!entry_ptr || !entry_frame || !entry_cluster10 || !eig12 || !sum10))) return VXS_ERR_ARG;
+  const int NCH = 4;
+  if (f->V != 0 || n_vox < 64 * NCH) return vxs_factor_push_voxels(f, n_vox, entry_ptr, entry_frame, entry_cluster10, fix10, coe, eig12, sum10);
+  vxs_ctx* ctx = f->ctx;
+  cudaSetDevice(ctx->device);
+  int rc = vxs_factor_wait_uploads(f);
+  if (rc) return rc;
+  const int64_t n_ent = entry_ptr[n_vox] - entry_ptr[0];
+  if (entry_ptr[0] != 0 || n_ent < 0) return vxs_fail(ctx, VXS_ERR_ARG, "entry_ptr must start at 0 and be non-decreasing");
+  rc = vxs_factor_reserve(f, size_t(n_vox), size_t(n_ent));
+  if (rc) return rc;
+  cudaStream_t s = ctx->stream, cs = ctx->copy_stream;
+  const size_t n = size_t(n_vox), ne = size_t(n_ent);
+  VXS_CUDA(ctx, ctx->stage.reserve(n * 12));
+  VXS_CUDA(ctx, ctx->stage2.reserve(ne * 10));
+  VXS_CUDA(ctx, ctx->stage_i64.reserve(n + 1));
+  if (!f->up_fence) VXS_CUDA(ctx, cudaEventCreateWithFlags(&f->up_fence, cudaEventDisableTiming));
+  for (int c = 0; c < NCH; c++) if (!f->up_ev[c]) VXS_CUDA(ctx, cudaEventCreateWithFlags(&f->up_ev[c], cudaEventDisableTiming));
+  // the copy stream starts behind whatever the ctx stream still does with this factor's arrays
+  VXS_CUDA(ctx, cudaEventRecord(f->up_fence, s));
+  VXS_CUDA(ctx, cudaStreamWaitEvent(cs, f->up_fence, 0));
+  // clusters + frame indices, chunked by voxel groups of 4 (the unit of the dense Jacobian / SYRK kernels)
+  const int64_t ngv = (n_vox + 3) / 4;
+  for (int c = 0; c < NCH; c++) {
+    const int64_t g0 = ngv * c / NCH, g1 = ngv * (c + 1) / NCH;
+    const int64_t v0 = std::min<int64_t>(4 * g0, n_vox), v1 = std::min<int64_t>(4 * g1, n_vox);
+    const size_t e0 = size_t(entry_ptr[v0]), e1 = size_t(entry_ptr[v1]);
+    if (e1 > e0) {
+      VXS_CUDA(ctx, cudaMemcpyAsync(ctx->stage2.p + e0 * 10, entry_cluster10 + e0 * 10, (e1 - e0) * 80, cudaMemcpyHostToDevice, cs));
+      VXS_CUDA(ctx, cudaMemcpyAsync(f->frame + e0, entry_frame + e0, (e1 - e0) * 4, cudaMemcpyHostToDevice, cs));
+      k_aos_to_soa<<<nblk((e1 - e0) * 10, 256), 256, 0, cs>>>(ctx->stage2.p + e0 * 10, f->cl, e1 - e0, 10, f->Ecap, e0);
+      ctx->launches++;
+    }
+    VXS_CUDA(ctx, cudaEventRecord(f->up_ev[c], cs));
+    f->up_group_end[c] = int(g1);
+  }
+  f->up_n = NCH; f->up_pending = NCH;
+  // CSR structure and per-voxel records on the ctx stream (small: 4 + 8 + 96 + 80 (+80) bytes per voxel)
+  VXS_CUDA(ctx, cudaMemcpyAsync(ctx->stage_i64.p, entry_ptr, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+  VXS_LAUNCH(ctx, "k_ptr_offset", k_ptr_offset, nblk(n + 1, 256), 256, 0, ctx->stage_i64.p, f->ptr, n + 1, int64_t(0));
+  if (fix10) {
+    VXS_CUDA(ctx, cudaMemcpyAsync(ctx->stage.p, fix10, n * 10 * 8, cudaMemcpyHostToDevice, s));
+    VXS_LAUNCH(ctx, "k_aos_to_soa", k_aos_to_soa, nblk(n * 10, 256), 256, 0, ctx->stage.p, f->fix, n, 10, f->Vcap, size_t(0));
+    bool any = false;
+    for (size_t i = 0; i < n && !any; i++) any = fix10[i * 10 + 9] != 0.0;
+    f->has_fix = f->has_fix || any;
+  } else {
+    VXS_LAUNCH(ctx, "k_zero_rows", k_zero_rows, nblk(n * 10, 256), 256, 0, f->fix, n, 10, f->Vcap, size_t(0));
+  }
+  if (coe) VXS_CUDA(ctx, cudaMemcpyAsync(f->coe, coe, n * 8, cudaMemcpyHostToDevice, s));
+  else VXS_LAUNCH(ctx, "k_fill", k_fill, nblk(n, 256), 256, 0, f->coe, n, 1.0);
+  VXS_CUDA(ctx, cudaMemcpyAsync(ctx->stage.p, eig12, n * 12 * 8, cudaMemcpyHostToDevice, s));
+  VXS_LAUNCH(ctx, "k_aos_to_soa", k_aos_to_soa, nblk(n * 12, 256), 256, 0, ctx->stage.p, f->eig, n, 12, f->Vcap, size_t(0));
+  VXS_CUDA(ctx, cudaMemcpyAsync(ctx->stage.p, sum10, n * 10 * 8, cudaMemcpyHostToDevice, s));
+  VXS_LAUNCH(ctx, "k_aos_to_soa", k_aos_to_soa, nblk(n * 10, 256), 256, 0, ctx->stage.p, f->sum, n, 10, f->Vcap, size_t(0));
+  f->V = n_vox; f->E = n_ent;
+  VXS_LAUNCH(ctx, "k_entry_to_voxel", k_entry_to_voxel, nblk(n, 128), 128, 0, f->ptr, f->vox, int64_t(0), f->V);
+  return VXS_OK;
+}
+
 extern "C" int vxs_factor_push_voxels_dense(vxs_factor* f, int64_t n_vox, const double* clusters10, const double* fix10, const double* coe,
                                             const double* eig12, const double* sum10) {
   if (!f || !f->ctx || n_vox < 0 || (n_vox > 0 && !clusters10)) return VXS_ERR_ARG;
@@ -361,6 +451,7 @@ extern "C" int vxs_factor_cache_save(vxs_factor* f) {
   cudaSetDevice(ctx->device);
   const size_t V = size_t(f->V);
   if (V == 0) { f->cache_copy_V = 0; return VXS_OK; }
+  { int rcw = vxs_factor_wait_uploads(f); if (rcw) return rcw; }
   VXS_CUDA(ctx, f->cache_copy.reserve(V * 22));
   VXS_CUDA(ctx, cudaMemcpy2DAsync(f->cache_copy.p, V * 8, f->eig, f->Vcap * 8, V * 8, 12, cudaMemcpyDeviceToDevice, ctx->stream));
   VXS_CUDA(ctx, cudaMemcpy2DAsync(f->cache_copy.p + V * 12, V * 8, f->sum, f->Vcap * 8, V * 8, 10, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -385,6 +476,7 @@ extern "C" int vxs_factor_read_back(vxs_factor* f, double* eig12, double* sum10)
   cudaSetDevice(ctx->device);
   const size_t n = size_t(f->V);
   if (n == 0) return VXS_OK;
+  { int rcw = vxs_factor_wait_uploads(f); if (rcw) return rcw; }
   cudaStream_t s = ctx->stream;
   VXS_CUDA(ctx, ctx->stage.reserve(n * 22));
   if (eig12) {
@@ -404,6 +496,7 @@ extern "C" int vxs_factor_read_structure(vxs_factor* f, int64_t* entry_ptr, int3
   vxs_ctx* ctx = f->ctx;
   cudaSetDevice(ctx->device);
   const size_t n = size_t(f->V), ne = size_t(f->E);
+  { int rcw = vxs_factor_wait_uploads(f); if (rcw) return rcw; }
   cudaStream_t s = ctx->stream;
   if (entry_ptr) {
     std::vector<int32_t> p32(n + 1, 0);

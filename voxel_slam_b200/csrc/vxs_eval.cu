@@ -324,7 +324,8 @@ __global__ void __launch_bounds__(128, 3) k_jac(FactorView f, const double* __re
 // voxels, so per-entry stores would be partial-sector writes from different warps.  Threads are 64-lane groups (lane = frame slot
 // in a sliding window), two voxels per round, two rounds per group; gradient / D sums as in k_jac.
 template <int LPV>   // lanes per voxel: 64 (W <= 64, two voxels per round) or 128 (W <= 128, one voxel per round) so that a lane keeps one frame slot
-__global__ void __launch_bounds__(128, 3) k_jac_slab(FactorView f, const double* __restrict__ poses, int pstride, double* __restrict__ XT, double* __restrict__ gD, int ngroups_vox) {
+__global__ void __launch_bounds__(128, 3) k_jac_slab(FactorView f, const double* __restrict__ poses, int pstride, double* __restrict__ XT, double* __restrict__ gD, int g_first,
+                                                     int ngroups_vox) {   // voxel groups [g_first, ngroups_vox)
   extern __shared__ __align__(16) double sm[];
   constexpr int VPR = 128 / LPV;                     // voxels per round
   const int tid = threadIdx.x, half = tid / LPV, lane = tid % LPV;
@@ -341,7 +342,7 @@ __global__ void __launch_bounds__(128, 3) k_jac_slab(FactorView f, const double*
 #pragma unroll
   for (int i = 0; i < 30; i++) acc[i * 128 + tid] = 0.0;
   stage_poses(sp, poses, pstride, W);
-  for (int G = blockIdx.x; G < ngroups_vox; G += gridDim.x) {
+  for (int G = g_first + blockIdx.x; G < ngroups_vox; G += gridDim.x) {
     {   // pull the next group's entries and voxel constants towards L2 while this one is computed
       const int Gn = G + gridDim.x;
 #pragma unroll
@@ -479,13 +480,13 @@ static SyrkGeom sy_geom(int W) {
 // the SM) busy on diagonal / remainder tiles, where a unit-per-warp mapping leaves one to three warps idle.
 struct SyPiece { int offI, offJ, ntI, ntJ, rowbase, colbase, nvalI, nvalJ; unsigned mask; };   // mask: bit ti*6+tj = tile needed
 
-__global__ void __launch_bounds__(SY_THREADS, 2) k_syrk(const double* __restrict__ XT, double* __restrict__ C, int ngroups_vox, int W, SyrkGeom g, int groups_per_chunk) {
+__global__ void __launch_bounds__(SY_THREADS, 2) k_syrk(const double* __restrict__ XT, double* __restrict__ C, int g_first, int ngroups_vox, int W, SyrkGeom g, int groups_per_chunk) {
   extern __shared__ __align__(16) double smem[];
   const int tile = blockIdx.x % g.ntiles, chunk = blockIdx.x / g.ntiles;
   int A = 0, rem = tile;
   while (rem >= g.nbp - A) { rem -= g.nbp - A; A++; }
   const int B = A + rem;
-  const int g_begin = chunk * groups_per_chunk, g_end = min(ngroups_vox, g_begin + groups_per_chunk);
+  const int g_begin = g_first + chunk * groups_per_chunk, g_end = min(ngroups_vox, g_begin + groups_per_chunk);   // voxel groups [g_first, ngroups_vox)
   if (g_begin >= g_end) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = 6 * W;
@@ -704,6 +705,7 @@ static size_t hess_block_doubles(int W) { return size_t(6 * W) * size_t(6 * W) +
 
 int vxs_eval_residual_dev(vxs_ctx* ctx, vxs_factor* f, const double* poses_dev, int pstride, double* residual_dev) {
   if (f->V == 0) { VXS_CUDA(ctx, cudaMemsetAsync(residual_dev, 0, 8, ctx->stream)); return VXS_OK; }
+  { int rcw = vxs_factor_wait_uploads(f); if (rcw) return rcw; }
   FactorView fv = make_view(f);
   const int G = pick_group(f);
   const unsigned blocks_v = nblk(size_t(f->V), 256);
@@ -751,39 +753,65 @@ int vxs_eval_hessian_dev(vxs_ctx* ctx, vxs_factor* f, const double* poses_dev, i
     unsigned gridj = unsigned(std::min<size_t>((size_t(f->V) * GJ + 127) / 128, size_t(ctx->sm_count) * 8));
     unsigned grid = unsigned(std::min<size_t>((size_t(f->V) * G + 127) / 128, size_t(ctx->sm_count) * 16));
 #define LAUNCH_JAC(GG, DD) { auto kp = k_jac<GG, DD>; VXS_LAUNCH(ctx, "k_jac", kp, gridj, 128, 0, fv, poses_dev, pstride, f->X.p, gD); }
+    // First build after vxs_factor_push_voxels_async: the clusters are still arriving in chunks of voxel groups; run the Jacobian and the
+    // SYRK chunk by chunk behind the upload events so that the PCIe transfer overlaps them (both kernels only accumulate: RED into C, g, D).
+    const bool chunked = f->up_pending > 0 && dense && W <= 128;
+    if (!chunked) { int rcw = vxs_factor_wait_uploads(f); if (rcw) return rcw; }
+    const int n_up = chunked ? f->up_n : 1;
     if (dense && W <= 128) {
       const int ngv = int((f->V + 3) / 4);
       const size_t smem = (size_t(30) * 128 + size_t(12) * 7 * W + size_t(12) * W) * 8;
-      const unsigned grids = unsigned(std::min<int>(ngv, ctx->sm_count * 3 * 2));
-      if (W <= 64) {
-        auto kp = k_jac_slab<64>;
-        VXS_CUDA(ctx, cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        VXS_LAUNCH(ctx, "k_jac", kp, grids, 128, smem, fv, poses_dev, pstride, f->X.p, gD, ngv);
-      } else {
-        auto kp = k_jac_slab<128>;
-        VXS_CUDA(ctx, cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        VXS_LAUNCH(ctx, "k_jac", kp, grids, 128, smem, fv, poses_dev, pstride, f->X.p, gD, ngv);
+      const SyrkGeom g = sy_geom(W);
+      static int waves = -1;
+      if (waves < 0) { const char* e = getenv("VXS_SYRK_WAVES"); waves = e ? std::max(1, atoi(e)) : 12; }
+      const size_t smem_sy = size_t(SY_STAGES) * SY_STAGE_DOUBLES * 8;
+      VXS_CUDA(ctx, cudaFuncSetAttribute(k_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_sy)));
+      int g0 = 0;
+      for (int uc = 0; uc < n_up; uc++) {
+        const int g1 = chunked ? std::min(f->up_group_end[uc], ngv) : ngv;
+        if (chunked) VXS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, f->up_ev[uc], 0));
+        if (g1 > g0) {
+          const int ng = g1 - g0;
+          const unsigned grids = unsigned(std::min<int>(ng, ctx->sm_count * 3 * 2));
+          if (W <= 64) {
+            auto kp = k_jac_slab<64>;
+            VXS_CUDA(ctx, cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+            VXS_LAUNCH(ctx, "k_jac", kp, grids, 128, smem, fv, poses_dev, pstride, f->X.p, gD, g0, g1);
+          } else {
+            auto kp = k_jac_slab<128>;
+            VXS_CUDA(ctx, cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+            VXS_LAUNCH(ctx, "k_jac", kp, grids, 128, smem, fv, poses_dev, pstride, f->X.p, gD, g0, g1);
+          }
+          // SYRK over the same groups.  Waves: CTA durations differ by 3x between tile kinds (full off-diagonal / diagonal / remainder) and
+          // the CTAs are dispatched in order, so the last wave leaves SMs idle for up to one CTA duration; ncu showed 68.6 % DMMA-pipe
+          // activity on average against 85.5 % on the busiest SM at 4 waves.  More, shorter CTAs shrink that tail (each pays one pipeline
+          // fill and one 96x96 RED epilogue); measured at the metric shape: 4 waves 0.781 ms, 8: 0.737, 12: 0.736, 16: 0.742, 24: 0.762.
+          const int target_ctas = std::max(1, ctx->sm_count * 2 * waves / n_up);
+          int nchunks = std::max(1, std::min<int>(target_ctas / g.ntiles, (ng + 7) / 8));
+          const int gpc = (ng + nchunks - 1) / nchunks;
+          nchunks = (ng + gpc - 1) / gpc;
+          VXS_LAUNCH(ctx, "k_syrk", k_syrk, unsigned(nchunks * g.ntiles), SY_THREADS, smem_sy, f->X.p, C, g0, g1, W, g, gpc);
+        }
+        g0 = g1;
       }
+      if (chunked) f->up_pending = 0;
     } else if (dense) { if (GJ == 64) LAUNCH_JAC(64, true) else if (GJ == 32) LAUNCH_JAC(32, true) else if (GJ == 16) LAUNCH_JAC(16, true) else LAUNCH_JAC(8, true) }
     else { if (GJ == 64) LAUNCH_JAC(64, false) else if (GJ == 32) LAUNCH_JAC(32, false) else if (GJ == 16) LAUNCH_JAC(16, false) else LAUNCH_JAC(8, false) }
 #undef LAUNCH_JAC
-    if (dense) {
+    if (dense && W <= 128) {
+      // k_syrk already launched with its Jacobian chunk above
+    } else if (dense) {
       const SyrkGeom g = sy_geom(W);
       const int ngv = int((f->V + 3) / 4);                 // voxel groups of 4 (12 rows of X each)
-      // enough chunks to fill the machine a few times over; tiles of one chunk are adjacent in launch order (L2 reuse of X)
-      // Waves: CTA durations differ by 3x between tile kinds (full off-diagonal / diagonal / remainder) and the CTAs are dispatched in order,
-      // so the last wave leaves SMs idle for up to one CTA duration; ncu showed 68.6 % DMMA-pipe activity on average against 85.5 % on
-      // the busiest SM at 4 waves.  More, shorter CTAs shrink that tail (each pays one pipeline fill and one 96x96 RED epilogue); measured at the
-      // metric shape: 4 waves 0.781 ms, 8: 0.737, 12: 0.736, 16: 0.742, 24: 0.762.
       static int waves = -1;
       if (waves < 0) { const char* e = getenv("VXS_SYRK_WAVES"); waves = e ? std::max(1, atoi(e)) : 12; }
       int target_ctas = ctx->sm_count * 2 * waves;
-      int nchunks = std::max(1, std::min<int>(target_ctas / g.ntiles, (ngv + 7) / 8));   // floor: CTAs fit whole waves of 2 per SM
+      int nchunks = std::max(1, std::min<int>(target_ctas / g.ntiles, (ngv + 7) / 8));
       int gpc = (ngv + nchunks - 1) / nchunks;
       nchunks = (ngv + gpc - 1) / gpc;
       const size_t smem = size_t(SY_STAGES) * SY_STAGE_DOUBLES * 8;
       VXS_CUDA(ctx, cudaFuncSetAttribute(k_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-      VXS_LAUNCH(ctx, "k_syrk", k_syrk, unsigned(nchunks * g.ntiles), SY_THREADS, smem, f->X.p, C, ngv, W, g, gpc);
+      VXS_LAUNCH(ctx, "k_syrk", k_syrk, unsigned(nchunks * g.ntiles), SY_THREADS, smem, f->X.p, C, 0, ngv, W, g, gpc);
     } else {
       if (G == 32) { auto kp = k_pairs<32>; VXS_LAUNCH(ctx, "k_pairs", kp, grid, 128, 0, fv, f->X.p, C); }
       else if (G == 16) { auto kp = k_pairs<16>; VXS_LAUNCH(ctx, "k_pairs", kp, grid, 128, 0, fv, f->X.p, C); }

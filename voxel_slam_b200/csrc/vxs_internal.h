@@ -35,6 +35,7 @@ struct DevBuf {  // grow-only device buffer
 };
 
 struct vxs_ctx {
+  DevBuf<double> stage2;             // AoS staging of an asynchronous cluster upload (lives until its conversion kernels ran)
   long long* ldlt_prof = nullptr;   // vxs_diag_ldlt_phases: device stamp buffer, otherwise null
   int device = 0;
   int sm_count = VXS_SM_COUNT_FALLBACK;
@@ -90,7 +91,16 @@ struct vxs_factor {
   DevBuf<double> vc;             // [8][Vcap] per-voxel constants for k_jac
   DevBuf<double> cache_copy;     // [22][Vcap] snapshot of eig | sum
   size_t cache_copy_V = 0;
+  // asynchronous chunked upload (vxs_factor_push_voxels_async): the clusters arrive on ctx->copy_stream in up_n chunks of whole voxel
+  // groups; up_ev[c] fires when chunk c (voxel groups < up_group_end[c]) is resident and converted to SoA.  up_pending > 0 until a
+  // consumer has ordered ctx->stream behind the events.
+  static const int UP_MAX = 8;
+  int up_pending = 0, up_n = 0;
+  int up_group_end[UP_MAX] = {0};
+  cudaEvent_t up_ev[UP_MAX] = {nullptr};
+  cudaEvent_t up_fence = nullptr;
 };
+int vxs_factor_wait_uploads(vxs_factor* f);   // orders ctx->stream behind every pending upload chunk (device-side wait, no host sync)
 
 inline int vxs_fail(vxs_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) {
   if (c) {
