@@ -260,6 +260,21 @@ def run_ours(args):
     roof_hess = roof(["k_jac", "k_syrk"], bytes_hess, flops_hess)
     roof_resid = roof(["k_cluster_sum", "k_eig_residual"], bytes_resid)
     roof_jac = roof(["k_jac"], E * 80 + V * 176 + E * 144)
+    # the dominant kernel (k_syrk: H -= X^T X on the fp64 tensor path) is compute-bound for k >~ 4 (SURVEY.md §7.3 / §8d "report both"):
+    # its roofline is the fp64 mma.sync (DMMA) throughput measured in this process; the HBM view of the whole Hessian build rides along
+    roof_main = roof_hess
+    if "k_syrk" in kern and kern["k_syrk"]["ms_per_step"] > 0:
+        try:
+            dmma_peak = ctx.dmma_tflops()
+        except Exception:
+            dmma_peak = fp64_peak
+        t_sy = kern["k_syrk"]["ms_per_step"] * 1e-3 / max(kern["k_syrk"]["launches_per_step"], 1.0)
+        fl_sy = V * 108.0 * kv * kv / max(kern["k_syrk"]["launches_per_step"], 1.0)      # 3 rank-1 rows x (6k)^2 / 2 MACs per voxel
+        roof_main = {"kernel": "k_syrk", "bound": "tensor", "achieved": fl_sy / t_sy / 1e12, "peak": dmma_peak, "unit": "TFLOP/s", "frac": fl_sy / t_sy / 1e12 / dmma_peak,
+                     "traffic": ncu_traffic(["k_syrk"]), "peak_source": "vxs_diag_dmma_tflops: mma.sync.m8n8k4.f64 (SASS DMMA) throughput measured in this process; "
+                     "MEASURED_PEAKS.json carries no fp64 figure", "algorithmic_flops": fl_sy, "us_per_launch": t_sy * 1e6,
+                     "traffic_source": "profiles/r01_ncu_full_ba_kernels.txt (ncu --set full of this command, DRAM read + write per launch)",
+                     "hbm_view_of_hessian_build": roof_hess}
     for r_, names_ in ((roof_hess, ["k_jac_slab", "k_syrk"]), (roof_resid, ["k_cluster_sum", "k_eig_residual"]), (roof_jac, ["k_jac_slab"])):
         if r_ is not None:
             r_["traffic"] = ncu_traffic(names_)
@@ -285,7 +300,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "iterations_per_call": it_call,
                     "call": "vxs_factor_push_voxels_async of the host LidarFactor (pinned CSR, 4 chunks overlapped with the first Hessian build) + LI_BA damping_iter (3 iterations) + read back poses, Hessian, eig/pcr_adds"},
             "gpu_launches": int(launches), "clocks": clocks,
-            "roofline": roof_hess, "roofline_residual": roof_resid, "roofline_jac": roof_jac, "dominant_kernel": dom,
+            "roofline": roof_main, "roofline_residual": roof_resid, "roofline_jac": roof_jac, "dominant_kernel": dom,
             "kernels": kern, "cpu_baseline": cpu, "c2_plane_fit": c2, "down_sampling": ds,
             "voxelize": {"ms_total": t_vox * 1e3, "points": int(W * pts), "stages_ms": {k: v[0] for k, v in vox_stages.items() if v[1] > 0}},
             "check": {"pose_err_before": err0, "pose_err_after_3_iters": err1, "trace": [[float(t["r1"]), float(t["r2"]), int(t["accepted"])] for t in o["trace"]]},
