@@ -209,6 +209,12 @@ int vxs_down_sampling_voxel(vxs_ctx* ctx, const float* pts, int stride_floats, i
 int vxs_down_sampling_close(vxs_ctx* ctx, const float* pts, int stride_floats, int64_t n, double voxel_size, float* xyz_out, float* count_out,
                             int64_t* picked_index_out, int64_t cap, int64_t* n_out);
 
+/* down_sampling_pvec (voxel_map.hpp:23-64, the scan pre-processing of the odometry): pointVar records (`stride_doubles` >= 12 apart: pnt at
+ * [0..2], the symmetric 3x3 var at [3..11]); per cell the running fp64 mean of pnt and var in input order; out: float(pnt), float(diag(var))
+ * (what the reference writes to x,y,z / normal_x,y,z), the cell's point count and the index of its first point; cells in ascending cell order. */
+int vxs_down_sampling_pvec(vxs_ctx* ctx, const double* pv, int stride_doubles, int64_t n, double voxel_size, float* xyz_out, float* var_diag_out,
+                           float* count_out, int64_t* first_index_out, int64_t cap, int64_t* n_out);
+
 /* Submap merge of HBA_add_edge (voxelslam.cpp:2428-2447): the clouds of the W keyframes of a window are moved into the frame of
  * keyframe 0 (v' = dR v + dp in fp64, dR = R_0^T R_i, dp = R_0^T (p_i - p_0), stored as float) and passed through
  * down_sampling_voxel(voxel_size) — the caller passes the reference's voxel_size / 8.  Outputs as vxs_down_sampling_voxel;

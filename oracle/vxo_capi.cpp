@@ -346,4 +346,15 @@ int64_t vxo_submap_merge(const float* pts, int stride, const int64_t* kf_offsets
   return int64_t(out.size());
 }
 
+// voxel_map.hpp:23-64 down_sampling_pvec
+int64_t vxo_down_sampling_pvec(const double* pv, int stride, int64_t n, double voxel_size, float* xyz_out, float* nrm_out, float* cnt_out, int64_t* idx_out, int64_t cap) {
+  std::vector<DsPvec> out;
+  down_sampling_pvec(pv, stride, n, voxel_size, out);
+  for (int64_t i = 0; i < int64_t(out.size()) && i < cap; i++) {
+    xyz_out[3 * i] = out[i].x; xyz_out[3 * i + 1] = out[i].y; xyz_out[3 * i + 2] = out[i].z;
+    nrm_out[3 * i] = out[i].nx; nrm_out[3 * i + 1] = out[i].ny; nrm_out[3 * i + 2] = out[i].nz; cnt_out[i] = out[i].cnt; idx_out[i] = out[i].idx;
+  }
+  return int64_t(out.size());
+}
+
 }  // extern "C"

@@ -456,6 +456,33 @@ inline bool down_sampling_close(const float* pts, int stride, int64_t n, double 
   return true;
 }
 
+// voxel_map.hpp:23-64 down_sampling_pvec: running fp64 mean of pnt and var per cell; pl_keep gets float(pnt) and float(diag(var)).
+// pv records `stride` doubles apart: pnt [0..2], var [3..11].  out.{x,y,z} = point, nrm = the three diagonal variances, idx = first point.
+struct DsPvec { float x, y, z, nx, ny, nz, cnt; int64_t idx; };
+inline void down_sampling_pvec(const double* pv, int stride, int64_t n, double voxel_size, std::vector<DsPvec>& out) {
+  struct Acc { double pnt[3]; double var[9]; int cnt; int64_t first; };
+  std::unordered_map<VoxelLoc, Acc, VoxelLocHash> feat_map;
+  for (int64_t i = 0; i < n; i++) {
+    const double* p = pv + size_t(i) * stride;
+    const VoxelLoc position = voxel_key(v3(p[0], p[1], p[2]), voxel_size);
+    auto it = feat_map.find(position);
+    if (it == feat_map.end()) {
+      Acc a; for (int k = 0; k < 3; k++) a.pnt[k] = p[k]; for (int k = 0; k < 9; k++) a.var[k] = p[3 + k]; a.cnt = 1; a.first = i;
+      feat_map[position] = a;
+    } else {
+      Acc& a = it->second;
+      for (int k = 0; k < 3; k++) a.pnt[k] = (a.pnt[k] * a.cnt + p[k]) / (a.cnt + 1);
+      for (int k = 0; k < 9; k++) a.var[k] = (a.var[k] * a.cnt + p[3 + k]) / (a.cnt + 1);
+      a.cnt += 1;
+    }
+  }
+  out.clear();
+  for (auto& kv : feat_map) {
+    const Acc& a = kv.second;
+    out.push_back(DsPvec{float(a.pnt[0]), float(a.pnt[1]), float(a.pnt[2]), float(a.var[0]), float(a.var[4]), float(a.var[8]), float(a.cnt), a.first});
+  }
+}
+
 // voxelslam.cpp:2428-2447: submap merge of HBA_add_edge.  xs: W poses (R row-major, p); clouds concatenated with kf_offsets.
 // merged (n x 3 float) receives the transformed points; then down_sampling_voxel(voxel_size) (the caller passes voxel_size / 8).
 inline bool submap_merge(const float* pts, int stride, const int64_t* kf_offsets, const double* poses12, int W, double voxel_size, std::vector<float>& merged,

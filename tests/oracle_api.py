@@ -203,6 +203,17 @@ def down_sampling(pts_f32, voxel_size, close=False, stride_floats=None):
     return dict(xyz=xyz[:m], count=cnt[:m], index=idx[:m])
 
 
+def down_sampling_pvec(pv_f64, voxel_size):
+    x = np.ascontiguousarray(pv_f64, dtype=np.float64)
+    n, stride = x.shape
+    xyz = np.zeros((max(n, 1), 3), dtype=np.float32); nrm = np.zeros((max(n, 1), 3), dtype=np.float32); cnt = np.zeros(max(n, 1), dtype=np.float32)
+    idx = np.zeros(max(n, 1), dtype=np.int64)
+    lib().vxo_down_sampling_pvec.restype = C.c_int64
+    m = lib().vxo_down_sampling_pvec(_dp(x), C.c_int(stride), C.c_int64(n), C.c_double(voxel_size), xyz.ctypes.data_as(C.POINTER(C.c_float)),
+                                     nrm.ctypes.data_as(C.POINTER(C.c_float)), cnt.ctypes.data_as(C.POINTER(C.c_float)), idx.ctypes.data_as(C.POINTER(C.c_int64)), C.c_int64(n))
+    return dict(xyz=xyz[:m], var_diag=nrm[:m], count=cnt[:m], index=idx[:m])
+
+
 def submap_merge(xyz_f32, kf_offsets, poses12, voxel_size, stride_floats=None):
     x = np.ascontiguousarray(xyz_f32, dtype=np.float32)
     stride = int(stride_floats) if stride_floats else (x.shape[1] if x.ndim == 2 else 3)

@@ -250,3 +250,25 @@ def test_submap_merge_parity(ctx, stride):
     # empty window and empty keyframes
     e = ctx.submap_merge(pts[:0], np.zeros(W + 1, dtype=np.int64), poses, 0.125, stride_floats=stride)
     assert len(e["index"]) == 0
+
+
+def test_down_sampling_pvec_parity(ctx):
+    """voxel_map.hpp:23-64 — bit-exact against the oracle (fp64 running means in input order, float outputs)."""
+    rng = np.random.default_rng(41)
+    n = 150000
+    pv = np.zeros((n, 12))
+    pv[:, :3] = rng.uniform(-30.0, 30.0, (n, 3))
+    pv[: n // 8, :3] = np.round(pv[: n // 8, :3] * 4) / 4
+    pv[n // 8: n // 4, :3] = pv[: n // 4 - n // 8, :3]
+    a = rng.uniform(-1e-2, 1e-2, (n, 3, 3))
+    pv[:, 3:] = (a @ a.transpose(0, 2, 1)).reshape(n, 9)
+    for vs in (0.5, 0.1):
+        g = ctx.down_sampling_pvec(pv, vs)
+        o = oa.down_sampling_pvec(pv, vs)
+        assert len(g["index"]) == len(o["index"])
+        go, oo = np.argsort(g["index"]), np.argsort(o["index"])
+        assert np.array_equal(g["index"][go], o["index"][oo])
+        assert np.array_equal(g["xyz"][go].view(np.uint32), o["xyz"][oo].view(np.uint32))
+        assert np.array_equal(g["var_diag"][go].view(np.uint32), o["var_diag"][oo].view(np.uint32))
+        assert np.array_equal(g["count"][go], o["count"][oo]) and int(g["count"].sum()) == n
+    assert len(ctx.down_sampling_pvec(pv[:0], 0.5)["index"]) == 0

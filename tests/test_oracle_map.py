@@ -188,3 +188,32 @@ def test_submap_merge_oracle_consistency():
     o = oa.submap_merge(pts, off, poses, 0.25)
     d = oa.down_sampling(raw["xyz"], 0.25)
     assert np.array_equal(np.sort(o["index"]), np.sort(d["index"])) and int(o["count"].sum()) == W * per
+
+
+def _pvec_cloud(n, seed):
+    rng = np.random.default_rng(seed)
+    pv = np.zeros((n, 12))
+    pv[:, :3] = rng.uniform(-9.0, 9.0, (n, 3))
+    pv[: n // 8, :3] = np.round(pv[: n // 8, :3] * 4) / 4            # on cell faces
+    a = rng.uniform(-1e-2, 1e-2, (n, 3, 3))
+    pv[:, 3:] = (a @ a.transpose(0, 2, 1)).reshape(n, 9)              # symmetric PSD covariances
+    return pv
+
+
+def test_down_sampling_pvec_oracle_matches_numpy():
+    """voxel_map.hpp:23-64 restated with numpy float64 scalars in input order."""
+    pv = _pvec_cloud(4000, 17)
+    for vs in (0.5, 0.25):
+        o = oa.down_sampling_pvec(pv, vs)
+        keys = oa.voxel_keys(pv[:, :3], vs)[0]
+        cells = {}
+        for i, k in enumerate(map(tuple, keys.tolist())):
+            cells.setdefault(k, []).append(i)
+        assert len(o["index"]) == len(cells)
+        pos = {i: t for t, i in enumerate(o["index"].tolist())}
+        for ids in cells.values():
+            m, cnt = pv[ids[0]].copy(), 1
+            for i in ids[1:]:
+                m = (m * cnt + pv[i]) / (cnt + 1); cnt += 1
+            t = pos[ids[0]]
+            assert np.array_equal(o["xyz"][t], m[:3].astype(np.float32)) and np.array_equal(o["var_diag"][t], m[[3, 7, 11]].astype(np.float32)) and o["count"][t] == cnt

@@ -372,6 +372,23 @@ def _down_sampling(self, pts_f32, voxel_size, close=False, stride_floats=None):
 Context.down_sampling = _down_sampling
 
 
+def _down_sampling_pvec(self, pv_f64, voxel_size):
+    """down_sampling_pvec (voxel_map.hpp:23-64): pv rows = pnt(3) | var(9)."""
+    x = np.ascontiguousarray(pv_f64, dtype=np.float64)
+    stride = x.shape[1]
+    n = x.shape[0]
+    xyz = np.zeros((max(n, 1), 3), dtype=np.float32); nrm = np.zeros((max(n, 1), 3), dtype=np.float32); cnt = np.zeros(max(n, 1), dtype=np.float32)
+    idx = np.zeros(max(n, 1), dtype=np.int64)
+    m = C.c_int64(0)
+    self._check(lib().vxs_down_sampling_pvec(self._p, _dp(x), C.c_int(stride), C.c_int64(n), C.c_double(voxel_size), xyz.ctypes.data_as(C.POINTER(C.c_float)),
+                                             nrm.ctypes.data_as(C.POINTER(C.c_float)), cnt.ctypes.data_as(C.POINTER(C.c_float)), idx.ctypes.data_as(C.POINTER(C.c_int64)),
+                                             C.c_int64(n), C.byref(m)))
+    return dict(xyz=xyz[: m.value], var_diag=nrm[: m.value], count=cnt[: m.value], index=idx[: m.value])
+
+
+Context.down_sampling_pvec = _down_sampling_pvec
+
+
 def _submap_merge(self, xyz_f32, kf_offsets, poses12, voxel_size, stride_floats=None):
     """Submap merge of HBA_add_edge (voxelslam.cpp:2428-2447): clouds into the frame of keyframe 0 + down_sampling_voxel."""
     x = np.ascontiguousarray(xyz_f32, dtype=np.float32)

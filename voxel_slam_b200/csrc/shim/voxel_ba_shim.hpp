@@ -247,6 +247,24 @@ inline void down_sampling_voxel(Context& ctx, pcl::PointCloud<PointType>& pl_fea
   }
   pl_feat.swap(out);
 }
+// down_sampling_pvec(pvec, voxel_size, pl_keep) — voxel_map.hpp:23 (call sites voxelslam.cpp:1146-1148 scan pre-processing).
+// pointVar = { Vector3d pnt; Matrix3d var } = 12 doubles, handed to the device as it is.
+inline void down_sampling_pvec(Context& ctx, PVec& pvec, double voxel_size, pcl::PointCloud<PointType>& pl_keep) {
+  static_assert(sizeof(pointVar) % sizeof(double) == 0, "pointVar is a plain fp64 record");
+  const int64_t n = int64_t(pvec.size());
+  std::vector<float> xyz(size_t(n) * 3), vd(size_t(n) * 3);
+  int64_t m = 0;
+  check(ctx.get(), vxs_down_sampling_pvec(ctx.get(), reinterpret_cast<const double*>(pvec.data()), int(sizeof(pointVar) / sizeof(double)), n, voxel_size,
+                                          xyz.data(), vd.data(), nullptr, nullptr, n, &m), "vxs_down_sampling_pvec");
+  pcl::PointCloud<PointType>().swap(pl_keep);
+  pl_keep.reserve(size_t(m));
+  PointType ap;
+  for (int64_t i = 0; i < m; i++) {
+    ap.x = xyz[3 * i]; ap.y = xyz[3 * i + 1]; ap.z = xyz[3 * i + 2];
+    ap.normal_x = vd[3 * i]; ap.normal_y = vd[3 * i + 1]; ap.normal_z = vd[3 * i + 2];
+    pl_keep.push_back(ap);
+  }
+}
 // down_sampling_close(pl_feat, voxel_size) — tools.hpp:240
 inline void down_sampling_close(Context& ctx, pcl::PointCloud<PointType>& pl_feat, double voxel_size) {
   const int64_t n = int64_t(pl_feat.size());

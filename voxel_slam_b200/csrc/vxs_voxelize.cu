@@ -638,10 +638,11 @@ static int build_factor(vxs_ctx* ctx, const vxs_map_params* mp, bool gba, const 
 // down_sampling_close keeps the input point nearest to the cell's float centroid (first minimum, distances in fp64, start value 100).
 // The reference iterates an unordered_map, so its output ORDER is unspecified; here cells come out in ascending (x, y, z) cell order and
 // every output carries the index of the first input point of its cell (the reference copies that point's other fields).
-__global__ void __launch_bounds__(256) k_ds_bbox(const float* __restrict__ pts, int stride, long long n, double voxel_size, long long* __restrict__ bbox) {
+template <class T>
+__global__ void __launch_bounds__(256) k_ds_bbox(const T* __restrict__ pts, int stride, long long n, double voxel_size, long long* __restrict__ bbox) {
   long long mn[3] = {LLONG_MAX, LLONG_MAX, LLONG_MAX}, mx[3] = {LLONG_MIN, LLONG_MIN, LLONG_MIN};
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float* p = pts + size_t(i) * stride;
+    const T* p = pts + size_t(i) * stride;
     for (int a = 0; a < 3; a++) { const long long k = quantise((double)p[a], voxel_size); mn[a] = min(mn[a], k); mx[a] = max(mx[a], k); }
   }
   for (int a = 0; a < 3; a++) {
@@ -649,11 +650,12 @@ __global__ void __launch_bounds__(256) k_ds_bbox(const float* __restrict__ pts, 
     if ((threadIdx.x & 31) == 0) { atomicMin(bbox + a, mn[a]); atomicMax(bbox + 3 + a, mx[a]); }
   }
 }
-__global__ void __launch_bounds__(256) k_ds_keys(const float* __restrict__ pts, int stride, long long n, double voxel_size, long long minx, long long miny, long long minz,
+template <class T>
+__global__ void __launch_bounds__(256) k_ds_keys(const T* __restrict__ pts, int stride, long long n, double voxel_size, long long minx, long long miny, long long minz,
                                                  unsigned long long ey, unsigned long long ez, unsigned long long* __restrict__ keys, unsigned int* __restrict__ idx) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float* p = pts + size_t(i) * stride;
+  const T* p = pts + size_t(i) * stride;
   const unsigned long long x = (unsigned long long)(quantise((double)p[0], voxel_size) - minx), y = (unsigned long long)(quantise((double)p[1], voxel_size) - miny),
                            z = (unsigned long long)(quantise((double)p[2], voxel_size) - minz);
   keys[i] = (x * ey + y) * ez + z;
@@ -702,16 +704,41 @@ __global__ void __launch_bounds__(128) k_ds_reduce(const float* __restrict__ pts
   }
 }
 
+// down_sampling_pvec (voxel_map.hpp:23-64): running fp64 mean of pnt and of var per cell, in input order; the cloud that comes out keeps
+// float(pnt) and float(diag(var)) — the recurrences are elementwise, so the three diagonal entries are all that has to be carried.
+// pv: pointVar records, `stride` doubles apart, pnt at [0..2], var (3x3, symmetric) at [3..11].
+__global__ void __launch_bounds__(128) k_ds_reduce_pvec(const double* __restrict__ pv, int stride, const unsigned int* __restrict__ idx, const unsigned int* __restrict__ seg_start,
+                                                        unsigned int nseg, float* __restrict__ xyz_out, float* __restrict__ cnt_out, long long* __restrict__ pick_out, float* __restrict__ nrm_out) {
+  const unsigned int sgi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sgi >= nseg) return;
+  const unsigned int b = seg_start[sgi], e = seg_start[sgi + 1];
+  const double* p0 = pv + size_t(idx[b]) * stride;
+  double m[6] = {p0[0], p0[1], p0[2], p0[3], p0[7], p0[11]};
+  int cnt = 1;
+  for (unsigned int j = b + 1; j < e; j++) {
+    const double* p = pv + size_t(idx[j]) * stride;
+    const double q[6] = {p[0], p[1], p[2], p[3], p[7], p[11]};
+    const double c = (double)cnt, c1 = (double)(cnt + 1);
+#pragma unroll
+    for (int k = 0; k < 6; k++) m[k] = __ddiv_rn(__dadd_rn(__dmul_rn(m[k], c), q[k]), c1);
+    cnt++;
+  }
+  for (int k = 0; k < 3; k++) { xyz_out[3 * size_t(sgi) + k] = __double2float_rn(m[k]); nrm_out[3 * size_t(sgi) + k] = __double2float_rn(m[3 + k]); }
+  cnt_out[sgi] = (float)cnt;
+  pick_out[sgi] = (long long)idx[b];
+}
+
 // pts_dev: device-resident cloud (n points, stride floats)
-static int down_sample_dev(vxs_ctx* ctx, int mode, const float* pts_dev, int stride, int64_t n, double voxel_size, float* xyz_out, float* count_out, int64_t* index_out,
-                           int64_t cap, int64_t* n_out) {
+template <class T>   // T = float (modes 0, 1) or double (mode 2, pointVar records; nrm_out receives diag(var))
+static int down_sample_dev(vxs_ctx* ctx, int mode, const T* pts_dev, int stride, int64_t n, double voxel_size, float* xyz_out, float* count_out, int64_t* index_out,
+                           int64_t cap, int64_t* n_out, float* nrm_out = nullptr) {
   VoxScratch* s = scratch(ctx);
   cudaStream_t st = ctx->stream;
   VXS_CUDA(ctx, s->totals.reserve(16));
   VXS_CUDA(ctx, s->bbox.reserve(6));
   const long long bb0[6] = {LLONG_MAX, LLONG_MAX, LLONG_MAX, LLONG_MIN, LLONG_MIN, LLONG_MIN};
   VXS_CUDA(ctx, cudaMemcpyAsync(s->bbox.p, bb0, sizeof bb0, cudaMemcpyHostToDevice, st));
-  VXS_LAUNCH(ctx, "k_ds_bbox", k_ds_bbox, std::min<unsigned>(nblk(size_t(n), 256), unsigned(ctx->sm_count) * 8), 256, 0, pts_dev, stride, (long long)n, voxel_size, s->bbox.p);
+  { auto kb = k_ds_bbox<T>; VXS_LAUNCH(ctx, "k_ds_bbox", kb, std::min<unsigned>(nblk(size_t(n), 256), unsigned(ctx->sm_count) * 8), 256, 0, pts_dev, stride, (long long)n, voxel_size, s->bbox.p); }
   long long bb[6];
   VXS_CUDA(ctx, cudaMemcpyAsync(bb, s->bbox.p, sizeof bb, cudaMemcpyDeviceToHost, st));
   VXS_CUDA(ctx, cudaStreamSynchronize(st));
@@ -720,8 +747,8 @@ static int down_sample_dev(vxs_ctx* ctx, int mode, const float* pts_dev, int str
   const int key_bits = bits_for((unsigned long long)(ex * ey * ez));
   VXS_CUDA(ctx, s->keysA.reserve(size_t(n))); VXS_CUDA(ctx, s->keysB.reserve(size_t(n)));
   VXS_CUDA(ctx, s->idxA.reserve(size_t(n))); VXS_CUDA(ctx, s->idxB.reserve(size_t(n)));
-  VXS_LAUNCH(ctx, "k_ds_keys", k_ds_keys, nblk(size_t(n), 256), 256, 0, pts_dev, stride, (long long)n, voxel_size, bb[0], bb[1], bb[2], (unsigned long long)ey, (unsigned long long)ez,
-             s->keysA.p, s->idxA.p);
+  { auto kk = k_ds_keys<T>; VXS_LAUNCH(ctx, "k_ds_keys", kk, nblk(size_t(n), 256), 256, 0, pts_dev, stride, (long long)n, voxel_size, bb[0], bb[1], bb[2], (unsigned long long)ey, (unsigned long long)ez,
+             s->keysA.p, s->idxA.p); }
   unsigned long long* ks; unsigned int* vs;
   int rc = radix_sort(ctx, s, s->keysA.p, s->idxA.p, s->keysB.p, s->idxB.p, size_t(n), key_bits, &ks, &vs);
   if (rc) return rc;
@@ -735,15 +762,20 @@ static int down_sample_dev(vxs_ctx* ctx, int mode, const float* pts_dev, int str
   VXS_CUDA(ctx, s->rec_start.reserve(size_t(R) + 1)); VXS_CUDA(ctx, s->rec_key.reserve(size_t(R)));
   VXS_LAUNCH(ctx, "k_write_records", k_write_records, nblk(size_t(n), 256), 256, 0, ks, s->flags.p, s->scanbuf.p, size_t(n), s->rec_start.p, s->rec_key.p, s->totals.p + 0);
   // outputs: reuse the cluster scratch (4 floats + 1 int64 per cell)
-  VXS_CUDA(ctx, s->rec_local.reserve(size_t(R) * 2 + 2)); VXS_CUDA(ctx, s->rec_world.reserve(size_t(R) + 1));
-  float* d_xyz = reinterpret_cast<float*>(s->rec_local.p); float* d_cnt = d_xyz + 3 * size_t(R);
+  VXS_CUDA(ctx, s->rec_local.reserve(size_t(R) * 4 + 4)); VXS_CUDA(ctx, s->rec_world.reserve(size_t(R) + 1));
+  float* d_xyz = reinterpret_cast<float*>(s->rec_local.p); float* d_cnt = d_xyz + 3 * size_t(R); float* d_nrm = d_cnt + size_t(R);
   long long* d_pick = reinterpret_cast<long long*>(s->rec_world.p);
-  VXS_LAUNCH(ctx, "k_ds_reduce", k_ds_reduce, nblk(size_t(R), 128), 128, 0, pts_dev, stride, vs, s->rec_start.p, R, mode, d_xyz, d_cnt, d_pick);
+  if constexpr (sizeof(T) == 8) {
+    VXS_LAUNCH(ctx, "k_ds_reduce_pvec", k_ds_reduce_pvec, nblk(size_t(R), 128), 128, 0, pts_dev, stride, vs, s->rec_start.p, R, d_xyz, d_cnt, d_pick, d_nrm);
+  } else {
+    VXS_LAUNCH(ctx, "k_ds_reduce", k_ds_reduce, nblk(size_t(R), 128), 128, 0, pts_dev, stride, vs, s->rec_start.p, R, mode, d_xyz, d_cnt, d_pick);
+  }
   *n_out = int64_t(R);
   const size_t ncopy = size_t(std::min<int64_t>(cap, int64_t(R)));
   if (xyz_out && ncopy) VXS_CUDA(ctx, cudaMemcpyAsync(xyz_out, d_xyz, ncopy * 12, cudaMemcpyDeviceToHost, st));
   if (count_out && ncopy) VXS_CUDA(ctx, cudaMemcpyAsync(count_out, d_cnt, ncopy * 4, cudaMemcpyDeviceToHost, st));
   if (index_out && ncopy) VXS_CUDA(ctx, cudaMemcpyAsync(index_out, d_pick, ncopy * 8, cudaMemcpyDeviceToHost, st));
+  if (nrm_out && ncopy) VXS_CUDA(ctx, cudaMemcpyAsync(nrm_out, d_nrm, ncopy * 12, cudaMemcpyDeviceToHost, st));
   VXS_CUDA(ctx, cudaStreamSynchronize(st));
   return VXS_OK;
 }
@@ -760,6 +792,19 @@ static int down_sample(vxs_ctx* ctx, int mode, const float* pts_host, int stride
   VXS_CUDA(ctx, s->pts_f.reserve(size_t(n) * stride));
   VXS_CUDA(ctx, cudaMemcpyAsync(s->pts_f.p, pts_host, size_t(n) * stride * 4, cudaMemcpyHostToDevice, ctx->stream));
   return down_sample_dev(ctx, mode, s->pts_f.p, stride, n, voxel_size, xyz_out, count_out, index_out, cap, n_out);
+}
+
+extern "C" int vxs_down_sampling_pvec(vxs_ctx* ctx, const double* pv, int stride_doubles, int64_t n, double voxel_size, float* xyz_out, float* var_diag_out, float* count_out,
+                                      int64_t* first_index_out, int64_t cap, int64_t* n_out) {
+  if (!ctx || !n_out || n < 0 || stride_doubles < 12 || (n > 0 && !pv) || !(voxel_size > 0)) return VXS_ERR_ARG;
+  *n_out = 0;
+  if (n == 0) return VXS_OK;
+  if (n >= (1ll << 32)) return vxs_fail(ctx, VXS_ERR_ARG, "more than 2^32 points in one down-sampling call");
+  cudaSetDevice(ctx->device);
+  VoxScratch* s = scratch(ctx);
+  VXS_CUDA(ctx, s->pts_d.reserve(size_t(n) * stride_doubles));
+  VXS_CUDA(ctx, cudaMemcpyAsync(s->pts_d.p, pv, size_t(n) * stride_doubles * 8, cudaMemcpyHostToDevice, ctx->stream));
+  return down_sample_dev<double>(ctx, 2, s->pts_d.p, stride_doubles, n, voxel_size, xyz_out, count_out, first_index_out, cap, n_out, var_diag_out);
 }
 
 // ------------------------------------------------------------------ submap merge of HBA_add_edge (voxelslam.cpp:2428-2447)
