@@ -357,4 +357,74 @@ int64_t vxo_down_sampling_pvec(const double* pv, int stride, int64_t n, double v
   return int64_t(out.size());
 }
 
+// ---------------------------------------------------------------- stateful local map (oracle only so far)
+// Build the window map from scratch with per-point variances (cov_add by-product on), recut + tras_opt (sets opt_state), then
+// margi(win_count = W, mgsize) with the identity slot map and the factor as built — i.e. the map state the odometry sees after a window slide.
+struct OracleLocalMap { LocalMap map; MapParams mp; int W; LidarFactor f; OracleLocalMap(int w) : W(w), f(w) {} ~OracleLocalMap() { local_map_free(map); } };
+void* vxo_local_map_build(const vxs_map_params* mp, const double* pts_body, const int64_t* scan_offsets, const double* poses12, int W, double var_diag, int mgsize) {
+  OracleLocalMap* h = new OracleLocalMap(W);
+  h->mp = to_map_params(mp, true);
+  auto xs = states_from_poses12(poses12, W);
+  std::vector<std::vector<PV>> scans(W);
+  M3 var = m3_zero(); var(0, 0) = var(1, 1) = var(2, 2) = var_diag;
+  for (int i = 0; i < W; i++) {
+    scans[i].resize(size_t(scan_offsets[i + 1] - scan_offsets[i]));
+    for (size_t k = 0; k < scans[i].size(); k++) { const double* p = pts_body + 3 * (scan_offsets[i] + k); scans[i][k].pnt = v3(p[0], p[1], p[2]); scans[i][k].var = var; }
+  }
+  build_window_factor(h->map, scans, xs, h->mp, 1, h->f, nullptr);
+  std::vector<int> slot(W);
+  for (int i = 0; i < W; i++) slot[i] = i;
+  for (auto& kv : h->map) if (!kv.second->margi(W, mgsize, xs, h->f, slot, h->mp)) { delete h; return nullptr; }
+  return h;
+}
+void vxo_local_map_free(void* h) { delete static_cast<OracleLocalMap*>(h); }
+static void collect_planes(OctoTree* o, std::vector<OctoTree*>& out) {
+  if (o->octo_state == 0) { if (o->is_plane && o->plane.radius > 0) out.push_back(o); return; }
+  for (auto c : o->leaves) if (c) collect_planes(c, out);
+}
+// per plane leaf (row of 52 doubles): center3 normal3 plane_var36 radius N voxel_center3 half_length cov_add-trace eig3
+int64_t vxo_local_map_planes(void* hh, double* rows52, int64_t cap) {
+  OracleLocalMap* h = static_cast<OracleLocalMap*>(hh);
+  std::vector<OctoTree*> pl;
+  for (auto& kv : h->map) collect_planes(kv.second, pl);
+  for (int64_t i = 0; i < int64_t(pl.size()) && i < cap; i++) {
+    double* r = rows52 + 52 * i; const OctoTree* o = pl[i];
+    for (int k = 0; k < 3; k++) { r[k] = o->plane.center[k]; r[3 + k] = o->plane.normal[k]; r[44 + k] = o->voxel_center[k]; r[49 + k] = o->eig_value[k]; }
+    for (int k = 0; k < 36; k++) r[6 + k] = o->plane.plane_var[k];
+    r[42] = o->plane.radius; r[43] = o->pcr_add.N; r[47] = double(o->quater_length) * 2;
+    double t = 0; for (int k = 0; k < 9; k++) t += o->cov_add[k * 9 + k];
+    r[48] = t;
+  }
+  return int64_t(pl.size());
+}
+// the points (world) and variances that formed plane leaf `idx` are not kept by the tree; tests rebuild them from the scene instead.
+int vxo_local_map_odom_accumulate(void* hh, const double* pv12, int64_t n, const double* pose12, const double* rot_var9, const double* tsl_var9, int passes, double* HTH36,
+                                  double* HTz6, double* nnt9, int32_t* flags) {
+  OracleLocalMap* h = static_cast<OracleLocalMap*>(hh);
+  std::vector<PV> pvec; pvec.resize(size_t(n));
+  for (int64_t i = 0; i < n; i++) {
+    const double* p = pv12 + 12 * i;
+    pvec[i].pnt = v3(p[0], p[1], p[2]);
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) pvec[i].var(r, c) = p[3 + 3 * r + c];
+  }
+  State x = states_from_poses12(pose12, 1)[0];
+  M3 rv, tv;
+  for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) { rv(r, c) = rot_var9[3 * r + c]; tv(r, c) = tsl_var9[3 * r + c]; }
+  std::vector<OctoTree*> octos;
+  int m = 0;
+  for (int pass = 0; pass < passes; pass++) m = odom_accumulate(h->map, pvec, x, rv, tv, h->mp.voxel_size, octos, HTH36, HTz6, nnt9);   // later passes use the leaf cache
+  if (flags) for (int64_t i = 0; i < n; i++) flags[i] = 0;
+  if (flags) {   // recompute the per-point flags once more for the tests (same calls, cache warm)
+    const M3 Rt = tr(x.R);
+    for (int64_t i = 0; i < n; i++) {
+      const M3 phat = hat(pvec[i].pnt);
+      const M3 var_world = (x.R * pvec[i].var * Rt + phat * rv * tr(phat)) + tv;
+      const V3 wld = x.R * pvec[i].pnt + x.p;
+      double sd = 0; const Plane* pla = nullptr; OctoTree* oc = nullptr;
+      flags[i] = match(h->map, wld, pla, var_world, sd, oc, h->mp.voxel_size);
+    }
+  }
+  return m;
+}
+
 }  // extern "C"

@@ -5,7 +5,10 @@
 //   tools.hpp:24-49          VOXEL_LOC + hash                                    -> VoxelLoc, voxel_hash
 //   voxel_map.hpp:896-930    SlideWindow
 //   voxel_map.hpp:935-1333   OctoTree: push/push_fix*/plane_judge/allocate/allocate_fix/fix_divide/
-//                            subdivide/recut/tras_opt      (margi/plane_update/match are "next" scope)
+//                            subdivide/recut/tras_opt
+//   voxel_map.hpp:66-81, 1118-1146, 1196-1305, 1335-1392, 1471-1480, 1674-1698
+//                            Plane, plane_update, margi, match, inside   (oracle only, no CUDA path yet)
+//   voxelslam.cpp:876-918    one accumulation pass of the odometry EKF (HTH, HTz, nnt, match count)
 //   voxel_map.hpp:1504-1540  cut_voxel (window)   :1641-1671 cut_voxel (fixed map points)
 //   voxelslam.cpp:600-628    build-from-scratch sequence (cut all scans, then recut + tras_opt)
 //   loop_refine.hpp:273-537  OctreeGBA, OctreeGBA_multi_recut
@@ -46,6 +49,15 @@ struct MapParams {
   double min_point[4] = {5, 5, 5, 5};              // voxelslam.cpp:812
   double plane_thre[8] = {.25, .25, .25, .25, .25, .25, .25, .25};  // plane_eigen_value_thre (already inverted, voxelslam.cpp:825)
   bool with_cov_add = false;         // voxel_map.hpp:990-992 by-product used only by plane_update (odometry)
+  int max_points = 100;              // voxel_map.hpp:86
+};
+
+// voxel_map.hpp:66-81 (is_plane lives on the OctoTree in this restatement)
+struct Plane {
+  V3 center = v3(0, 0, 0), normal = v3(0, 0, 0);
+  double plane_var[36];   // row-major 6x6: [normal | center]
+  float radius = 0;
+  Plane() { for (double& x : plane_var) x = 0; }
 };
 
 struct PV { V3 pnt; M3 var; };  // voxel_map.hpp:14-19 pointVar
@@ -83,6 +95,8 @@ struct OctoTree {  // voxel_map.hpp:935-1502
   bool is_plane = false, isexist = false;
   V3 eig_value; M3 eig_vector;
   int opt_state = -1;
+  int last_num = 0;
+  Plane plane;
   VoxelLoc root{0, 0, 0}; int path = 0;  // bookkeeping for tests only
 
   OctoTree(int l, int w) : layer(l), wdsize(w) { for (auto& p : leaves) p = nullptr; std::memset(cov_add, 0, sizeof cov_add); }
@@ -154,6 +168,113 @@ struct OctoTree {  // voxel_map.hpp:935-1502
     }
     for (auto c : leaves) if (c) c->recut(win_count, x_buf, mp_);
   }
+  // voxel_map.hpp:1118-1146: plane centre, normal and their 6x6 covariance propagated from cov_add (the 9x9 covariance of the
+  // cluster parameters [P(6) | v(3)] accumulated by bf_var) through d(normal)/d(cluster) = sum_k u_k f_kl / (N (lambda_l - lambda_k))
+  void plane_update() {
+    const double N = pcr_add.N;
+    plane.center = v3(pcr_add.v[0] / N, pcr_add.v[1] / N, pcr_add.v[2] / N);
+    const int l = 0;
+    V3 u[3];
+    for (int k = 0; k < 3; k++) u[k] = v3(eig_vector(0, k), eig_vector(1, k), eig_vector(2, k));
+    const double nv = 1.0 / N;
+    double u_c[3][9];
+    for (auto& r : u_c) for (double& x : r) x = 0;
+    for (int k = 0; k < 3; k++) {
+      if (k == l) continue;
+      double ukl[3][3];
+      for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) ukl[a][b] = u[k][a] * u[l][b];
+      double fkl[9] = {ukl[0][0], ukl[1][0] + ukl[0][1], ukl[2][0] + ukl[0][2], ukl[1][1], ukl[1][2] + ukl[2][1], ukl[2][2], 0, 0, 0};
+      const double dk = dot(u[k], plane.center), dl = dot(u[l], plane.center);
+      for (int a = 0; a < 3; a++) fkl[6 + a] = -(dk * u[l][a] + dl * u[k][a]);
+      const double s = nv / (eig_value[l] - eig_value[k]);
+      for (int a = 0; a < 3; a++) for (int c = 0; c < 9; c++) u_c[a][c] += s * u[k][a] * fkl[c];
+    }
+    double Jc[3][9];
+    for (int a = 0; a < 3; a++) for (int c = 0; c < 9; c++) { double t = 0; for (int m = 0; m < 9; m++) t += u_c[a][m] * cov_add[m * 9 + c]; Jc[a][c] = t; }
+    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) {
+      double t = 0; for (int m = 0; m < 9; m++) t += Jc[a][m] * u_c[b][m];
+      plane.plane_var[a * 6 + b] = t;
+      const double jn = nv * Jc[a][6 + b];
+      plane.plane_var[a * 6 + 3 + b] = jn;
+      plane.plane_var[(3 + b) * 6 + a] = jn;
+      plane.plane_var[(3 + a) * 6 + 3 + b] = nv * nv * cov_add[(6 + a) * 9 + 6 + b];
+    }
+    plane.normal = u[0];
+    plane.radius = float(eig_value[2]);
+  }
+  // voxel_map.hpp:1196-1305: marginalise the oldest `mgsize` scans of the window out of every leaf.  mp[] = logical window position ->
+  // slide-window slot (voxel_map.hpp:934).  The "opt_state >= size" printf+exit of the reference is an assert-like guard (returns false).
+  bool margi(int win_count, int mgsize, const std::vector<State>& x_buf, const LidarFactor& vox_opt, const std::vector<int>& mp, const MapParams& mp_) {
+    if (octo_state == 0 && layer >= 0) {
+      if (!isexist || sw == nullptr) return true;
+      std::vector<PC> pcrs_world(wdsize);
+      if (opt_state >= int(vox_opt.pcr_adds.size())) return false;
+      if (opt_state >= 0) {
+        pcr_add = vox_opt.pcr_adds[opt_state];
+        eig_value = vox_opt.eig_values[opt_state];
+        eig_vector = vox_opt.eig_vectors[opt_state];
+        opt_state = -1;
+        for (int i = 0; i < mgsize; i++)
+          if (sw->pcrs_local[mp[i]].N != 0) pcrs_world[i].transform(sw->pcrs_local[mp[i]], x_buf[i].R, x_buf[i].p);
+      } else {
+        pcr_add = pcr_fix;
+        for (int i = 0; i < win_count; i++)
+          if (sw->pcrs_local[mp[i]].N != 0) { pcrs_world[i].transform(sw->pcrs_local[mp[i]], x_buf[i].R, x_buf[i].p); pcr_add += pcrs_world[i]; }
+        if (is_plane) eig3_sym(pcr_add.cov(), eig_value, eig_vector);
+      }
+      if (pcr_fix.N < mp_.max_points && is_plane)
+        if (pcr_add.N - last_num >= 5 || last_num <= 10) { plane_update(); last_num = int(pcr_add.N); }
+      if (pcr_fix.N < mp_.max_points) {
+        for (int i = 0; i < mgsize; i++)
+          if (pcrs_world[i].N != 0) {
+            pcr_fix += pcrs_world[i];
+            for (PV pv : sw->points[mp[i]]) { pv.pnt = x_buf[i].R * pv.pnt + x_buf[i].p; point_fix.push_back(pv); }
+          }
+      } else {
+        for (int i = 0; i < mgsize; i++) if (pcrs_world[i].N != 0) pcr_add -= pcrs_world[i];
+        if (!point_fix.empty()) std::vector<PV>().swap(point_fix);
+      }
+      for (int i = 0; i < mgsize; i++)
+        if (sw->pcrs_local[mp[i]].N != 0) { sw->pcrs_local[mp[i]].clear(); sw->points[mp[i]].clear(); }
+      isexist = !(pcr_fix.N >= pcr_add.N);
+      return true;
+    }
+    isexist = false;
+    bool ok = true;
+    for (auto c : leaves) if (c) { ok = c->margi(win_count, mgsize, x_buf, vox_opt, mp, mp_) && ok; isexist = isexist || c->isexist; }
+    return ok;
+  }
+  bool inside(const V3& wld) const {  // voxel_map.hpp:1471-1480
+    const double hl = quater_length * 2;
+    for (int k = 0; k < 3; k++) if (!(wld[k] >= voxel_center[k] - hl && wld[k] <= voxel_center[k] + hl)) return false;
+    return true;
+  }
+  // voxel_map.hpp:1335-1392: descend to the leaf that contains wld; accept its plane if the point lies within 3 sqrt(radius) of the
+  // centre (in-plane) and within 3 sigma of the plane, sigma^2 = J plane_var J^T + n^T var_wld n.  float intermediates as in the reference.
+  int match(const V3& wld, const Plane*& pla, const M3& var_wld, double& sigma_d, OctoTree*& oc) {
+    int flag = 0;
+    if (octo_state == 0) {
+      if (is_plane) {
+        const V3 d = wld - plane.center;
+        const float dis_to_plane = float(std::fabs(dot(plane.normal, d)));
+        const float dis_to_center = float(dot(d, d));
+        const float range_dis = dis_to_center - dis_to_plane * dis_to_plane;
+        if (range_dis <= 3 * 3 * plane.radius) {
+          const double J[6] = {d[0], d[1], d[2], -plane.normal[0], -plane.normal[1], -plane.normal[2]};
+          double sigma_l = 0;
+          for (int a = 0; a < 6; a++) { double t = 0; for (int b = 0; b < 6; b++) t += plane.plane_var[a * 6 + b] * J[b]; sigma_l += J[a] * t; }
+          sigma_l += dot(plane.normal, var_wld * plane.normal);
+          if (dis_to_plane < 3 * std::sqrt(sigma_l)) { oc = this; sigma_d = sigma_l; pla = &plane; flag = 1; }
+        }
+      }
+    } else {
+      int xyz[3] = {0, 0, 0};
+      for (int k = 0; k < 3; k++) if (wld[k] > voxel_center[k]) xyz[k] = 1;
+      const int leafnum = 4 * xyz[0] + 2 * xyz[1] + xyz[2];
+      if (leaves[leafnum] != nullptr) flag = leaves[leafnum]->match(wld, pla, var_wld, sigma_d, oc);
+    }
+    return flag;
+  }
   void tras_opt(LidarFactor& vox_opt, std::vector<VoxelId>* ids) {  // :1308-1333
     if (octo_state == 0) {
       if (layer >= 0 && isexist && is_plane && sw != nullptr) {
@@ -171,6 +292,44 @@ struct OctoTree {  // voxel_map.hpp:935-1502
 
 using LocalMap = std::unordered_map<VoxelLoc, OctoTree*, VoxelLocHash>;
 inline void local_map_free(LocalMap& m) { for (auto& kv : m) delete kv.second; m.clear(); }
+
+// voxel_map.hpp:1674-1698: root-cell lookup, then OctoTree::match
+inline int match(LocalMap& feat_map, const V3& wld, const Plane*& pla, const M3& var_wld, double& sigma_d, OctoTree*& oc, double voxel_size) {
+  auto it = feat_map.find(voxel_key(wld, voxel_size));
+  if (it == feat_map.end()) return 0;
+  return it->second->match(wld, pla, var_wld, sigma_d, oc);
+}
+// voxelslam.cpp:876-918: one pass over the scan inside the odometry EKF iteration.  octos: per-point cache of the matched leaf
+// (voxelslam.cpp:866-867, 892-900).  HTH 6x6 row-major, HTz 6, nnt 3x3 row-major.  Returns the number of matched points.
+inline int odom_accumulate(LocalMap& surf_map, const std::vector<PV>& pvec, const State& x, const M3& rot_var, const M3& tsl_var, double voxel_size,
+                           std::vector<OctoTree*>& octos, double HTH[36], double HTz[6], double nnt[9]) {
+  for (int i = 0; i < 36; i++) HTH[i] = 0;
+  for (int i = 0; i < 6; i++) HTz[i] = 0;
+  for (int i = 0; i < 9; i++) nnt[i] = 0;
+  int match_num = 0;
+  octos.resize(pvec.size(), nullptr);
+  const M3 Rt = tr(x.R);
+  for (size_t i = 0; i < pvec.size(); i++) {
+    const PV& pv = pvec[i];
+    const M3 phat = hat(pv.pnt);
+    const M3 var_world = (x.R * pv.var * Rt + phat * rot_var * tr(phat)) + tsl_var;
+    const V3 wld = x.R * pv.pnt + x.p;
+    double sigma_d = 0;
+    const Plane* pla = nullptr;
+    int flag;
+    if (octos[i] != nullptr && octos[i]->inside(wld)) flag = octos[i]->match(wld, pla, var_world, sigma_d, octos[i]);
+    else flag = match(surf_map, wld, pla, var_world, sigma_d, octos[i], voxel_size);
+    if (!flag) continue;
+    const double R_inv = 1.0 / (0.0005 + sigma_d);
+    const double resi = dot(pla->normal, wld - pla->center);
+    const V3 jh = phat * (Rt * pla->normal);
+    const double jac[6] = {jh[0], jh[1], jh[2], pla->normal[0], pla->normal[1], pla->normal[2]};
+    for (int a = 0; a < 6; a++) { for (int b = 0; b < 6; b++) HTH[a * 6 + b] += R_inv * jac[a] * jac[b]; HTz[a] -= R_inv * jac[a] * resi; }
+    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) nnt[a * 3 + b] += pla->normal[a] * pla->normal[b];
+    match_num++;
+  }
+  return match_num;
+}
 
 // voxel_map.hpp:1504-1540 (feat_tem_map bookkeeping dropped: in a from-scratch build slide map == map)
 inline void cut_voxel(LocalMap& feat_map, const std::vector<PV>& pvec, int win_count, int wdsize, const std::vector<V3>& pwld, const MapParams& mp_) {

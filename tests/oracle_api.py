@@ -239,3 +239,36 @@ def hba_window(coarse, fine, xyz_f32, kf_offsets, poses12, max_iter, thread_num=
     rc = lib().vxo_hba_window(C.byref(coarse), C.byref(fine), x.ctypes.data_as(C.POINTER(C.c_float)), C.c_int(stride_floats), off.ctypes.data_as(C.POINTER(C.c_int64)), _dp(p),
                               C.c_int(W), C.c_int(max_iter), C.c_int(thread_num), _dp(H), _dp(log), C.byref(it))
     return dict(poses=p, hess=H, resis_log=log[: 2 * it.value], outer_iters=it.value, status=rc)
+
+
+# ---------------------------------------------------------------- SURVEY 8f ranks 1 / 3 (oracle only): stateful local map after margi
+class LocalMap:
+    def __init__(self, mp, pts_body, scan_offsets, poses12, var_diag, mgsize=0):
+        pts = _f64(pts_body).reshape(-1, 3)
+        off = np.ascontiguousarray(scan_offsets, dtype=np.int64)
+        self.W = off.shape[0] - 1
+        lib().vxo_local_map_build.restype = C.c_void_p
+        self._h = lib().vxo_local_map_build(C.byref(mp), _dp(pts), off.ctypes.data_as(C.POINTER(C.c_int64)), _dp(_f64(poses12)), C.c_int(self.W), C.c_double(var_diag), C.c_int(mgsize))
+        if not self._h:
+            raise RuntimeError("vxo_local_map_build failed")
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().vxo_local_map_free(C.c_void_p(self._h)); self._h = None
+
+    def planes(self):
+        lib().vxo_local_map_planes.restype = C.c_int64
+        n = lib().vxo_local_map_planes(C.c_void_p(self._h), None, C.c_int64(0))
+        rows = np.zeros((max(n, 1), 52))
+        lib().vxo_local_map_planes(C.c_void_p(self._h), _dp(rows), C.c_int64(n))
+        r = rows[:n]
+        return dict(center=r[:, 0:3], normal=r[:, 3:6], plane_var=r[:, 6:42].reshape(-1, 6, 6), radius=r[:, 42], N=r[:, 43], voxel_center=r[:, 44:47], half=r[:, 47],
+                    eig=r[:, 49:52])
+
+    def odom_accumulate(self, pv12, pose12, rot_var, tsl_var, passes=1):
+        pv = _f64(pv12).reshape(-1, 12)
+        HTH, HTz, nnt = np.zeros((6, 6)), np.zeros(6), np.zeros((3, 3))
+        flags = np.zeros(pv.shape[0], dtype=np.int32)
+        m = lib().vxo_local_map_odom_accumulate(C.c_void_p(self._h), _dp(pv), C.c_int64(pv.shape[0]), _dp(_f64(pose12)), _dp(_f64(rot_var)), _dp(_f64(tsl_var)), C.c_int(passes),
+                                                _dp(HTH), _dp(HTz), _dp(nnt), flags.ctypes.data_as(C.POINTER(C.c_int32)))
+        return dict(n=m, HTH=HTH, HTz=HTz, nnt=nnt, flags=flags)

@@ -1,0 +1,121 @@
+"""CPU pins for the oracle of SURVEY §8f ranks 1 and 3 (plane_update / margi / match / odometry accumulation, voxel_map.hpp:1118-1392,
+voxelslam.cpp:876-918).  There is no CUDA path for these rows yet; the oracle is pinned so that the next round can build against it."""
+import numpy as np
+import pytest
+
+import oracle_api as oa
+import scenes
+import voxel_slam_b200 as vx
+
+SIGMA = 0.01
+
+
+@pytest.fixture(scope="module")
+def world():
+    W, L = 4, 6.0
+    tr, est = scenes.poses_true_est(W, L, 5)
+    pts, off = scenes.make_points(W, 6000, L, 5, tr)
+    mp = vx.MapParams.make(voxel_size=1.0, max_layer=2)
+    lm = oa.LocalMap(mp, pts, off, tr, SIGMA ** 2, mgsize=0)
+    # world points at the poses the map was built with
+    pw = np.concatenate([pts[off[i]:off[i + 1]] @ tr[i, :9].reshape(3, 3).T + tr[i, 9:] for i in range(W)])
+    return dict(W=W, L=L, tr=tr, pts=pts, off=off, lm=lm, pw=pw, planes=lm.planes())
+
+
+def _points_of(world, k):
+    c, h = world["planes"]["voxel_center"][k], world["planes"]["half"][k]
+    inside = np.all(np.abs(world["pw"] - c) < h * (1 - 1e-9), axis=1)
+    return world["pw"][inside]
+
+
+def test_plane_update_matches_monte_carlo(world):
+    """plane_var (covariance of [normal | centre]) against the sample covariance of planes refitted to re-noised points."""
+    P = world["planes"]
+    assert len(P["N"]) > 20
+    rng = np.random.default_rng(1)
+    checked = 0
+    for k in np.argsort(-P["N"])[:40]:
+        pts = _points_of(world, k)
+        if pts.shape[0] != int(P["N"][k]) or P["eig"][k, 1] < 20 * P["eig"][k, 0]:   # points on the cube faces / badly conditioned patches: skip
+            continue
+        n0, c0 = P["normal"][k], P["center"][k]
+        assert np.allclose(c0, pts.mean(0), atol=1e-12)
+        T = 3000
+        noisy = pts[None] + SIGMA * rng.standard_normal((T,) + pts.shape)
+        c = noisy.mean(1)
+        d = noisy - c[:, None]
+        cov = np.einsum("tni,tnj->tij", d, d) / pts.shape[0]
+        w, U = np.linalg.eigh(cov)
+        nrm = U[:, :, 0]
+        nrm *= np.sign(nrm @ n0)[:, None]
+        S = np.cov(np.concatenate([nrm, c], axis=1).T)
+        V = P["plane_var"][k]
+        # the refitted plane sees the original scatter PLUS the added noise, so the prediction is compared block-wise with 25 % slack
+        for blk in (slice(0, 3), slice(3, 6)):
+            assert abs(np.trace(S[blk, blk]) - np.trace(V[blk, blk])) < 0.25 * np.trace(V[blk, blk])
+        assert np.linalg.norm(S - V) < 0.3 * np.linalg.norm(V)
+        assert abs(P["radius"][k] - np.float32(P["eig"][k, 2])) == 0
+        checked += 1
+    assert checked >= 8
+
+
+def test_margi_moves_scans_into_the_fixed_part(world):
+    """After margi(mgsize=2) the two oldest scans live in pcr_fix: the plane table is unchanged (same points) and a second map built with
+    those scans marginalised still matches the same points."""
+    mp = vx.MapParams.make(voxel_size=1.0, max_layer=2)
+    lm2 = oa.LocalMap(mp, world["pts"], world["off"], world["tr"], SIGMA ** 2, mgsize=2)
+    a, b = world["planes"], lm2.planes()
+    assert len(a["N"]) == len(b["N"])
+    ia, ib = np.lexsort(a["voxel_center"].T), np.lexsort(b["voxel_center"].T)
+    assert np.array_equal(a["voxel_center"][ia], b["voxel_center"][ib])
+    assert np.allclose(a["center"][ia], b["center"][ib], atol=1e-12) and np.allclose(a["plane_var"][ia], b["plane_var"][ib], rtol=1e-9, atol=1e-18)
+
+
+def _brute_force(world, pv, pose, rot_var, tsl_var):
+    P = world["planes"]
+    R, p = pose[:9].reshape(3, 3), pose[9:]
+    HTH, HTz, nnt, flags = np.zeros((6, 6)), np.zeros(6), np.zeros((3, 3)), np.zeros(pv.shape[0], dtype=np.int32)
+    f32 = np.float32
+    for i in range(pv.shape[0]):
+        x, var = pv[i, :3], pv[i, 3:].reshape(3, 3)
+        phat = np.array([[0, -x[2], x[1]], [x[2], 0, -x[0]], [-x[1], x[0], 0]])
+        vw = R @ var @ R.T + phat @ rot_var @ phat.T + tsl_var
+        w = R @ x + p
+        inside = np.where(np.all(np.abs(w - P["voxel_center"]) < P["half"][:, None], axis=1))[0]
+        if inside.size != 1:
+            continue
+        k = inside[0]
+        d = w - P["center"][k]
+        dp = f32(abs(P["normal"][k] @ d)); dc = f32(d @ d)
+        if f32(dc - f32(dp * dp)) > f32(9) * f32(P["radius"][k]):
+            continue
+        J = np.concatenate([d, -P["normal"][k]])
+        sig = J @ P["plane_var"][k] @ J + P["normal"][k] @ vw @ P["normal"][k]
+        if not (float(dp) < 3 * np.sqrt(sig)):
+            continue
+        rinv = 1.0 / (0.0005 + sig)
+        res = P["normal"][k] @ d
+        jac = np.concatenate([phat @ R.T @ P["normal"][k], P["normal"][k]])
+        HTH += rinv * np.outer(jac, jac); HTz -= rinv * jac * res; nnt += np.outer(P["normal"][k], P["normal"][k]); flags[i] = 1
+    return HTH, HTz, nnt, flags
+
+
+def test_odom_accumulate_matches_brute_force(world):
+    """voxelslam.cpp:876-918 against a numpy loop over the exported plane table (independent leaf search by cube containment)."""
+    rng = np.random.default_rng(3)
+    W, L = world["W"], world["L"]
+    pose_true = vx.true_pose(L, W)                                  # the next scan of the trajectory
+    body = vx.gen_scan(L, W, 1500, pose_true, seed=0x5EED0000 + 77)
+    pose = vx.perturb_pose(pose_true, 99, 2e-3, 1e-2)
+    var = np.tile((SIGMA ** 2 * np.eye(3)).reshape(1, 9), (body.shape[0], 1)) * rng.uniform(0.5, 2.0, (body.shape[0], 1))
+    pv = np.concatenate([body, var], axis=1)
+    rot_var, tsl_var = 1e-6 * np.eye(3), 1e-4 * np.eye(3)
+    o = world["lm"].odom_accumulate(pv, pose, rot_var, tsl_var, passes=1)
+    HTH, HTz, nnt, flags = _brute_force(world, pv, pose, rot_var, tsl_var)
+    assert o["n"] == int(flags.sum()) > 300
+    assert np.array_equal(o["flags"], flags)
+    for a, b in ((o["HTH"], HTH), (o["HTz"], HTz), (o["nnt"], nnt)):
+        assert np.max(np.abs(a - b)) < 1e-9 * np.max(np.abs(b))
+    # the per-point leaf cache of the EKF loop (voxelslam.cpp:892-900) does not change the result
+    o2 = world["lm"].odom_accumulate(pv, pose, rot_var, tsl_var, passes=3)
+    assert o2["n"] == o["n"] and np.array_equal(o2["HTH"], o["HTH"]) and np.array_equal(o2["HTz"], o["HTz"])
