@@ -53,3 +53,34 @@ def test_cpp_shim_plain_layer_compiles():
         f.write('#include "voxel_slam_b200/csrc/shim/voxel_ba_shim.hpp"\nint main() { vxs_shim::Lidar_BA_Optimizer o; return o.thd_num == 2 ? 0 : 1; }\n')
     r = subprocess.run(["g++", "-std=c++14", "-fsyntax-only", "-I", root, f.name], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_cpp_shim_typed_layer_type_checks_against_reference_signatures():
+    """The Eigen/PCL-typed layer of the shim (push_voxel, damping_iter wrappers, IMU adapter, down-sampling, submap merge) type-checks against
+    stand-ins that mirror the reference's names, members and call signatures (tests/shim_stubs/reference_stubs.hpp; Eigen/PCL are not
+    installed here), instantiated the way voxelslam.cpp calls them."""
+    import subprocess
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = r'''
+#include "tests/shim_stubs/reference_stubs.hpp"
+#define VXS_SHIM_WITH_REFERENCE_TYPES
+#include "voxel_slam_b200/csrc/shim/voxel_ba_shim.hpp"
+void use(vxs_shim::Context& c, std::vector<IMUST>& xs, std::deque<IMU_PRE*>& imus, std::vector<Keyframe*>& smps, PVec& pvec, pcl::PointCloud<PointType>& pl) {
+  vxs_shim::LidarFactor f(c, int(xs.size()));
+  std::vector<PointCluster> pcrs(xs.size()); PointCluster fix, add; Eigen::Vector3d ev; Eigen::Matrix3d U;
+  vxs_shim::push_voxel(f, pcrs, fix, 1.0, ev, U, add);
+  Eigen::MatrixXd hess; std::vector<double> resis;
+  vxs_shim::li_ba_damping_iter(xs, f, imus, &hess, 1e-4);
+  vxs_shim::lidar_ba_damping_iter(xs, f, &hess, resis, 3, 2);
+  vxs_shim::down_sampling_voxel(c, pl, 0.1);
+  vxs_shim::down_sampling_close(c, pl, 0.1);
+  vxs_shim::down_sampling_pvec(c, pvec, 0.1, pl);
+  vxs_shim::submap_merge(c, xs, smps, 1.0, pl);
+}
+int main() { return 0; }
+'''
+    with tempfile.NamedTemporaryFile("w", suffix=".cpp", delete=False) as f:
+        f.write(src)
+    r = subprocess.run(["g++", "-std=c++14", "-fsyntax-only", "-I", root, f.name], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
