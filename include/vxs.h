@@ -223,6 +223,19 @@ int vxs_down_sampling_pvec(vxs_ctx* ctx, const double* pv, int stride_doubles, i
 int vxs_submap_merge(vxs_ctx* ctx, const float* xyz, int stride_floats, const int64_t* kf_offsets, const double* poses12, int W,
                      double voxel_size, float* xyz_out, float* count_out, int64_t* first_index_out, int64_t cap, int64_t* n_out);
 
+/* ---------------------------------------------------------------- odometry association
+ * The per-point loop of the EKF update (voxelslam.cpp:876-918): world point and its covariance, match() against the voxel map
+ * (voxel_map.hpp:1674-1698, 1335-1392), HTH += R_inv jac jac^T, HTz -= R_inv jac resi, nnt += n n^T, match_num++.
+ * vxs_odom_set_planes: the plane leaves of the current map, exported by the caller after every marginalisation (the octree stays on
+ * the host until §8f rank 1 lands): cube centre (OctoTree::voxel_center) and layer, plane.center / normal / plane_var (6x6 row-major)
+ * / radius as written by plane_update (voxel_map.hpp:1118-1146).  Leaves with plane.radius == 0 never match and may be left out.
+ * vxs_odom_accumulate: pv12 = n pointVar records (pnt 3 | var 3x3 row-major), NULL = re-use the scan of the previous call;
+ * pose12 = R row-major | p of x_curr; rot_var9 / tsl_var9 = x_curr.cov blocks (0,0) and (3,3).  flags (may be NULL): 1 where the point matched. */
+int vxs_odom_set_planes(vxs_ctx* ctx, const vxs_map_params* mp, int64_t n, const double* voxel_center, const int32_t* layer, const double* center,
+                        const double* normal, const double* plane_var36, const float* radius);
+int vxs_odom_accumulate(vxs_ctx* ctx, const double* pv12, int64_t n, const double* pose12, const double* rot_var9, const double* tsl_var9,
+                        double* HTH36, double* HTz6, double* nnt9, int64_t* match_num, int32_t* flags);
+
 #ifdef __cplusplus
 }
 #endif

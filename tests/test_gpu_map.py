@@ -272,3 +272,35 @@ def test_down_sampling_pvec_parity(ctx):
         assert np.array_equal(g["var_diag"][go].view(np.uint32), o["var_diag"][oo].view(np.uint32))
         assert np.array_equal(g["count"][go], o["count"][oo]) and int(g["count"].sum()) == n
     assert len(ctx.down_sampling_pvec(pv[:0], 0.5)["index"]) == 0
+
+
+def test_odom_accumulate_parity(ctx):
+    """voxelslam.cpp:876-918 + voxel_map.hpp:1335-1392, 1674-1698 — point -> plane-leaf association bit-exact against the oracle's octree
+    descent (flags equal), accumulated HTH / HTz / nnt to 1e-9 (warp-tree + RED summation order)."""
+    W, L, sigma = 4, 6.0, 0.01
+    tr, _ = scenes.poses_true_est(W, L, 5)
+    pts, off = scenes.make_points(W, 6000, L, 5, tr)
+    mp = vx.MapParams.make(voxel_size=1.0, max_layer=2)
+    lm = oa.LocalMap(mp, pts, off, tr, sigma ** 2, mgsize=1)
+    P = lm.planes()
+    layer = np.rint(np.log2(1.0 / (2.0 * P["half"]))).astype(np.int32)
+    assert layer.min() >= 0 and layer.max() <= 2 and len(layer) > 50
+    ctx.odom_set_planes(mp, P["voxel_center"], layer, P["center"], P["normal"], P["plane_var"], P["radius"])
+    rng = np.random.default_rng(3)
+    pose_true = vx.true_pose(L, W)
+    body = vx.gen_scan(L, W, 20000, pose_true, seed=0x5EED0000 + 77)
+    var = np.tile((sigma ** 2 * np.eye(3)).reshape(1, 9), (body.shape[0], 1)) * rng.uniform(0.5, 2.0, (body.shape[0], 1))
+    pv = np.concatenate([body, var], axis=1)
+    rot_var, tsl_var = 1e-6 * np.eye(3), 1e-4 * np.eye(3)
+    for k, (rs, ps) in enumerate([(2e-3, 1e-2), (0.0, 0.0), (2e-2, 5e-2)]):
+        pose = vx.perturb_pose(pose_true, 99 + k, rs, ps) if rs > 0 else pose_true
+        g = ctx.odom_accumulate(pv if k == 0 else None, pose, rot_var, tsl_var, n=pv.shape[0])      # later passes re-use the resident scan
+        o = lm.odom_accumulate(pv, pose, rot_var, tsl_var)
+        assert g["n"] == o["n"] and (k == 2 or o["n"] > 3000)
+        assert np.array_equal(g["flags"], o["flags"])
+        for a, b in ((g["HTH"], o["HTH"]), (g["HTz"], o["HTz"]), (g["nnt"], o["nnt"])):
+            assert np.max(np.abs(a - b)) <= 1e-9 * max(np.max(np.abs(b)), 1e-300)
+    # empty plane table: nothing matches
+    ctx.odom_set_planes(mp, P["voxel_center"][:0], layer[:0], P["center"][:0], P["normal"][:0], P["plane_var"][:0], P["radius"][:0])
+    e = ctx.odom_accumulate(pv, pose_true, rot_var, tsl_var)
+    assert e["n"] == 0 and not e["flags"].any() and not e["HTH"].any()

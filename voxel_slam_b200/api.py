@@ -389,6 +389,30 @@ def _down_sampling_pvec(self, pv_f64, voxel_size):
 Context.down_sampling_pvec = _down_sampling_pvec
 
 
+def _odom_set_planes(self, mp, voxel_center, layer, center, normal, plane_var, radius):
+    vc, c, nr, pv = _f64(voxel_center).reshape(-1, 3), _f64(center).reshape(-1, 3), _f64(normal).reshape(-1, 3), _f64(plane_var).reshape(-1, 36)
+    ly = np.ascontiguousarray(layer, dtype=np.int32)
+    rd = np.ascontiguousarray(radius, dtype=np.float32)
+    self._check(lib().vxs_odom_set_planes(self._p, C.byref(mp), C.c_int64(vc.shape[0]), _dp(vc), ly.ctypes.data_as(C.POINTER(C.c_int32)), _dp(c), _dp(nr), _dp(pv),
+                                          rd.ctypes.data_as(C.POINTER(C.c_float))))
+
+
+def _odom_accumulate(self, pv12, pose12, rot_var, tsl_var, n=None, want_flags=True):
+    """One accumulation pass of the odometry EKF (voxelslam.cpp:876-918).  pv12=None re-uses the resident scan (pass n)."""
+    pv = _f64(pv12).reshape(-1, 12) if pv12 is not None else None
+    n = pv.shape[0] if pv is not None else int(n)
+    HTH, HTz, nnt = np.zeros((6, 6)), np.zeros(6), np.zeros((3, 3))
+    flags = np.zeros(max(n, 1), dtype=np.int32) if want_flags else None
+    m = C.c_int64(0)
+    self._check(lib().vxs_odom_accumulate(self._p, _dp(pv), C.c_int64(n), _dp(_f64(pose12)), _dp(_f64(rot_var)), _dp(_f64(tsl_var)), _dp(HTH), _dp(HTz), _dp(nnt), C.byref(m),
+                                          flags.ctypes.data_as(C.POINTER(C.c_int32)) if want_flags else None))
+    return dict(n=m.value, HTH=HTH, HTz=HTz, nnt=nnt, flags=flags[:n] if want_flags else None)
+
+
+Context.odom_set_planes = _odom_set_planes
+Context.odom_accumulate = _odom_accumulate
+
+
 def _submap_merge(self, xyz_f32, kf_offsets, poses12, voxel_size, stride_floats=None):
     """Submap merge of HBA_add_edge (voxelslam.cpp:2428-2447): clouds into the frame of keyframe 0 + down_sampling_voxel."""
     x = np.ascontiguousarray(xyz_f32, dtype=np.float32)

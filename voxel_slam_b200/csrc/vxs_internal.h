@@ -36,6 +36,7 @@ struct DevBuf {  // grow-only device buffer
 
 struct vxs_ctx {
   DevBuf<double> stage2;             // AoS staging of an asynchronous cluster upload (lives until its conversion kernels ran)
+  void* odom_scratch = nullptr;      // vxs_odom.cu: plane table + resident scan
   long long* ldlt_prof = nullptr;   // vxs_diag_ldlt_phases: device stamp buffer, otherwise null
   int device = 0;
   int sm_count = VXS_SM_COUNT_FALLBACK;
@@ -100,6 +101,7 @@ struct vxs_factor {
   cudaEvent_t up_ev[UP_MAX] = {nullptr};
   cudaEvent_t up_fence = nullptr;
 };
+void vxs_odom_release(vxs_ctx* c);
 int vxs_factor_wait_uploads(vxs_factor* f);   // orders ctx->stream behind every pending upload chunk (device-side wait, no host sync)
 
 inline int vxs_fail(vxs_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) {

@@ -1,0 +1,261 @@
+// Odometry association + EKF normal-equation accumulation on the device:
+//   match()            voxel_map.hpp:1674-1698  root-cell lookup
+//   OctoTree::match()  voxel_map.hpp:1335-1392  descent to the leaf, 3-sigma gates, sigma_d
+//   the per-point loop of the EKF update, voxelslam.cpp:876-918: HTH += R_inv jac jac^T, HTz -= R_inv jac resi, nnt += n n^T, match_num++
+//
+// The octree itself stays where the reference keeps it (host) until the stateful map moves to the device (§8f rank 1): after every
+// marginalisation the caller exports the plane leaves once (vxs_odom_set_planes: cube centre + layer, plane centre / normal / 6x6
+// covariance / radius — the fields plane_update writes, voxel_map.hpp:1118-1146) and every EKF iteration is then one kernel over the
+// scan.  Leaves partition space, so "descend from the root" == "probe the sorted leaf table with the (root cell, layer, octant path)
+// key of every layer"; the octant path follows the reference's comparisons and float quarter lengths exactly (same routine as the map
+// build), so the point -> leaf assignment is bit-exact.
+#include <algorithm>
+#include <vector>
+#include "vxs_internal.h"
+#include "vxs_math.cuh"
+
+using namespace vxs;
+
+namespace {
+
+// ---- bit-exact cell arithmetic (same as vxs_voxelize.cu; kept local so that the validated map-build unit stays untouched)
+__host__ __device__ inline long long od_quantise(double pw, double voxel_size) {
+#ifdef __CUDA_ARCH__
+  float loc = __double2float_rn(__ddiv_rn(pw, voxel_size));
+  if (loc < 0.0f) loc = __fsub_rn(loc, 1.0f);
+  return __float2ll_rz(loc);
+#else
+  float loc = float(pw / voxel_size);
+  if (loc < 0) loc -= 1;
+  return (long long)loc;
+#endif
+}
+__device__ __forceinline__ double od_dot3(double a0, double a1, double a2, double x, double y, double z, double t) {
+  return __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(a0, x), __dmul_rn(a1, y)), __dmul_rn(a2, z)), t);
+}
+// octants of the deeper layers, 3 bits per layer, layer 1 in the low bits (voxel_map.hpp:1029-1040)
+__device__ __forceinline__ unsigned int od_octants(double wx, double wy, double wz, long long kx, long long ky, long long kz, double voxel_size, int max_layer) {
+  double cx = __dmul_rn(__dadd_rn(0.5, (double)kx), voxel_size), cy = __dmul_rn(__dadd_rn(0.5, (double)ky), voxel_size), cz = __dmul_rn(__dadd_rn(0.5, (double)kz), voxel_size);
+  float q = __double2float_rn(__ddiv_rn(voxel_size, 4.0));
+  unsigned int bits = 0;
+  for (int l = 0; l < max_layer; l++) {
+    const int bx = wx > cx, by = wy > cy, bz = wz > cz;
+    bits |= (unsigned int)(4 * bx + 2 * by + bz) << (3 * l);
+    cx = __dadd_rn(cx, (double)__fmul_rn((float)(2 * bx - 1), q));
+    cy = __dadd_rn(cy, (double)__fmul_rn((float)(2 * by - 1), q));
+    cz = __dadd_rn(cz, (double)__fmul_rn((float)(2 * bz - 1), q));
+    q = __fdiv_rn(q, 2.0f);
+  }
+  return bits;
+}
+// key of a node: linear root id | layer | path (path = octants most-significant first, as OctoTree numbers its children)
+__host__ __device__ inline unsigned long long od_key(unsigned long long root_lin, int layer, unsigned int path) { return (root_lin << 12) | ((unsigned long long)layer << 9) | path; }
+__device__ __forceinline__ unsigned int od_path_prefix(unsigned int bits, int depth) {
+  unsigned int p = 0;
+  for (int j = 0; j < depth; j++) p = p * 8 + ((bits >> (3 * j)) & 7u);
+  return p;
+}
+
+#define OD_ROW 28   // per plane: centre 3, normal 3, plane_var upper triangle 21, radius 1
+
+struct OdomScratch {
+  DevBuf<unsigned long long> keys;
+  DevBuf<double> rows, pts, out, st;
+  DevBuf<int> flags;
+  long long n_planes = 0, n_pts = 0;
+  long long minx = 0, miny = 0, minz = 0, ex = 0, ey = 0, ez = 0;
+  double voxel_size = 1.0;
+  int max_layer = 0;
+};
+
+__global__ void __launch_bounds__(256) k_odom_accumulate(const double* __restrict__ pv, long long n, const double* __restrict__ st /* R9 p3 rotvar9 tslvar9 */,
+                                                         const unsigned long long* __restrict__ keys, const double* __restrict__ rows, long long n_planes, long long minx,
+                                                         long long miny, long long minz, long long ex, long long ey, long long ez, double voxel_size, int max_layer,
+                                                         double* __restrict__ out /* HTH 36 | HTz 6 | nnt 9 | count */, int* __restrict__ flags) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double acc[34];
+#pragma unroll
+  for (int k = 0; k < 34; k++) acc[k] = 0.0;
+  int hit = 0;
+  if (i < n) {
+    const double* p = pv + 12 * i;
+    const double x = p[0], y = p[1], z = p[2];
+    const double R[9] = {st[0], st[1], st[2], st[3], st[4], st[5], st[6], st[7], st[8]};
+    const double wx = od_dot3(R[0], R[1], R[2], x, y, z, st[9]), wy = od_dot3(R[3], R[4], R[5], x, y, z, st[10]), wz = od_dot3(R[6], R[7], R[8], x, y, z, st[11]);
+    const long long kx = od_quantise(wx, voxel_size), ky = od_quantise(wy, voxel_size), kz = od_quantise(wz, voxel_size);
+    const long long rx = kx - minx, ry = ky - miny, rz = kz - minz;
+    if (rx >= 0 && ry >= 0 && rz >= 0 && rx < ex && ry < ey && rz < ez) {
+      const unsigned long long root_lin = ((unsigned long long)rx * (unsigned long long)ey + (unsigned long long)ry) * (unsigned long long)ez + (unsigned long long)rz;
+      const unsigned int bits = od_octants(wx, wy, wz, kx, ky, kz, voxel_size, max_layer);
+      long long found = -1;
+      for (int l = 0; l <= max_layer && found < 0; l++) {
+        const unsigned long long key = od_key(root_lin, l, od_path_prefix(bits, l));
+        long long lo = 0, hi = n_planes;                       // first key >= wanted
+        while (lo < hi) { const long long mid = (lo + hi) >> 1; if (keys[mid] < key) lo = mid + 1; else hi = mid; }
+        if (lo < n_planes && keys[lo] == key) found = lo;
+      }
+      if (found >= 0) {
+        const double* r = rows + OD_ROW * found;
+        const double c[3] = {r[0], r[1], r[2]}, nr[3] = {r[3], r[4], r[5]};
+        const double d[3] = {wx - c[0], wy - c[1], wz - c[2]};
+        const double nd = (nr[0] * d[0] + nr[1] * d[1]) + nr[2] * d[2];
+        const float dis_to_plane = (float)fabs(nd);
+        const float dis_to_center = (float)((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]);
+        const float range_dis = __fsub_rn(dis_to_center, __fmul_rn(dis_to_plane, dis_to_plane));
+        if (range_dis <= __fmul_rn(9.0f, (float)r[27])) {
+          // sigma_l = J plane_var J^T + n^T var_world n,  J = [d | -n]
+          const double J[6] = {d[0], d[1], d[2], -nr[0], -nr[1], -nr[2]};
+          double sigma_l = 0.0;
+          int t = 6;
+#pragma unroll
+          for (int a = 0; a < 6; a++)
+#pragma unroll
+            for (int b = a; b < 6; b++) { const double v = r[t++]; sigma_l += (a == b ? 1.0 : 2.0) * v * J[a] * J[b]; }
+          // var_world = R var R^T + phat rot_var phat^T + tsl_var; only n^T (.) n is needed:  (R^T n)^T var (R^T n) + (phat^T n)^T rot_var (phat^T n) + n^T tsl_var n
+          const double a1[3] = {R[0] * nr[0] + R[3] * nr[1] + R[6] * nr[2], R[1] * nr[0] + R[4] * nr[1] + R[7] * nr[2], R[2] * nr[0] + R[5] * nr[1] + R[8] * nr[2]};   // R^T n
+          const double a2[3] = {-(z * nr[1] - y * nr[2]), -(x * nr[2] - z * nr[0]), -(y * nr[0] - x * nr[1])};   // phat^T n = -(p x n)
+          const double* var = p + 3;
+          const double* rv = st + 12; const double* tv = st + 21;
+          double q = 0.0;
+#pragma unroll
+          for (int a = 0; a < 3; a++)
+#pragma unroll
+            for (int b = 0; b < 3; b++) q += a1[a] * var[3 * a + b] * a1[b] + a2[a] * rv[3 * a + b] * a2[b] + nr[a] * tv[3 * a + b] * nr[b];
+          sigma_l += q;
+          if ((double)dis_to_plane < 3.0 * sqrt(sigma_l)) {
+            hit = 1;
+            const double R_inv = 1.0 / (0.0005 + sigma_l);
+            // jac.head(3) = phat R^T n = p x (R^T n),  jac.tail(3) = n
+            const double jac[6] = {y * a1[2] - z * a1[1], z * a1[0] - x * a1[2], x * a1[1] - y * a1[0], nr[0], nr[1], nr[2]};
+            int u = 0;
+#pragma unroll
+            for (int a = 0; a < 6; a++)
+#pragma unroll
+              for (int b = a; b < 6; b++) acc[u++] = R_inv * jac[a] * jac[b];           // 21: upper triangle of HTH
+#pragma unroll
+            for (int a = 0; a < 6; a++) acc[21 + a] = -R_inv * jac[a] * nd;                // HTz
+            acc[27] = nr[0] * nr[0]; acc[28] = nr[0] * nr[1]; acc[29] = nr[0] * nr[2]; acc[30] = nr[1] * nr[1]; acc[31] = nr[1] * nr[2]; acc[32] = nr[2] * nr[2];
+            acc[33] = 1.0;
+          }
+        }
+      }
+    }
+    if (flags) flags[i] = hit;
+  }
+  // warp reduction, one fp64 RED per value and warp
+#pragma unroll
+  for (int k = 0; k < 34; k++) {
+    double v = acc[k];
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(out + k, v);
+  }
+}
+
+OdomScratch* odom_scratch(vxs_ctx* c) { if (!c->odom_scratch) c->odom_scratch = new OdomScratch(); return static_cast<OdomScratch*>(c->odom_scratch); }
+
+}  // namespace
+
+void vxs_odom_release(vxs_ctx* c) {
+  if (!c->odom_scratch) return;
+  OdomScratch* s = static_cast<OdomScratch*>(c->odom_scratch);
+  s->keys.release(); s->rows.release(); s->pts.release(); s->out.release(); s->st.release(); s->flags.release();
+  delete s;
+  c->odom_scratch = nullptr;
+}
+
+extern "C" int vxs_odom_set_planes(vxs_ctx* ctx, const vxs_map_params* mp, int64_t n, const double* voxel_center, const int32_t* layer, const double* center, const double* normal,
+                                   const double* plane_var36, const float* radius) {
+  if (!ctx || !mp || n < 0 || (n > 0 && (!voxel_center || !layer || !center || !normal || !plane_var36 || !radius))) return VXS_ERR_ARG;
+  if (mp->max_layer < 0 || mp->max_layer > 3 || !(mp->voxel_size > 0)) return vxs_fail(ctx, VXS_ERR_ARG, "max_layer must be 0..3 and voxel_size > 0");
+  cudaSetDevice(ctx->device);
+  OdomScratch* s = odom_scratch(ctx);
+  s->n_planes = 0; s->voxel_size = mp->voxel_size; s->max_layer = mp->max_layer;
+  if (n == 0) return VXS_OK;
+  const double vs = mp->voxel_size;
+  std::vector<long long> root(size_t(n) * 3);
+  std::vector<unsigned int> path(n);
+  long long mn[3] = {LLONG_MAX, LLONG_MAX, LLONG_MAX}, mx[3] = {LLONG_MIN, LLONG_MIN, LLONG_MIN};
+  for (int64_t i = 0; i < n; i++) {
+    if (layer[i] < 0 || layer[i] > mp->max_layer) return vxs_fail(ctx, VXS_ERR_ARG, "vxs_odom_set_planes: layer outside 0..max_layer");
+    const double* vc = voxel_center + 3 * i;
+    long long k[3];
+    for (int a = 0; a < 3; a++) { k[a] = od_quantise(vc[a], vs); root[3 * size_t(i) + a] = k[a]; mn[a] = std::min(mn[a], k[a]); mx[a] = std::max(mx[a], k[a]); }
+    // replay the descent from the root cell to this cube (voxel_map.hpp:1029-1040): the cube centre picks its own octants
+    double c[3] = {(0.5 + double(k[0])) * vs, (0.5 + double(k[1])) * vs, (0.5 + double(k[2])) * vs};
+    float q = float(vs / 4.0);
+    unsigned int pth = 0;
+    for (int l = 0; l < layer[i]; l++) {
+      int b[3];
+      for (int a = 0; a < 3; a++) { b[a] = vc[a] > c[a]; c[a] = c[a] + double(float(2 * b[a] - 1) * q); }
+      pth = pth * 8 + unsigned(4 * b[0] + 2 * b[1] + b[2]);
+      q = q / 2.0f;
+    }
+    path[i] = pth;
+  }
+  const long double ex = (long double)mx[0] - mn[0] + 1, ey = (long double)mx[1] - mn[1] + 1, ez = (long double)mx[2] - mn[2] + 1;
+  if (ex * ey * ez >= (long double)(1ull << 50)) return vxs_fail(ctx, VXS_ERR_RANGE, "plane table spans more than 2^50 root cells");
+  s->minx = mn[0]; s->miny = mn[1]; s->minz = mn[2]; s->ex = (long long)ex; s->ey = (long long)ey; s->ez = (long long)ez;
+  std::vector<unsigned long long> key(n);
+  std::vector<int64_t> order(n);
+  for (int64_t i = 0; i < n; i++) {
+    const unsigned long long lin = ((unsigned long long)(root[3 * size_t(i)] - mn[0]) * (unsigned long long)s->ey + (unsigned long long)(root[3 * size_t(i) + 1] - mn[1])) * (unsigned long long)s->ez +
+                                   (unsigned long long)(root[3 * size_t(i) + 2] - mn[2]);
+    key[i] = od_key(lin, layer[i], path[i]);
+    order[i] = i;
+  }
+  std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return key[a] < key[b]; });
+  std::vector<unsigned long long> skey(n);
+  std::vector<double> rows(size_t(n) * OD_ROW);
+  for (int64_t t = 0; t < n; t++) {
+    const int64_t i = order[t];
+    skey[t] = key[i];
+    if (t > 0 && skey[t] == skey[t - 1]) return vxs_fail(ctx, VXS_ERR_ARG, "vxs_odom_set_planes: two planes in the same cube");
+    double* r = rows.data() + size_t(t) * OD_ROW;
+    for (int a = 0; a < 3; a++) { r[a] = center[3 * i + a]; r[3 + a] = normal[3 * i + a]; }
+    int u = 6;
+    for (int a = 0; a < 6; a++) for (int b = a; b < 6; b++) r[u++] = plane_var36[36 * i + 6 * a + b];
+    r[27] = double(radius[i]);
+  }
+  VXS_CUDA(ctx, s->keys.reserve(size_t(n)));
+  VXS_CUDA(ctx, s->rows.reserve(size_t(n) * OD_ROW));
+  VXS_CUDA(ctx, cudaMemcpyAsync(s->keys.p, skey.data(), size_t(n) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  VXS_CUDA(ctx, cudaMemcpyAsync(s->rows.p, rows.data(), rows.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  VXS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  s->n_planes = n;
+  return VXS_OK;
+}
+
+extern "C" int vxs_odom_accumulate(vxs_ctx* ctx, const double* pv12, int64_t n, const double* pose12, const double* rot_var9, const double* tsl_var9, double* HTH36, double* HTz6,
+                                   double* nnt9, int64_t* match_num, int32_t* flags) {
+  if (!ctx || n < 0 || !pose12 || !rot_var9 || !tsl_var9 || !HTH36 || !HTz6 || !nnt9 || !match_num) return VXS_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  OdomScratch* s = odom_scratch(ctx);
+  if (pv12) {   // NULL re-uses the scan of the previous call (the EKF loop re-associates the same scan up to four times)
+    VXS_CUDA(ctx, s->pts.reserve(size_t(std::max<int64_t>(n, 1)) * 12));
+    if (n) VXS_CUDA(ctx, cudaMemcpyAsync(s->pts.p, pv12, size_t(n) * 96, cudaMemcpyHostToDevice, ctx->stream));
+    s->n_pts = n;
+  } else if (n != s->n_pts) return vxs_fail(ctx, VXS_ERR_ARG, "vxs_odom_accumulate: no resident scan of this size");
+  double st[30];
+  for (int k = 0; k < 12; k++) st[k] = pose12[k];
+  for (int k = 0; k < 9; k++) { st[12 + k] = rot_var9[k]; st[21 + k] = tsl_var9[k]; }
+  VXS_CUDA(ctx, s->st.reserve(30)); VXS_CUDA(ctx, s->out.reserve(34));
+  VXS_CUDA(ctx, cudaMemcpyAsync(s->st.p, st, sizeof st, cudaMemcpyHostToDevice, ctx->stream));
+  VXS_CUDA(ctx, cudaMemsetAsync(s->out.p, 0, 34 * 8, ctx->stream));
+  int* dflags = nullptr;
+  if (flags) { VXS_CUDA(ctx, s->flags.reserve(size_t(std::max<int64_t>(n, 1)))); dflags = s->flags.p; }
+  if (n > 0 && s->n_planes > 0)
+    VXS_LAUNCH(ctx, "k_odom_accumulate", k_odom_accumulate, unsigned((n + 255) / 256), 256, 0, s->pts.p, (long long)n, s->st.p, s->keys.p, s->rows.p, s->n_planes, s->minx, s->miny, s->minz,
+               s->ex, s->ey, s->ez, s->voxel_size, s->max_layer, s->out.p, dflags);
+  else if (flags && n > 0) VXS_CUDA(ctx, cudaMemsetAsync(dflags, 0, size_t(n) * 4, ctx->stream));
+  double out[34];
+  VXS_CUDA(ctx, cudaMemcpyAsync(out, s->out.p, sizeof out, cudaMemcpyDeviceToHost, ctx->stream));
+  if (flags && n > 0) VXS_CUDA(ctx, cudaMemcpyAsync(flags, dflags, size_t(n) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  VXS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  int u = 0;
+  for (int a = 0; a < 6; a++) for (int b = a; b < 6; b++) { HTH36[6 * a + b] = out[u]; HTH36[6 * b + a] = out[u]; u++; }
+  for (int a = 0; a < 6; a++) HTz6[a] = out[21 + a];
+  const int sy[9] = {27, 28, 29, 28, 30, 31, 29, 31, 32};
+  for (int k = 0; k < 9; k++) nnt9[k] = out[sy[k]];
+  *match_num = int64_t(out[33] + 0.5);
+  return VXS_OK;
+}
