@@ -427,4 +427,54 @@ int vxo_local_map_odom_accumulate(void* hh, const double* pv12, int64_t n, const
   return m;
 }
 
+// ---------------------------------------------------------------- sliding-window simulator (map side of voxelslam.cpp:1599-1686)
+void* vxo_sliding_sim_create(const vxs_map_params* mp, int win_size, int mgsize, int max_points) {
+  MapParams m = to_map_params(mp, true);
+  m.max_points = max_points;
+  return new SlidingWindowSim(m, win_size, mgsize);
+}
+void vxo_sliding_sim_free(void* h) { delete static_cast<SlidingWindowSim*>(h); }
+void vxo_sliding_sim_add_scan(void* h, const double* pts_body, int64_t n, const double* pose12, double var_diag) {
+  SlidingWindowSim* sim = static_cast<SlidingWindowSim*>(h);
+  std::vector<PV> scan; scan.resize(size_t(n));
+  M3 var = m3_zero(); var(0, 0) = var(1, 1) = var(2, 2) = var_diag;
+  for (int64_t k = 0; k < n; k++) { scan[k].pnt = v3(pts_body[3 * k], pts_body[3 * k + 1], pts_body[3 * k + 2]); scan[k].var = var; }
+  sim->add_scan(scan, states_from_poses12(pose12, 1)[0]);
+}
+static void collect_leaves(OctoTree* o, std::vector<OctoTree*>& out) {
+  if (o->octo_state == 0) { out.push_back(o); return; }
+  for (auto c : o->leaves) if (c) collect_leaves(c, out);
+}
+// state: win_count, win_base, ring[W], poses of x_buf (win_count x 12).  Leaves of ALL roots of the map (slide or not): per leaf a row of
+// 12 + 10 + 10 + 10*W doubles: voxel_center3 half layer is_plane isexist has_sw in_slide opt_state last_num n_point_fix | pcr_add10 | pcr_fix10 | pcrs_local[ring[i]] for i < W
+int64_t vxo_sliding_sim_state(void* h, int32_t* head /* win_count, win_base, ring[W] */, double* poses12, double* rows, int64_t cap) {
+  SlidingWindowSim* sim = static_cast<SlidingWindowSim*>(h);
+  const int W = sim->win_size;
+  head[0] = sim->win_count; head[1] = sim->win_base;
+  for (int i = 0; i < W; i++) head[2 + i] = sim->ring[i];
+  for (int i = 0; i < sim->win_count; i++) {
+    const State& x = sim->x_buf[i];
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) poses12[12 * i + 3 * r + c] = x.R(r, c);
+    for (int k = 0; k < 3; k++) poses12[12 * i + 9 + k] = x.p[k];
+  }
+  std::vector<OctoTree*> lv;
+  std::vector<char> in_slide;
+  for (auto& kv : sim->surf_map) {
+    const size_t b = lv.size();
+    collect_leaves(kv.second, lv);
+    in_slide.resize(lv.size(), sim->slide.count(kv.first) ? 1 : 0);
+    (void)b;
+  }
+  const int rw = 32 + 10 * W;
+  for (int64_t t = 0; t < int64_t(lv.size()) && t < cap; t++) {
+    double* r = rows + size_t(t) * rw; const OctoTree* o = lv[t];
+    for (int k = 0; k < 3; k++) r[k] = o->voxel_center[k];
+    r[3] = double(o->quater_length) * 2; r[4] = o->layer; r[5] = o->is_plane; r[6] = o->isexist; r[7] = o->sw != nullptr; r[8] = in_slide[t]; r[9] = o->opt_state; r[10] = o->last_num;
+    r[11] = double(o->point_fix.size());
+    pc_pack(o->pcr_add, r + 12); pc_pack(o->pcr_fix, r + 22);
+    for (int i = 0; i < W; i++) { if (o->sw) pc_pack(o->sw->pcrs_local[sim->ring[i]], r + 32 + 10 * i); else for (int k = 0; k < 10; k++) r[32 + 10 * i + k] = 0; }
+  }
+  return int64_t(lv.size());
+}
+
 }  // extern "C"

@@ -50,6 +50,8 @@ struct MapParams {
   double plane_thre[8] = {.25, .25, .25, .25, .25, .25, .25, .25};  // plane_eigen_value_thre (already inverted, voxelslam.cpp:825)
   bool with_cov_add = false;         // voxel_map.hpp:990-992 by-product used only by plane_update (odometry)
   int max_points = 100;              // voxel_map.hpp:86
+  const int* ring = nullptr;         // voxel_map.hpp:934 `int* mp`: logical window position -> slide-window slot (null = identity: from-scratch builds)
+  int slot(int i) const { return ring ? ring[i] : i; }
 };
 
 // voxel_map.hpp:66-81 (is_plane lives on the OctoTree in this restatement)
@@ -102,11 +104,12 @@ struct OctoTree {  // voxel_map.hpp:935-1502
   OctoTree(int l, int w) : layer(l), wdsize(w) { for (auto& p : leaves) p = nullptr; std::memset(cov_add, 0, sizeof cov_add); }
   ~OctoTree() { for (auto p : leaves) delete p; delete sw; }
 
-  void push(int ord, const PV& pv, const V3& pw, const MapParams& mp_) {  // :969-994 (mp[] ring map = identity in a from-scratch build)
+  void push(int ord, const PV& pv, const V3& pw, const MapParams& mp_) {  // :969-994 (the slide-window pool `sws` is an allocation detail)
     if (!sw) sw = new SlideWindow(wdsize);
     isexist = true;
-    if (layer < mp_.max_layer) sw->points[ord].push_back(pv);
-    sw->pcrs_local[ord].push(pv.pnt);
+    const int mord = mp_.slot(ord);
+    if (layer < mp_.max_layer) sw->points[mord].push_back(pv);
+    sw->pcrs_local[mord].push(pv.pnt);
     pcr_add.push(pw);
     if (mp_.with_cov_add) { double Bi[81]; bf_var(pv, Bi, pw); for (int i = 0; i < 81; i++) cov_add[i] += Bi[i]; }
   }
@@ -145,7 +148,7 @@ struct OctoTree {  // voxel_map.hpp:935-1502
   }
   void fix_divide(const MapParams& mp_) { for (const PV& pv : point_fix) child_for(pv.pnt)->push_fix(pv, mp_); }  // :1074-1094
   void subdivide(int si, const State& xx, const MapParams& mp_) {  // :1096-1116 — world point re-derived with the CURRENT pose
-    for (const PV& pv : sw->points[si]) {
+    for (const PV& pv : sw->points[mp_.slot(si)]) {
       V3 pw = xx.R * pv.pnt + xx.p;
       child_for(pw)->push(si, pv, pw, mp_);
     }
@@ -275,18 +278,22 @@ struct OctoTree {  // voxel_map.hpp:935-1502
     }
     return flag;
   }
-  void tras_opt(LidarFactor& vox_opt, std::vector<VoxelId>* ids) {  // :1308-1333
+  void tras_opt(LidarFactor& vox_opt, std::vector<VoxelId>* ids, const int* ring_ = nullptr) {  // :1308-1333
     if (octo_state == 0) {
       if (layer >= 0 && isexist && is_plane && sw != nullptr) {
         if (eig_value[0] / eig_value[1] > 0.12) return;
         std::vector<PC> pcrs(wdsize);
-        for (int i = 0; i < wdsize; i++) pcrs[i] = sw->pcrs_local[i];
+        for (int i = 0; i < wdsize; i++) pcrs[i] = sw->pcrs_local[ring_ ? ring_[i] : i];   // :1317-1319 pcrs[i] = sw->pcrs_local[mp[i]]
         opt_state = int(vox_opt.size());
         vox_opt.push_voxel(pcrs, pcr_fix, 1.0, eig_value, eig_vector, pcr_add);
         if (ids) ids->push_back(VoxelId{root.x, root.y, root.z, layer, path});
       }
     } else
-      for (auto c : leaves) if (c) c->tras_opt(vox_opt, ids);
+      for (auto c : leaves) if (c) c->tras_opt(vox_opt, ids, ring_);
+  }
+  void clear_slwd() {  // :1482-1500 (the windows go back to a pool in the reference; here they are freed)
+    if (octo_state != 0) for (auto c : leaves) if (c) c->clear_slwd();
+    if (sw) { delete sw; sw = nullptr; }
   }
 };
 
@@ -665,5 +672,62 @@ inline bool submap_merge(const float* pts, int stride, const int64_t* kf_offsets
   }
   return down_sampling_voxel(merged.data(), 3, n, voxel_size, out);
 }
+
+// ------------------------------------------------------------------ sliding-window local mapping, map side only
+// voxelslam.cpp:1599-1686 without the odometry, the IMU and the BA solve (poses are given): per scan cut_voxel into the map and the
+// slide map, multi_recut (+ tras_opt) on the slide map, and once the window is full multi_margi(mgsize), erase of the dead roots from
+// the slide map, rotation of the slot ring and shift of the pose buffer.  Single-threaded (the thread split of multi_recut / multi_margi
+// only partitions the roots).  The state after every scan is what the next round's device map has to reproduce.
+struct SlidingWindowSim {
+  MapParams mp_;
+  int win_size, mgsize;
+  std::vector<int> ring;
+  LocalMap surf_map;                                   // owns the trees
+  std::unordered_map<VoxelLoc, OctoTree*, VoxelLocHash> slide;   // roots touched inside the current window (not owning)
+  std::vector<State> x_buf;
+  int win_count = 0, win_base = 0;
+  LidarFactor voxhess;
+  SlidingWindowSim(const MapParams& m, int w, int mg) : mp_(m), win_size(w), mgsize(mg), ring(w), voxhess(w) {
+    for (int i = 0; i < w; i++) ring[i] = i;
+    mp_.with_cov_add = true;
+    mp_.ring = ring.data();
+  }
+  ~SlidingWindowSim() { local_map_free(surf_map); }
+  SlidingWindowSim(const SlidingWindowSim&) = delete;
+  SlidingWindowSim& operator=(const SlidingWindowSim&) = delete;
+
+  void add_scan(const std::vector<PV>& scan, const State& x) {
+    win_count++;
+    x_buf.push_back(x);
+    voxhess.clear(); voxhess.win_size = win_size;
+    for (const PV& pv : scan) {                        // cut_voxel, voxel_map.hpp:1504-1540
+      const V3 pw = x.R * pv.pnt + x.p;
+      const VoxelLoc position = voxel_key(pw, mp_.voxel_size);
+      auto it = surf_map.find(position);
+      OctoTree* ot;
+      if (it != surf_map.end()) { ot = it->second; ot->allocate(win_count - 1, pv, pw, mp_); ot->isexist = true; }
+      else {
+        ot = new OctoTree(0, win_size);
+        ot->root = position;
+        ot->allocate(win_count - 1, pv, pw, mp_);
+        for (int k = 0; k < 3; k++) ot->voxel_center[k] = (0.5 + (k == 0 ? position.x : k == 1 ? position.y : position.z)) * mp_.voxel_size;
+        ot->quater_length = float(mp_.voxel_size / 4.0);
+        surf_map[position] = ot;
+      }
+      slide[position] = ot;
+    }
+    for (auto& kv : slide) kv.second->recut(win_count, x_buf, mp_);            // multi_recut, voxelslam.cpp:1398-1446
+    for (auto& kv : slide) kv.second->tras_opt(voxhess, nullptr, ring.data());
+    if (win_count >= win_size) {
+      std::vector<int> rg(ring);
+      for (auto& kv : slide) kv.second->margi(win_count, mgsize, x_buf, voxhess, rg, mp_);   // multi_margi, :1321-1395
+      for (auto it = slide.begin(); it != slide.end();) { if (it->second->isexist) ++it; else { it->second->clear_slwd(); it = slide.erase(it); } }
+      for (int i = 0; i < win_size; i++) { ring[i] += mgsize; if (ring[i] >= win_size) ring[i] -= win_size; }   // :1658-1662
+      for (int i = mgsize; i < win_count; i++) x_buf[i - mgsize] = x_buf[i];
+      for (int i = 0; i < mgsize; i++) x_buf.pop_back();
+      win_base += mgsize; win_count -= mgsize;
+    }
+  }
+};
 
 }  // namespace vxo

@@ -272,3 +272,33 @@ class LocalMap:
         m = lib().vxo_local_map_odom_accumulate(C.c_void_p(self._h), _dp(pv), C.c_int64(pv.shape[0]), _dp(_f64(pose12)), _dp(_f64(rot_var)), _dp(_f64(tsl_var)), C.c_int(passes),
                                                 _dp(HTH), _dp(HTz), _dp(nnt), flags.ctypes.data_as(C.POINTER(C.c_int32)))
         return dict(n=m, HTH=HTH, HTz=HTz, nnt=nnt, flags=flags)
+
+
+class SlidingSim:
+    """Map side of the sliding-window loop (voxelslam.cpp:1599-1686): cut + recut + tras_opt per scan, margi + ring rotation when full."""
+
+    def __init__(self, mp, win_size, mgsize=1, max_points=100):
+        self.W = win_size
+        lib().vxo_sliding_sim_create.restype = C.c_void_p
+        self._h = lib().vxo_sliding_sim_create(C.byref(mp), C.c_int(win_size), C.c_int(mgsize), C.c_int(max_points))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().vxo_sliding_sim_free(C.c_void_p(self._h)); self._h = None
+
+    def add_scan(self, pts_body, pose12, var_diag=1e-4):
+        p = _f64(pts_body).reshape(-1, 3)
+        lib().vxo_sliding_sim_add_scan(C.c_void_p(self._h), _dp(p), C.c_int64(p.shape[0]), _dp(_f64(pose12)), C.c_double(var_diag))
+
+    def state(self):
+        W = self.W
+        head = np.zeros(2 + W, dtype=np.int32)
+        poses = np.zeros((W, 12))
+        lib().vxo_sliding_sim_state.restype = C.c_int64
+        n = lib().vxo_sliding_sim_state(C.c_void_p(self._h), head.ctypes.data_as(C.POINTER(C.c_int32)), _dp(poses), None, C.c_int64(0))
+        rows = np.zeros((max(n, 1), 32 + 10 * W))
+        lib().vxo_sliding_sim_state(C.c_void_p(self._h), head.ctypes.data_as(C.POINTER(C.c_int32)), _dp(poses), _dp(rows), C.c_int64(n))
+        r = rows[:n]
+        return dict(win_count=int(head[0]), win_base=int(head[1]), ring=head[2:].copy(), poses=poses[: int(head[0])], voxel_center=r[:, 0:3], half=r[:, 3], layer=r[:, 4].astype(int),
+                    is_plane=r[:, 5] > 0, isexist=r[:, 6] > 0, has_sw=r[:, 7] > 0, in_slide=r[:, 8] > 0, opt_state=r[:, 9].astype(int), last_num=r[:, 10].astype(int),
+                    n_point_fix=r[:, 11].astype(int), pcr_add=r[:, 12:22], pcr_fix=r[:, 22:32], slots=r[:, 32:].reshape(n, W, 10))

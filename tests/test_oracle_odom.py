@@ -119,3 +119,56 @@ def test_odom_accumulate_matches_brute_force(world):
     # the per-point leaf cache of the EKF loop (voxelslam.cpp:892-900) does not change the result
     o2 = world["lm"].odom_accumulate(pv, pose, rot_var, tsl_var, passes=3)
     assert o2["n"] == o["n"] and np.array_equal(o2["HTH"], o["HTH"]) and np.array_equal(o2["HTz"], o["HTz"])
+
+
+# ---------------------------------------------------------------------------------------------------------------- sliding window
+def _transform_cluster(c10, pose):
+    """PointCluster::transform (tools.hpp:357-363) on the packed form Pxx Pxy Pxz Pyy Pyz Pzz vx vy vz N."""
+    R, t = pose[:9].reshape(3, 3), pose[9:]
+    P = np.array([[c10[0], c10[1], c10[2]], [c10[1], c10[3], c10[4]], [c10[2], c10[4], c10[5]]]); v = c10[6:9]; N = c10[9]
+    Rv = R @ v
+    Pw = R @ P @ R.T + np.outer(Rv, t) + np.outer(t, Rv) + N * np.outer(t, t)
+    vw = Rv + N * t
+    return np.array([Pw[0, 0], Pw[0, 1], Pw[0, 2], Pw[1, 1], Pw[1, 2], Pw[2, 2], vw[0], vw[1], vw[2], N])
+
+
+@pytest.mark.parametrize("max_points", [10 ** 9, 100])
+def test_sliding_window_bookkeeping(max_points):
+    """voxelslam.cpp:1599-1686 (map side): after every scan, in every leaf, pcr_add == pcr_fix + sum over the window of the slot clusters
+    moved to the world with the pose of their LOGICAL window position (the slot ring rotates on every slide), the slots beyond the
+    window are empty, and — while nothing has been dropped at max_points — every point ever cut is in exactly one leaf."""
+    W, L, n_scans, per = 5, 6.0, 13, 1500
+    mp = vx.MapParams.make(voxel_size=1.0, max_layer=2)
+    sim = oa.SlidingSim(mp, W, mgsize=1, max_points=max_points)
+    all_world = []
+    for k in range(n_scans):
+        pose = vx.true_pose(L, k)
+        body = vx.gen_scan(L, k, per, pose, seed=0x5EED0000 + 9)
+        sim.add_scan(body, pose, var_diag=1e-4)
+        all_world.append(body @ pose[:9].reshape(3, 3).T + pose[9:])
+        st = sim.state()
+        assert st["win_count"] == min(k + 1, W - 1) and st["win_base"] == max(0, k + 2 - W)
+        assert sorted(st["ring"].tolist()) == list(range(W)) and st["ring"][0] == st["win_base"] % W
+        live = st["has_sw"]
+        assert live.sum() > 30
+        # slots of logical positions outside the window are empty
+        assert not st["slots"][:, st["win_count"]:, 9].any()
+        # cluster bookkeeping (N exactly, first and second moments to rounding)
+        for t in np.where(live)[0]:
+            acc = st["pcr_fix"][t].copy()
+            for i in range(st["win_count"]):
+                if st["slots"][t, i, 9] != 0:
+                    acc += _transform_cluster(st["slots"][t, i], st["poses"][i])
+            assert acc[9] == st["pcr_add"][t, 9]
+            assert np.max(np.abs(acc - st["pcr_add"][t])) <= 1e-9 * max(1.0, np.max(np.abs(acc)))
+        if max_points >= 10 ** 9:
+            # conservation: the leaves partition space and nothing was dropped
+            pw = np.concatenate(all_world)
+            total = 0
+            for t in range(len(st["half"])):
+                inside = np.all(np.abs(pw - st["voxel_center"][t]) < st["half"][t], axis=1).sum()
+                assert inside == int(st["pcr_add"][t, 9]), (k, t, inside, st["pcr_add"][t, 9])
+                total += inside
+            assert total == pw.shape[0]
+        else:
+            assert np.all(st["pcr_fix"][:, 9] <= st["pcr_add"][:, 9])
