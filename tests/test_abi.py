@@ -84,3 +84,21 @@ int main() { return 0; }
         f.write(src)
     r = subprocess.run(["g++", "-std=c++14", "-fsyntax-only", "-I", root, f.name], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_bench_reference_arm_contract_on_cpu():
+    """`bench.py --impl reference` needs no GPU: one JSON line with the contract keys (tiny window so that it runs in seconds)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--win", "6", "--pts-per-scan", "4000", "--L", "8", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, cwd=root, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "e2e", "cpu_baseline", "config"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] == 0 and d["cpu_baseline"]["kind"] == "port"
+    assert d["cpu_baseline"]["all_cores_variant"].get("value", 0) > 0
