@@ -40,3 +40,32 @@ def states_from_poses(poses12, vel=(0.5, 0.3, 0.0), g=(0.0, 0.0, -9.8)):
     s[:, 12:15] = vel
     s[:, 21:24] = g
     return s
+
+
+# ---------------------------------------------------------------- golden vectors of the down-sampling rows (tests/golden/downsample.json)
+def load_downsample_golden():
+    import json
+    import os
+    doc = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "downsample.json")))
+    pts = np.array([[float.fromhex(v) for v in p] for p in doc["points_f32"]], dtype=np.float32)
+    pv = np.array([[float.fromhex(v) for v in p] for p in doc["pvec_f64"]], dtype=np.float64)
+    return pts, pv, doc["cases"]
+
+
+def check_downsample_against_golden(run_voxel, run_close, run_pvec):
+    """run_*(array, voxel_size) -> dict(xyz, count, index[, var_diag]) from the implementation under test (oracle or CUDA); compared
+    bit-exactly with the committed vectors (cells identified by the index they report: first point / picked point)."""
+    pts, pv, cases = load_downsample_golden()
+    for case in cases:
+        vs = case["voxel_size"]
+        for name, out, src in (("voxel", run_voxel(pts, vs), pts), ("close", run_close(pts, vs), pts), ("pvec", run_pvec(pv, vs), pv)):
+            gold = case[name]
+            assert len(out["index"]) == len(gold), (name, vs)
+            for t, i in enumerate(out["index"].tolist()):
+                g = gold[str(i)]
+                want = np.array([float.fromhex(v) for v in g["xyz"]], dtype=np.float32)
+                assert np.array_equal(out["xyz"][t].view(np.uint32), want.view(np.uint32)), (name, vs, i)
+                assert out["count"][t] == g["count"], (name, vs, i)
+                if name == "pvec":
+                    wv = np.array([float.fromhex(v) for v in g["var_diag"]], dtype=np.float32)
+                    assert np.array_equal(out["var_diag"][t].view(np.uint32), wv.view(np.uint32)), (name, vs, i)

@@ -304,3 +304,8 @@ def test_odom_accumulate_parity(ctx):
     ctx.odom_set_planes(mp, P["voxel_center"][:0], layer[:0], P["center"][:0], P["normal"][:0], P["plane_var"][:0], P["radius"][:0])
     e = ctx.odom_accumulate(pv, pose_true, rot_var, tsl_var)
     assert e["n"] == 0 and not e["flags"].any() and not e["HTH"].any()
+
+
+def test_down_sampling_golden_vectors(ctx):
+    """The CUDA down-sampling kernels against the committed golden vectors (tests/golden/downsample.json), bit-exact."""
+    scenes.check_downsample_against_golden(lambda p, vs: ctx.down_sampling(p, vs), lambda p, vs: ctx.down_sampling(p, vs, close=True), lambda pv, vs: ctx.down_sampling_pvec(pv, vs))

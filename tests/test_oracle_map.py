@@ -217,3 +217,8 @@ def test_down_sampling_pvec_oracle_matches_numpy():
                 m = (m * cnt + pv[i]) / (cnt + 1); cnt += 1
             t = pos[ids[0]]
             assert np.array_equal(o["xyz"][t], m[:3].astype(np.float32)) and np.array_equal(o["var_diag"][t], m[[3, 7, 11]].astype(np.float32)) and o["count"][t] == cnt
+
+
+def test_down_sampling_oracle_matches_golden_vectors():
+    """tests/golden/downsample.json (independent numpy restatement, generator committed beside it) — bit-exact."""
+    scenes.check_downsample_against_golden(lambda p, vs: oa.down_sampling(p, vs), lambda p, vs: oa.down_sampling(p, vs, close=True), lambda pv, vs: oa.down_sampling_pvec(pv, vs))
