@@ -27,6 +27,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))   # synth (scene generator / IMU stand-in) and oracle_api (CPU baseline legs only)
+
+import synth  # noqa: E402  (tests/synth.py: seeded scenes + IMU stand-in; test / bench infrastructure)
 
 METRIC = "local-BA LM iterations/sec (W=50 window, 1M pts/scan)"
 UNIT = "iterations/s"
@@ -94,16 +97,16 @@ class ClockSampler:
 
 
 def scene_points(vx, W, pts, L, seed):
-    tr = np.stack([vx.true_pose(L, i) for i in range(W)])
+    tr = np.stack([synth.true_pose(L, i) for i in range(W)])
     est = tr.copy()
     for i in range(1, W):
         # odometry-grade initial error.  SURVEY §8d suggests (2e-3 rad, 1e-2 m); at L=130 m a 2e-3 rad error moves far points by 0.2 m,
         # which breaks every plane of the initial map (the window leaves the convergence basin and k collapses), so the rotation
         # noise is scaled with the lever arm: 1e-4 rad * 90 m = 9 mm, the size of the point noise.
-        est[i] = vx.perturb_pose(tr[i], seed * 1000 + i, 1e-4, 5e-3)
+        est[i] = synth.perturb_pose(tr[i], seed * 1000 + i, 1e-4, 5e-3)
     p = np.empty((W * pts, 3), dtype=np.float64)
     for i in range(W):
-        vx.gen_scan(L, i, pts, tr[i], seed=0x5EED0000 + seed, out=p[i * pts:(i + 1) * pts])
+        synth.gen_scan(L, i, pts, tr[i], seed=0x5EED0000 + seed, out=p[i * pts:(i + 1) * pts])
     off = np.arange(W + 1, dtype=np.int64) * pts
     return tr, est, p, off
 
@@ -171,7 +174,7 @@ def run_ours(args):
     eig0, sum0 = f.read_back()
     f.cache_save()
     st0 = states_from(est)
-    imu = vx.ImuWindow(tr)
+    imu = synth.ImuWindow(tr)
     n = 15 * W
 
     def step():
@@ -351,8 +354,8 @@ def c2_leg(vx, ctx, hbm):
     """BASELINE.json configs[1]: per-voxel covariance + 3x3 eigensolve over 1 M points / ~100 k voxels (L=183, max_layer 0):
     the GPU voxel-map build on device-resident-after-upload points; kernel times from CUDA events."""
     L, n = 183.0, 1000000
-    pose = vx.true_pose(L, 0)
-    pts = vx.gen_scan(L, 0, n, pose, seed=0x5EED0000 + 2000)
+    pose = synth.true_pose(L, 0)
+    pts = synth.gen_scan(L, 0, n, pose, seed=0x5EED0000 + 2000)
     off = np.array([0, n], dtype=np.int64)
     mp = vx.MapParams.make(voxel_size=1.0, min_eigen_value=0.0025, max_layer=0)
     f = vx.Factor(ctx, 1)
@@ -384,7 +387,7 @@ def oracle_factor_from_csr(W, ptr, fr, cl, eig, s):
 def cpu_baseline_from_structure(vx, W, ptr, fr, cl, eig, s, st0, tr, reps=2):
     """The oracle (CPU restatement of the reference, reference thread structure: 5 threads) on the SAME factor, timed on this host."""
     of = oracle_factor_from_csr(W, ptr, fr, cl, eig, s)
-    imu = vx.ImuWindow(tr)
+    imu = synth.ImuWindow(tr)
     ts = []
     for _ in range(reps):
         imu.reset()
@@ -438,7 +441,7 @@ def run_reference(args):
     V = of.size()
     log(f"[reference] oracle map build from {W}x{pts_map} points: {t_map:.1f}s, V={V}")
     st0 = states_from(est)
-    imu = vx.ImuWindow(tr)
+    imu = synth.ImuWindow(tr)
     ex = of.export()
     cl, eig, s = ex["clusters10"], ex["eig12"], ex["sum10"]
     # probe one iteration, then bound the sample so the whole run stays within a few minutes
@@ -499,11 +502,11 @@ def run_gba(args):
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(uid[0], rank, world)
     t0 = time.time()
-    tr = np.stack([vx.lawnmower_pose(i, per_row) for i in range(K)])
-    est = np.stack([tr[0]] + [vx.perturb_pose(tr[i], 100 + i, 1e-3, 1e-2) for i in range(1, K)])
+    tr = np.stack([synth.lawnmower_pose(i, per_row) for i in range(K)])
+    est = np.stack([tr[0]] + [synth.perturb_pose(tr[i], 100 + i, 1e-3, 1e-2) for i in range(1, K)])
     xyz = np.empty((K * n, 3), dtype=np.float32)
     for i in range(K):
-        vx.gen_scan_city(i, n, tr[i], out=xyz[i * n:(i + 1) * n])
+        synth.gen_scan_city(i, n, tr[i], out=xyz[i * n:(i + 1) * n])
     off = np.arange(K + 1, dtype=np.int64) * n
     mp = vx.MapParams.make(voxel_size=args.gba_voxel, min_eigen_value=0.1 if args.gba_voxel >= 2 else 0.0025, max_layer=2)
     f = vx.Factor(ctx, K)

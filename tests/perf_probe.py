@@ -9,6 +9,7 @@ sys.path.insert(0, ".")
 sys.path.insert(0, "tests")
 import oracle_api as oa  # noqa: E402
 import scenes  # noqa: E402
+import synth
 import voxel_slam_b200 as vx  # noqa: E402
 
 W, pts, L = int(sys.argv[1]), int(sys.argv[2]), float(sys.argv[3])
@@ -24,7 +25,7 @@ t0 = time.time()
 f.push_voxels_dense(sc["clusters10"], sc["eig12"], sc["sum10"])
 print(f"push {time.time() - t0:.3f}s", flush=True)
 st = scenes.states_from_poses(sc["poses_est"])
-imu = vx.ImuWindow(sc["poses_true"])
+imu = synth.ImuWindow(sc["poses_true"])
 for name, fn in [("residual", lambda: ctx.evaluate_residual(f, sc["poses_est"])),
                  ("hessian", lambda: ctx.evaluate_hessian(f, sc["poses_est"])),
                  ("lidar_ba_1it", lambda: ctx.lidar_ba(f, sc["poses_est"], max_iter=1, want_hess=False)),

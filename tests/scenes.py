@@ -3,21 +3,22 @@ ORACLE voxel map to obtain the factor (clusters, cached eig, sums) the reference
 import numpy as np
 
 import oracle_api as oa
+import synth
 import voxel_slam_b200 as vx
 
 
 def poses_true_est(W, L, seed, rot_sigma=2e-3, pos_sigma=1e-2):
-    tr = np.stack([vx.true_pose(L, i) for i in range(W)])
+    tr = np.stack([synth.true_pose(L, i) for i in range(W)])
     est = tr.copy()
     for i in range(1, W):
-        est[i] = vx.perturb_pose(tr[i], seed * 1000 + i, rot_sigma, pos_sigma)
+        est[i] = synth.perturb_pose(tr[i], seed * 1000 + i, rot_sigma, pos_sigma)
     return tr, est
 
 
 def make_points(W, pts_per_scan, L, seed, poses_true, dtype=np.float64):
     pts = np.empty((W * pts_per_scan, 3), dtype=dtype)
     for i in range(W):
-        vx.gen_scan(L, i, pts_per_scan, poses_true[i], seed=0x5EED0000 + seed, dtype=dtype, out=pts[i * pts_per_scan:(i + 1) * pts_per_scan])
+        synth.gen_scan(L, i, pts_per_scan, poses_true[i], seed=0x5EED0000 + seed, dtype=dtype, out=pts[i * pts_per_scan:(i + 1) * pts_per_scan])
     off = np.arange(W + 1, dtype=np.int64) * pts_per_scan
     return pts, off
 

@@ -5,6 +5,7 @@ import os
 import pytest
 import torch
 
+import synth
 import voxel_slam_b200 as vx
 
 
@@ -18,11 +19,11 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_harness_library_loads():
-    p = vx.true_pose(20.0, 3)
+    p = synth.true_pose(20.0, 3)
     assert p.shape == (12,) and abs(p[9] - 10.15) < 1e-12
-    pts = vx.gen_scan(20.0, 0, 1000, vx.true_pose(20.0, 0))
+    pts = synth.gen_scan(20.0, 0, 1000, synth.true_pose(20.0, 0))
     assert pts.shape == (1000, 3) and abs(pts).max() < 40
-    assert (vx.gen_scan(20.0, 0, 1000, vx.true_pose(20.0, 0)) == pts).all()          # seeded, reproducible
+    assert (synth.gen_scan(20.0, 0, 1000, synth.true_pose(20.0, 0)) == pts).all()          # seeded, reproducible
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")

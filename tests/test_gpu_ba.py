@@ -8,6 +8,7 @@ import pytest
 
 import oracle_api as oa
 import scenes
+import synth
 import voxel_slam_b200 as vx
 
 pytestmark = pytest.mark.gpu
@@ -85,7 +86,7 @@ def test_sparse_window_path(ctx):
     n = sc["eig12"].shape[0]
     cl = np.zeros((n, W2, 10))
     cl[:, ::stride, :] = sc["clusters10"]
-    poses = np.stack([vx.true_pose(6.0, 0)] * W2)
+    poses = np.stack([synth.true_pose(6.0, 0)] * W2)
     poses[::stride] = sc["poses_est"]
     f = vx.Factor(ctx, W2)
     f.push_voxels_dense(cl, sc["eig12"], sc["sum10"], fix10=sc["fix10"])
@@ -152,8 +153,8 @@ def test_li_ba_parity(ctx, gravity, iters):
     of = sc["oracle_factor"]
     st = scenes.states_from_poses(sc["poses_est"])
     st[:, 12:15] += 0.02 * np.random.default_rng(0).standard_normal((W, 3))
-    imu_g = vx.ImuWindow(sc["poses_true"])
-    imu_r = vx.ImuWindow(sc["poses_true"])
+    imu_g = synth.ImuWindow(sc["poses_true"])
+    imu_r = synth.ImuWindow(sc["poses_true"])
     g = ctx.li_ba(f, st, imu_g, with_gravity=gravity, max_iter=iters)
     r = of.li_ba(st, imu_r, with_gravity=gravity, max_iter=iters)
     assert len(g["trace"]) == len(r["trace"]) >= 1

@@ -9,6 +9,7 @@ import pytest
 
 import oracle_api as oa
 import scenes
+import synth
 import voxel_slam_b200 as vx
 
 pytestmark = pytest.mark.gpu
@@ -96,7 +97,7 @@ def test_window_factor_negative_coordinates_and_plane_on_cell_boundary(ctx):
 def test_window_factor_with_fixed_map_points(ctx):
     W, pts, L = 4, 6000, 5.0
     sc = scenes.make_window(W=W, pts_per_scan=pts, L=L, seed=29)
-    fixp = vx.gen_scan(L, 77, 9000, vx.true_pose(L, 0), seed=99)            # body frame of pose 0 ...
+    fixp = synth.gen_scan(L, 77, 9000, synth.true_pose(L, 0), seed=99)            # body frame of pose 0 ...
     R0, t0 = sc["poses_true"][0, :9].reshape(3, 3), sc["poses_true"][0, 9:]
     fixw = fixp @ R0.T + t0                                                  # ... moved to the world: the "fixed map"
     of = oa.build_window_factor(sc["mp"], sc["pts"], sc["offsets"], sc["poses_est"], fix_pts=fixw)
@@ -234,7 +235,7 @@ def test_submap_merge_parity(ctx, stride):
     """voxelslam.cpp:2428-2447 — merged cloud and its down-sampling bit-exact against the oracle."""
     rng = np.random.default_rng(31 + stride)
     W, per = 10, 30000
-    poses = np.stack([vx.true_pose(20.0, i) for i in range(W)])
+    poses = np.stack([synth.true_pose(20.0, i) for i in range(W)])
     pts = np.zeros((W * per, stride), dtype=np.float32)
     pts[:, :3] = rng.uniform(-25, 25, (W * per, 3)).astype(np.float32)
     off = np.arange(W + 1, dtype=np.int64) * per
@@ -287,13 +288,13 @@ def test_odom_accumulate_parity(ctx):
     assert layer.min() >= 0 and layer.max() <= 2 and len(layer) > 50
     ctx.odom_set_planes(mp, P["voxel_center"], layer, P["center"], P["normal"], P["plane_var"], P["radius"])
     rng = np.random.default_rng(3)
-    pose_true = vx.true_pose(L, W)
-    body = vx.gen_scan(L, W, 20000, pose_true, seed=0x5EED0000 + 77)
+    pose_true = synth.true_pose(L, W)
+    body = synth.gen_scan(L, W, 20000, pose_true, seed=0x5EED0000 + 77)
     var = np.tile((sigma ** 2 * np.eye(3)).reshape(1, 9), (body.shape[0], 1)) * rng.uniform(0.5, 2.0, (body.shape[0], 1))
     pv = np.concatenate([body, var], axis=1)
     rot_var, tsl_var = 1e-6 * np.eye(3), 1e-4 * np.eye(3)
     for k, (rs, ps) in enumerate([(2e-3, 1e-2), (0.0, 0.0), (2e-2, 5e-2)]):
-        pose = vx.perturb_pose(pose_true, 99 + k, rs, ps) if rs > 0 else pose_true
+        pose = synth.perturb_pose(pose_true, 99 + k, rs, ps) if rs > 0 else pose_true
         g = ctx.odom_accumulate(pv if k == 0 else None, pose, rot_var, tsl_var, n=pv.shape[0])      # later passes re-use the resident scan
         o = lm.odom_accumulate(pv, pose, rot_var, tsl_var)
         assert g["n"] == o["n"] and (k == 2 or o["n"] > 3000)

@@ -5,6 +5,7 @@ import pytest
 
 import oracle_api as oa
 import scenes
+import synth
 import voxel_slam_b200 as vx
 
 
@@ -176,7 +177,7 @@ def test_submap_merge_oracle_consistency():
     W, per = 4, 800
     poses = np.stack([scenes.true_pose(12.0, i) for i in range(W)]) if hasattr(scenes, "true_pose") else None
     if poses is None:
-        poses = np.stack([vx.true_pose(12.0, i) for i in range(W)])
+        poses = np.stack([synth.true_pose(12.0, i) for i in range(W)])
     pts = rng.uniform(-8, 8, (W * per, 3)).astype(np.float32)
     off = np.arange(W + 1, dtype=np.int64) * per
     raw = oa.submap_merge(pts, off, poses, 0.0)          # < 0.001: merged cloud returned as it is

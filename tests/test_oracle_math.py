@@ -9,6 +9,7 @@ from scipy.spatial.transform import Rotation
 
 import oracle_api as oa
 import scenes
+import synth
 import voxel_slam_b200 as vx
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -188,7 +189,7 @@ def test_li_ba_oracle_runs_and_decreases(gravity):
     W = 6
     sc = scenes.make_window(W=W, pts_per_scan=4000, L=6.0, seed=14)
     st = scenes.states_from_poses(sc["poses_est"])
-    imu = vx.ImuWindow(sc["poses_true"])
+    imu = synth.ImuWindow(sc["poses_true"])
     out = sc["oracle_factor"].li_ba(st, imu, with_gravity=gravity, max_iter=3)
     tr = out["trace"]
     assert len(tr) >= 1 and tr[0]["accepted"] == 1 and tr[-1]["r2"] < tr[0]["r1"]

@@ -5,6 +5,7 @@ import pytest
 
 import oracle_api as oa
 import scenes
+import synth
 import voxel_slam_b200 as vx
 
 SIGMA = 0.01
@@ -104,9 +105,9 @@ def test_odom_accumulate_matches_brute_force(world):
     """voxelslam.cpp:876-918 against a numpy loop over the exported plane table (independent leaf search by cube containment)."""
     rng = np.random.default_rng(3)
     W, L = world["W"], world["L"]
-    pose_true = vx.true_pose(L, W)                                  # the next scan of the trajectory
-    body = vx.gen_scan(L, W, 1500, pose_true, seed=0x5EED0000 + 77)
-    pose = vx.perturb_pose(pose_true, 99, 2e-3, 1e-2)
+    pose_true = synth.true_pose(L, W)                                  # the next scan of the trajectory
+    body = synth.gen_scan(L, W, 1500, pose_true, seed=0x5EED0000 + 77)
+    pose = synth.perturb_pose(pose_true, 99, 2e-3, 1e-2)
     var = np.tile((SIGMA ** 2 * np.eye(3)).reshape(1, 9), (body.shape[0], 1)) * rng.uniform(0.5, 2.0, (body.shape[0], 1))
     pv = np.concatenate([body, var], axis=1)
     rot_var, tsl_var = 1e-6 * np.eye(3), 1e-4 * np.eye(3)
@@ -142,8 +143,8 @@ def test_sliding_window_bookkeeping(max_points):
     sim = oa.SlidingSim(mp, W, mgsize=1, max_points=max_points)
     all_world = []
     for k in range(n_scans):
-        pose = vx.true_pose(L, k)
-        body = vx.gen_scan(L, k, per, pose, seed=0x5EED0000 + 9)
+        pose = synth.true_pose(L, k)
+        body = synth.gen_scan(L, k, per, pose, seed=0x5EED0000 + 9)
         sim.add_scan(body, pose, var_diag=1e-4)
         all_world.append(body @ pose[:9].reshape(3, 3).T + pose[9:])
         st = sim.state()

@@ -5,11 +5,7 @@ mirror used by the tests and ``bench.py``.  There is no CPU fallback: importing 
 CPU-only checks can verify the ABI), but every compute entry point needs a CUDA device and raises otherwise.
 """
 from .api import (  # noqa: F401
-    VxsError, lib, harness, Context, Factor, ImuWindow, MapParams, LmTrace, VoxelId,
-    gen_scan, true_pose, perturb_pose, declared_symbols, LIB_PATH, HARNESS_PATH, lawnmower_pose, gen_scan_city,
+    VxsError, lib, Context, Factor, MapParams, LmTrace, VoxelId, ImuHooks, declared_symbols, LIB_PATH,
 )
 
-__all__ = [
-    "VxsError", "lib", "harness", "Context", "Factor", "ImuWindow", "MapParams", "LmTrace", "VoxelId",
-    "gen_scan", "true_pose", "perturb_pose", "declared_symbols", "LIB_PATH", "HARNESS_PATH",
-]
+__all__ = ["VxsError", "lib", "Context", "Factor", "MapParams", "LmTrace", "VoxelId", "ImuHooks", "declared_symbols", "LIB_PATH"]
