@@ -67,6 +67,10 @@ int vxs_diag_dmma_tflops(vxs_ctx* ctx, double* tflops);
  * checked on the host, out[9..11] reserved (0).
  * VXS_LDLT_LOOKAHEAD_CTA=0 in the environment keeps the look-ahead on CTA 0 (A/B switch). */
 int vxs_diag_ldlt_phases(vxs_ctx* ctx, int n, double out[12]);
+/* the damped, gauge-fixed solve of the LM drivers on a caller-supplied n x n system (column-major hess, jact; host buffers):
+ * rows / columns < gauge zeroed with an identity block, D = diag, dx = (H + u D)^-1 (-jact) by the pivoted LDL^T the solvers use
+ * (voxel_map.hpp:397-403, 591-597, 800-811).  For parity tests of the solver at the headline sizes (n = 750, 753, ...). */
+int vxs_diag_solve_damped(vxs_ctx* ctx, const double* hess, const double* jact, int n, int gauge, double u, double* dx, int* singular);
 
 /* ---------------------------------------------------------------- multi-GPU (one process per GPU; NCCL over NVLink)
  * Voxel-sharded BA: every rank holds the factor voxels it owns and the replicated poses; [H_lidar, g, r] are
@@ -140,7 +144,8 @@ typedef struct vxs_imu_hooks {
   int (*rollback)(void* user);
 } vxs_imu_hooks;
 
-/* LI_BA_Optimizer::damping_iter (voxel_map.hpp:562-653; with_gravity=0, n=15W, the reference hard-codes 3 iterations)
+/* LI_BA_Optimizer::damping_iter (voxel_map.hpp:562-653; with_gravity=0, n=15W; the reference hard-codes 3 iterations, :581 —
+ * max_iter > 3 is clamped to 3, smaller values step fewer iterations)
  * and LI_BA_OptimizerGravity::damping_iter (:775-862; with_gravity=1, n=15W+3, max_iter default 2).
  * states24 in/out (W x 24); hess_out (n x n col-major, may be NULL); resis[2] as above; imu_coef = voxel_map.hpp:446. */
 int vxs_li_ba(vxs_ctx* ctx, vxs_factor* f, double* states24, int with_gravity, int max_iter, double imu_coef,
@@ -191,7 +196,9 @@ int vxs_hba_window(vxs_ctx* ctx, const vxs_map_params* coarse, const vxs_map_par
 /* PGO edge extraction of HBA_add_edge (voxelslam.cpp:2405-2427) from the raw Hessian of the LAST vxs_lidar_ba / vxs_hba_window
  * on this ctx, without downloading the Hessian: for every pair i<j whose six diagonal entries of block (i,j) are all >= 1e-6 in
  * magnitude, one edge with variance v6[k] = 1/|H(6i+k, 6j+k)|, rot = R_i^T R_j (row-major), tra = R_i^T (p_j - p_i).
- * edge_ij: [cap][2] int32, v6: [cap][6], rot: [cap][9], tra: [cap][3]; *n_edges = number found (may exceed cap: truncated). */
+ * edge_ij: [cap][2] int32, v6: [cap][6], rot: [cap][9], tra: [cap][3]; *n_edges = number found (may exceed cap: truncated).
+ * Edges come out in the reference's lexicographic (i, j) order, the same on every run (and the first `cap` of them when truncated).
+ * VXS_ERR_ARG when the Hessian resident on the ctx is not the lidar-only 6W system of a BA with this W. */
 int vxs_hba_edges(vxs_ctx* ctx, int W, const double* poses12, int64_t cap, int32_t* edge_ij, double* v6, double* rot, double* tra,
                   int64_t* n_edges);
 

@@ -1,5 +1,5 @@
-"""Multi-GPU parity check for the voxel-sharded global-BA step (run under torchrun on the GPU box, not collected by pytest):
-   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multi_gpu_check.py
+"""Multi-GPU parity worker for the voxel-sharded global-BA step; launched under torchrun by tests/test_gpu_multi.py (pytest -m gpu, >= 2 GPUs):
+   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multi_gpu_worker.py
 Every rank builds the same seeded window with the ORACLE map, keeps the voxels it owns (reference hash of the root cell mod n),
 pushes them to its GPU and runs Lidar_BA_Optimizer::damping_iter with the NCCL all-reduce of [C | g | D | r] inside libvxs.
 Rank 0 compares poses / residuals / Hessian with the single-process oracle solve."""
@@ -45,6 +45,24 @@ def main():
             print(f"[multi-gpu x{world}] W={W}: shard sizes {int(mine.sum())}/{len(mine)}  pose {e_pose:.2e}  hess {e_h:.2e}  resid {e_r:.2e} {e_r2:.2e}  -> {'OK' if ok else 'FAIL'}", flush=True)
             ok_all = ok_all and ok
         f.close()
+    # a rank that owns NO voxel (hash(root cell) mod n can leave a shard empty) must still enter both all-reduces (vxs_eval.cu):
+    # everything on rank 0, nothing on the others
+    sc = scenes.make_window(W=6, pts_per_scan=6000, L=6.0, seed=5)
+    f = vx.Factor(ctx, 6)
+    if rank == 0:
+        f.push_voxels_dense(sc["clusters10"], sc["eig12"], sc["sum10"], fix10=sc["fix10"])
+    g = ctx.lidar_ba(f, sc["poses_est"], max_iter=4, thd_num=1)
+    r_all = ctx.evaluate_residual(f, sc["poses_true"])
+    ref = sc["oracle_factor"].lidar_ba(sc["poses_est"], max_iter=4)
+    r_ref = sc["oracle_factor"].residual(sc["poses_true"])
+    inc = np.max(np.abs(ref["poses"] - sc["poses_est"]))
+    ok = (np.max(np.abs(g["poses"] - ref["poses"])) / inc < 1e-5 and abs(r_all - r_ref) / r_ref < 1e-9 and len(g["trace"]) == len(ref["trace"])
+          and all(a["accepted"] == b["accepted"] for a, b in zip(g["trace"], ref["trace"])))
+    print(f"[multi-gpu x{world}] rank {rank} empty-shard case (V={f.counts()[0]}): {'OK' if ok else 'FAIL'}", flush=True)
+    okt = torch.tensor([1 if ok else 0], device=f"cuda:{local}")
+    dist.all_reduce(okt, op=dist.ReduceOp.MIN)          # every rank must have followed the same LM path
+    ok_all = ok_all and int(okt.item()) == 1
+    f.close()
     # hierarchical-GBA window: every rank sees all keyframe clouds, builds only the octrees it owns, all-reduces the Hessian
     import oracle_api as oa
     W = 10

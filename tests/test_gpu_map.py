@@ -154,8 +154,19 @@ def test_hba_edges_on_device(ctx):
     e = ctx.hba_edges(W, g["poses"])
     r = oa.hba_window(coarse, fine, xyz, off, est, max_iter=3, thread_num=2)
     eo = oa.hba_edges(r["hess"], W, r["poses"])
-    assert e["n"] == eo["n"] > 0 and np.array_equal(e["ij"], eo["ij"])
+    assert e["n"] == eo["n"] > 0 and np.array_equal(e["ij"], eo["ij"])         # same edges in the reference's lexicographic (i, j) order, unsorted
     assert np.max(np.abs(e["v6"] - eo["v6"]) / eo["v6"]) < 1e-6
+    cap = e["n"] // 2                                                          # truncation keeps the FIRST cap edges, deterministically
+    e2 = ctx.hba_edges(W, g["poses"], cap=cap)
+    assert e2["n"] == e["n"] and np.array_equal(e2["ij"], e["ij"][:cap]) and np.array_equal(e2["v6"], e["v6"][:cap])
+    # a different system on the ctx (n = 15 W) must be refused instead of being read with the wrong stride
+    sc = scenes.make_window(W=W, pts_per_scan=3000, L=6.0, seed=2)
+    f = vx.Factor(ctx, W)
+    f.push_voxels_dense(sc["clusters10"], sc["eig12"], sc["sum10"], fix10=sc["fix10"])
+    ctx.li_ba(f, scenes.states_from_poses(sc["poses_est"]), synth.ImuWindow(sc["poses_true"]), max_iter=1)
+    with pytest.raises(vx.VxsError):
+        ctx.hba_edges(W, g["poses"])
+    f.close()
     assert np.max(np.abs(e["rot"] - eo["rot"])) < 1e-9 and np.max(np.abs(e["tra"] - eo["tra"])) < 1e-8
 
 

@@ -158,6 +158,16 @@ class Context:
         return list(out)
 
     # --- multi-GPU
+    def solve_damped(self, hess, jact, gauge, u):
+        """vxs_diag_solve_damped: the LM drivers' gauge-fixed damped LDL^T solve on a host system (n x n, any layout: symmetric)."""
+        H = np.asfortranarray(hess, dtype=np.float64)
+        g = _f64(jact)
+        n = g.shape[0]
+        dx = np.zeros(n)
+        sing = C.c_int(0)
+        self._check(lib().vxs_diag_solve_damped(self._p, H.ctypes.data_as(C.POINTER(C.c_double)), _dp(g), C.c_int(n), C.c_int(gauge), C.c_double(u), _dp(dx), C.byref(sing)))
+        return dx, sing.value
+
     @staticmethod
     def comm_unique_id():
         buf = (C.c_ubyte * 128)()
@@ -262,9 +272,8 @@ def _hba_edges(self, W, poses12, cap=None):
     eij = np.zeros((max(cap, 1), 2), dtype=np.int32); v6 = np.zeros((max(cap, 1), 6)); rot = np.zeros((max(cap, 1), 9)); tra = np.zeros((max(cap, 1), 3))
     n = C.c_int64(0)
     self._check(lib().vxs_hba_edges(self._p, C.c_int(W), _dp(p), C.c_int64(cap), eij.ctypes.data_as(C.POINTER(C.c_int32)), _dp(v6), _dp(rot), _dp(tra), C.byref(n)))
-    m = min(n.value, cap)
-    order = np.lexsort((eij[:m, 1], eij[:m, 0]))
-    return dict(n=n.value, ij=eij[:m][order], v6=v6[:m][order], rot=rot[:m][order], tra=tra[:m][order])
+    m = min(n.value, cap)      # the library returns the edges in the reference's lexicographic (i, j) order
+    return dict(n=n.value, ij=eij[:m], v6=v6[:m], rot=rot[:m], tra=tra[:m])
 
 
 Context.hba_edges = _hba_edges

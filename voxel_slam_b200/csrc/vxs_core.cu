@@ -1,5 +1,6 @@
 // Context, timing and the device-resident LidarFactor container (CSR over observing frames, SoA clusters).
 // Reference: voxel_map.hpp:109-130,281-286 (LidarFactor members, push_voxel, clear).
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include "vxs_internal.h"
@@ -28,6 +29,8 @@ extern "C" int vxs_ctx_create(int device, vxs_ctx** out) {
   cudaEventCreate(&c->ev_t0); cudaEventCreate(&c->ev_t1);
   c->scal.reserve(64);
   c->flags.reserve(16);
+  { const char* e = getenv("VXS_LDLT_LOOKAHEAD_CTA"); c->ldlt_lookahead = (e && e[0] == '0') ? 0 : 1; }
+  { const char* e = getenv("VXS_SYRK_WAVES"); c->syrk_waves = e ? std::max(1, atoi(e)) : 12; }
   *out = c;
   return VXS_OK;
 }

@@ -704,7 +704,11 @@ static int pick_group_jac(const vxs_factor* f) {   // one lane per frame slot of
 static size_t hess_block_doubles(int W) { return size_t(6 * W) * size_t(6 * W) + size_t(30) * W + 1; }
 
 int vxs_eval_residual_dev(vxs_ctx* ctx, vxs_factor* f, const double* poses_dev, int pstride, double* residual_dev) {
-  if (f->V == 0) { VXS_CUDA(ctx, cudaMemsetAsync(residual_dev, 0, 8, ctx->stream)); return VXS_OK; }
+  if (f->V == 0) {   // a rank of a voxel-sharded run may own no voxel at all: it still has to take part in the scalar all-reduce
+    VXS_CUDA(ctx, cudaMemsetAsync(residual_dev, 0, 8, ctx->stream));
+    if (ctx->nranks > 1) return vxs_comm_allreduce(ctx, residual_dev, 1);
+    return VXS_OK;
+  }
   { int rcw = vxs_factor_wait_uploads(f); if (rcw) return rcw; }
   FactorView fv = make_view(f);
   const int G = pick_group(f);
@@ -762,8 +766,7 @@ int vxs_eval_hessian_dev(vxs_ctx* ctx, vxs_factor* f, const double* poses_dev, i
       const int ngv = int((f->V + 3) / 4);
       const size_t smem = (size_t(30) * 128 + size_t(12) * 7 * W + size_t(12) * W) * 8;
       const SyrkGeom g = sy_geom(W);
-      static int waves = -1;
-      if (waves < 0) { const char* e = getenv("VXS_SYRK_WAVES"); waves = e ? std::max(1, atoi(e)) : 12; }
+      const int waves = ctx->syrk_waves;
       const size_t smem_sy = size_t(SY_STAGES) * SY_STAGE_DOUBLES * 8;
       VXS_CUDA(ctx, cudaFuncSetAttribute(k_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_sy)));
       int g0 = 0;
@@ -803,8 +806,7 @@ int vxs_eval_hessian_dev(vxs_ctx* ctx, vxs_factor* f, const double* poses_dev, i
     } else if (dense) {
       const SyrkGeom g = sy_geom(W);
       const int ngv = int((f->V + 3) / 4);                 // voxel groups of 4 (12 rows of X each)
-      static int waves = -1;
-      if (waves < 0) { const char* e = getenv("VXS_SYRK_WAVES"); waves = e ? std::max(1, atoi(e)) : 12; }
+      const int waves = ctx->syrk_waves;
       int target_ctas = ctx->sm_count * 2 * waves;
       int nchunks = std::max(1, std::min<int>(target_ctas / g.ntiles, (ngv + 7) / 8));
       int gpc = (ngv + nchunks - 1) / nchunks;
@@ -831,6 +833,7 @@ int vxs_assemble_dev(vxs_ctx* ctx, vxs_factor* f, int S, int n, const double* bl
   VXS_CUDA(ctx, ctx->jact.reserve(size_t(n)));
   const double* C = f->C.p; const double* gD = C + nl * nl;
   VXS_LAUNCH(ctx, "k_assemble", k_assemble, nblk(size_t(n) * n, 256), 256, 0, C, gD, blocks, gvec, bs, imu_coef, W, S, n, ctx->Hraw.p, ctx->jact.p);
+  ctx->hraw_n = n; ctx->hraw_S = S;
   return VXS_OK;
 }
 double* vxs_hess_r1_dev(vxs_factor* f) { return f->C.p + size_t(6 * f->W) * size_t(6 * f->W) + size_t(30) * f->W; }

@@ -54,6 +54,13 @@ struct vxs_ctx {
   // NCCL
   void* comm = nullptr;
   int rank = 0, nranks = 1;
+  // per-ctx (= per-device) launch configuration, filled once in vxs_ctx_create (a ctx is used by one thread at a time)
+  int coop = -1;                  // cooperative launch of k_ldlt_all possible on this device (-1 = not probed yet)
+  int ldlt_blocks_per_sm = 0;
+  int ldlt_lookahead = 1;         // VXS_LDLT_LOOKAHEAD_CTA=0 keeps the look-ahead on CTA 0 (A/B switch)
+  int syrk_waves = 12;            // VXS_SYRK_WAVES
+  // what ctx->Hraw currently holds (vxs_hba_edges refuses anything but a lidar-only 6W system)
+  int hraw_n = 0, hraw_S = 0;
   // solver scratch (n = system size)
   DevBuf<double> Hraw, Mp, Lm, himu, gimu, jact, dvec, rhs, dx, dtmp, states_a, states_b;
   DevBuf<int> perm;

@@ -11,6 +11,7 @@
 #include <math.h>
 #include <string.h>
 #include <algorithm>
+#include <mutex>
 #include <vector>
 #include "vxs_internal.h"
 #include "vxs_math.cuh"
@@ -32,9 +33,8 @@ struct NcclApi {
 };
 static NcclApi* nccl_api() {
   static NcclApi api;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  static std::once_flag once;
+  std::call_once(once, [] {
     const char* names[] = {"libnccl.so.2", "libnccl.so"};
     for (const char* nm : names) { api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (api.lib) break; }
     if (api.lib) {
@@ -45,7 +45,7 @@ static NcclApi* nccl_api() {
       api.GetErrorString = (const char* (*)(int))dlsym(api.lib, "ncclGetErrorString");
       if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy) api.lib = nullptr;
     }
-  }
+  });
   return api.lib ? &api : nullptr;
 }
 extern "C" int vxs_comm_unique_id(unsigned char id[128]) {
@@ -226,6 +226,9 @@ extern "C" int vxs_li_ba(vxs_ctx* ctx, vxs_factor* f, double* states24, int with
   c.ctx = ctx; c.f = f; c.W = f->W; c.S = 15; c.n = 15 * f->W + (with_gravity ? 3 : 0); c.gauge = with_gravity ? 6 : 15; c.sst = 24;
   int rc = lm_prepare(c);
   if (rc) return rc;
+  // LI_BA_Optimizer::damping_iter hard-codes `for(int i=0; i<3; i++)` (voxel_map.hpp:581): never more than 3 iterations without gravity,
+  // whatever the caller passes (fewer are allowed so that a single iteration can be stepped / timed); the gravity variant honours max_iter (:796)
+  if (!with_gravity && max_iter > 3) max_iter = 3;
   const int W = c.W, n = c.n, bs = with_gravity ? 33 : 30;
   c.x.assign(states24, states24 + size_t(W) * 24);
   c.xt = c.x;
@@ -296,46 +299,101 @@ extern "C" int vxs_li_ba(vxs_ctx* ctx, vxs_factor* f, double* states24, int with
 }
 
 // ------------------------------------------------------------------ PGO edges from the raw Hessian (voxelslam.cpp:2405-2427)
-__global__ void k_hba_edges(const double* __restrict__ H, int n, int W, const double* __restrict__ poses, unsigned int* __restrict__ count, long long cap,
-                            int* __restrict__ eij, double* __restrict__ v6, double* __restrict__ rot, double* __restrict__ tra) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)W * W) return;
-  const int i = int(idx / W), j = int(idx % W);
-  if (j <= i) return;
-  double v[6];
+// The reference emits the edges in lexicographic (i, j) order (two nested loops); so does this: one CTA per row i counts its edges, a
+// single-CTA scan turns the counts into row offsets, and the emit pass compacts every row in j order (ballot prefix), so the output — and
+// the subset that survives when it does not fit `cap` — is the same on every run.
+__device__ __forceinline__ bool edge_ok(const double* __restrict__ H, int n, int i, int j, double* v) {
   for (int k = 0; k < 6; k++) {
     const double hc = fabs(H[size_t(6 * j + k) * n + 6 * i + k]);
-    if (hc < 1e-6) return;
-    v[k] = 1.0 / hc;
+    if (hc < 1e-6) return false;
+    if (v) v[k] = 1.0 / hc;
   }
-  const unsigned int slot = atomicAdd(count, 1u);
-  if ((long long)slot >= cap) return;
-  eij[2 * slot] = i; eij[2 * slot + 1] = j;
-  for (int k = 0; k < 6; k++) v6[6 * slot + k] = v[k];
-  const rot3 Ri = load_rot(poses + 12 * i), Rj = load_rot(poses + 12 * j);
-  const d3 dp = mk3(poses[12 * j + 9] - poses[12 * i + 9], poses[12 * j + 10] - poses[12 * i + 10], poses[12 * j + 11] - poses[12 * i + 11]);
-  const d3 t = mulT(Ri, dp);
-  tra[3 * slot] = t.x; tra[3 * slot + 1] = t.y; tra[3 * slot + 2] = t.z;
-  // R_i^T R_j
-  const double a[9] = {Ri.r00, Ri.r01, Ri.r02, Ri.r10, Ri.r11, Ri.r12, Ri.r20, Ri.r21, Ri.r22}, b[9] = {Rj.r00, Rj.r01, Rj.r02, Rj.r10, Rj.r11, Rj.r12, Rj.r20, Rj.r21, Rj.r22};
-  for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) rot[9 * slot + 3 * r + c] = a[r] * b[c] + a[3 + r] * b[3 + c] + a[6 + r] * b[6 + c];
+  return true;
+}
+__global__ void __launch_bounds__(256) k_hba_edge_count(const double* __restrict__ H, int n, int W, unsigned int* __restrict__ rowcnt) {
+  const int i = blockIdx.x;
+  int c = 0;
+  for (int j = i + 1 + threadIdx.x; j < W; j += blockDim.x) c += edge_ok(H, n, i, j, nullptr) ? 1 : 0;
+  __shared__ int sh[8];
+  for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 8; w++) t += sh[w]; rowcnt[i] = (unsigned int)t; }
+}
+__global__ void __launch_bounds__(1024) k_hba_edge_scan(unsigned int* __restrict__ rowcnt, int W, unsigned int* __restrict__ total) {
+  // exclusive scan of W counts in place, W small (<= a few thousand): chunks of 1024 with a carried offset
+  __shared__ unsigned int buf[1024];
+  __shared__ unsigned int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < W; base += 1024) {
+    const int idx = base + threadIdx.x;
+    const unsigned int v = idx < W ? rowcnt[idx] : 0u;
+    buf[threadIdx.x] = v;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+      const unsigned int t = threadIdx.x >= off ? buf[threadIdx.x - off] : 0u;
+      __syncthreads();
+      buf[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (idx < W) rowcnt[idx] = carry + buf[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += buf[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+__global__ void __launch_bounds__(256) k_hba_edge_emit(const double* __restrict__ H, int n, int W, const double* __restrict__ poses, const unsigned int* __restrict__ rowoff, long long cap,
+                                                       int* __restrict__ eij, double* __restrict__ v6, double* __restrict__ rot, double* __restrict__ tra) {
+  const int i = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ unsigned int wcnt[8];
+  __shared__ unsigned int run;
+  if (threadIdx.x == 0) run = rowoff[i];
+  __syncthreads();
+  for (int j0 = i + 1; j0 < W; j0 += blockDim.x) {
+    const int j = j0 + threadIdx.x;
+    double v[6];
+    const bool ok = j < W && edge_ok(H, n, i, j, v);
+    const unsigned int bal = __ballot_sync(0xffffffffu, ok);
+    if (lane == 0) wcnt[warp] = __popc(bal);
+    __syncthreads();
+    unsigned int before = run;
+    for (int w = 0; w < warp; w++) before += wcnt[w];
+    const long long slot = (long long)before + __popc(bal & ((1u << lane) - 1u));
+    if (ok && slot < cap) {
+      eij[2 * slot] = i; eij[2 * slot + 1] = j;
+      for (int k = 0; k < 6; k++) v6[6 * slot + k] = v[k];
+      const rot3 Ri = load_rot(poses + 12 * i), Rj = load_rot(poses + 12 * j);
+      const d3 dp = mk3(poses[12 * j + 9] - poses[12 * i + 9], poses[12 * j + 10] - poses[12 * i + 10], poses[12 * j + 11] - poses[12 * i + 11]);
+      const d3 t = mulT(Ri, dp);
+      tra[3 * slot] = t.x; tra[3 * slot + 1] = t.y; tra[3 * slot + 2] = t.z;
+      const double a[9] = {Ri.r00, Ri.r01, Ri.r02, Ri.r10, Ri.r11, Ri.r12, Ri.r20, Ri.r21, Ri.r22}, b[9] = {Rj.r00, Rj.r01, Rj.r02, Rj.r10, Rj.r11, Rj.r12, Rj.r20, Rj.r21, Rj.r22};
+      for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) rot[9 * slot + 3 * r + c] = a[r] * b[c] + a[3 + r] * b[3 + c] + a[6 + r] * b[6 + c];   // R_i^T R_j
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { unsigned int t = 0; for (int w = 0; w < 8; w++) t += wcnt[w]; run += t; }
+    __syncthreads();
+  }
 }
 
 extern "C" int vxs_hba_edges(vxs_ctx* ctx, int W, const double* poses12, int64_t cap, int32_t* edge_ij, double* v6, double* rot, double* tra, int64_t* n_edges) {
   if (!ctx || W <= 0 || !poses12 || cap < 0 || !n_edges) return VXS_ERR_ARG;
   const int n = 6 * W;
-  if (ctx->Hraw.cap < size_t(n) * n) return vxs_fail(ctx, VXS_ERR_ARG, "vxs_hba_edges: no Hessian of this size on the ctx (run vxs_lidar_ba / vxs_hba_window first)");
+  if (ctx->hraw_n != n || ctx->hraw_S != 6 || ctx->Hraw.cap < size_t(n) * n)
+    return vxs_fail(ctx, VXS_ERR_ARG, "vxs_hba_edges: the Hessian resident on this ctx is not a lidar-only 6W system of this W (run vxs_lidar_ba / vxs_hba_window first)");
   cudaSetDevice(ctx->device);
   const size_t c = size_t(std::max<int64_t>(cap, 1));
   VXS_CUDA(ctx, ctx->stage.reserve(c * 18 + size_t(W) * 12));
-  VXS_CUDA(ctx, ctx->stage_i64.reserve(c + 2));
+  VXS_CUDA(ctx, ctx->stage_i64.reserve(c + size_t(W) / 2 + 4));
   double* d_v6 = ctx->stage.p; double* d_rot = d_v6 + c * 6; double* d_tra = d_rot + c * 9; double* d_pose = d_tra + c * 3;
   int* d_eij = reinterpret_cast<int*>(ctx->stage_i64.p);
+  unsigned int* d_row = reinterpret_cast<unsigned int*>(ctx->stage_i64.p + c);
   unsigned int* d_cnt = reinterpret_cast<unsigned int*>(ctx->flags.p + 8);
-  VXS_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, sizeof(unsigned int), ctx->stream));
   VXS_CUDA(ctx, cudaMemcpyAsync(d_pose, poses12, size_t(W) * 96, cudaMemcpyHostToDevice, ctx->stream));
-  const unsigned blocks = unsigned((size_t(W) * W + 255) / 256);
-  VXS_LAUNCH(ctx, "k_hba_edges", k_hba_edges, blocks, 256, 0, ctx->Hraw.p, n, W, d_pose, d_cnt, (long long)cap, d_eij, d_v6, d_rot, d_tra);
+  VXS_LAUNCH(ctx, "k_hba_edges", k_hba_edge_count, unsigned(W), 256, 0, ctx->Hraw.p, n, W, d_row);
+  VXS_LAUNCH(ctx, "k_hba_edges", k_hba_edge_scan, 1, 1024, 0, d_row, W, d_cnt);
+  VXS_LAUNCH(ctx, "k_hba_edges", k_hba_edge_emit, unsigned(W), 256, 0, ctx->Hraw.p, n, W, d_pose, d_row, (long long)cap, d_eij, d_v6, d_rot, d_tra);
   unsigned int cnt = 0;
   VXS_CUDA(ctx, cudaMemcpyAsync(&cnt, d_cnt, sizeof cnt, cudaMemcpyDeviceToHost, ctx->stream));
   VXS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
