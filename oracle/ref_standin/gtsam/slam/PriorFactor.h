@@ -1,0 +1,2 @@
+// STAND-IN (test infrastructure): see gtsam/geometry/Pose3.h
+#include "../geometry/Pose3.h"

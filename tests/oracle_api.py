@@ -8,13 +8,32 @@ from voxel_slam_b200.api import LM_TRACE_DTYPE, VOXEL_ID_DTYPE, LmTrace, MapPara
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_PATH = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
+REF_PATH = os.path.join(ROOT, "oracle", "_ref", "libvxref.so")
+# Two libraries export the same entry points: the hand-written restatement (oracle/vxo_*.hpp, prefix vxo_) and the reference's OWN sources
+# compiled against the Eigen / PCL / ROS stand-ins (oracle/ref_capi.cpp, prefix vxr_).  This module is executed once per backend:
+# `import oracle_api` binds to the restatement, `import ref_api` re-executes it with BACKEND = "ref" (tests/ref_api.py).
+BACKEND = globals().get("BACKEND", "oracle")
 _lib = None
+
+
+class _Prefixed:
+    """CDLL view that maps the vxo_ names used below onto the backend's prefix."""
+
+    def __init__(self, cdll, prefix):
+        self._cdll, self._prefix = cdll, prefix
+
+    def __getattr__(self, name):
+        return getattr(self._cdll, self._prefix + name[4:] if name.startswith("vxo_") else name)
+
+
+def available():
+    return os.path.exists(REF_PATH if BACKEND == "ref" else ORACLE_PATH)
 
 
 def lib():
     global _lib
     if _lib is None:
-        _lib = C.CDLL(ORACLE_PATH)
+        _lib = _Prefixed(C.CDLL(REF_PATH), "vxr_") if BACKEND == "ref" else _Prefixed(C.CDLL(ORACLE_PATH), "vxo_")
         _lib.vxo_factor_create.restype = C.c_void_p
         _lib.vxo_build_window_factor.restype = C.c_void_p
         _lib.vxo_build_gba_factor.restype = C.c_void_p
@@ -149,7 +168,9 @@ class OracleFactor:
         H, resis = np.zeros((n, n), order="F"), np.zeros(2)
         tl = C.c_int(0)
         tr = np.zeros(trace_cap, dtype=LM_TRACE_DTYPE)
-        rc = lib().vxo_li_ba(self._h, _dp(s), C.c_int(int(with_gravity)), C.c_int(max_iter), C.c_double(imu_coef), C.byref(imu.hooks), _dp(H), _dp(resis),
+        # the restatement calls back through vxs_imu_hooks (harness stand-in); the reference build drives real IMU_PRE objects (RefImuWindow)
+        imu_arg = imu._h if BACKEND == "ref" else C.byref(imu.hooks)
+        rc = lib().vxo_li_ba(self._h, _dp(s), C.c_int(int(with_gravity)), C.c_int(max_iter), C.c_double(imu_coef), imu_arg, _dp(H), _dp(resis),
                              tr.ctypes.data_as(C.POINTER(LmTrace)), C.c_int(trace_cap), C.byref(tl))
         return dict(states=s, hess=H, resis=resis, trace=tr[: tl.value], status=rc)
 
@@ -241,7 +262,34 @@ def hba_window(coarse, fine, xyz_f32, kf_offsets, poses12, max_iter, thread_num=
     return dict(poses=p, hess=H, resis_log=log[: 2 * it.value], outer_iters=it.value, status=rc)
 
 
-# ---------------------------------------------------------------- SURVEY 8f ranks 1 / 3 (oracle only): stateful local map after margi
+class RefImuWindow:
+    """W-1 real IMU_PRE objects of the reference build (BACKEND == "ref" only), fed with the same seeded samples as synth.ImuWindow."""
+
+    def __init__(self, poses12_true, T=0.1, samples=20, gyr_noise=1e-3, acc_noise=1e-2, seed=7):
+        p = _f64(poses12_true).reshape(-1, 12)
+        self.W = p.shape[0]
+        lib().vxo_imu_create.restype = C.c_void_p
+        self._h = C.c_void_p(lib().vxo_imu_create(_dp(p), C.c_int(self.W), C.c_double(T), C.c_int(samples), C.c_double(gyr_noise), C.c_double(acc_noise), C.c_uint64(seed)))
+
+    def reset(self):
+        lib().vxo_imu_reset(self._h)
+
+    def eval(self, states24, with_gravity=False, want_jac=True):
+        s = _f64(states24)
+        bs = 33 if with_gravity else 30
+        blocks, gvec, cost = np.zeros((self.W - 1, bs * bs)), np.zeros((self.W - 1, bs)), C.c_double(0)
+        lib().vxo_imu_eval(self._h, _dp(s), C.c_int(self.W), C.c_int(int(with_gravity)), C.c_int(int(want_jac)), _dp(blocks), _dp(gvec), C.byref(cost))
+        return cost.value, blocks, gvec
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().vxo_imu_destroy(self._h); self._h = None
+        except Exception:
+            pass
+
+
+# ---------------------------------------------------------------- SURVEY 8f ranks 1 / 3: stateful local map after margi
 class LocalMap:
     def __init__(self, mp, pts_body, scan_offsets, poses12, var_diag, mgsize=0):
         pts = _f64(pts_body).reshape(-1, 3)
