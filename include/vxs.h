@@ -243,6 +243,37 @@ int vxs_odom_set_planes(vxs_ctx* ctx, const vxs_map_params* mp, int64_t n, const
 int vxs_odom_accumulate(vxs_ctx* ctx, const double* pv12, int64_t n, const double* pose12, const double* rot_var9, const double* tsl_var9,
                         double* HTH36, double* HTz6, double* nnt9, int64_t* match_num, int32_t* flags);
 
+/* ---------------------------------------------------------------- persistent local map of the sliding-window loop
+ * The device-resident counterpart of `surf_map` / `surf_map_slide` (unordered_map<VOXEL_LOC, OctoTree*>, voxelslam.hpp) and of the per-scan
+ * calls around the BA in thd_odometry_localmapping (voxelslam.cpp:1599-1712).  A scan is uploaded ONCE; the map, the slide windows
+ * (SlideWindow, voxel_map.hpp:896-930), the raw points that are still re-cuttable and the marginalised points kept in point_fix stay in HBM.
+ *   vxs_map_push_scan = cut_voxel_multi (voxel_map.hpp:1543-1639; single-thread form cut_voxel :1504-1540) of the NEW scan at window position
+ *                       win_count-1 + multi_recut (voxelslam.cpp:1398-1453: OctoTree::recut :1148-1194 on every slide root, then tras_opt
+ *                       :1308-1333) — `out` receives the LidarFactor of the window (cleared first; may be NULL).
+ *                       pv12: n pointVar records (body-frame pnt 3 | var 3x3 row-major, as pvec_update left it, voxelslam.hpp:203-214);
+ *                       poses12: x_buf, win_count poses INCLUDING the new scan's (R row-major | p).
+ *   vxs_map_margi     = multi_margi (voxelslam.cpp:1321-1395: OctoTree::margi voxel_map.hpp:1196-1305 with plane_update :1118-1146, erase of the
+ *                       roots that ceased to exist + clear_slwd :1482-1500) with x_buf AFTER the BA and the factor the BA ran on (its cached
+ *                       eig / pcr_adds are read in place, nothing is downloaded), then the slot-ring rotation mp[i] += mgsize
+ *                       (voxelslam.cpp:1689-1693).  The caller shifts its own x_buf / pvec_buf / imu_pre_buf (:1695-1712).
+ *                       multi_margi hard-codes mgsize 1 (:1360); 1..4 are accepted.
+ * The reference's silent early-outs when there are fewer roots than threads (voxel_map.hpp:1597, voxelslam.cpp:1343, 1409) are not
+ * reproduced: the work is always done.  One map belongs to one ctx (and its thread). */
+typedef struct vxs_map vxs_map;
+int vxs_map_create(vxs_ctx* ctx, const vxs_map_params* mp, int win_size, int max_points /* voxel_map.hpp:86, default 100 */, vxs_map** out);
+int vxs_map_destroy(vxs_map* m);
+int vxs_map_push_scan(vxs_map* m, const double* pv12, int64_t n, const double* poses12, int win_count, vxs_factor* out);
+int vxs_map_margi(vxs_map* m, const double* poses12, int win_count, int mgsize, vxs_factor* f);
+/* bookkeeping: nodes in the table, points in the point_fix pool, resident scans, ring[win_size] = slot of every logical window position */
+int vxs_map_counts(const vxs_map* m, int64_t* n_nodes, int64_t* n_fix_points, int* win_count, int32_t* ring);
+/* Every leaf of the map, 32 + 10 * win_size doubles each (for tests and debugging): voxel_center 3 | cube half length | layer | is_plane |
+ * isexist | has a slide window | root in the slide map | opt_state | last_num | points in point_fix | pcr_add 10 | pcr_fix 10 | the window
+ * clusters pcrs_local[mp[i]], i < win_size.  *n_out = number of leaves (rows are written when cap suffices). */
+int vxs_map_read_leaves(vxs_map* m, double* rows, int64_t cap, int64_t* n_out);
+/* Plane leaves (is_plane, radius > 0) as plane_update left them, 52 doubles each: plane centre 3 | normal 3 | plane_var 6x6 row-major | radius |
+ * N | voxel_center 3 | cube half length | trace(cov_add) | eig_value 3;  ids5 (may be NULL): root x, y, z, layer, octant path. */
+int vxs_map_read_planes(vxs_map* m, double* rows52, int64_t* ids5, int64_t cap, int64_t* n_out);
+
 #ifdef __cplusplus
 }
 #endif

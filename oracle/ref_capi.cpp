@@ -395,10 +395,8 @@ int64_t vxr_local_map_planes(void* hh, double* rows52, int64_t cap) {
   return int64_t(pl.size());
 }
 // the per-point loop of lio_state_estimation (voxelslam.cpp:876-918) around the reference's match()
-int vxr_local_map_odom_accumulate(void* hh, const double* pv12, int64_t n, const double* pose12, const double* rot_var9, const double* tsl_var9, int passes, double* HTH36, double* HTz6,
+static int odom_accum_impl(unordered_map<VOXEL_LOC, OctoTree*>& the_map, const double* pv12, int64_t n, const double* pose12, const double* rot_var9, const double* tsl_var9, int passes, double* HTH36, double* HTz6,
                                   double* nnt9, int32_t* flags) {
-  RefLocalMap* h = static_cast<RefLocalMap*>(hh);
-  set_local_params(&h->mp);
   IMUST x_curr = state_from12(pose12);
   Eigen::Matrix3d rot_var, tsl_var;
   for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) { rot_var(r, c) = rot_var9[3 * r + c]; tsl_var(r, c) = tsl_var9[3 * r + c]; }
@@ -420,7 +418,7 @@ int vxr_local_map_odom_accumulate(void* hh, const double* pv12, int64_t n, const
       Plane* pla = nullptr;
       int flag = 0;
       if (octos[size_t(i)] != nullptr && octos[size_t(i)]->inside(wld)) { double max_prob = 0; flag = octos[size_t(i)]->match(wld, pla, max_prob, var_world, sigma_d, octos[size_t(i)]); }
-      else flag = match(h->map, wld, pla, var_world, sigma_d, octos[size_t(i)]);
+      else flag = match(the_map, wld, pla, var_world, sigma_d, octos[size_t(i)]);
       if (flags && pass == passes - 1) flags[i] = flag;
       if (flag) {
         Plane& pp = *pla;
@@ -441,6 +439,13 @@ int vxr_local_map_odom_accumulate(void* hh, const double* pv12, int64_t n, const
   return match_num;
 }
 
+int vxr_local_map_odom_accumulate(void* hh, const double* pv12, int64_t n, const double* pose12, const double* rot_var9, const double* tsl_var9, int passes, double* HTH36, double* HTz6,
+                                  double* nnt9, int32_t* flags) {
+  RefLocalMap* h = static_cast<RefLocalMap*>(hh);
+  set_local_params(&h->mp);
+  return odom_accum_impl(h->map, pv12, n, pose12, rot_var9, tsl_var9, passes, HTH36, HTz6, nnt9, flags);
+}
+
 // ---------------------------------------------------------------- the per-scan map sequence of thd_odometry_localmapping (voxelslam.cpp:1599-1615, 1669-1712), poses given
 struct RefSlidingSim {
   vxs_map_params mp; int win_size, mgsize, max_pts;
@@ -457,19 +462,30 @@ struct RefSlidingSim {
 };
 void* vxr_sliding_sim_create(const vxs_map_params* mpar, int win_size, int mgsize, int max_pts) { return mgsize == 1 ? new RefSlidingSim(*mpar, win_size, mgsize, max_pts) : nullptr; }
 void vxr_sliding_sim_free(void* h) { delete static_cast<RefSlidingSim*>(h); }
-void vxr_sliding_sim_add_scan(void* hh, const double* pts_body, int64_t n, const double* pose12, double var_diag) {
-  RefSlidingSim* s = static_cast<RefSlidingSim*>(hh);
+static void ref_sim_add(RefSlidingSim* s, PVecPtr pv, const double* pose12, int ba_iters);
+void vxr_sliding_sim_add_scan(void* hh, const double* pts_body, int64_t n, const double* pose12, double var_diag) { ref_sim_add(static_cast<RefSlidingSim*>(hh), make_pvec(pts_body, n, var_diag), pose12, 0); }
+void vxr_sliding_sim_add_scan_pv(void* hh, const double* pv12, int64_t n, const double* pose12, int ba_iters) {
+  PVecPtr pv(new PVec(size_t(n)));
+  for (int64_t k = 0; k < n; k++) { const double* p = pv12 + 12 * k; (*pv)[size_t(k)].pnt = Eigen::Vector3d(p[0], p[1], p[2]); for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) (*pv)[size_t(k)].var(r, c) = p[3 + 3 * r + c]; }
+  ref_sim_add(static_cast<RefSlidingSim*>(hh), pv, pose12, ba_iters);
+}
+void* vxr_sliding_sim_factor(void* hh) { RefSlidingSim* s = static_cast<RefSlidingSim*>(hh); RefFactor* rf = new RefFactor(s->win_size); rf->f = s->voxhess; return rf; }
+static void ref_sim_add(RefSlidingSim* s, PVecPtr pv, const double* pose12, int ba_iters) {
   s->bind();
   IMUST x = state_from12(pose12);
   s->win_count++; s->x_buf.push_back(x);                                                   // :1599-1601
   s->voxhess.clear(); s->voxhess.win_size = s->win_size;                                   // :1609
-  PVecPtr pv = make_pvec(pts_body, n, var_diag);
   PLV(3) pwld;
   for (pointVar& p : *pv) pwld.push_back(x.R * p.pnt + x.p);
   cut_voxel(s->surf_map, pv, s->win_count - 1, s->surf_map_slide, s->win_size, pwld, s->sws);   // :1611 (the single-thread form of :1612)
   for (auto& kv : s->surf_map_slide) kv.second->recut(s->win_count, s->x_buf, s->sws);     // multi_recut :1420-1424
   for (auto& kv : s->surf_map_slide) kv.second->tras_opt(s->voxhess);                      // :1450-1451
   if (s->win_count >= s->win_size) {
+    if (ba_iters > 0 && s->voxhess.plvec_voxels.size() >= 2) {                               // the BA between recut and margi (:1637-1654), pose-only flavour
+      Lidar_BA_Optimizer opt; opt.thd_num = 2;
+      Eigen::MatrixXd hess; vector<double> resis;
+      opt.damping_iter(s->x_buf, s->voxhess, &hess, resis, ba_iters, false);
+    }
     for (auto& kv : s->surf_map_slide) kv.second->margi(s->win_count, 1, s->x_buf, s->voxhess);   // multi_margi :1356-1362
     for (auto it = s->surf_map_slide.begin(); it != s->surf_map_slide.end();) { if (it->second->isexist) it++; else { it->second->clear_slwd(s->sws); s->surf_map_slide.erase(it++); } }   // :1379-1388
     for (int i = 0; i < s->win_size; i++) { s->ring[size_t(i)] += s->mgsize; if (s->ring[size_t(i)] >= s->win_size) s->ring[size_t(i)] -= s->win_size; }                              // :1689-1693
@@ -500,6 +516,27 @@ int64_t vxr_sliding_sim_state(void* hh, int32_t* head, double* poses12, double* 
     for (int i = 0; i < W; i++) { if (o->sw) pc_pack(o->sw->pcrs_local[size_t(s->ring[size_t(i)])], r + 32 + 10 * i); else for (int k = 0; k < 10; k++) r[32 + 10 * i + k] = 0; }
   }
   return int64_t(lv.size());
+}
+
+int64_t vxr_sliding_sim_planes(void* hh, double* rows52, int64_t cap) {
+  RefSlidingSim* s = static_cast<RefSlidingSim*>(hh);
+  vector<OctoTree*> pl;
+  for (auto& kv : s->surf_map) collect_planes(kv.second, pl);
+  for (int64_t i = 0; i < int64_t(pl.size()) && i < cap; i++) {
+    double* r = rows52 + 52 * i; OctoTree* o = pl[size_t(i)];
+    for (int k = 0; k < 3; k++) { r[k] = o->plane.center[k]; r[3 + k] = o->plane.normal[k]; r[44 + k] = o->voxel_center[k]; r[49 + k] = o->eig_value[k]; }
+    for (int a = 0; a < 6; a++) for (int b = 0; b < 6; b++) r[6 + 6 * a + b] = o->plane.plane_var(a, b);
+    r[42] = o->plane.radius; r[43] = o->pcr_add.N; r[47] = double(o->quater_length) * 2;
+    double t = 0; for (int k = 0; k < 9; k++) t += o->cov_add(k, k);
+    r[48] = t;
+  }
+  return int64_t(pl.size());
+}
+int vxr_sliding_sim_odom_accumulate(void* hh, const double* pv12, int64_t n, const double* pose12, const double* rot_var9, const double* tsl_var9, double* HTH36, double* HTz6, double* nnt9,
+                                    int32_t* flags) {
+  RefSlidingSim* s = static_cast<RefSlidingSim*>(hh);
+  s->bind();
+  return odom_accum_impl(s->surf_map, pv12, n, pose12, rot_var9, tsl_var9, 1, HTH36, HTz6, nnt9, flags);
 }
 
 }  // extern "C"

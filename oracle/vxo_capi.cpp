@@ -441,6 +441,56 @@ void vxo_sliding_sim_add_scan(void* h, const double* pts_body, int64_t n, const 
   for (int64_t k = 0; k < n; k++) { scan[k].pnt = v3(pts_body[3 * k], pts_body[3 * k + 1], pts_body[3 * k + 2]); scan[k].var = var; }
   sim->add_scan(scan, states_from_poses12(pose12, 1)[0]);
 }
+// full pointVar records (pnt 3 | var 3x3 row-major) and an optional pose-only BA between tras_opt and margi
+void vxo_sliding_sim_add_scan_pv(void* h, const double* pv12, int64_t n, const double* pose12, int ba_iters) {
+  SlidingWindowSim* sim = static_cast<SlidingWindowSim*>(h);
+  std::vector<PV> scan; scan.resize(size_t(n));
+  for (int64_t k = 0; k < n; k++) { const double* p = pv12 + 12 * k; scan[k].pnt = v3(p[0], p[1], p[2]); for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) scan[k].var(r, c) = p[3 + 3 * r + c]; }
+  sim->add_scan(scan, states_from_poses12(pose12, 1)[0], ba_iters);
+}
+// copy of the factor the last add_scan extracted (tras_opt), as a factor handle
+void* vxo_sliding_sim_factor(void* h) {
+  SlidingWindowSim* sim = static_cast<SlidingWindowSim*>(h);
+  OracleFactor* of = new OracleFactor(sim->win_size);
+  of->f = sim->voxhess;
+  return of;
+}
+int64_t vxo_sliding_sim_planes(void* hh, double* rows52, int64_t cap) {
+  SlidingWindowSim* sim = static_cast<SlidingWindowSim*>(hh);
+  std::vector<OctoTree*> pl;
+  for (auto& kv : sim->surf_map) collect_planes(kv.second, pl);
+  for (int64_t i = 0; i < int64_t(pl.size()) && i < cap; i++) {
+    double* r = rows52 + 52 * i; const OctoTree* o = pl[i];
+    for (int k = 0; k < 3; k++) { r[k] = o->plane.center[k]; r[3 + k] = o->plane.normal[k]; r[44 + k] = o->voxel_center[k]; r[49 + k] = o->eig_value[k]; }
+    for (int k = 0; k < 36; k++) r[6 + k] = o->plane.plane_var[k];
+    r[42] = o->plane.radius; r[43] = o->pcr_add.N; r[47] = double(o->quater_length) * 2;
+    double t = 0; for (int k = 0; k < 9; k++) t += o->cov_add[k * 9 + k];
+    r[48] = t;
+  }
+  return int64_t(pl.size());
+}
+int vxo_sliding_sim_odom_accumulate(void* hh, const double* pv12, int64_t n, const double* pose12, const double* rot_var9, const double* tsl_var9, double* HTH36, double* HTz6, double* nnt9,
+                                    int32_t* flags) {
+  SlidingWindowSim* sim = static_cast<SlidingWindowSim*>(hh);
+  std::vector<PV> pvec; pvec.resize(size_t(n));
+  for (int64_t i = 0; i < n; i++) { const double* p = pv12 + 12 * i; pvec[i].pnt = v3(p[0], p[1], p[2]); for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) pvec[i].var(r, c) = p[3 + 3 * r + c]; }
+  State x = states_from_poses12(pose12, 1)[0];
+  M3 rv, tv;
+  for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) { rv(r, c) = rot_var9[3 * r + c]; tv(r, c) = tsl_var9[3 * r + c]; }
+  std::vector<OctoTree*> octos;
+  const int m = odom_accumulate(sim->surf_map, pvec, x, rv, tv, sim->mp_.voxel_size, octos, HTH36, HTz6, nnt9);
+  if (flags) {
+    const M3 Rt = tr(x.R);
+    for (int64_t i = 0; i < n; i++) {
+      const M3 phat = hat(pvec[i].pnt);
+      const M3 var_world = (x.R * pvec[i].var * Rt + phat * rv * tr(phat)) + tv;
+      const V3 wld = x.R * pvec[i].pnt + x.p;
+      double sd = 0; const Plane* pla = nullptr; OctoTree* oc = nullptr;
+      flags[i] = match(sim->surf_map, wld, pla, var_world, sd, oc, sim->mp_.voxel_size);
+    }
+  }
+  return m;
+}
 static void collect_leaves(OctoTree* o, std::vector<OctoTree*>& out) {
   if (o->octo_state == 0) { out.push_back(o); return; }
   for (auto c : o->leaves) if (c) collect_leaves(c, out);

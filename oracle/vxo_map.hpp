@@ -696,7 +696,9 @@ struct SlidingWindowSim {
   SlidingWindowSim(const SlidingWindowSim&) = delete;
   SlidingWindowSim& operator=(const SlidingWindowSim&) = delete;
 
-  void add_scan(const std::vector<PV>& scan, const State& x) {
+  // ba_iters > 0: a pose-only BA (Lidar_BA_Optimizer::damping_iter) runs between tras_opt and margi once the window is full, as the LI-BA does in
+  // the reference loop (voxelslam.cpp:1637-1654): x_buf moves and the factor's cached eig / pcr_adds are overwritten before margi reads them
+  void add_scan(const std::vector<PV>& scan, const State& x, int ba_iters = 0) {
     win_count++;
     x_buf.push_back(x);
     voxhess.clear(); voxhess.win_size = win_size;
@@ -719,6 +721,7 @@ struct SlidingWindowSim {
     for (auto& kv : slide) kv.second->recut(win_count, x_buf, mp_);            // multi_recut, voxelslam.cpp:1398-1446
     for (auto& kv : slide) kv.second->tras_opt(voxhess, nullptr, ring.data());
     if (win_count >= win_size) {
+      if (ba_iters > 0 && int(voxhess.size()) >= 2) { Mat hess; std::vector<double> resis; int status = 0; lidar_ba_damping_iter(x_buf, voxhess, &hess, resis, ba_iters, 2, nullptr, &status); }
       std::vector<int> rg(ring);
       for (auto& kv : slide) kv.second->margi(win_count, mgsize, x_buf, voxhess, rg, mp_);   // multi_margi, :1321-1395
       for (auto it = slide.begin(); it != slide.end();) { if (it->second->isexist) ++it; else { it->second->clear_slwd(); it = slide.erase(it); } }

@@ -338,6 +338,32 @@ class SlidingSim:
         p = _f64(pts_body).reshape(-1, 3)
         lib().vxo_sliding_sim_add_scan(C.c_void_p(self._h), _dp(p), C.c_int64(p.shape[0]), _dp(_f64(pose12)), C.c_double(var_diag))
 
+    def add_scan_pv(self, pv12, pose12, ba_iters=0):
+        """full pointVar records (pnt | var 3x3); ba_iters > 0 runs a pose-only BA between tras_opt and margi once the window is full"""
+        p = _f64(pv12).reshape(-1, 12)
+        lib().vxo_sliding_sim_add_scan_pv(C.c_void_p(self._h), _dp(p), C.c_int64(p.shape[0]), _dp(_f64(pose12)), C.c_int(ba_iters))
+
+    def factor(self):
+        lib().vxo_sliding_sim_factor.restype = C.c_void_p
+        return OracleFactor(lib().vxo_sliding_sim_factor(C.c_void_p(self._h)), self.W)
+
+    def planes(self):
+        lib().vxo_sliding_sim_planes.restype = C.c_int64
+        n = lib().vxo_sliding_sim_planes(C.c_void_p(self._h), None, C.c_int64(0))
+        rows = np.zeros((max(n, 1), 52))
+        lib().vxo_sliding_sim_planes(C.c_void_p(self._h), _dp(rows), C.c_int64(n))
+        r = rows[:n]
+        return dict(center=r[:, 0:3], normal=r[:, 3:6], plane_var=r[:, 6:42].reshape(-1, 6, 6), radius=r[:, 42], N=r[:, 43], voxel_center=r[:, 44:47], half=r[:, 47],
+                    cov_trace=r[:, 48], eig=r[:, 49:52])
+
+    def odom_accumulate(self, pv12, pose12, rot_var, tsl_var):
+        pv = _f64(pv12).reshape(-1, 12)
+        HTH, HTz, nnt = np.zeros((6, 6)), np.zeros(6), np.zeros((3, 3))
+        flags = np.zeros(pv.shape[0], dtype=np.int32)
+        m = lib().vxo_sliding_sim_odom_accumulate(C.c_void_p(self._h), _dp(pv), C.c_int64(pv.shape[0]), _dp(_f64(pose12)), _dp(_f64(rot_var)), _dp(_f64(tsl_var)), _dp(HTH), _dp(HTz),
+                                                  _dp(nnt), flags.ctypes.data_as(C.POINTER(C.c_int32)))
+        return dict(n=m, HTH=HTH, HTz=HTz, nnt=nnt, flags=flags)
+
     def state(self):
         W = self.W
         head = np.zeros(2 + W, dtype=np.int32)

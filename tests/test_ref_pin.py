@@ -269,3 +269,50 @@ def test_sliding_window_map_sequence():
             assert np.array_equal(x[..., 9], y[..., 9]), (i, f)
             assert np.max(np.abs(x - y) / (np.abs(y) + 1e-6)) < 1e-11, (i, f)
     assert sa["win_base"] == nscan - Wn + 1 and int(np.sum(sa["pcr_fix"][:, 9] > 0)) > 10       # scans were marginalised into pcr_fix
+
+
+def _pv_records(scan, seed):
+    """pointVar records with a full (symmetric positive) per-point variance, as pvec_update leaves them"""
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((scan.shape[0], 3, 3)) * 0.01
+    var = A @ np.transpose(A, (0, 2, 1)) + np.eye(3) * 1e-5
+    return np.concatenate([scan, var.reshape(-1, 9)], axis=1)
+
+
+def test_sliding_window_with_ba_between_recut_and_margi():
+    """The loop as the reference runs it: per scan cut + recut + tras_opt, then (window full) a BA that moves x_buf and overwrites the factor cache,
+    then margi reads pcr_add / eig back from the factor (opt_state path) — reference build vs restatement, plus the plane table and one odometry pass."""
+    Wn, L, nscan = 6, 6.0, 16
+    mp = vx.MapParams.make(voxel_size=1.0, max_layer=2)
+    a, b = ra.SlidingSim(mp, Wn, 1, max_points=60), oa.SlidingSim(mp, Wn, 1, max_points=60)
+    for i in range(nscan):
+        pose = synth.true_pose(L, i)
+        est = synth.perturb_pose(pose, 900 + i, 2e-3, 1e-2) if i else pose
+        pv = _pv_records(synth.gen_scan(L, i, 2500, pose, seed=0x5EED0000 + 33), i)
+        a.add_scan_pv(pv, est, ba_iters=2); b.add_scan_pv(pv, est, ba_iters=2)
+        sa, sb = a.state(), b.state()
+        assert sa["win_count"] == sb["win_count"] and np.array_equal(sa["ring"], sb["ring"])
+        assert np.max(np.abs(sa["poses"] - sb["poses"])) < 1e-9                                   # x_buf after the BA
+        key = lambda s: np.lexsort(np.concatenate([np.round(s["voxel_center"], 9), s["layer"][:, None]], axis=1).T)
+        ka, kb = key(sa), key(sb)
+        for f in ("voxel_center", "layer", "is_plane", "isexist", "has_sw", "in_slide", "last_num", "n_point_fix"):
+            assert np.array_equal(sa[f][ka], sb[f][kb]), (i, f)
+        for f in ("pcr_add", "pcr_fix", "slots"):
+            x, y = sa[f][ka], sb[f][kb]
+            assert np.array_equal(x[..., 9], y[..., 9]), (i, f)
+            assert np.max(np.abs(x - y) / (np.abs(y) + 1e-6)) < 1e-8, (i, f)
+    fa, fb = a.factor().export(), b.factor().export()
+    assert len(fa["sum10"]) == len(fb["sum10"]) > 20
+    pa, pb = a.planes(), b.planes()
+    assert len(pa["N"]) == len(pb["N"]) > 20
+    ka, kb = np.lexsort(np.round(pa["voxel_center"], 9).T), np.lexsort(np.round(pb["voxel_center"], 9).T)
+    assert np.array_equal(pa["N"][ka], pb["N"][kb]) and np.max(np.abs(pa["center"][ka] - pb["center"][kb])) < 1e-9
+    assert np.max(np.abs(pa["cov_trace"][ka] - pb["cov_trace"][kb]) / pb["cov_trace"][kb]) < 1e-10      # the Bf_var accumulation with full variances
+    sgn = np.sign(np.sum(pa["normal"][ka] * pb["normal"][kb], axis=1))
+    Vb = pb["plane_var"][kb].copy(); Vb[:, :3, 3:] *= sgn[:, None, None]; Vb[:, 3:, :3] *= sgn[:, None, None]
+    assert np.max(np.abs(pa["plane_var"][ka] - Vb) / np.max(np.abs(Vb), axis=(1, 2), keepdims=True)) < 1e-5
+    pose = synth.perturb_pose(synth.true_pose(L, nscan), 78, 1e-3, 5e-3)
+    pv = _pv_records(synth.gen_scan(L, nscan, 3000, synth.true_pose(L, nscan), seed=0x5EED0000 + 33), 99)
+    oa_, ob_ = a.odom_accumulate(pv, pose, np.eye(3) * 1e-6, np.eye(3) * 1e-5), b.odom_accumulate(pv, pose, np.eye(3) * 1e-6, np.eye(3) * 1e-5)
+    assert oa_["n"] == ob_["n"] > 300 and np.array_equal(oa_["flags"], ob_["flags"])
+    assert relinf(oa_["HTH"], ob_["HTH"]) < 1e-8 and relinf(oa_["HTz"], ob_["HTz"]) < 1e-8

@@ -5,7 +5,7 @@ mirror used by the tests and ``bench.py``.  There is no CPU fallback: importing 
 CPU-only checks can verify the ABI), but every compute entry point needs a CUDA device and raises otherwise.
 """
 from .api import (  # noqa: F401
-    VxsError, lib, Context, Factor, MapParams, LmTrace, VoxelId, ImuHooks, declared_symbols, LIB_PATH,
+    VxsError, lib, Context, Factor, LocalMap, MapParams, LmTrace, VoxelId, ImuHooks, declared_symbols, LIB_PATH,
 )
 
-__all__ = ["VxsError", "lib", "Context", "Factor", "MapParams", "LmTrace", "VoxelId", "ImuHooks", "declared_symbols", "LIB_PATH"]
+__all__ = ["VxsError", "lib", "Context", "Factor", "LocalMap", "MapParams", "LmTrace", "VoxelId", "ImuHooks", "declared_symbols", "LIB_PATH"]

@@ -446,6 +446,64 @@ class Factor:
         return ptr, fr, cl, fx, co
 
 
+class LocalMap:
+    """vxs_map: the device-resident `surf_map` / `surf_map_slide` of the sliding-window loop (voxelslam.cpp:1599-1712)."""
+
+    def __init__(self, ctx, mp, win_size, max_points=100):
+        self.ctx, self.W = ctx, win_size
+        self._p = C.c_void_p()
+        ctx._check(lib().vxs_map_create(ctx._p, C.byref(mp), C.c_int(win_size), C.c_int(max_points), C.byref(self._p)))
+
+    def close(self):
+        if self._p:
+            lib().vxs_map_destroy(self._p)
+            self._p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def push_scan(self, pv12, poses12, factor=None):
+        """cut_voxel_multi + multi_recut + tras_opt of one new scan; pv12 rows = body pnt (3) | var (9); poses12 = x_buf incl. the new scan."""
+        pv = _f64(pv12).reshape(-1, 12)
+        p = _f64(poses12).reshape(-1, 12)
+        self.ctx._check(lib().vxs_map_push_scan(self._p, _dp(pv), C.c_int64(pv.shape[0]), _dp(p), C.c_int(p.shape[0]), factor._p if factor is not None else None))
+
+    def margi(self, poses12, factor, mgsize=1):
+        p = _f64(poses12).reshape(-1, 12)
+        self.ctx._check(lib().vxs_map_margi(self._p, _dp(p), C.c_int(p.shape[0]), C.c_int(mgsize), factor._p))
+
+    def counts(self):
+        nn, nf, wc = C.c_int64(0), C.c_int64(0), C.c_int(0)
+        ring = np.zeros(self.W, dtype=np.int32)
+        self.ctx._check(lib().vxs_map_counts(self._p, C.byref(nn), C.byref(nf), C.byref(wc), ring.ctypes.data_as(C.POINTER(C.c_int32))))
+        return dict(nodes=nn.value, fix_points=nf.value, win_count=wc.value, ring=ring)
+
+    def leaves(self):
+        """every leaf, same fields as the oracle's SlidingSim.state()"""
+        W = self.W
+        n = C.c_int64(0)
+        self.ctx._check(lib().vxs_map_read_leaves(self._p, None, C.c_int64(0), C.byref(n)))
+        rows = np.zeros((max(n.value, 1), 32 + 10 * W))
+        self.ctx._check(lib().vxs_map_read_leaves(self._p, _dp(rows), C.c_int64(n.value), C.byref(n)))
+        r = rows[: n.value]
+        c = self.counts()
+        return dict(win_count=c["win_count"], ring=c["ring"], voxel_center=r[:, 0:3], half=r[:, 3], layer=r[:, 4].astype(int), is_plane=r[:, 5] > 0, isexist=r[:, 6] > 0,
+                    has_sw=r[:, 7] > 0, in_slide=r[:, 8] > 0, opt_state=r[:, 9].astype(int), last_num=r[:, 10].astype(int), n_point_fix=r[:, 11].astype(int),
+                    pcr_add=r[:, 12:22], pcr_fix=r[:, 22:32], slots=r[:, 32:].reshape(n.value, W, 10))
+
+    def planes(self):
+        n = C.c_int64(0)
+        self.ctx._check(lib().vxs_map_read_planes(self._p, None, None, C.c_int64(0), C.byref(n)))
+        rows = np.zeros((max(n.value, 1), 52)); ids = np.zeros((max(n.value, 1), 5), dtype=np.int64)
+        self.ctx._check(lib().vxs_map_read_planes(self._p, _dp(rows), ids.ctypes.data_as(C.POINTER(C.c_int64)), C.c_int64(n.value), C.byref(n)))
+        r = rows[: n.value]
+        return dict(center=r[:, 0:3], normal=r[:, 3:6], plane_var=r[:, 6:42].reshape(-1, 6, 6), radius=r[:, 42], N=r[:, 43], voxel_center=r[:, 44:47], half=r[:, 47],
+                    cov_trace=r[:, 48], eig=r[:, 49:52], ids=ids[: n.value])
+
+
 def host_alloc(nbytes):
     p = C.c_void_p()
     rc = lib().vxs_host_alloc(C.byref(p), C.c_uint64(nbytes))
