@@ -186,7 +186,8 @@ def run_ours(args):
 
     # ---- value: K steps, factor resident in HBM
     sampler = ClockSampler(local); sampler.start()
-    for _ in range(max(Wu, 3)):
+    first_step = step()
+    for _ in range(max(Wu, 3) - 1):
         step()
     launches0 = ctx.launches
     barrier(dist, local)
@@ -291,6 +292,28 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline_from_structure(vx, W, ptr, fr, hp["cl"], eig0, sum0, st0, tr, reps=2)
+    # ---- parity of what was timed, at the metric shape itself (the oracle is the checker here, never the thing measured)
+    parity = None
+    if rank == 0:
+        try:
+            parity = parity_block(vx, ctx, W, ptr, fr, hp["cl"], eig0, sum0, est, first_step, cpu)
+        except Exception as e:   # never lose the bench line over the checker
+            parity = {"error": repr(e)}
+    # ---- the full local-mapping step on the persistent device map (SURVEY §8d "also report the full local-mapping step")
+    lmap = None
+    if rank == 0 and world == 1 and not args.no_local_mapping:
+        try:
+            f.close()
+            lmap = local_mapping_leg(vx, ctx, W, pts, L, args.lm_steps)
+        except Exception as e:
+            lmap = {"error": repr(e)}
+    # ---- the path that shards: one voxel-sharded global-BA window over all ranks, NCCL all-reduce of the pose Hessian (strong scaling)
+    gba = None
+    if not args.no_gba:
+        try:
+            gba = gba_sharded_leg(vx, local, rank, world, dist, args)
+        except Exception as e:
+            gba = {"error": repr(e)}
 
     if rank == 0:
         line = {
@@ -304,13 +327,151 @@ def run_ours(args):
                     "call": "vxs_factor_push_voxels_async of the host LidarFactor (pinned CSR, 4 chunks overlapped with the first Hessian build) + LI_BA damping_iter (3 iterations) + read back poses, Hessian, eig/pcr_adds"},
             "gpu_launches": int(launches), "clocks": clocks,
             "roofline": roof_main, "roofline_residual": roof_resid, "roofline_jac": roof_jac, "dominant_kernel": dom,
-            "kernels": kern, "cpu_baseline": cpu, "c2_plane_fit": c2, "down_sampling": ds,
+            "kernels": kern, "cpu_baseline": cpu, "parity": parity, "local_mapping": lmap, "gba": gba, "c2_plane_fit": c2, "down_sampling": ds,
             "voxelize": {"ms_total": t_vox * 1e3, "points": int(W * pts), "stages_ms": {k: v[0] for k, v in vox_stages.items() if v[1] > 0}},
             "check": {"pose_err_before": err0, "pose_err_after_3_iters": err1, "trace": [[float(t["r1"]), float(t["r2"]), int(t["accepted"])] for t in o["trace"]]},
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier(); dist.destroy_process_group()
+
+
+def parity_block(vx, ctx, W, ptr, fr, cl, eig, s, est, first_step, cpu):
+    """CUDA vs oracle AT the metric shape: (1) acc_evaluate2 on an evenly spaced ~2 % voxel sample (same sample on both sides: Hessian, gradient,
+    residual), (2) the first LM iteration of the timed step against the oracle's full-size iteration that cpu_baseline ran (r1, r2, state increment)."""
+    import oracle_api as oa
+    V = ptr.shape[0] - 1
+    sel = np.linspace(0, V - 1, max(64, V // 50)).astype(np.int64)
+    cnt = np.diff(ptr)[sel]
+    ent = np.concatenate([np.arange(ptr[v], ptr[v + 1]) for v in sel])
+    sp = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+    fs = vx.Factor(ctx, W)
+    fs.push_voxels(sp, fr[ent], np.ascontiguousarray(cl[ent]), eig[sel], s[sel])
+    H, J, r = ctx.evaluate_hessian(fs, est)
+    fs.close()
+    of = oracle_factor_from_csr(W, sp, fr[ent], cl[ent], eig[sel], s[sel])
+    Hr, Jr, rr = of.hessian(est)
+    rel = lambda a, b: float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / max(np.max(np.abs(b)), 1e-300))
+    out = {"shape": f"W={W}, V={V}", "hessian_sample": {"voxels": int(len(sel)), "H_relinf": rel(H, Hr), "g_relinf": rel(J, Jr), "residual_rel": abs(r - rr) / abs(rr)},
+           "tolerance": "north_star: 1e-5 relative on residuals / solved increments; fp64 kernels are far inside"}
+    if cpu is not None and cpu.get("first_iteration") is not None:
+        o = cpu["first_iteration"]
+        g = first_step
+        d_ref = np.max(np.abs(o["states"] - o["st0"]))
+        out["first_iteration"] = {"r1_rel": abs(g["trace"][0]["r1"] - o["r1"]) / o["r1"], "r2_rel": abs(g["trace"][0]["r2"] - o["r2"]) / o["r2"],
+                                  "accepted": [int(g["trace"][0]["accepted"]), int(o["accepted"])],
+                                  "dx_rel": float(np.max(np.abs(g["states"] - o["states"])) / d_ref), "dx_inf": float(d_ref)}
+        cpu.pop("first_iteration")
+    return out
+
+
+def local_mapping_leg(vx, ctx, W, pts, L, steps):
+    """One step of the sliding-window local-mapping loop (voxelslam.cpp:1599-1712) on the persistent device map, window full:
+    vxs_map_push_scan (upload of ONE scan from pinned memory, cut_voxel_multi, multi_recut, tras_opt) -> LI_BA damping_iter (<= 3 iterations, IMU
+    callbacks on the CPU) -> vxs_map_margi (multi_margi, plane_update, ring rotation).  Round 1 rebuilt the whole window per scan (~120 ms)."""
+    from voxel_slam_b200 import api
+    mp = vx.MapParams.make(voxel_size=1.0, min_eigen_value=0.0025, max_layer=2)
+    dm = vx.LocalMap(ctx, mp, W, max_points=100)
+    f = vx.Factor(ctx, W)
+    nscan = W - 1 + steps + 2
+    pv = api.pinned_array((pts, 12), np.float64)
+    pv[:, 3:] = 0.0
+    pv[:, [3, 7, 11]] = 1e-4
+    x_buf, tr_buf = [], []
+    t_fill = time.perf_counter()
+    stage_ms = {}
+    walls, iters = [], 0
+    for i in range(nscan):
+        tr = synth.true_pose(L, i)
+        est = synth.perturb_pose(tr, 77000 + i, 1e-4, 5e-3) if i else tr
+        synth.gen_scan(L, i, pts, tr, seed=0x5EED0000 + 9, out=pv[:, :3])
+        x_buf.append(est); tr_buf.append(tr)
+        timed = i >= W - 1 + 2                              # window full and two warm steps behind us
+        if timed:
+            ctx.timing(True); ctx.timing_reset()
+        t0 = time.perf_counter()
+        dm.push_scan(pv, np.stack(x_buf), f)
+        t1 = time.perf_counter()
+        if len(x_buf) >= W:
+            st = states_from(np.stack(x_buf))
+            imu = synth.ImuWindow(np.stack(tr_buf))
+            o = ctx.li_ba(f, st, imu, with_gravity=False, max_iter=3, want_hess=False, trace_cap=8)
+            t2 = time.perf_counter()
+            xs = o["states"][:, :12]
+            dm.margi(xs, f, mgsize=1)
+            x_buf = [p for p in xs[1:]]; tr_buf = tr_buf[1:]
+            t3 = time.perf_counter()
+            if timed:
+                walls.append((t1 - t0, t2 - t1, t3 - t2)); iters += len(o["trace"])
+                for k, v in ctx.timing_read().items():
+                    if v[1] > 0:
+                        stage_ms[k] = stage_ms.get(k, 0.0) + v[0]
+                ctx.timing(False)
+    w = np.array(walls) * 1e3
+    c = dm.counts()
+    V, E, _ = f.counts()
+    res = {"workload": f"W={W} window full, {pts} pts/scan, L={L}: push_scan + LI-BA (<=3 it) + margi per new scan; map holds {c['nodes']} nodes, {c['fix_points']} point_fix points; factor V={V}, E={E}",
+           "steps": int(len(walls)), "steps_per_s": float(1e3 / w.sum(axis=1).mean()), "ms_per_step": float(w.sum(axis=1).mean()),
+           "ms_push_scan": float(w[:, 0].mean()), "ms_ba": float(w[:, 1].mean()), "ms_margi": float(w[:, 2].mean()), "lm_iterations_per_step": iters / max(len(walls), 1),
+           "h2d_bytes_per_step": int(pts * 96), "timing": "host wall clock around the three synchronous C-ABI calls (pinned host scan; includes the 96 MB H2D)",
+           "kernel_ms_per_step": {k: v / max(len(walls), 1) for k, v in sorted(stage_ms.items(), key=lambda kv: -kv[1])[:14]},
+           "round1_from_scratch_rebuild_ms": 120.0, "fill_s": time.perf_counter() - t_fill}
+    dm.close(); f.close()
+    return res
+
+
+def gba_sharded_leg(vx, local, rank, world, dist, args):
+    """The step that shards (north_star): ONE pose-only global-BA window whose voxel factor is sharded over the ranks by the reference
+    hash of the root cell; a step = one LM iteration = sharded Hessian build -> NCCL all-reduce of [C | g | D | r] -> replicated LDLT -> sharded
+    residual -> scalar all-reduce.  STRONG scaling: the same window for every N.  Own ctx, so the local-BA legs above stay unsharded."""
+    import torch
+    W, pts, L, K = args.gba_win, args.gba_win_pts, args.gba_L, args.gba_steps
+    ctx = vx.Context(local)
+    if world > 1:
+        uid = [vx.Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(uid[0], rank, world)
+    tr, est, p, off = scene_points(vx, W, pts, L, seed=1)
+    mp = vx.MapParams.make(voxel_size=1.0, min_eigen_value=0.0025, max_layer=2)
+    f = vx.Factor(ctx, W)
+    t0 = time.time()
+    ctx.build_window_factor(mp, p, off, est, f)          # every rank keeps the octrees whose root cell it owns
+    t_vox = time.time() - t0
+    del p
+    V, E, _ = f.counts()
+    f.cache_save()
+
+    def step():
+        f.cache_restore()
+        return ctx.lidar_ba(f, est, max_iter=1, thd_num=1, want_hess=False)
+
+    o = None
+    for _ in range(3):
+        o = step()
+    barrier(dist, local)
+    ctx.timer_start(); t0 = time.perf_counter()
+    for _ in range(K):
+        step()
+    ms = max(ctx.timer_stop(), (time.perf_counter() - t0) * 1e3)
+    ms = barrier_max(dist, local, ms)
+    ctx.timing(True); ctx.timing_reset()
+    for _ in range(3):
+        step()
+    stages = ctx.timing_read(); ctx.timing(False)
+    mine = [float(V), float(E)] + [stages.get(k, (0.0, 0))[0] / 3 for k in ("k_syrk", "k_jac", "k_pairs", "k_cluster_sum", "nccl_allreduce", "k_ldlt_all")]
+    per_rank = [mine]
+    if dist is not None:
+        g = [torch.zeros(len(mine), dtype=torch.float64, device=f"cuda:{local}") for _ in range(world)]
+        dist.all_gather(g, torch.tensor(mine, dtype=torch.float64, device=f"cuda:{local}"))
+        per_rank = [x.cpu().tolist() for x in g]
+    res = {"metric": "global-BA LM iterations/sec, one voxel-sharded pose-only BA (strong scaling)", "value": K / (ms * 1e-3), "unit": "iterations/s", "ms_per_step": ms / K, "steps": K,
+           "scaling": "strong", "n_gpus": world, "workload": f"W={W} keyframes x {pts} pts, L={L} m -> {int(sum(r[0] for r in per_rank))} plane voxels, {int(sum(r[1] for r in per_rank))} clusters; n=6W={6 * W}",
+           "allreduce_bytes_per_step": 8 * ((6 * W) ** 2 + 30 * W + 2), "allreduce_ms": max(r[6] for r in per_rank), "map_build_ms_rank0": t_vox * 1e3,
+           "per_rank_[V,E,syrk,jac,pairs,cluster_sum,nccl,ldlt]_ms": [[round(x, 3) for x in r] for r in per_rank],
+           "comm": "NCCL all-reduce issued by libvxs on its own communicator (vxs_ctx_comm_init)" if world > 1 else "single GPU: no collective",
+           "check": {"trace": [[float(t["r1"]), float(t["r2"]), int(t["accepted"])] for t in o["trace"]]}}
+    f.close(); ctx.close()
+    return res
 
 
 def ncu_traffic(kernels):
@@ -388,12 +549,14 @@ def cpu_baseline_from_structure(vx, W, ptr, fr, cl, eig, s, st0, tr, reps=2):
     """The oracle (CPU restatement of the reference, reference thread structure: 5 threads) on the SAME factor, timed on this host."""
     of = oracle_factor_from_csr(W, ptr, fr, cl, eig, s)
     imu = synth.ImuWindow(tr)
-    ts = []
+    ts, first = [], None
     for _ in range(reps):
         imu.reset()
         t0 = time.perf_counter()
-        of.li_ba(st0, imu, with_gravity=False, max_iter=1)
+        o = of.li_ba(st0, imu, with_gravity=False, max_iter=1)
         ts.append(time.perf_counter() - t0)
+        if first is None:
+            first = {"r1": float(o["trace"][0]["r1"]), "r2": float(o["trace"][0]["r2"]), "accepted": int(o["trace"][0]["accepted"]), "states": o["states"], "st0": np.array(st0)}
     t = min(ts)
     try:
         n = 15 * W
@@ -404,7 +567,7 @@ def cpu_baseline_from_structure(vx, W, ptr, fr, cl, eig, s, st0, tr, reps=2):
         allc = {"error": str(e)}
     return {"value": 1.0 / t, "unit": UNIT, "cores": 5, "kind": "port", "host_cores": os.cpu_count(),
             "sample": f"{reps} full-size LM iterations (all {ptr.shape[0] - 1} voxels) of the oracle LI_BA_Optimizer, best of {reps}; 5 threads as voxel_map.hpp:467,531 hard-code",
-            "all_cores_variant": allc}
+            "all_cores_variant": allc, "first_iteration": first}
 
 
 def all_cores_variant(of, poses12, t_fix, scale=1.0):
@@ -620,6 +783,13 @@ def main():
     ap.add_argument("--L", type=float, default=130.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="local_ba", choices=["local_ba", "gba", "gba_window"])
+    ap.add_argument("--no-local-mapping", action="store_true")
+    ap.add_argument("--lm-steps", type=int, default=6)
+    ap.add_argument("--no-gba", action="store_true")
+    ap.add_argument("--gba-win", type=int, default=100)
+    ap.add_argument("--gba-win-pts", type=int, default=200000)
+    ap.add_argument("--gba-L", type=float, default=260.0)
+    ap.add_argument("--gba-steps", type=int, default=10)
     ap.add_argument("--gba-keyframes", type=int, default=400)
     ap.add_argument("--gba-pts", type=int, default=50000)
     ap.add_argument("--gba-per-row", type=int, default=20)

@@ -1,47 +1,35 @@
-"""Scratch performance probe (not a test, not bench.py): builds a window with the ORACLE map, pushes it to the GPU and
-prints per-kernel CUDA-event timings.  Usage: python tests/perf_probe.py W pts_per_scan L [reps]"""
+"""Scratch probe (not a test): per-tile-kind cost of k_syrk at the metric shape.  Usage on the GPU box: python tests/perf_probe.py"""
+import os
+import subprocess
 import sys
-import time
 
-import numpy as np
-
-sys.path.insert(0, ".")
-sys.path.insert(0, "tests")
-import oracle_api as oa  # noqa: E402
-import scenes  # noqa: E402
-import synth
-import voxel_slam_b200 as vx  # noqa: E402
-
-W, pts, L = int(sys.argv[1]), int(sys.argv[2]), float(sys.argv[3])
-reps = int(sys.argv[4]) if len(sys.argv) > 4 else 5
-t0 = time.time()
-sc = scenes.make_window(W=W, pts_per_scan=pts, L=L, seed=1, threads=8)
-V = sc["eig12"].shape[0]
-E = int((sc["clusters10"][:, :, 9] > 0).sum())
-print(f"scene W={W} pts/scan={pts} L={L}: V={V} E={E} k_avg={E / V:.1f}  (gen+oracle map {time.time() - t0:.1f}s, cut+recut {sc['oracle_factor'].build_seconds:.2f}s)", flush=True)
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CODE = r'''
+import sys, os, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "tests"))
+import synth, voxel_slam_b200 as vx
+W, pts, L = 50, 200000, 130.0
+tr = np.stack([synth.true_pose(L, i) for i in range(W)])
+p = np.empty((W * pts, 3))
+for i in range(W):
+    synth.gen_scan(L, i, pts, tr[i], seed=0x5EED0000 + 1, out=p[i * pts:(i + 1) * pts])
+off = np.arange(W + 1, dtype=np.int64) * pts
 ctx = vx.Context(0)
 f = vx.Factor(ctx, W)
-t0 = time.time()
-f.push_voxels_dense(sc["clusters10"], sc["eig12"], sc["sum10"])
-print(f"push {time.time() - t0:.3f}s", flush=True)
-st = scenes.states_from_poses(sc["poses_est"])
-imu = synth.ImuWindow(sc["poses_true"])
-for name, fn in [("residual", lambda: ctx.evaluate_residual(f, sc["poses_est"])),
-                 ("hessian", lambda: ctx.evaluate_hessian(f, sc["poses_est"])),
-                 ("lidar_ba_1it", lambda: ctx.lidar_ba(f, sc["poses_est"], max_iter=1, want_hess=False)),
-                 ("li_ba_1it", lambda: (imu.reset(), ctx.li_ba(f, st, imu, max_iter=1, want_hess=False)))]:
-    fn(); fn()
-    ctx.timing(True); ctx.timing_reset()
-    t0 = time.time()
-    for _ in range(reps):
-        fn()
-    wall = (time.time() - t0) / reps
-    tm = ctx.timing_read(); ctx.timing(False)
-    print(f"--- {name}: wall {wall * 1e3:.3f} ms/call")
-    for k, (ms, calls) in sorted(tm.items(), key=lambda kv: -kv[1][0]):
-        if calls:
-            print(f"    {k:18s} {ms / reps:9.4f} ms/call  ({calls // reps} launches/call, {ms / calls * 1e3:8.1f} us each)")
-nthr = 5
-ts, _ = sc["oracle_factor"].time_hessian(sc["poses_est"], nthr, 1)
-tr, _ = sc["oracle_factor"].time_residual(sc["poses_est"], nthr, 1)
-print(f"CPU oracle ({nthr} threads): hessian {ts * 1e3:.1f} ms, residual {tr * 1e3:.1f} ms")
+ctx.build_window_factor(vx.MapParams.make(), p, off, tr, f)
+for _ in range(3):
+    ctx.evaluate_hessian(f, tr)
+ctx.timing(True); ctx.timing_reset()
+for _ in range(5):
+    ctx.evaluate_hessian(f, tr)
+st = ctx.timing_read()
+print(os.environ.get("VXS_SYRK_ONLY_TILE", "all"), os.environ.get("VXS_SYRK_STREAMK", "1"), f.counts()[:2], "k_syrk ms", st["k_syrk"][0] / 5)
+''' % (ROOT, ROOT)
+for tile in ["all"] + [str(t) for t in range(10)]:
+    env = dict(os.environ, VXS_SYRK_STREAMK="0")
+    if tile != "all":
+        env["VXS_SYRK_ONLY_TILE"] = tile
+    r = subprocess.run([sys.executable, "-c", CODE], env=env, capture_output=True, text=True)
+    print(r.stdout.strip() or r.stderr[-500:])
+r = subprocess.run([sys.executable, "-c", CODE], env=dict(os.environ, VXS_SYRK_STREAMK="1"), capture_output=True, text=True)
+print(r.stdout.strip() or r.stderr[-500:])

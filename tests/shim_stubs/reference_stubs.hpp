@@ -41,5 +41,9 @@ template <class T> struct PointCloud {
 }  // namespace pcl
 typedef pcl::PointXYZINormal PointType;                                                                  // tools.hpp:19
 struct pointVar { Eigen::Vector3d pnt; Eigen::Matrix3d var; };                                           // voxel_map.hpp:14-19
-using PVec = std::vector<pointVar>;                                                                      // voxel_map.hpp:21
+using PVec = std::vector<pointVar>;
+using PVecPtr = std::shared_ptr<std::vector<pointVar>>;                                                 // voxel_map.hpp:22
+struct SlideWindow { std::vector<PVec> points; std::vector<PointCluster> pcrs_local; };                   // voxel_map.hpp:896-930
+namespace Eigen { template <class T> using aligned_allocator = std::allocator<T>; }
+#define PLV(a) std::vector<Eigen::Vector3d, Eigen::aligned_allocator<Eigen::Vector3d>>                 // tools.hpp:13 (only PLV(3) is used)                                                                      // voxel_map.hpp:21
 struct Keyframe { IMUST x0; pcl::PointCloud<PointType>::Ptr plptr; int exist, id, mp; float jour; };     // voxel_map.hpp:867-874

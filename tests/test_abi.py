@@ -9,6 +9,37 @@ import synth
 import voxel_slam_b200 as vx
 
 
+SHIM_USE = r'''
+#define VXS_SHIM_WITH_REFERENCE_TYPES
+#include "voxel_slam_b200/csrc/shim/voxel_ba_shim.hpp"
+// the call sites of voxelslam.cpp, with the reference's own argument types
+void use(std::vector<IMUST>& xs, std::deque<IMU_PRE*>& imus, std::vector<Keyframe*>& smps, PVec& pvec, PVecPtr pptr, pcl::PointCloud<PointType>& pl,
+         std::vector<std::vector<SlideWindow*>>& sws, PLV(3)& pwld, vxs_map_params& mpar) {
+  vxs_shim::LidarFactor f(int(xs.size()));                                   // LidarFactor voxhess(win_size)            voxel_map.hpp:120
+  std::vector<PointCluster> pcrs(xs.size()); PointCluster fix, add; Eigen::Vector3d ev; Eigen::Matrix3d U;
+  vxs_shim::push_voxel(f, pcrs, fix, 1.0, ev, U, add);                        // voxel_map.hpp:1321
+  Eigen::MatrixXd hess; std::vector<double> resis;
+  vxs_shim::li_ba_damping_iter(xs, f, imus, &hess, 1e-4);                     // voxelslam.cpp:1652-1653
+  vxs_shim::li_ba_gravity_damping_iter(xs, f, imus, resis, &hess, 5, 1e-4);   // voxelslam.cpp:632-634, 1643-1645
+  vxs_shim::lidar_ba_damping_iter(xs, f, &hess, resis, 4, 2);                 // voxelslam.cpp:2381-2384
+  vxs_shim::SurfMap surf_map(mpar, int(xs.size()));
+  vxs_shim::cut_voxel_multi(surf_map, pptr, int(xs.size()) - 1, surf_map, int(xs.size()), pwld, sws);   // voxelslam.cpp:1612
+  vxs_shim::cut_voxel(surf_map, pptr, int(xs.size()) - 1, surf_map, int(xs.size()), pwld, sws[0]);      // voxelslam.cpp:619, 1176
+  vxs_shim::multi_recut(surf_map, int(xs.size()), xs, f, sws);                // voxelslam.cpp:1615
+  vxs_shim::multi_margi(surf_map, 0.0, int(xs.size()), xs, f, sws[0]);        // voxelslam.cpp:1669
+  vxs_shim::GbaMap oct_map(mpar);
+  vxs_shim::OctreeGBA_cut_voxel(oct_map, xs[0], smps[0]->plptr, 0, int(xs.size()));   // voxelslam.cpp:2376
+  vxs_shim::OctreeGBA_multi_recut(oct_map, f, 2);                             // voxelslam.cpp:2379
+  vxs_shim::Context& c = vxs_shim::default_context();
+  vxs_shim::down_sampling_voxel(c, pl, 0.1);
+  vxs_shim::down_sampling_close(c, pl, 0.1);
+  vxs_shim::down_sampling_pvec(c, pvec, 0.1, pl);
+  vxs_shim::submap_merge(c, xs, smps, 1.0, pl);
+}
+int main() { return 0; }
+'''
+
+
 def test_library_exports_every_declared_symbol():
     syms = vx.declared_symbols()
     assert len(syms) >= 25 and "vxs_li_ba" in syms and "vxs_build_window_factor" in syms
@@ -63,28 +94,31 @@ def test_cpp_shim_typed_layer_type_checks_against_reference_signatures():
     import subprocess
     import tempfile
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    src = r'''
-#include "tests/shim_stubs/reference_stubs.hpp"
-#define VXS_SHIM_WITH_REFERENCE_TYPES
-#include "voxel_slam_b200/csrc/shim/voxel_ba_shim.hpp"
-void use(vxs_shim::Context& c, std::vector<IMUST>& xs, std::deque<IMU_PRE*>& imus, std::vector<Keyframe*>& smps, PVec& pvec, pcl::PointCloud<PointType>& pl) {
-  vxs_shim::LidarFactor f(c, int(xs.size()));
-  std::vector<PointCluster> pcrs(xs.size()); PointCluster fix, add; Eigen::Vector3d ev; Eigen::Matrix3d U;
-  vxs_shim::push_voxel(f, pcrs, fix, 1.0, ev, U, add);
-  Eigen::MatrixXd hess; std::vector<double> resis;
-  vxs_shim::li_ba_damping_iter(xs, f, imus, &hess, 1e-4);
-  vxs_shim::lidar_ba_damping_iter(xs, f, &hess, resis, 3, 2);
-  vxs_shim::down_sampling_voxel(c, pl, 0.1);
-  vxs_shim::down_sampling_close(c, pl, 0.1);
-  vxs_shim::down_sampling_pvec(c, pvec, 0.1, pl);
-  vxs_shim::submap_merge(c, xs, smps, 1.0, pl);
-}
-int main() { return 0; }
-'''
+    src = '#include "tests/shim_stubs/reference_stubs.hpp"\n' + SHIM_USE
     with tempfile.NamedTemporaryFile("w", suffix=".cpp", delete=False) as f:
         f.write(src)
     r = subprocess.run(["g++", "-std=c++14", "-fsyntax-only", "-I", root, f.name], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+
+
+def test_cpp_shim_typed_layer_compiles_against_the_reference_headers():
+    """The typed layer against the reference's REAL tools.hpp / preintegration.hpp / voxel_map.hpp (IMUST, PointCluster, IMU_PRE, pointVar,
+    SlideWindow, Keyframe, PLV ...), with the stand-in Eigen / PCL / ROS headers of oracle/ref_standin; skipped where /root/reference is absent
+    (the stub-based check above still runs there).  Also checks the layout assumptions (sizeof(pointVar), sizeof(PointType))."""
+    import subprocess
+    import tempfile
+    import pytest
+    ref = "/root/reference/VoxelSLAM/src"
+    if not os.path.exists(os.path.join(ref, "voxel_map.hpp")):
+        pytest.skip("reference sources not present on this box")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = '#include "voxel_map.hpp"\nstatic_assert(sizeof(pointVar) == 96 && sizeof(PointType) == 48, "record layouts the C-ABI relies on");\n' + SHIM_USE
+    with tempfile.NamedTemporaryFile("w", suffix=".cpp", delete=False) as f:
+        f.write(src)
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-w", "-I", os.path.join(root, "oracle", "ref_standin"), "-I", ref, "-I", root, f.name], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-4000:]
 
 
 def test_bench_reference_arm_contract_on_cpu():

@@ -8,9 +8,10 @@
 //
 // Two layers:
 //   * a plain layer (no Eigen): flat arrays in, flat arrays out — compile-tested in this repository (tests/test_abi.py);
-//   * an Eigen/reference-typed layer behind VXS_SHIM_WITH_REFERENCE_TYPES: include it AFTER the reference's tools.hpp and
-//     preintegration.hpp (it uses their IMUST, PointCluster, IMU_PRE, DIM).  Eigen is not installed in the build container, so this
-//     layer is written against the reference headers but could not be compiled here (INTEGRATION.md says how to enable it).
+//   * an Eigen/reference-typed layer behind VXS_SHIM_WITH_REFERENCE_TYPES: include it AFTER the reference's tools.hpp, preintegration.hpp and
+//     voxel_map.hpp (it uses their IMUST, PointCluster, IMU_PRE, DIM, pointVar, PVecPtr, SlideWindow, Keyframe).  tests/test_abi.py compiles
+//     this layer against the reference's REAL headers from /root/reference (with stand-in headers for the Eigen / PCL /
+//     ROS headers this image lacks) and, on boxes without the reference, against tests/shim_stubs/reference_stubs.hpp.
 #pragma once
 #include <cstring>
 #include <deque>
@@ -39,6 +40,9 @@ class Context {
   vxs_ctx* ctx_ = nullptr;
 };
 
+// `LidarFactor voxhess(win_size);` (voxel_map.hpp:120) keeps compiling: one lazily created context per calling thread
+inline Context& default_context() { static thread_local Context c(0); return c; }
+
 // page-locked std::vector storage for the bulk of the staged factor, so that vxs_factor_push_voxels_async really overlaps PCIe and compute
 template <class T>
 struct PinnedAllocator {
@@ -60,6 +64,7 @@ class LidarFactor {
   std::vector<double> sum10;   // [V][10]  pcr_adds
 
   LidarFactor(Context& c, int w) : win_size(w), ctx_(c.get()) { check(ctx_, vxs_factor_create(ctx_, w, &dev_), "vxs_factor_create"); }
+  explicit LidarFactor(int w) : LidarFactor(default_context(), w) {}   // the reference's constructor (voxel_map.hpp:120)
   ~LidarFactor() { vxs_factor_destroy(dev_); }
   LidarFactor(const LidarFactor&) = delete;
   LidarFactor& operator=(const LidarFactor&) = delete;
@@ -78,9 +83,15 @@ class LidarFactor {
   void clear() {  // voxel_map.hpp:281-286
     ptr_.assign(1, 0); frame_.clear(); cl_.clear(); fix_.clear(); coe_.clear(); eig12.clear(); sum10.clear();
     check(ctx_, vxs_factor_clear(dev_), "vxs_factor_clear");
-    dirty_ = false;
+    dirty_ = false; device_filled_ = false;
   }
-  size_t size() const { return ptr_.size() - 1; }
+  size_t size() const {
+    if (!device_filled_) return ptr_.size() - 1;
+    int64_t v = 0; vxs_factor_counts(dev_, &v, nullptr, nullptr); return size_t(v);
+  }
+  // the factor was filled on the device (vxs_map_push_scan / vxs_build_*_factor): nothing is staged on the host, and margi reads the cached
+  // eig / pcr_adds in place, so no read-back happens either
+  vxs_factor* device_fill_target() { ptr_.assign(1, 0); frame_.clear(); cl_.clear(); fix_.clear(); coe_.clear(); eig12.clear(); sum10.clear(); dirty_ = false; device_filled_ = true; return dev_; }
 
   vxs_factor* device() {  // flush staged voxels
     if (dirty_) {
@@ -93,7 +104,10 @@ class LidarFactor {
     }
     return dev_;
   }
-  void sync_back() { if (size()) check(ctx_, vxs_factor_read_back(dev_, eig12.data(), sum10.data()), "vxs_factor_read_back"); }
+  void sync_back() {
+    if (device_filled_) { const size_t v = size(); eig12.resize(v * 12); sum10.resize(v * 10); }
+    if (size()) check(ctx_, vxs_factor_read_back(dev_, eig12.data(), sum10.data()), "vxs_factor_read_back");
+  }
   vxs_ctx* ctx() const { return ctx_; }
 
  private:
@@ -103,7 +117,7 @@ class LidarFactor {
   std::vector<int32_t, PinnedAllocator<int32_t>> frame_;
   std::vector<double, PinnedAllocator<double>> cl_;
   std::vector<double> fix_, coe_;
-  bool dirty_ = false;
+  bool dirty_ = false, device_filled_ = false;
 };
 
 // Lidar_BA_Optimizer (flat layer): poses12 = W x 12 in/out, hess = (6W)^2 column-major out (may be null), resis gets 2 entries appended
@@ -303,6 +317,87 @@ inline void submap_merge(Context& ctx, const std::vector<IMUST>& xs, const Keyfr
     pp.x = xyz[3 * k]; pp.y = xyz[3 * k + 1]; pp.z = xyz[3 * k + 2]; pp.curvature = cnt[k]; pp.intensity = smps[kf]->mp;
     out.push_back(pp);
   }
+}
+
+// LI_BA_OptimizerGravity::damping_iter(x_stats, voxhess, imus_factor, resis, hess, max_iter) — voxel_map.hpp:775, call sites voxelslam.cpp:632-634, 1643-1645
+inline void li_ba_gravity_damping_iter(std::vector<IMUST>& x_stats, LidarFactor& voxhess, std::deque<IMU_PRE*>& imus_factor, std::vector<double>& resis, Eigen::MatrixXd* hess,
+                                       int max_iter, double imu_coef) {
+  const int W = voxhess.win_size;
+  std::vector<double> st(size_t(W) * 24);
+  for (int i = 0; i < W; i++) pack_state(x_stats[i], &st[24 * i]);
+  hess->resize(W * DIM + 3, W * DIM + 3);
+  ImuAdapter ad{&imus_factor};
+  LI_BA_OptimizerGravity opt; opt.imu_coef = imu_coef;
+  opt.damping_iter(st.data(), voxhess, ad.hooks(), resis, hess->data(), max_iter);
+  for (int i = 0; i < W; i++) unpack_state(&st[24 * i], x_stats[i]);     // g is broadcast to every state by the solver (voxel_map.hpp:821)
+}
+
+// ---------------------------------------------------------------- the per-scan map calls of thd_odometry_localmapping on the device-resident map
+// SurfMap stands for BOTH `surf_map` and `surf_map_slide` (unordered_map<VOXEL_LOC, OctoTree*>, voxelslam.hpp): the octree, the slide windows
+// and the resident scans live in HBM (vxs_map).  The three reference calls keep their names and argument lists:
+//   cut_voxel_multi(surf_map, pvec_buf[win_count-1], win_count-1, surf_map_slide, win_size, pwld, sws);      voxelslam.cpp:1612
+//   multi_recut(surf_map_slide, win_count, x_buf, voxhess, sws);                                              voxelslam.cpp:1615
+//   multi_margi(surf_map_slide, jour, win_count, x_buf, voxhess, sws[0]);                                     voxelslam.cpp:1669
+// cut + recut are one device call (vxs_map_push_scan), so cut_voxel_multi only notes the scan and multi_recut does the work; multi_margi also
+// rotates the slot ring, so the caller's `mp[i] += mgsize` loop (voxelslam.cpp:1689-1693) becomes a no-op on an unused array.
+class SurfMap {
+ public:
+  SurfMap(Context& c, const vxs_map_params& p, int win_size, int max_pts = 100) : ctx_(c.get()) { check(ctx_, vxs_map_create(ctx_, &p, win_size, max_pts, &m_), "vxs_map_create"); }
+  SurfMap(const vxs_map_params& p, int win_size, int max_pts = 100) : SurfMap(default_context(), p, win_size, max_pts) {}
+  ~SurfMap() { vxs_map_destroy(m_); }
+  SurfMap(const SurfMap&) = delete;
+  SurfMap& operator=(const SurfMap&) = delete;
+  vxs_map* get() const { return m_; }
+  vxs_ctx* ctx() const { return ctx_; }
+  PVecPtr pending;          // the scan cut_voxel_multi was called with, consumed by multi_recut
+ private:
+  vxs_ctx* ctx_; vxs_map* m_ = nullptr;
+};
+inline void cut_voxel_multi(SurfMap& feat_map, PVecPtr pvec, int /*win_count*/, SurfMap& /*feat_tem_map*/, int /*wdsize*/, PLV(3)& /*pwld: recomputed on the device, bit-exact*/,
+                            std::vector<std::vector<SlideWindow*>>& /*sws*/) { feat_map.pending = pvec; }
+inline void cut_voxel(SurfMap& feat_map, PVecPtr pvec, int /*win_count*/, SurfMap& /*feat_tem_map*/, int /*wdsize*/, PLV(3)& /*pwld*/, std::vector<SlideWindow*>& /*sws*/) { feat_map.pending = pvec; }
+inline void multi_recut(SurfMap& feat_map, int win_count, std::vector<IMUST>& xs, LidarFactor& voxopt, std::vector<std::vector<SlideWindow*>>& /*sws*/) {
+  static_assert(sizeof(pointVar) == 12 * sizeof(double), "pointVar = { Vector3d pnt; Matrix3d var } is handed to the device as 12 doubles (var is symmetric: storage order is irrelevant)");
+  std::vector<double> p(size_t(win_count) * 12), st(24);
+  for (int i = 0; i < win_count; i++) { pack_state(xs[i], st.data()); std::memcpy(&p[12 * size_t(i)], st.data(), 96); }
+  const PVecPtr& pv = feat_map.pending;
+  check(feat_map.ctx(), vxs_map_push_scan(feat_map.get(), pv ? reinterpret_cast<const double*>(pv->data()) : nullptr, pv ? int64_t(pv->size()) : 0, p.data(), win_count,
+                                          voxopt.device_fill_target()), "vxs_map_push_scan");
+  feat_map.pending.reset();
+}
+inline void multi_margi(SurfMap& feat_map, double /*jour*/, int win_count, std::vector<IMUST>& xs, LidarFactor& voxopt, std::vector<SlideWindow*>& /*sw*/) {
+  std::vector<double> p(size_t(win_count) * 12), st(24);
+  for (int i = 0; i < win_count; i++) { pack_state(xs[i], st.data()); std::memcpy(&p[12 * size_t(i)], st.data(), 96); }
+  check(feat_map.ctx(), vxs_map_margi(feat_map.get(), p.data(), win_count, 1 /* multi_margi hard-codes margi(win_cnt, 1, ...), voxelslam.cpp:1360 */, voxopt.device()), "vxs_map_margi");
+}
+
+// ---------------------------------------------------------------- the map rebuild of an HBA pass (voxelslam.cpp:2374-2379)
+//   OctreeGBA::cut_voxel(oct_map, xs[i], smps[i]->plptr, i, wdsize);   loop_refine.hpp:446      -> notes the keyframe
+//   OctreeGBA_multi_recut(oct_map, voxhess, thread_num);               loop_refine.hpp:483      -> one vxs_build_gba_factor over all of them
+class GbaMap {
+ public:
+  explicit GbaMap(const vxs_map_params& p) : params(p) {}
+  vxs_map_params params;
+  std::vector<pcl::PointCloud<PointType>::Ptr> clouds;
+  std::vector<double> poses12;
+  void clear() { clouds.clear(); poses12.clear(); }
+};
+inline void OctreeGBA_cut_voxel(GbaMap& feat_map, IMUST& xc, pcl::PointCloud<PointType>::Ptr plptr, int win_count, int /*wdsize*/) {
+  if (int(feat_map.clouds.size()) <= win_count) { feat_map.clouds.resize(size_t(win_count) + 1); feat_map.poses12.resize((size_t(win_count) + 1) * 12); }
+  feat_map.clouds[size_t(win_count)] = plptr;
+  double st[24]; pack_state(xc, st);
+  std::memcpy(&feat_map.poses12[12 * size_t(win_count)], st, 96);
+}
+inline void OctreeGBA_multi_recut(GbaMap& feat_map, LidarFactor& voxhess, int /*thd_num*/) {
+  const int W = int(feat_map.clouds.size());
+  std::vector<int64_t> off(size_t(W) + 1, 0);
+  for (int i = 0; i < W; i++) off[size_t(i) + 1] = off[size_t(i)] + int64_t(feat_map.clouds[size_t(i)] ? feat_map.clouds[size_t(i)]->size() : 0);
+  std::vector<PointType, PinnedAllocator<PointType>> all; all.reserve(size_t(off[size_t(W)]));
+  for (int i = 0; i < W; i++) if (feat_map.clouds[size_t(i)]) all.insert(all.end(), feat_map.clouds[size_t(i)]->points.begin(), feat_map.clouds[size_t(i)]->points.end());
+  int64_t nv = 0;
+  check(voxhess.ctx(), vxs_build_gba_factor(voxhess.ctx(), &feat_map.params, reinterpret_cast<const float*>(all.data()), int(sizeof(PointType) / sizeof(float)), off.data(),
+                                            feat_map.poses12.data(), W, voxhess.device_fill_target(), nullptr, 0, &nv), "vxs_build_gba_factor");
+  feat_map.clear();          // the reference consumes (deletes) the octrees here too (loop_refine.hpp:503-509)
 }
 
 }  // namespace vxs_shim

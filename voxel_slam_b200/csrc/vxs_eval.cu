@@ -15,6 +15,7 @@
 //   k_assemble      dense n x n system from the block accumulators (+ the CPU-evaluated IMU 30x30 blocks), mirror of the lower triangle.
 #include <algorithm>
 #include <cstdlib>
+#include <vector>
 #include "vxs_internal.h"
 #include "vxs_math.cuh"
 
@@ -480,9 +481,9 @@ static SyrkGeom sy_geom(int W) {
 // the SM) busy on diagonal / remainder tiles, where a unit-per-warp mapping leaves one to three warps idle.
 struct SyPiece { int offI, offJ, ntI, ntJ, rowbase, colbase, nvalI, nvalJ; unsigned mask; };   // mask: bit ti*6+tj = tile needed
 
-__global__ void __launch_bounds__(SY_THREADS, 2) k_syrk(const double* __restrict__ XT, double* __restrict__ C, int g_first, int ngroups_vox, int W, SyrkGeom g, int groups_per_chunk) {
+__global__ void __launch_bounds__(SY_THREADS, 2) k_syrk(const double* __restrict__ XT, double* __restrict__ C, int g_first, int ngroups_vox, int W, SyrkGeom g, int groups_per_chunk, int only_tile) {
   extern __shared__ __align__(16) double smem[];
-  const int tile = blockIdx.x % g.ntiles, chunk = blockIdx.x / g.ntiles;
+  const int tile = only_tile >= 0 ? only_tile : int(blockIdx.x % g.ntiles), chunk = only_tile >= 0 ? int(blockIdx.x) : int(blockIdx.x / g.ntiles);   // only_tile: diagnostic (cost of one tile kind)
   int A = 0, rem = tile;
   while (rem >= g.nbp - A) { rem -= g.nbp - A; A++; }
   const int B = A + rem;
@@ -615,6 +616,149 @@ __global__ void __launch_bounds__(SY_THREADS, 2) k_syrk(const double* __restrict
   }
 }
 
+// Stream-K form of the same kernel: ONE wave of CTAs (2 per SM), every CTA owns a contiguous, equal-cost stretch of the flattened
+// (tile, voxel group) work line computed on the host (sy_plan) — so no in-order dispatch tail, no imbalance between the cheap (diagonal /
+// remainder) and the full tiles, and ~1.3 RED epilogues per CTA instead of one per (tile, chunk) CTA (12 waves x 296 CTAs x 9216 fp64 REDs
+// on the same 45 k addresses before).  seg[b] .. seg[b+1] are CTA b's segments: (tile, first group, end group).
+struct SySeg { int tile, g_begin, g_end; };
+__global__ void __launch_bounds__(SY_THREADS, 2) k_syrk_sk(const double* __restrict__ XT, double* __restrict__ C, int W, SyrkGeom g, const int* __restrict__ seg_ptr, const SySeg* __restrict__ segs) {
+  extern __shared__ __align__(16) double smem[];
+  for (int si = seg_ptr[blockIdx.x]; si < seg_ptr[blockIdx.x + 1]; si++) {
+  const int tile = segs[si].tile;
+  int A = 0, rem = tile;
+  while (rem >= g.nbp - A) { rem -= g.nbp - A; A++; }
+  const int B = A + rem;
+  const int g_begin = segs[si].g_begin, g_end = segs[si].g_end;
+  if (g_begin >= g_end) continue;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n = 6 * W;
+  // part geometry: part I = blocks 2A, 2A+1 (contiguous frames), part J = blocks 2B, 2B+1
+  const int colI0 = 6 * sy_gstart(g, 2 * A), ncolI = 6 * (sy_glen(g, 2 * A) + sy_glen(g, 2 * A + 1));
+  const int colJ0 = 6 * sy_gstart(g, 2 * B), ncolJ = 6 * (sy_glen(g, 2 * B) + sy_glen(g, 2 * B + 1));
+
+  // enumerate the pieces of this tile in a fixed order and keep those with index % 4 == warp (warp-uniform, <= 3)
+  SyPiece pc[3];
+  int npc = 0;
+  {
+    int q = 0;
+    for (int u = 0; u < 4; u++) {
+      const int wy = u >> 1, wx = u & 1, ga = 2 * A + wy, gb = 2 * B + wx;
+      if (!(ga < g.ngc && gb < g.ngc && ga <= gb)) continue;
+      const int nvalI = 6 * sy_glen(g, ga), nvalJ = 6 * sy_glen(g, gb);
+      const int ntI = (nvalI + 7) >> 3, ntJ = (nvalJ + 7) >> 3;
+      for (int t0 = 0; t0 < ntI; t0 += 2, q++) {
+        if ((q & 3) != warp || npc >= 3) continue;
+        SyPiece P;
+        P.offI = (wy ? 6 * sy_glen(g, 2 * A) : 0) + 8 * t0;
+        P.offJ = wx ? 6 * sy_glen(g, 2 * B) : 0;
+        P.ntI = min(2, ntI - t0); P.ntJ = ntJ;
+        P.rowbase = 6 * sy_gstart(g, ga) + 8 * t0; P.colbase = 6 * sy_gstart(g, gb);
+        P.nvalI = nvalI - 8 * t0; P.nvalJ = nvalJ;
+        // tiles of a diagonal unit whose rows all belong to later frames than all of their columns hold only pairs with
+        // frame(i) > frame(j): never stored, so never computed (11 of the 36 tiles of a full diagonal unit)
+        P.mask = 0u;
+        for (int ti = 0; ti < P.ntI; ti++)
+          for (int tj = 0; tj < P.ntJ; tj++)
+            if (!(ga == gb && (8 * (t0 + ti)) / 6 > (8 * tj + 7) / 6)) P.mask |= 1u << (ti * 6 + tj);
+        if (npc == 0) pc[0] = P; else if (npc == 1) pc[1] = P; else pc[2] = P;
+        npc++;
+      }
+    }
+  }
+
+  double acc[72];
+#pragma unroll
+  for (int i = 0; i < 72; i++) acc[i] = 0.0;
+
+  const int nsteps = g_end - g_begin;                  // one voxel group (4 voxels, 3 k-chunks) per step
+  constexpr int CH_PER_RUN = SY_PCOLS * 2;             // 16-B chunks per (k-chunk, part) run: 96 cols x 32 B
+  constexpr int CH_PER_STAGE = 3 * 2 * CH_PER_RUN;     // 1152
+  constexpr int CH_PER_THREAD = CH_PER_STAGE / SY_THREADS;   // 9
+  // the loader's address arithmetic does not depend on the step: do it once (source offset inside a voxel group, smem offset, predicate)
+  int ld_src[CH_PER_THREAD], ld_dst[CH_PER_THREAD];
+  unsigned ld_ok = 0;
+#pragma unroll
+  for (int j = 0; j < CH_PER_THREAD; j++) {
+    const int ch = tid + j * SY_THREADS;
+    const int run = ch / CH_PER_RUN, off = ch - run * CH_PER_RUN;      // run = part*3 + kchunk
+    const int part = run / 3, kc = run - part * 3;
+    const int col = off >> 1;                                            // column inside the part
+    const bool ok = col < (part ? ncolJ : ncolI);
+    ld_src[j] = (kc * n + (part ? colJ0 : colI0) + (ok ? col : 0)) * 4 + (off & 1) * 2;
+    ld_dst[j] = part * SY_PART + (kc * SY_PCOLS + col) * 4 + (off & 1) * 2;
+    ld_ok |= (ok ? 1u : 0u) << j;
+  }
+  const size_t group_stride = size_t(3) * n * 4;
+  auto issue = [&](int step) {
+    double* sbase = smem + size_t(step % SY_STAGES) * SY_STAGE_DOUBLES;
+    const double* gbase = XT + size_t(g_begin + step) * group_stride;
+#pragma unroll
+    for (int j = 0; j < CH_PER_THREAD; j++) cp_async16_zfill(sbase + ld_dst[j], gbase + ld_src[j], (ld_ok >> j) & 1u);
+  };
+  for (int s = 0; s < SY_STAGES - 1; s++) { if (s < nsteps) issue(s); cp_async_commit(); }
+  for (int step = 0; step < nsteps; step++) {
+    cp_async_wait<SY_STAGES - 2>();
+    __syncthreads();
+    if (step + SY_STAGES - 1 < nsteps) issue(step + SY_STAGES - 1);
+    cp_async_commit();
+    const double* sI = smem + size_t(step % SY_STAGES) * SY_STAGE_DOUBLES + lane;
+    const double* sJ = sI + SY_PART;
+#pragma unroll
+    for (int p = 0; p < 3; p++) {
+      if (p < npc) {
+        const double* pI = sI + size_t(pc[p].offI) * 4;
+        const double* pJ = sJ + size_t(pc[p].offJ) * 4;
+        const bool full = pc[p].mask == 0xFFFu;
+#pragma unroll
+        for (int kc = 0; kc < 3; kc++) {
+          double fa[2], fb[6];
+#pragma unroll
+          for (int t = 0; t < 2; t++) fa[t] = pI[(kc * SY_PCOLS + 8 * t) * 4];
+#pragma unroll
+          for (int t = 0; t < 6; t++) fb[t] = pJ[(kc * SY_PCOLS + 8 * t) * 4];
+          if (full) {
+#pragma unroll
+            for (int ti = 0; ti < 2; ti++)
+#pragma unroll
+              for (int tj = 0; tj < 6; tj++) dmma884(acc[p * 24 + 2 * (ti * 6 + tj)], acc[p * 24 + 2 * (ti * 6 + tj) + 1], fa[ti], fb[tj]);
+          } else {
+#pragma unroll
+            for (int ti = 0; ti < 2; ti++)
+#pragma unroll
+              for (int tj = 0; tj < 6; tj++)
+                if ((pc[p].mask >> (ti * 6 + tj)) & 1u) dmma884(acc[p * 24 + 2 * (ti * 6 + tj)], acc[p * 24 + 2 * (ti * 6 + tj) + 1], fa[ti], fb[tj]);
+          }
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+  // epilogue: lane holds C[8ti + lane/4][8tj + 2(lane%4) + {0,1}] of every tile; H_ij -= x_i x_j^T for frame(i) <= frame(j)
+  const int rl = lane >> 2, cl = 2 * (lane & 3);
+#pragma unroll
+  for (int p = 0; p < 3; p++) {
+    if (p < npc) {
+#pragma unroll
+      for (int ti = 0; ti < 2; ti++)
+#pragma unroll
+        for (int tj = 0; tj < 6; tj++) {
+          const int r = 8 * ti + rl;
+          if (((pc[p].mask >> (ti * 6 + tj)) & 1u) && r < pc[p].nvalI) {
+            const int R = pc[p].rowbase + r;
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+              const int c = 8 * tj + cl + e;
+              const int Cc = pc[p].colbase + c;
+              if (c < pc[p].nvalJ && (R / 6) <= (Cc / 6)) atomicAdd(C + size_t(Cc) * n + R, -acc[p * 24 + 2 * (ti * 6 + tj) + e]);
+            }
+          }
+        }
+    }
+  }
+  __syncthreads();   // the next segment re-fills the stages
+  }
+}
+
 // ------------------------------------------------------------------ dense system assembly
 // H (n x n col-major) from the lidar block accumulator C (upper block triangle), block-diagonal D, gradient g, and the
 // host-evaluated IMU part (already summed over factors, unscaled).  S = dofs per frame (6 or 15); rows >= W*S are the gravity dofs.
@@ -690,6 +834,78 @@ __global__ void k_assemble(const double* __restrict__ C, const double* __restric
 
 // ------------------------------------------------------------------ host drivers
 static inline unsigned nblk(size_t n, unsigned b) { return unsigned((n + b - 1) / b); }
+
+// cost of one voxel group (one pipeline stage) of a tile = the busiest warp's DMMA count (the warps meet at the stage barrier), by the same
+// piece enumeration as the kernel, + a constant for the stage's barrier / loads
+static int sy_tile_cost(const SyrkGeom& g, int tile) {
+  int A = 0, rem = tile;
+  while (rem >= g.nbp - A) { rem -= g.nbp - A; A++; }
+  const int B = A + rem;
+  int cnt[4] = {0, 0, 0, 0}, npc[4] = {0, 0, 0, 0}, q = 0;
+  for (int u = 0; u < 4; u++) {
+    const int wy = u >> 1, wx = u & 1, ga = 2 * A + wy, gb = 2 * B + wx;
+    if (!(ga < g.ngc && gb < g.ngc && ga <= gb)) continue;
+    const int nvalI = 6 * sy_glen(g, ga), nvalJ = 6 * sy_glen(g, gb), ntI = (nvalI + 7) >> 3, ntJ = (nvalJ + 7) >> 3;
+    for (int t0 = 0; t0 < ntI; t0 += 2, q++) {
+      const int w = q & 3;
+      if (npc[w] >= 3) continue;
+      npc[w]++;
+      for (int ti = 0; ti < std::min(2, ntI - t0); ti++)
+        for (int tj = 0; tj < ntJ; tj++)
+          if (!(ga == gb && (8 * (t0 + ti)) / 6 > (8 * tj + 7) / 6)) cnt[w]++;
+    }
+  }
+  return 3 * std::max(std::max(cnt[0], cnt[1]), std::max(cnt[2], cnt[3])) + 6;
+}
+// equal-cost contiguous stretches of the (tile, group) work line for `nctas` CTAs; table = seg_ptr[nctas + 1] | segments x 3 ints
+static int sy_plan(vxs_ctx* ctx, vxs_factor* f, int W, const SyrkGeom& g, int g0, int g1, int nctas) {
+  if (f->sk_key[0] == W && f->sk_key[1] == g0 && f->sk_key[2] == g1 && f->sk_key[3] == nctas && f->sk_tab.p) return VXS_OK;
+  const int ng = g1 - g0;
+  std::vector<double> pre(size_t(g.ntiles) + 1, 0.0);
+  std::vector<int> cost(size_t(g.ntiles));
+  for (int t = 0; t < g.ntiles; t++) { cost[size_t(t)] = sy_tile_cost(g, t); pre[size_t(t) + 1] = pre[size_t(t)] + double(cost[size_t(t)]) * ng; }
+  const double T = pre[size_t(g.ntiles)];
+  // boundary b -> (tile, group) position
+  std::vector<int> bt(size_t(nctas) + 1), bg(size_t(nctas) + 1);
+  for (int b = 0; b <= nctas; b++) {
+    const double c = T * double(b) / double(nctas);
+    int t = 0;
+    while (t < g.ntiles - 1 && pre[size_t(t) + 1] <= c) t++;
+    int o = int((c - pre[size_t(t)]) / double(cost[size_t(t)]) + 0.5);
+    o = std::max(0, std::min(ng, o));
+    bt[size_t(b)] = t; bg[size_t(b)] = o;
+  }
+  bt[size_t(nctas)] = g.ntiles - 1; bg[size_t(nctas)] = ng;
+  std::vector<int> tab(size_t(nctas) + 1);
+  std::vector<int> segs;
+  for (int b = 0; b < nctas; b++) {
+    tab[size_t(b)] = int(segs.size() / 3);
+    int t = bt[size_t(b)], o = bg[size_t(b)];
+    const int te = bt[size_t(b) + 1], oe = bg[size_t(b) + 1];
+    while (t < te) { if (o < ng) { segs.push_back(t); segs.push_back(g0 + o); segs.push_back(g0 + ng); } t++; o = 0; }
+    if (o < oe) { segs.push_back(t); segs.push_back(g0 + o); segs.push_back(g0 + oe); }
+  }
+  tab[size_t(nctas)] = int(segs.size() / 3);
+  const size_t nptr = size_t(nctas) + 1;
+  std::vector<int> all(tab);
+  all.insert(all.end(), segs.begin(), segs.end());
+  VXS_CUDA(ctx, f->sk_tab.reserve(all.size() + 3));
+  VXS_CUDA(ctx, cudaMemcpyAsync(f->sk_tab.p, all.data(), all.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  VXS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // `all` goes out of scope; plans are cached, so this happens once per window shape
+  f->sk_key[0] = W; f->sk_key[1] = g0; f->sk_key[2] = g1; f->sk_key[3] = nctas;
+  (void)nptr;
+  return VXS_OK;
+}
+static int launch_syrk_sk(vxs_ctx* ctx, vxs_factor* f, double* C, int W, const SyrkGeom& g, int g0, int g1, size_t smem_sy) {
+  const int nctas = ctx->sm_count * 2;
+  int rc = sy_plan(ctx, f, W, g, g0, g1, nctas);
+  if (rc) return rc;
+  VXS_CUDA(ctx, cudaFuncSetAttribute(k_syrk_sk, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_sy)));
+  const int* seg_ptr = f->sk_tab.p;
+  const SySeg* segs = reinterpret_cast<const SySeg*>(f->sk_tab.p + nctas + 1);
+  VXS_LAUNCH(ctx, "k_syrk", k_syrk_sk, unsigned(nctas), SY_THREADS, smem_sy, f->X.p, C, W, g, seg_ptr, segs);
+  return VXS_OK;
+}
 static int pick_group(const vxs_factor* f) {
   const double avg = f->V > 0 ? double(f->E) / double(f->V) : 1.0;
   return avg > 16.0 ? 32 : (avg > 8.0 ? 16 : 8);
@@ -789,11 +1005,17 @@ int vxs_eval_hessian_dev(vxs_ctx* ctx, vxs_factor* f, const double* poses_dev, i
           // the CTAs are dispatched in order, so the last wave leaves SMs idle for up to one CTA duration; ncu showed 68.6 % DMMA-pipe
           // activity on average against 85.5 % on the busiest SM at 4 waves.  More, shorter CTAs shrink that tail (each pays one pipeline
           // fill and one 96x96 RED epilogue); measured at the metric shape: 4 waves 0.781 ms, 8: 0.737, 12: 0.736, 16: 0.742, 24: 0.762.
-          const int target_ctas = std::max(1, ctx->sm_count * 2 * waves / n_up);
-          int nchunks = std::max(1, std::min<int>(target_ctas / g.ntiles, (ng + 7) / 8));
-          const int gpc = (ng + nchunks - 1) / nchunks;
-          nchunks = (ng + gpc - 1) / gpc;
-          VXS_LAUNCH(ctx, "k_syrk", k_syrk, unsigned(nchunks * g.ntiles), SY_THREADS, smem_sy, f->X.p, C, g0, g1, W, g, gpc);
+          if (!chunked && ctx->syrk_streamk && ng >= 8 * ctx->sm_count) {
+            int rcs = launch_syrk_sk(ctx, f, C, W, g, g0, g1, smem_sy);
+            if (rcs) return rcs;
+          } else {
+            const int target_ctas = std::max(1, ctx->sm_count * 2 * waves / n_up);
+            int nchunks = std::max(1, std::min<int>(target_ctas / g.ntiles, (ng + 7) / 8));
+            const int gpc = (ng + nchunks - 1) / nchunks;
+            nchunks = (ng + gpc - 1) / gpc;
+            const int only = ctx->syrk_only_tile;
+            VXS_LAUNCH(ctx, "k_syrk", k_syrk, unsigned(only >= 0 ? nchunks : nchunks * g.ntiles), SY_THREADS, smem_sy, f->X.p, C, g0, g1, W, g, gpc, only);
+          }
         }
         g0 = g1;
       }
@@ -812,8 +1034,13 @@ int vxs_eval_hessian_dev(vxs_ctx* ctx, vxs_factor* f, const double* poses_dev, i
       int gpc = (ngv + nchunks - 1) / nchunks;
       nchunks = (ngv + gpc - 1) / gpc;
       const size_t smem = size_t(SY_STAGES) * SY_STAGE_DOUBLES * 8;
-      VXS_CUDA(ctx, cudaFuncSetAttribute(k_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-      VXS_LAUNCH(ctx, "k_syrk", k_syrk, unsigned(nchunks * g.ntiles), SY_THREADS, smem, f->X.p, C, 0, ngv, W, g, gpc);
+      if (ctx->syrk_streamk && ngv >= 8 * ctx->sm_count) {
+        int rcs = launch_syrk_sk(ctx, f, C, W, g, 0, ngv, smem);
+        if (rcs) return rcs;
+      } else {
+        VXS_CUDA(ctx, cudaFuncSetAttribute(k_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        VXS_LAUNCH(ctx, "k_syrk", k_syrk, unsigned(nchunks * g.ntiles), SY_THREADS, smem, f->X.p, C, 0, ngv, W, g, gpc, -1);
+      }
     } else {
       if (G == 32) { auto kp = k_pairs<32>; VXS_LAUNCH(ctx, "k_pairs", kp, grid, 128, 0, fv, f->X.p, C); }
       else if (G == 16) { auto kp = k_pairs<16>; VXS_LAUNCH(ctx, "k_pairs", kp, grid, 128, 0, fv, f->X.p, C); }

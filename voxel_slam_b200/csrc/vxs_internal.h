@@ -59,6 +59,8 @@ struct vxs_ctx {
   int ldlt_blocks_per_sm = 0;
   int ldlt_lookahead = 1;         // VXS_LDLT_LOOKAHEAD_CTA=0 keeps the look-ahead on CTA 0 (A/B switch)
   int syrk_waves = 12;            // VXS_SYRK_WAVES
+  int syrk_only_tile = -1;        // VXS_SYRK_ONLY_TILE: diagnostic, run a single tile kind of k_syrk (results are then incomplete)
+  int syrk_streamk = 1;           // VXS_SYRK_STREAMK=0: the (tile, chunk) grid of k_syrk instead of the one-wave stream-K plan (A/B switch)
   // what ctx->Hraw currently holds (vxs_hba_edges refuses anything but a lidar-only 6W system)
   int hraw_n = 0, hraw_S = 0;
   // solver scratch (n = system size)
@@ -97,6 +99,8 @@ struct vxs_factor {
   DevBuf<double> partial;        // block partial sums for the residual
   DevBuf<unsigned int> counter;
   DevBuf<double> vc;             // [8][Vcap] per-voxel constants for k_jac
+  DevBuf<int> sk_tab;            // stream-K plan of k_syrk_sk: seg_ptr[nctas+1] | segments (tile, g_begin, g_end)
+  int sk_key[4] = {-1, -1, -1, -1};   // (W, g0, g1, nctas) the plan was made for
   DevBuf<double> cache_copy;     // [22][Vcap] snapshot of eig | sum
   size_t cache_copy_V = 0;
   // asynchronous chunked upload (vxs_factor_push_voxels_async): the clusters arrive on ctx->copy_stream in up_n chunks of whole voxel

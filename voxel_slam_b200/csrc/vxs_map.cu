@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(256) k_map_locate(NodeView nv, unsigned int* _
       }
       v = old;
     }
-    if (v == MAP_CLAIM) { leaf_out[i] = MAP_RETRY; return; }
+    if (v == MAP_CLAIM) { leaf_out[i] = MAP_RETRY; atomicAdd(count + 7, 1); return; }
     const int r = int(v - 1u);
     if (nv.rkey[r] == kx && nv.rkey[nv.cap + r] == ky && nv.rkey[2 * nv.cap + r] == kz) { node = r; break; }
     h = (h + 1u) & tmask;
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(256) k_map_locate(NodeView nv, unsigned int* _
   atomicOr(nv.flags + node, F_EXIST | F_SLIDE);          // iter->second->isexist = true; feat_tem_map[position] = ...   :1523-1526
   while (*((volatile unsigned int*)(nv.flags + node)) & F_INNER) {
     const int c = child_find_or_create(nv, node, octant_of(nv, node, w), count);
-    if (c == MAP_RETRY) { leaf_out[i] = MAP_RETRY; return; }
+    if (c == MAP_RETRY) { leaf_out[i] = MAP_RETRY; atomicAdd(count + 7, 1); return; }
     node = c;
   }
   leaf_out[i] = node;
@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(256) k_map_subdiv_assign(NodeView nv, VirtPts 
   const int c = child_find_or_create(nv, parent, octant_of(nv, parent, w), count);
   idx[o] = o;
   refs[o] = ((unsigned long long)slot << 32) | (unsigned long long)li;
-  if (c == MAP_RETRY) { keys[o] = ~0ull; return; }
+  if (c == MAP_RETRY) { keys[o] = ~0ull; atomicAdd(count + 7, 1); return; }
   keys[o] = ((unsigned long long)(unsigned int)c << 8) | (unsigned long long)slot;
   // fixed points are only kept re-cuttable below max_layer (push_fix :998-999); window points keep their leaf at every layer
   lf[li] = (slot == W && nv.layer[c] >= max_layer) ? -1 : c;
@@ -636,7 +636,7 @@ __global__ void __launch_bounds__(128) k_map_leaf_flags(NodeView nv, int n_nodes
   const int nd = blockIdx.x * blockDim.x + threadIdx.x;
   if (nd < n_nodes) flag[nd] = (nv.flags[nd] & F_INNER) ? 0u : 1u;
 }
-// row layout of the oracle's vxo_sliding_sim_state: 32 + 10 W doubles per leaf
+// row layout documented at vxs_map_read_leaves (include/vxs.h): 32 + 10 W doubles per leaf
 __global__ void __launch_bounds__(128) k_map_leaf_rows(NodeView nv, int n_nodes, int W, const int* __restrict__ ring, const double* __restrict__ swp, const unsigned int* __restrict__ flag,
                                                        const unsigned int* __restrict__ pos, const int* __restrict__ fixcnt, double* __restrict__ rows) {
   const int nd = blockIdx.x * blockDim.x + threadIdx.x;
@@ -655,7 +655,7 @@ __global__ void __launch_bounds__(128) k_map_plane_flags(NodeView nv, int n_node
   const int nd = blockIdx.x * blockDim.x + threadIdx.x;
   if (nd < n_nodes) { const unsigned int f = nv.flags[nd]; flag[nd] = (!(f & F_INNER) && (f & F_PLANE) && nv.plane[27 * nv.cap + nd] > 0.0) ? 1u : 0u; }
 }
-// 52 doubles per plane leaf, the oracle's vxo_local_map_planes layout: centre3 normal3 plane_var36 radius N voxel_center3 half cov-trace eig3
+// 52 doubles per plane leaf (vxs_map_read_planes): centre3 normal3 plane_var36 radius N voxel_center3 half cov-trace eig3
 __global__ void __launch_bounds__(128) k_map_plane_rows(NodeView nv, int n_nodes, const unsigned int* __restrict__ flag, const unsigned int* __restrict__ pos, double* __restrict__ rows,
                                                         long long* __restrict__ ids) {
   const int nd = blockIdx.x * blockDim.x + threadIdx.x;
@@ -842,12 +842,17 @@ static int map_recut(vxs_map* m, int wc) {
       if (rc) return rc;
       VXS_CUDA(ctx, m->keysA.reserve(na)); VXS_CUDA(ctx, m->keysB.reserve(na)); VXS_CUDA(ctx, m->idxA.reserve(na)); VXS_CUDA(ctx, m->idxB.reserve(na)); VXS_CUDA(ctx, m->refs.reserve(na));
       // the flag / scan buffers are reused by accumulate_sorted: keep the compaction positions in idxB until the assignment ran
-      for (int pass = 0; pass < 2; pass++)
+      int c2[8];
+      for (int pass = 0;; pass++) {
+        VXS_CUDA(ctx, cudaMemsetAsync(m->counters.p + 7, 0, 4, ctx->stream));
         VXS_LAUNCH(ctx, "k_map_subdiv_assign", k_map_subdiv_assign, nblk(size_t(total), 256), 256, 0, view(m), vp, point_srcs(m), leaf_ptrs, m->d_ring.p, wc, total, m->flagbuf.p, m->scanbuf.p,
                    m->counters.p, int(m->mp.max_layer), m->keysA.p, m->idxA.p, m->refs.p, pass);
-      int c2[8];
-      rc = read_counters(m, c2);
-      if (rc) return rc;
+        if (pass == 0) continue;
+        rc = read_counters(m, c2);
+        if (rc) return rc;
+        if (c2[7] == 0) break;
+        if (pass > 64) return vxs_fail(ctx, VXS_ERR_CUDA, "vxs_map_push_scan: child creation did not settle");
+      }
       m->n_nodes = c2[0];
       rc = accumulate_sorted(m, na, bits_for((unsigned long long)m->n_nodes) + 8);
       if (rc) return rc;
@@ -943,12 +948,19 @@ extern "C" int vxs_map_push_scan(vxs_map* m, const double* pv12, int64_t n, cons
   if (n) {
     // ---- cut_voxel: leaf of every point (two passes: the second one serves the points that met a node being created)
     const unsigned int tmask = (unsigned int)(m->tcap - 1);
-    for (int pass = 0; pass < 2; pass++)
+    // a point that meets a node being created by another thread is served by a later pass; a later pass can create nodes itself (a root whose
+    // hash slot was claimed for ANOTHER root in the pass before), so the passes repeat until no point is left over (2-3 in practice)
+    int c8[8];
+    for (int pass = 0;; pass++) {
+      VXS_CUDA(ctx, cudaMemsetAsync(m->counters.p + 7, 0, 4, st));
       VXS_LAUNCH(ctx, "k_map_locate", k_map_locate, nblk(size_t(n), 256), 256, 0, view(m), m->table.p, tmask, m->counters.p, pv.p, (long long)n, m->d_poses.p + size_t(win_count - 1) * 12,
                  m->mp.voxel_size, lf.p, pass);
-    int c8[8];
-    rc = read_counters(m, c8);
-    if (rc) return rc;
+      if (pass == 0) continue;
+      rc = read_counters(m, c8);
+      if (rc) return rc;
+      if (c8[7] == 0) break;
+      if (pass > 64) return vxs_fail(ctx, VXS_ERR_CUDA, "vxs_map_push_scan: node creation did not settle");
+    }
     m->n_nodes = c8[0];
     // ---- push: accumulate the scan into its leaves
     VXS_CUDA(ctx, m->keysA.reserve(size_t(n))); VXS_CUDA(ctx, m->keysB.reserve(size_t(n))); VXS_CUDA(ctx, m->idxA.reserve(size_t(n))); VXS_CUDA(ctx, m->idxB.reserve(size_t(n)));
