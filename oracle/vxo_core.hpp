@@ -460,7 +460,8 @@ inline void li_ba_damping_iter(std::vector<State>& x_stats, LidarFactor& voxhess
   double residual1 = 0, residual2 = 0, q;
   bool is_calc_hess = true;
   std::vector<State> x_temp = x_stats;
-  const int iters = gravity ? max_iter : 3;
+  // LI_BA_Optimizer hard-codes 3 iterations (voxel_map.hpp:581); a SMALLER max_iter steps fewer (single-iteration parity / timing), as vxs_li_ba does
+  const int iters = gravity ? max_iter : (max_iter < 3 ? max_iter : 3);
   for (int it = 0; it < iters; it++) {
     if (is_calc_hess) {
       // divide_thread  voxel_map.hpp:465-523 / 673-736 (IMU part on the calling thread, then hess_plus)

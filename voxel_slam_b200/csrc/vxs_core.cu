@@ -32,7 +32,11 @@ extern "C" int vxs_ctx_create(int device, vxs_ctx** out) {
   { const char* e = getenv("VXS_LDLT_LOOKAHEAD_CTA"); c->ldlt_lookahead = (e && e[0] == '0') ? 0 : 1; }
   { const char* e = getenv("VXS_SYRK_WAVES"); c->syrk_waves = e ? std::max(1, atoi(e)) : 12; }
   { const char* e = getenv("VXS_SYRK_ONLY_TILE"); c->syrk_only_tile = e ? atoi(e) : -1; }
-  { const char* e = getenv("VXS_SYRK_STREAMK"); c->syrk_streamk = (e && e[0] == '0') ? 0 : 1; }
+  { const char* e = getenv("VXS_RESID_STREAM"); c->resid_stream = (e && e[0] == '0') ? 0 : 1; }
+  { const char* e = getenv("VXS_RESID_TE"); if (e) c->resid_te = atoi(e); }
+  cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  { const char* e = getenv("VXS_SYRK_BULK"); c->syrk_bulk = (e && e[0] == '1') ? 1 : 0; }
+  { const char* e = getenv("VXS_SYRK_STREAMK"); c->syrk_streamk = (e && e[0] == '1') ? 1 : 0; }
   *out = c;
   return VXS_OK;
 }

@@ -16,63 +16,8 @@
 #include <algorithm>
 #include <cstdlib>
 #include <vector>
-#include "vxs_internal.h"
-#include "vxs_math.cuh"
-
-using namespace vxs;
-
-struct FactorView {
-  const int32_t* ptr; const int32_t* frame;
-  const double* cl; size_t Ecap;
-  const double* fix; const double* coe;
-  double* eig; double* sum; size_t Vcap;
-  const double* vc;     // [8][Vcap] per-voxel constants of acc_evaluate2 (k_voxel_consts)
-  int V; int W; int has_fix;
-};
-static FactorView make_view(const vxs_factor* f) {
-  FactorView v;
-  v.ptr = f->ptr; v.frame = f->frame; v.cl = f->cl; v.Ecap = f->Ecap; v.fix = f->fix; v.coe = f->coe; v.eig = f->eig; v.sum = f->sum;
-  v.Vcap = f->Vcap; v.V = int(f->V); v.W = f->W; v.has_fix = f->has_fix ? 1 : 0; v.vc = f->vc.p;
-  return v;
-}
-
-__device__ __forceinline__ cluster load_cluster_soa(const double* __restrict__ base, size_t stride, size_t i) {
-  cluster c;
-  c.P.xx = __ldg(base + i); c.P.xy = __ldg(base + stride + i); c.P.xz = __ldg(base + 2 * stride + i);
-  c.P.yy = __ldg(base + 3 * stride + i); c.P.yz = __ldg(base + 4 * stride + i); c.P.zz = __ldg(base + 5 * stride + i);
-  c.v.x = __ldg(base + 6 * stride + i); c.v.y = __ldg(base + 7 * stride + i); c.v.z = __ldg(base + 8 * stride + i);
-  c.n = __ldg(base + 9 * stride + i);
-  return c;
-}
-__device__ __forceinline__ void load_pose(const double* __restrict__ poses, int stride, int fr, rot3& R, d3& t) {
-  const double* p = poses + size_t(fr) * stride;
-  R.r00 = __ldg(p); R.r01 = __ldg(p + 1); R.r02 = __ldg(p + 2); R.r10 = __ldg(p + 3); R.r11 = __ldg(p + 4); R.r12 = __ldg(p + 5);
-  R.r20 = __ldg(p + 6); R.r21 = __ldg(p + 7); R.r22 = __ldg(p + 8);
-  t = mk3(__ldg(p + 9), __ldg(p + 10), __ldg(p + 11));
-}
-
-// Poses staged once per CTA in shared memory, component-major [12][W]: lanes of a group read consecutive frames, so each of the 12
-// reads is one conflict-free wavefront instead of a 96-byte-strided global gather (the LSU, not DRAM, bounds these kernels).
-#define POSE_SMEM_MAX_W 512
-__device__ __forceinline__ void stage_poses(double* sp, const double* __restrict__ poses, int pstride, int W) {
-  for (int i = threadIdx.x; i < 12 * W; i += blockDim.x) { const int fr = i / 12, c = i - fr * 12; sp[c * W + fr] = __ldg(poses + size_t(fr) * pstride + c); }
-  __syncthreads();
-}
-__device__ __forceinline__ void load_pose_s(const double* sp, int W, int fr, rot3& R, d3& t) {
-  R.r00 = sp[fr]; R.r01 = sp[W + fr]; R.r02 = sp[2 * W + fr]; R.r10 = sp[3 * W + fr]; R.r11 = sp[4 * W + fr]; R.r12 = sp[5 * W + fr];
-  R.r20 = sp[6 * W + fr]; R.r21 = sp[7 * W + fr]; R.r22 = sp[8 * W + fr];
-  t = mk3(sp[9 * W + fr], sp[10 * W + fr], sp[11 * W + fr]);
-}
-
-// L2 prefetch of the cluster columns (and frame index) of entry e: the evaluation kernels are latency-bound at their register-limited
-// occupancy (ncu: long-scoreboard stalls dominate), so each group pulls the entries of its NEXT voxel towards L2 one iteration ahead.
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-__device__ __forceinline__ void prefetch_entry(const FactorView& f, int e) {
-  if (size_t(e) >= f.Ecap) return;
-#pragma unroll
-  for (int c = 0; c < 10; c++) prefetch_l2(f.cl + size_t(c) * f.Ecap + e);
-  prefetch_l2(f.frame + e);
-}
+#include "vxs_factor_view.cuh"
+#include "vxs_pipe.cuh"
 
 // ------------------------------------------------------------------ residual: transform + sum
 template <int G, bool SP>
@@ -616,6 +561,169 @@ __global__ void __launch_bounds__(SY_THREADS, 2) k_syrk(const double* __restrict
   }
 }
 
+// mbarrier / bulk-copy form of k_syrk (the default): same tiling, pieces and epilogue, but
+//   * XT is staged by 1-D bulk copies (cp.async.bulk, 3 KB runs: one k-chunk of one part is contiguous in XT) that complete on an mbarrier —
+//     no per-thread loader arithmetic, no cp.async groups, no CTA-wide barrier per stage (the old loop spent ~9 LDGSTS + address math per
+//     thread and one __syncthreads per 108 DMMA per warp; ncu: barrier 1.3 + wait 3.6 stall cycles per issue);
+//   * the warps only meet through the stage barriers: a warp waits for full[s], runs its pieces, arrives on empty[s]; the issuing role
+//     rotates over the warps (lane 0 of warp step%4 refills the stage freed one step ago), so no warp is a dedicated producer and the
+//     2 CTAs x 4 warps x 252 registers still fit the register file;
+//   * the operand fragments of the next (piece, k-chunk) are loaded while the 12 DMMA of the current one issue (explicit double buffer);
+//   * a diagonal tile stages its part once (parts I and J are the same columns).
+#define SYB_STAGES 5
+__global__ void __launch_bounds__(SY_THREADS, 2) k_syrk_bulk(const double* __restrict__ XT, double* __restrict__ C, int g_first, int ngroups_vox, int W, SyrkGeom g, int groups_per_chunk) {
+  extern __shared__ __align__(128) double smem[];
+  __shared__ __align__(8) uint64_t bars[2 * SYB_STAGES];
+  uint64_t* full = bars; uint64_t* empty = bars + SYB_STAGES;
+  const int tile = int(blockIdx.x % g.ntiles), chunk = int(blockIdx.x / g.ntiles);
+  int A = 0, rem = tile;
+  while (rem >= g.nbp - A) { rem -= g.nbp - A; A++; }
+  const int B = A + rem;
+  const int g_begin = g_first + chunk * groups_per_chunk, g_end = min(ngroups_vox, g_begin + groups_per_chunk);
+  if (g_begin >= g_end) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n = 6 * W;
+  const bool diag = (A == B);
+  const int colI0 = 6 * sy_gstart(g, 2 * A), ncolI = 6 * (sy_glen(g, 2 * A) + sy_glen(g, 2 * A + 1));
+  const int colJ0 = 6 * sy_gstart(g, 2 * B), ncolJ = 6 * (sy_glen(g, 2 * B) + sy_glen(g, 2 * B + 1));
+
+  SyPiece pc[3];
+  int npc = 0;
+  {
+    int q = 0;
+    for (int u = 0; u < 4; u++) {
+      const int wy = u >> 1, wx = u & 1, ga = 2 * A + wy, gb = 2 * B + wx;
+      if (!(ga < g.ngc && gb < g.ngc && ga <= gb)) continue;
+      const int nvalI = 6 * sy_glen(g, ga), nvalJ = 6 * sy_glen(g, gb);
+      const int ntI = (nvalI + 7) >> 3, ntJ = (nvalJ + 7) >> 3;
+      for (int t0 = 0; t0 < ntI; t0 += 2, q++) {
+        if ((q & 3) != warp || npc >= 3) continue;
+        SyPiece P;
+        P.offI = (wy ? 6 * sy_glen(g, 2 * A) : 0) + 8 * t0;
+        P.offJ = wx ? 6 * sy_glen(g, 2 * B) : 0;
+        P.ntI = min(2, ntI - t0); P.ntJ = ntJ;
+        P.rowbase = 6 * sy_gstart(g, ga) + 8 * t0; P.colbase = 6 * sy_gstart(g, gb);
+        P.nvalI = nvalI - 8 * t0; P.nvalJ = nvalJ;
+        P.mask = 0u;
+        for (int ti = 0; ti < P.ntI; ti++)
+          for (int tj = 0; tj < P.ntJ; tj++)
+            if (!(ga == gb && (8 * (t0 + ti)) / 6 > (8 * tj + 7) / 6)) P.mask |= 1u << (ti * 6 + tj);
+        if (npc == 0) pc[0] = P; else if (npc == 1) pc[1] = P; else pc[2] = P;
+        npc++;
+      }
+    }
+  }
+
+  // the bulk copies only ever write the valid columns of a part: clear the stages once so that the tail columns of a short part hold zeros
+  for (int i = tid; i < SYB_STAGES * SY_STAGE_DOUBLES / 2; i += SY_THREADS) reinterpret_cast<double2*>(smem)[i] = make_double2(0.0, 0.0);
+  if (tid == 0) {
+    for (int s = 0; s < SYB_STAGES; s++) { mbar_init(full + s, 1); mbar_init(empty + s, SY_THREADS / 32); }
+    mbar_fence_init();
+  }
+  fence_proxy_async_smem();
+  __syncthreads();
+
+  const int nsteps = g_end - g_begin;                  // one voxel group (4 voxels, 3 k-chunks) per step
+  const size_t group_stride = size_t(3) * n * 4;
+  const unsigned tx_bytes = 3u * unsigned(ncolI + (diag ? 0 : ncolJ)) * 32u;
+  auto issue = [&](int j) {                            // called by ONE lane
+    const int s = j % SYB_STAGES;
+    mbar_wait(empty + s, (((unsigned)(j / SYB_STAGES)) & 1u) ^ 1u);
+    double* sbase = smem + size_t(s) * SY_STAGE_DOUBLES;
+    const double* gbase = XT + size_t(g_begin + j) * group_stride;
+    mbar_arrive_expect_tx(full + s, tx_bytes);
+#pragma unroll
+    for (int kc = 0; kc < 3; kc++) {
+      bulk_g2s(sbase + kc * SY_PCOLS * 4, gbase + (size_t(kc) * n + colI0) * 4, unsigned(ncolI) * 32u, full + s);
+      if (!diag) bulk_g2s(sbase + SY_PART + kc * SY_PCOLS * 4, gbase + (size_t(kc) * n + colJ0) * 4, unsigned(ncolJ) * 32u, full + s);
+    }
+  };
+  if (tid == 0) for (int j = 0; j < SYB_STAGES - 1 && j < nsteps; j++) issue(j);
+
+  double acc[72];
+#pragma unroll
+  for (int i = 0; i < 72; i++) acc[i] = 0.0;
+
+  for (int step = 0; step < nsteps; step++) {
+    const int s = step % SYB_STAGES;
+    // refill the stage that was consumed one step ago (all four warps arrive on its empty barrier when they leave that step)
+    if (warp == (step & 3) && lane == 0 && step + SYB_STAGES - 1 < nsteps) issue(step + SYB_STAGES - 1);
+    mbar_wait(full + s, ((unsigned)(step / SYB_STAGES)) & 1u);
+    const double* sI = smem + size_t(s) * SY_STAGE_DOUBLES + lane;
+    const double* sJ = diag ? sI : sI + SY_PART;
+    // fragments of (piece 0, chunk 0)
+    double fa[2][2], fb[2][6];
+    if (npc > 0) {
+      const double* pI = sI + size_t(pc[0].offI) * 4; const double* pJ = sJ + size_t(pc[0].offJ) * 4;
+#pragma unroll
+      for (int t = 0; t < 2; t++) fa[0][t] = pI[(8 * t) * 4];
+#pragma unroll
+      for (int t = 0; t < 6; t++) fb[0][t] = pJ[(8 * t) * 4];
+    }
+#pragma unroll
+    for (int p = 0; p < 3; p++) {
+      if (p < npc) {
+        const bool full_piece = pc[p].mask == 0xFFFu;
+#pragma unroll
+        for (int kc = 0; kc < 3; kc++) {
+          constexpr int dummy = 0; (void)dummy;
+          const int cur = (p * 3 + kc) & 1, nxt = cur ^ 1;
+          // prefetch the fragments of the next (piece, chunk)
+          if (kc < 2) {
+            const double* pI = sI + size_t(pc[p].offI) * 4; const double* pJ = sJ + size_t(pc[p].offJ) * 4;
+#pragma unroll
+            for (int t = 0; t < 2; t++) fa[nxt][t] = pI[((kc + 1) * SY_PCOLS + 8 * t) * 4];
+#pragma unroll
+            for (int t = 0; t < 6; t++) fb[nxt][t] = pJ[((kc + 1) * SY_PCOLS + 8 * t) * 4];
+          } else if (p + 1 < 3 && p + 1 < npc) {
+            const double* pI = sI + size_t(pc[(p + 1) % 3].offI) * 4; const double* pJ = sJ + size_t(pc[(p + 1) % 3].offJ) * 4;
+#pragma unroll
+            for (int t = 0; t < 2; t++) fa[nxt][t] = pI[(8 * t) * 4];
+#pragma unroll
+            for (int t = 0; t < 6; t++) fb[nxt][t] = pJ[(8 * t) * 4];
+          }
+          if (full_piece) {
+#pragma unroll
+            for (int ti = 0; ti < 2; ti++)
+#pragma unroll
+              for (int tj = 0; tj < 6; tj++) dmma884(acc[p * 24 + 2 * (ti * 6 + tj)], acc[p * 24 + 2 * (ti * 6 + tj) + 1], fa[cur][ti], fb[cur][tj]);
+          } else {
+#pragma unroll
+            for (int ti = 0; ti < 2; ti++)
+#pragma unroll
+              for (int tj = 0; tj < 6; tj++)
+                if ((pc[p].mask >> (ti * 6 + tj)) & 1u) dmma884(acc[p * 24 + 2 * (ti * 6 + tj)], acc[p * 24 + 2 * (ti * 6 + tj) + 1], fa[cur][ti], fb[cur][tj]);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + s);
+  }
+  // epilogue: lane holds C[8ti + lane/4][8tj + 2(lane%4) + {0,1}] of every tile; H_ij -= x_i x_j^T for frame(i) <= frame(j)
+  const int rl = lane >> 2, cl = 2 * (lane & 3);
+#pragma unroll
+  for (int p = 0; p < 3; p++) {
+    if (p < npc) {
+#pragma unroll
+      for (int ti = 0; ti < 2; ti++)
+#pragma unroll
+        for (int tj = 0; tj < 6; tj++) {
+          const int r = 8 * ti + rl;
+          if (((pc[p].mask >> (ti * 6 + tj)) & 1u) && r < pc[p].nvalI) {
+            const int R = pc[p].rowbase + r;
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+              const int c = 8 * tj + cl + e;
+              const int Cc = pc[p].colbase + c;
+              if (c < pc[p].nvalJ && (R / 6) <= (Cc / 6)) atomicAdd(C + size_t(Cc) * n + R, -acc[p * 24 + 2 * (ti * 6 + tj) + e]);
+            }
+          }
+        }
+    }
+  }
+}
+
 // Stream-K form of the same kernel: ONE wave of CTAs (2 per SM), every CTA owns a contiguous, equal-cost stretch of the flattened
 // (tile, voxel group) work line computed on the host (sy_plan) — so no in-order dispatch tail, no imbalance between the cheap (diagonal /
 // remainder) and the full tiles, and ~1.3 RED epilogues per CTA instead of one per (tile, chunk) CTA (12 waves x 296 CTAs x 9216 fp64 REDs
@@ -926,10 +1034,16 @@ int vxs_eval_residual_dev(vxs_ctx* ctx, vxs_factor* f, const double* poses_dev, 
     return VXS_OK;
   }
   { int rcw = vxs_factor_wait_uploads(f); if (rcw) return rcw; }
+  {   // one streaming kernel (vxs_resid.cu); the two-kernel form below is the A/B alternative
+    int ran = 0;
+    int rcs = vxs_residual_stream_launch(ctx, f, poses_dev, pstride, residual_dev, &ran);
+    if (rcs) return rcs;
+    if (ran) { if (ctx->nranks > 1) return vxs_comm_allreduce(ctx, residual_dev, 1); return VXS_OK; }
+  }
   FactorView fv = make_view(f);
   const int G = pick_group(f);
   const unsigned blocks_v = nblk(size_t(f->V), 256);
-  VXS_CUDA(ctx, f->partial.reserve(blocks_v));
+  VXS_CUDA(ctx, f->partial.reserve(std::max<size_t>(blocks_v, size_t(ctx->sm_count))));
   if (!f->counter.p) { VXS_CUDA(ctx, f->counter.reserve(4)); VXS_CUDA(ctx, cudaMemsetAsync(f->counter.p, 0, 16, ctx->stream)); }
   {
     const size_t groups_needed = size_t(f->V);
@@ -1014,6 +1128,11 @@ int vxs_eval_hessian_dev(vxs_ctx* ctx, vxs_factor* f, const double* poses_dev, i
             const int gpc = (ng + nchunks - 1) / nchunks;
             nchunks = (ng + gpc - 1) / gpc;
             const int only = ctx->syrk_only_tile;
+            if (ctx->syrk_bulk && only < 0) {
+              const size_t smem_b = size_t(SYB_STAGES) * SY_STAGE_DOUBLES * 8;
+              VXS_CUDA(ctx, cudaFuncSetAttribute(k_syrk_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_b)));
+              VXS_LAUNCH(ctx, "k_syrk", k_syrk_bulk, unsigned(nchunks * g.ntiles), SY_THREADS, smem_b, f->X.p, C, g0, g1, W, g, gpc);
+            } else
             VXS_LAUNCH(ctx, "k_syrk", k_syrk, unsigned(only >= 0 ? nchunks : nchunks * g.ntiles), SY_THREADS, smem_sy, f->X.p, C, g0, g1, W, g, gpc, only);
           }
         }
@@ -1038,8 +1157,14 @@ int vxs_eval_hessian_dev(vxs_ctx* ctx, vxs_factor* f, const double* poses_dev, i
         int rcs = launch_syrk_sk(ctx, f, C, W, g, 0, ngv, smem);
         if (rcs) return rcs;
       } else {
+        if (ctx->syrk_bulk) {
+          const size_t smem_b = size_t(SYB_STAGES) * SY_STAGE_DOUBLES * 8;
+          VXS_CUDA(ctx, cudaFuncSetAttribute(k_syrk_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_b)));
+          VXS_LAUNCH(ctx, "k_syrk", k_syrk_bulk, unsigned(nchunks * g.ntiles), SY_THREADS, smem_b, f->X.p, C, 0, ngv, W, g, gpc);
+        } else {
         VXS_CUDA(ctx, cudaFuncSetAttribute(k_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         VXS_LAUNCH(ctx, "k_syrk", k_syrk, unsigned(nchunks * g.ntiles), SY_THREADS, smem, f->X.p, C, 0, ngv, W, g, gpc, -1);
+        }
       }
     } else {
       if (G == 32) { auto kp = k_pairs<32>; VXS_LAUNCH(ctx, "k_pairs", kp, grid, 128, 0, fv, f->X.p, C); }

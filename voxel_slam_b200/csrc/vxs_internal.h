@@ -60,7 +60,12 @@ struct vxs_ctx {
   int ldlt_lookahead = 1;         // VXS_LDLT_LOOKAHEAD_CTA=0 keeps the look-ahead on CTA 0 (A/B switch)
   int syrk_waves = 12;            // VXS_SYRK_WAVES
   int syrk_only_tile = -1;        // VXS_SYRK_ONLY_TILE: diagnostic, run a single tile kind of k_syrk (results are then incomplete)
-  int syrk_streamk = 1;           // VXS_SYRK_STREAMK=0: the (tile, chunk) grid of k_syrk instead of the one-wave stream-K plan (A/B switch)
+  int resid_stream = 1;           // VXS_RESID_STREAM=0: k_cluster_sum + k_eig_residual instead of the one streaming kernel (A/B switch)
+  int resid_te = 128;             // VXS_RESID_TE: entries per tile (= consumer threads per CTA) of k_residual_stream: 512 (1 CTA/SM), 256 (2), 128 (4)
+  int smem_optin = 0;             // cudaDevAttrMaxSharedMemoryPerBlockOptin
+  int syrk_bulk = 0;              // VXS_SYRK_BULK=1: the bulk-copy / mbarrier form of k_syrk (A/B switch; measured 0.796 vs 0.737 ms for the cp.async form at the metric shape)
+  int syrk_streamk = 0;           // VXS_SYRK_STREAMK=1: one-wave stream-K plan instead of the (tile, chunk) grid of k_syrk (A/B switch; measured SLOWER at the metric
+                                  // shape, 1.06 vs 0.74 ms: tiles of one voxel chunk no longer run together, so every tile re-reads its XT columns from HBM instead of L2)
   // what ctx->Hraw currently holds (vxs_hba_edges refuses anything but a lidar-only 6W system)
   int hraw_n = 0, hraw_S = 0;
   // solver scratch (n = system size)
@@ -156,6 +161,7 @@ struct vxs_eval_out {
 int vxs_eval_residual_dev(vxs_ctx* ctx, vxs_factor* f, const double* poses_dev, int pose_stride, double* residual_dev);
 int vxs_eval_hessian_dev(vxs_ctx* ctx, vxs_factor* f, const double* poses_dev, int pose_stride, double* r1_dev);
 int vxs_comm_allreduce(vxs_ctx* ctx, double* buf, size_t n);
+int vxs_residual_stream_launch(vxs_ctx* ctx, vxs_factor* f, const double* poses_dev, int pstride, double* residual_dev, int* ran);   // vxs_resid.cu
 
 // solver (vxs_solve.cu)
 int vxs_solve_damped(vxs_ctx* ctx, const double* Hraw, const double* jact, int n, int gauge, double u, double* dx_dev, double* D_dev, double* rhs_dev, int* singular_flag_host);

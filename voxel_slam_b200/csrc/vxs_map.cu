@@ -73,7 +73,7 @@ struct vxs_map {
   std::vector<DevBuf<double>*> scan_pv; std::vector<DevBuf<int>*> scan_leaf; std::vector<long long> scan_n;
   DevBuf<unsigned long long> scan_ptrs;     // [2][W+1] device pointers (pv12, leaf) per slot; entry W = fix pool
   // fix pool (point_fix of all leaves)
-  DevBuf<double> fix_pv; DevBuf<int> fix_leaf; long long fix_n = 0, fix_dead = 0;
+  DevBuf<double> fix_pv, fix_pv2; DevBuf<int> fix_leaf, fix_leaf2; long long fix_n = 0, fix_dead = 0;   // *2 = spare pool of the compaction (ping-pong)
   // ring: logical window position -> slot (voxel_map.hpp:934 `int* mp`)
   std::vector<int> ring;
   DevBuf<int> d_ring;        // [W] ring | [W+1] inverse (slot -> logical, entry W = W for the fix pseudo slot)
@@ -919,7 +919,7 @@ extern "C" int vxs_map_destroy(vxs_map* m) {
   for (auto b : m->scan_leaf) { b->release(); delete b; }
   m->n_root.release(); m->n_child.release(); m->n_layer.release(); m->n_path.release(); m->n_sw.release(); m->n_opt.release(); m->n_last.release(); m->n_flags.release(); m->n_rkey.release();
   m->n_center.release(); m->n_add.release(); m->n_fix.release(); m->n_cov.release(); m->n_eig.release(); m->n_plane.release(); m->n_quater.release(); m->table.release(); m->counters.release();
-  m->swp.release(); m->sw_free.release(); m->scan_ptrs.release(); m->fix_pv.release(); m->fix_leaf.release(); m->d_ring.release(); m->d_poses.release(); m->d_off.release();
+  m->swp.release(); m->sw_free.release(); m->scan_ptrs.release(); m->fix_pv.release(); m->fix_leaf.release(); m->fix_pv2.release(); m->fix_leaf2.release(); m->d_ring.release(); m->d_poses.release(); m->d_off.release();
   m->ss.hist.release(); m->ss.blocksums.release(); m->ss.totals.release(); m->keysA.release(); m->keysB.release(); m->refs.release(); m->rec_key.release(); m->idxA.release(); m->idxB.release();
   m->flagbuf.release(); m->scanbuf.release(); m->rec_start.release(); m->node_of_rec.release(); m->node_rec_start.release(); m->nflag.release(); m->sel.release(); m->nent.release();
   m->voff.release(); m->eoff.release();
@@ -1040,13 +1040,15 @@ extern "C" int vxs_map_margi(vxs_map* m, const double* poses12, int win_count, i
     unsigned int live = 0;
     VXS_CUDA(ctx, cudaMemcpyAsync(&live, m->ss.totals.p + 7, 4, cudaMemcpyDeviceToHost, st));
     VXS_CUDA(ctx, cudaStreamSynchronize(st));
-    double* np = nullptr; int* nl = nullptr;
-    const size_t nc = std::max<size_t>(size_t(live) * 2, 1 << 16);
-    VXS_CUDA(ctx, cudaMalloc((void**)&np, nc * 96)); VXS_CUDA(ctx, cudaMalloc((void**)&nl, nc * 4));
-    VXS_LAUNCH(ctx, "k_map_fix_compact", k_map_fix_compact, nblk(n, 256), 256, 0, m->fix_pv.p, m->fix_leaf.p, m->fix_n, m->flagbuf.p, m->scanbuf.p, np, nl);
-    VXS_CUDA(ctx, cudaStreamSynchronize(st));
-    cudaFree(m->fix_pv.p); cudaFree(m->fix_leaf.p);
-    m->fix_pv.p = np; m->fix_pv.cap = nc * 12; m->fix_leaf.p = nl; m->fix_leaf.cap = nc;
+    // compact into the spare pool (same capacity as the live one, allocated once and kept) and swap: no cudaMalloc / cudaFree per compaction —
+    // a 400 MB cudaFree + cudaMalloc pair every other scan cost ~80 ms of host time in the first version
+    if (m->fix_pv2.cap < m->fix_pv.cap || m->fix_leaf2.cap < m->fix_leaf.cap) {
+      m->fix_pv2.release(); m->fix_leaf2.release();
+      VXS_CUDA(ctx, m->fix_pv2.reserve(m->fix_pv.cap)); VXS_CUDA(ctx, m->fix_leaf2.reserve(m->fix_leaf.cap));
+    }
+    VXS_LAUNCH(ctx, "k_map_fix_compact", k_map_fix_compact, nblk(n, 256), 256, 0, m->fix_pv.p, m->fix_leaf.p, m->fix_n, m->flagbuf.p, m->scanbuf.p, m->fix_pv2.p, m->fix_leaf2.p);
+    std::swap(m->fix_pv.p, m->fix_pv2.p); std::swap(m->fix_pv.cap, m->fix_pv2.cap);
+    std::swap(m->fix_leaf.p, m->fix_leaf2.p); std::swap(m->fix_leaf.cap, m->fix_leaf2.cap);
     m->fix_n = live; m->fix_dead = 0;
   }
   // ---- ring rotation (voxelslam.cpp:1689-1693); the caller shifts its pose buffer (:1695-1712)
