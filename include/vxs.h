@@ -243,6 +243,17 @@ int vxs_odom_set_planes(vxs_ctx* ctx, const vxs_map_params* mp, int64_t n, const
 int vxs_odom_accumulate(vxs_ctx* ctx, const double* pv12, int64_t n, const double* pose12, const double* rot_var9, const double* tsl_var9,
                         double* HTH36, double* HTz6, double* nnt9, int64_t* match_num, int32_t* flags);
 
+/* Point variances of a scan (voxelslam.hpp:187-214; call sites voxelslam.cpp:1246-1250, 1584-1594), the step between down-sampling and the EKF:
+ *   vxs_var_init    = var_init: per point calcBodyVar (voxelslam.hpp:163-184: range / bearing noise, dept_err and beam_err narrow to float at the
+ *                     call as in the reference; a point with z == 0 gets z = 0.0001) then the extrinsic, pnt = ext.R pnt + ext.p,
+ *                     var = ext.R var ext.R^T.  pts: x, y, z float at the start of each point, stride_floats apart (12 for PointType).
+ *                     pv12_out (host, may be NULL): n pointVar records (pnt 3 | var 3x3 row-major).  The records also STAY on the device as the
+ *                     ctx's resident scan: vxs_odom_accumulate / vxs_map_odom_accumulate / vxs_pvec_update / vxs_map_push_scan take pv12 = NULL.
+ *   vxs_pvec_update = pvec_update: var = R var R^T + hat(pnt) rot_var hat(pnt)^T + tsl_var in place (pnt stays in the body frame),
+ *                     pwld = R pnt + p.  pv12 (host) may be NULL = the resident scan; pv12_out / pwld_out (host, n x 12 / n x 3) may be NULL. */
+int vxs_var_init(vxs_ctx* ctx, const float* pts, int stride_floats, int64_t n, const double* ext_R9, const double* ext_p3, double dept_err, double beam_err, double* pv12_out);
+int vxs_pvec_update(vxs_ctx* ctx, const double* pv12, int64_t n, const double* pose12, const double* rot_var9, const double* tsl_var9, double* pv12_out, double* pwld_out);
+
 /* ---------------------------------------------------------------- persistent local map of the sliding-window loop
  * The device-resident counterpart of `surf_map` / `surf_map_slide` (unordered_map<VOXEL_LOC, OctoTree*>, voxelslam.hpp) and of the per-scan
  * calls around the BA in thd_odometry_localmapping (voxelslam.cpp:1599-1712).  A scan is uploaded ONCE; the map, the slide windows
@@ -250,7 +261,8 @@ int vxs_odom_accumulate(vxs_ctx* ctx, const double* pv12, int64_t n, const doubl
  *   vxs_map_push_scan = cut_voxel_multi (voxel_map.hpp:1543-1639; single-thread form cut_voxel :1504-1540) of the NEW scan at window position
  *                       win_count-1 + multi_recut (voxelslam.cpp:1398-1453: OctoTree::recut :1148-1194 on every slide root, then tras_opt
  *                       :1308-1333) — `out` receives the LidarFactor of the window (cleared first; may be NULL).
- *                       pv12: n pointVar records (body-frame pnt 3 | var 3x3 row-major, as pvec_update left it, voxelslam.hpp:203-214);
+ *                       pv12: n pointVar records (body-frame pnt 3 | var 3x3 row-major, as pvec_update left it, voxelslam.hpp:203-214); NULL = the ctx's
+ *                       resident scan (vxs_var_init / vxs_pvec_update), copied device to device;
  *                       poses12: x_buf, win_count poses INCLUDING the new scan's (R row-major | p).
  *   vxs_map_margi     = multi_margi (voxelslam.cpp:1321-1395: OctoTree::margi voxel_map.hpp:1196-1305 with plane_update :1118-1146, erase of the
  *                       roots that ceased to exist + clear_slwd :1482-1500) with x_buf AFTER the BA and the factor the BA ran on (its cached
@@ -264,6 +276,12 @@ int vxs_map_create(vxs_ctx* ctx, const vxs_map_params* mp, int win_size, int max
 int vxs_map_destroy(vxs_map* m);
 int vxs_map_push_scan(vxs_map* m, const double* pv12, int64_t n, const double* poses12, int win_count, vxs_factor* out);
 int vxs_map_margi(vxs_map* m, const double* poses12, int win_count, int mgsize, vxs_factor* f);
+/* The per-point loop of the EKF update (voxelslam.cpp:876-918; match voxel_map.hpp:1674-1698, OctoTree::match :1335-1392) against the RESIDENT map:
+ * root cell through the map's root hash, descent by centre comparison, 3-sigma gates on the plane row plane_update left in the leaf — nothing is
+ * exported (vxs_odom_set_planes / vxs_odom_accumulate are the path for a caller that keeps the reference's host octree).  Arguments and outputs as
+ * vxs_odom_accumulate; pv12 = NULL uses the ctx's resident scan (vxs_var_init). */
+int vxs_map_odom_accumulate(vxs_map* m, const double* pv12, int64_t n, const double* pose12, const double* rot_var9, const double* tsl_var9, double* HTH36, double* HTz6,
+                            double* nnt9, int64_t* match_num, int32_t* flags);
 /* bookkeeping: nodes in the table, points in the point_fix pool, resident scans, ring[win_size] = slot of every logical window position */
 int vxs_map_counts(const vxs_map* m, int64_t* n_nodes, int64_t* n_fix_points, int* win_count, int32_t* ring);
 /* Every leaf of the map, 32 + 10 * win_size doubles each (for tests and debugging): voxel_center 3 | cube half length | layer | is_plane |

@@ -18,6 +18,10 @@
 #include "voxel_map.hpp"      // -I /root/reference/VoxelSLAM/src  (pulls tools.hpp, preintegration.hpp)
 #include "loop_refine.hpp"
 #include "../tests/harness/synth.hpp"   // the seeded IMU sample generator shared with the harness (so both arms integrate the same samples)
+#ifndef DEG2RAD
+#define DEG2RAD(x) ((x)*0.017453293)   // pcl/pcl_macros.h (PCL 1.10), used by calcBodyVar
+#endif
+#include "_ref/vh_pointvar.inc"         // calcBodyVar / var_init / pvec_update cut out of voxelslam.hpp:163-214 by the Makefile (see there)
 
 namespace {
 
@@ -93,6 +97,28 @@ PVecPtr make_pvec(const double* pts, int64_t n, double var_diag) {
 extern "C" {
 
 int vxr_standin_eigen(void) { return VXREF_EIGEN_STANDIN; }
+// var_init / pvec_update: the reference's own functions (voxelslam.hpp:187-214)
+void vxr_var_init(const float* pts, int stride, int64_t n, const double* ext_R9, const double* ext_p3, double dept_err_, double beam_err_, double* pv12) {
+  IMUST ext;
+  for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) ext.R(r, c) = ext_R9[3 * r + c];
+  for (int k = 0; k < 3; k++) ext.p[k] = ext_p3[k];
+  pcl::PointCloud<PointType> pl;
+  for (int64_t i = 0; i < n; i++) { PointType ap; ap.x = pts[size_t(i) * stride]; ap.y = pts[size_t(i) * stride + 1]; ap.z = pts[size_t(i) * stride + 2]; pl.push_back(ap); }
+  PVecPtr pptr(new PVec);
+  var_init(ext, pl, pptr, dept_err_, beam_err_);
+  for (int64_t i = 0; i < n; i++) { const pointVar& pv = (*pptr)[size_t(i)]; for (int k = 0; k < 3; k++) pv12[12 * i + k] = pv.pnt[k]; for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) pv12[12 * i + 3 + 3 * r + c] = pv.var(r, c); }
+}
+void vxr_pvec_update(double* pv12, int64_t n, const double* pose12, const double* rot_var9, const double* tsl_var9, double* pwld_out) {
+  PVecPtr pptr(new PVec(size_t(n)));
+  for (int64_t i = 0; i < n; i++) { pointVar& pv = (*pptr)[size_t(i)]; pv.pnt = Eigen::Vector3d(pv12[12 * i], pv12[12 * i + 1], pv12[12 * i + 2]); for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) pv.var(r, c) = pv12[12 * i + 3 + 3 * r + c]; }
+  IMUST x = state_from12(pose12);
+  x.cov.setZero();
+  for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) { x.cov(r, c) = rot_var9[3 * r + c]; x.cov(3 + r, 3 + c) = tsl_var9[3 * r + c]; }
+  PLV(3) pwld;
+  pvec_update(pptr, x, pwld);
+  for (int64_t i = 0; i < n; i++) { const pointVar& pv = (*pptr)[size_t(i)]; for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) pv12[12 * i + 3 + 3 * r + c] = pv.var(r, c); for (int k = 0; k < 3; k++) pwld_out[3 * i + k] = pwld[size_t(i)][k]; }
+}
+
 
 // ---------------------------------------------------------------- primitives
 void vxr_eig3(const double* A9_rowmajor, double* w3, double* U9_rowmajor) {

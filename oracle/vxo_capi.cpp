@@ -428,6 +428,23 @@ int vxo_local_map_odom_accumulate(void* hh, const double* pv12, int64_t n, const
 }
 
 // ---------------------------------------------------------------- sliding-window simulator (map side of voxelslam.cpp:1599-1686)
+// var_init / pvec_update (voxelslam.hpp:187-214)
+void vxo_var_init(const float* pts, int stride, int64_t n, const double* ext_R9, const double* ext_p3, double dept_err, double beam_err, double* pv12) {
+  M3 R; for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) R(r, c) = ext_R9[3 * r + c];
+  std::vector<PV> out;
+  var_init(R, v3(ext_p3[0], ext_p3[1], ext_p3[2]), pts, stride, n, dept_err, beam_err, out);
+  for (int64_t i = 0; i < n; i++) { for (int k = 0; k < 3; k++) pv12[12 * i + k] = out[size_t(i)].pnt[k]; for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) pv12[12 * i + 3 + 3 * r + c] = out[size_t(i)].var(r, c); }
+}
+void vxo_pvec_update(double* pv12, int64_t n, const double* pose12, const double* rot_var9, const double* tsl_var9, double* pwld) {
+  std::vector<PV> pv(static_cast<size_t>(n));
+  for (int64_t i = 0; i < n; i++) { pv[size_t(i)].pnt = v3(pv12[12 * i], pv12[12 * i + 1], pv12[12 * i + 2]); for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) pv[size_t(i)].var(r, c) = pv12[12 * i + 3 + 3 * r + c]; }
+  State x = states_from_poses12(pose12, 1)[0];
+  M3 rv, tv; for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) { rv(r, c) = rot_var9[3 * r + c]; tv(r, c) = tsl_var9[3 * r + c]; }
+  std::vector<V3> pw;
+  pvec_update(pv, x, rv, tv, pw);
+  for (int64_t i = 0; i < n; i++) { for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) pv12[12 * i + 3 + 3 * r + c] = pv[size_t(i)].var(r, c); for (int k = 0; k < 3; k++) pwld[3 * i + k] = pw[size_t(i)][k]; }
+}
+
 void* vxo_sliding_sim_create(const vxs_map_params* mp, int win_size, int mgsize, int max_points) {
   MapParams m = to_map_params(mp, true);
   m.max_points = max_points;

@@ -338,6 +338,49 @@ inline int odom_accumulate(LocalMap& surf_map, const std::vector<PV>& pvec, cons
   return match_num;
 }
 
+// voxelslam.hpp:163-184 calcBodyVar: range / bearing noise of one point in the sensor frame.  The reference's float intermediates are kept
+// (`const float range_inc, degree_inc` parameters, `float range`, `float range_var`); DEG2RAD(x) = ((x)*0.017453293) (pcl_macros.h).
+inline void calc_body_var(V3& pb, const float range_inc, const float degree_inc, M3& var) {
+  if (pb[2] == 0) pb[2] = 0.0001;
+  float range = std::sqrt(pb[0] * pb[0] + pb[1] * pb[1] + pb[2] * pb[2]);
+  float range_var = range_inc * range_inc;
+  const double dv = std::pow(std::sin(degree_inc * 0.017453293), 2);
+  const double nrm = std::sqrt((pb[0] * pb[0] + pb[1] * pb[1]) + pb[2] * pb[2]);
+  const V3 direction = v3(pb[0] / nrm, pb[1] / nrm, pb[2] / nrm);
+  const M3 direction_hat = hat(direction);
+  V3 b1 = v3(1, 1, -(direction[0] + direction[1]) / direction[2]);
+  { const double l = std::sqrt((b1[0] * b1[0] + b1[1] * b1[1]) + b1[2] * b1[2]); b1 = v3(b1[0] / l, b1[1] / l, b1[2] / l); }
+  V3 b2 = v3(b1[1] * direction[2] - b1[2] * direction[1], b1[2] * direction[0] - b1[0] * direction[2], b1[0] * direction[1] - b1[1] * direction[0]);   // base_vector1.cross(direction)
+  { const double l = std::sqrt((b2[0] * b2[0] + b2[1] * b2[1]) + b2[2] * b2[2]); b2 = v3(b2[0] / l, b2[1] / l, b2[2] / l); }
+  // A = range * direction_hat * N,  N = [b1 b2] (3 x 2)
+  double A[3][2];
+  for (int a = 0; a < 3; a++) {
+    A[a][0] = ((double(range) * direction_hat(a, 0)) * b1[0] + (double(range) * direction_hat(a, 1)) * b1[1]) + (double(range) * direction_hat(a, 2)) * b1[2];
+    A[a][1] = ((double(range) * direction_hat(a, 0)) * b2[0] + (double(range) * direction_hat(a, 1)) * b2[1]) + (double(range) * direction_hat(a, 2)) * b2[2];
+  }
+  for (int a = 0; a < 3; a++)
+    for (int b = 0; b < 3; b++) var(a, b) = (direction[a] * double(range_var)) * direction[b] + ((A[a][0] * dv) * A[b][0] + (A[a][1] * dv) * A[b][1]);
+}
+// voxelslam.hpp:187-203 var_init: pts = x, y, z float (PointType), stride floats apart
+inline void var_init(const M3& ext_R, const V3& ext_p, const float* pts, int stride, int64_t n, double dept_err, double beam_err, std::vector<PV>& out) {
+  out.resize(size_t(n));
+  for (int64_t i = 0; i < n; i++) {
+    PV& pv = out[size_t(i)];
+    pv.pnt = v3(pts[size_t(i) * stride], pts[size_t(i) * stride + 1], pts[size_t(i) * stride + 2]);
+    calc_body_var(pv.pnt, float(dept_err), float(beam_err), pv.var);
+    pv.pnt = ext_R * pv.pnt + ext_p;
+    pv.var = ext_R * pv.var * tr(ext_R);
+  }
+}
+// voxelslam.hpp:205-214 pvec_update
+inline void pvec_update(std::vector<PV>& pvec, const State& x, const M3& rot_var, const M3& tsl_var, std::vector<V3>& pwld) {
+  for (PV& pv : pvec) {
+    const M3 phat = hat(pv.pnt);
+    pv.var = (x.R * pv.var * tr(x.R) + phat * rot_var * tr(phat)) + tsl_var;
+    pwld.push_back(x.R * pv.pnt + x.p);
+  }
+}
+
 // voxel_map.hpp:1504-1540 (feat_tem_map bookkeeping dropped: in a from-scratch build slide map == map)
 inline void cut_voxel(LocalMap& feat_map, const std::vector<PV>& pvec, int win_count, int wdsize, const std::vector<V3>& pwld, const MapParams& mp_) {
   for (size_t i = 0; i < pvec.size(); i++) {

@@ -262,6 +262,24 @@ def hba_window(coarse, fine, xyz_f32, kf_offsets, poses12, max_iter, thread_num=
     return dict(poses=p, hess=H, resis_log=log[: 2 * it.value], outer_iters=it.value, status=rc)
 
 
+def var_init(pts_f32, ext_R, ext_p, dept_err, beam_err, stride_floats=None):
+    """var_init (voxelslam.hpp:187-203) -> n x 12 pointVar records (pnt | var row-major)"""
+    x = np.ascontiguousarray(pts_f32, dtype=np.float32)
+    stride = int(stride_floats) if stride_floats else (x.shape[1] if x.ndim == 2 else 3)
+    n = x.size // stride
+    out = np.zeros((max(n, 1), 12))
+    lib().vxo_var_init(x.ctypes.data_as(C.POINTER(C.c_float)), C.c_int(stride), C.c_int64(n), _dp(_f64(ext_R)), _dp(_f64(ext_p)), C.c_double(dept_err), C.c_double(beam_err), _dp(out))
+    return out[:n]
+
+
+def pvec_update(pv12, pose12, rot_var, tsl_var):
+    """pvec_update (voxelslam.hpp:205-214) -> (pv with the world variance, pwld)"""
+    pv = _f64(pv12).reshape(-1, 12).copy()
+    pw = np.zeros((max(pv.shape[0], 1), 3))
+    lib().vxo_pvec_update(_dp(pv), C.c_int64(pv.shape[0]), _dp(_f64(pose12)), _dp(_f64(rot_var)), _dp(_f64(tsl_var)), _dp(pw))
+    return pv, pw[: pv.shape[0]]
+
+
 class RefImuWindow:
     """W-1 real IMU_PRE objects of the reference build (BACKEND == "ref" only), fed with the same seeded samples as synth.ImuWindow."""
 

@@ -109,6 +109,18 @@ def test_sliding_window_map_sequence(ctx, Wn, pts, max_layer, max_points, ba_ite
     Vo = po["plane_var"][ko].copy(); Vo[:, :3, 3:] *= sgn[:, None, None]; Vo[:, 3:, :3] *= sgn[:, None, None]
     assert np.max(np.abs(pg["plane_var"][kg] - Vo) / np.max(np.abs(Vo), axis=(1, 2), keepdims=True)) < 1e-5
     assert np.array_equal(pg["radius"][kg].astype(np.float32), po["radius"][ko].astype(np.float32)) or np.max(np.abs(pg["radius"][kg] - po["radius"][ko]) / po["radius"][ko]) < 1e-6
+    # one association pass of the odometry EKF (voxelslam.cpp:876-918) against the RESIDENT map: no plane table is exported
+    pose = synth.perturb_pose(synth.true_pose(6.0, nscan), 991, 1e-3, 5e-3)
+    scan = pv_records(synth.gen_scan(6.0, nscan, 6000, synth.true_pose(6.0, nscan), seed=0x5EED0000 + 5), 77, True)
+    rng = np.random.default_rng(3)
+    A = rng.standard_normal((3, 3)) * 1e-3; B = rng.standard_normal((3, 3)) * 1e-2
+    rot_var, tsl_var = A @ A.T, B @ B.T
+    og, oo = dm.odom_accumulate(scan, pose, rot_var, tsl_var), sim.odom_accumulate(scan, pose, rot_var, tsl_var)
+    assert oo["n"] > 500 and og["n"] == oo["n"] and np.array_equal(og["flags"], oo["flags"])
+    for k in ("HTH", "HTz", "nnt"):
+        assert np.max(np.abs(og[k] - oo[k])) / np.max(np.abs(oo[k])) < 1e-9, k
+    og2 = dm.odom_accumulate(None, pose, rot_var, tsl_var, n=scan.shape[0])      # the scan stayed resident
+    assert og2["n"] == og["n"] and np.array_equal(og2["HTH"] != 0, og["HTH"] != 0) and np.max(np.abs(og2["HTH"] - og["HTH"])) / np.max(np.abs(og["HTH"])) < 1e-12
     dm.close(); f.close()
 
 

@@ -316,3 +316,29 @@ def test_sliding_window_with_ba_between_recut_and_margi():
     oa_, ob_ = a.odom_accumulate(pv, pose, np.eye(3) * 1e-6, np.eye(3) * 1e-5), b.odom_accumulate(pv, pose, np.eye(3) * 1e-6, np.eye(3) * 1e-5)
     assert oa_["n"] == ob_["n"] > 300 and np.array_equal(oa_["flags"], ob_["flags"])
     assert relinf(oa_["HTH"], ob_["HTH"]) < 1e-8 and relinf(oa_["HTz"], ob_["HTz"]) < 1e-8
+
+
+def test_var_init_and_pvec_update_against_the_reference_functions():
+    """calcBodyVar / var_init / pvec_update (voxelslam.hpp:163-214, cut out of voxelslam.hpp at build time): the restatement vs the reference's code,
+    incl. a point with z == 0 (the reference moves it to z = 1e-4) and points on the axes' neighbourhood."""
+    rng = np.random.default_rng(5)
+    n = 4000
+    pts = np.zeros((n, 12), dtype=np.float32)                       # PointType stride (12 floats)
+    pts[:, :3] = rng.uniform(-40, 40, (n, 3)).astype(np.float32)
+    pts[0, :3] = (3.0, -2.0, 0.0)                                  # z == 0 trap (voxelslam.hpp:165)
+    pts[1, :3] = (0.01, 0.02, 35.0)
+    pts[2, :3] = (25.0, -25.0, 1e-3)
+    ext_R = oa.so3_exp(np.array([0.02, -0.01, 0.03])); ext_p = np.array([0.05, -0.02, 0.1])
+    a = oa.var_init(pts, ext_R, ext_p, 0.02, 0.05)
+    b = ra.var_init(pts, ext_R, ext_p, 0.02, 0.05)
+    assert np.array_equal(a[:, :3], b[:, :3])
+    assert np.max(np.abs(a[:, 3:] - b[:, 3:]) / (np.max(np.abs(b[:, 3:]), axis=1, keepdims=True))) < 1e-12
+    assert abs(a[0, 2] - (ext_R @ np.array([3.0, -2.0, 1e-4]) + ext_p)[2]) < 1e-15
+    pose = np.concatenate([oa.so3_exp(np.array([0.3, 0.1, -0.2])).ravel(), [5.0, -3.0, 1.0]])
+    A = rng.standard_normal((3, 3)) * 1e-3; rot_var = A @ A.T
+    B = rng.standard_normal((3, 3)) * 1e-2; tsl_var = B @ B.T
+    pa, wa = oa.pvec_update(a, pose, rot_var, tsl_var)
+    pb, wb = ra.pvec_update(a, pose, rot_var, tsl_var)
+    assert np.array_equal(pa[:, :3], a[:, :3])                      # pnt stays in the body frame
+    assert np.max(np.abs(wa - wb)) < 1e-12
+    assert np.max(np.abs(pa[:, 3:] - pb[:, 3:]) / np.max(np.abs(pb[:, 3:]), axis=1, keepdims=True)) < 1e-12

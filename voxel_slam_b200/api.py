@@ -335,6 +335,29 @@ def _odom_accumulate(self, pv12, pose12, rot_var, tsl_var, n=None, want_flags=Tr
     return dict(n=m.value, HTH=HTH, HTz=HTz, nnt=nnt, flags=flags[:n] if want_flags else None)
 
 
+def _var_init(self, pts_f32, ext_R, ext_p, dept_err, beam_err, want_out=True, stride_floats=None):
+    """var_init (voxelslam.hpp:187-203): pointVar records of a scan; they also stay on the device as the ctx's resident scan."""
+    x = np.ascontiguousarray(pts_f32, dtype=np.float32)
+    stride = int(stride_floats) if stride_floats else (x.shape[1] if x.ndim == 2 else 3)
+    n = x.size // stride
+    out = np.zeros((max(n, 1), 12)) if want_out else None
+    self._check(lib().vxs_var_init(self._p, x.ctypes.data_as(C.POINTER(C.c_float)), C.c_int(stride), C.c_int64(n), _dp(_f64(ext_R)), _dp(_f64(ext_p)), C.c_double(dept_err), C.c_double(beam_err),
+                                   _dp(out)))
+    return out[:n] if want_out else n
+
+
+def _pvec_update(self, pv12, pose12, rot_var, tsl_var, n=None, want_pv=True, want_pwld=True):
+    """pvec_update (voxelslam.hpp:205-214); pv12=None works on the resident scan (pass n)."""
+    pv = _f64(pv12).reshape(-1, 12) if pv12 is not None else None
+    n = pv.shape[0] if pv is not None else int(n)
+    out = np.zeros((max(n, 1), 12)) if want_pv else None
+    pw = np.zeros((max(n, 1), 3)) if want_pwld else None
+    self._check(lib().vxs_pvec_update(self._p, _dp(pv), C.c_int64(n), _dp(_f64(pose12)), _dp(_f64(rot_var)), _dp(_f64(tsl_var)), _dp(out), _dp(pw)))
+    return dict(pv=out[:n] if want_pv else None, pwld=pw[:n] if want_pwld else None)
+
+
+Context.var_init = _var_init
+Context.pvec_update = _pvec_update
 Context.odom_set_planes = _odom_set_planes
 Context.odom_accumulate = _odom_accumulate
 
@@ -465,11 +488,23 @@ class LocalMap:
         except Exception:
             pass
 
-    def push_scan(self, pv12, poses12, factor=None):
+    def push_scan(self, pv12, poses12, factor=None, n=None):
         """cut_voxel_multi + multi_recut + tras_opt of one new scan; pv12 rows = body pnt (3) | var (9); poses12 = x_buf incl. the new scan."""
-        pv = _f64(pv12).reshape(-1, 12)
+        pv = _f64(pv12).reshape(-1, 12) if pv12 is not None else None      # None: the ctx's resident scan (var_init / pvec_update), pass n
         p = _f64(poses12).reshape(-1, 12)
-        self.ctx._check(lib().vxs_map_push_scan(self._p, _dp(pv), C.c_int64(pv.shape[0]), _dp(p), C.c_int(p.shape[0]), factor._p if factor is not None else None))
+        nn = pv.shape[0] if pv is not None else int(n)
+        self.ctx._check(lib().vxs_map_push_scan(self._p, _dp(pv), C.c_int64(nn), _dp(p), C.c_int(p.shape[0]), factor._p if factor is not None else None))
+
+    def odom_accumulate(self, pv12, pose12, rot_var, tsl_var, n=None, want_flags=True):
+        """vxs_map_odom_accumulate: the EKF accumulation pass (voxelslam.cpp:876-918) against the resident map; pv12=None = resident scan (pass n)."""
+        pv = _f64(pv12).reshape(-1, 12) if pv12 is not None else None
+        n = pv.shape[0] if pv is not None else int(n)
+        HTH, HTz, nnt = np.zeros((6, 6)), np.zeros(6), np.zeros((3, 3))
+        flags = np.zeros(max(n, 1), dtype=np.int32) if want_flags else None
+        m = C.c_int64(0)
+        self.ctx._check(lib().vxs_map_odom_accumulate(self._p, _dp(pv), C.c_int64(n), _dp(_f64(pose12)), _dp(_f64(rot_var)), _dp(_f64(tsl_var)), _dp(HTH), _dp(HTz), _dp(nnt), C.byref(m),
+                                                      flags.ctypes.data_as(C.POINTER(C.c_int32)) if want_flags else None))
+        return dict(n=m.value, HTH=HTH, HTz=HTz, nnt=nnt, flags=flags[:n] if want_flags else None)
 
     def margi(self, poses12, factor, mgsize=1):
         p = _f64(poses12).reshape(-1, 12)

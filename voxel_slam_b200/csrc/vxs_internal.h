@@ -61,7 +61,8 @@ struct vxs_ctx {
   int syrk_waves = 12;            // VXS_SYRK_WAVES
   int syrk_only_tile = -1;        // VXS_SYRK_ONLY_TILE: diagnostic, run a single tile kind of k_syrk (results are then incomplete)
   int resid_stream = 1;           // VXS_RESID_STREAM=0: k_cluster_sum + k_eig_residual instead of the one streaming kernel (A/B switch)
-  int resid_te = 128;             // VXS_RESID_TE: entries per tile (= consumer threads per CTA) of k_residual_stream: 512 (1 CTA/SM), 256 (2), 128 (4)
+  int resid_te = 256;             // VXS_RESID_TE: entries per tile (= consumer threads per CTA) of k_residual_stream: 512 (1 CTA/SM), 256 (2), 128 (4)
+  int resid_stages = 2, resid_per_sm = 3;   // VXS_RESID_STAGES (2..4), VXS_RESID_PER_SM (CTAs per SM the batches are cut for; 0 = by tile size)
   int smem_optin = 0;             // cudaDevAttrMaxSharedMemoryPerBlockOptin
   int syrk_bulk = 0;              // VXS_SYRK_BULK=1: the bulk-copy / mbarrier form of k_syrk (A/B switch; measured 0.796 vs 0.737 ms for the cp.async form at the metric shape)
   int syrk_streamk = 0;           // VXS_SYRK_STREAMK=1: one-wave stream-K plan instead of the (tile, chunk) grid of k_syrk (A/B switch; measured SLOWER at the metric
@@ -118,6 +119,8 @@ struct vxs_factor {
   cudaEvent_t up_fence = nullptr;
 };
 void vxs_odom_release(vxs_ctx* c);
+int vxs_odom_resident_scan(vxs_ctx* ctx, double** pv12_dev, long long* n);            // the scan var_init / odom_accumulate / pvec_update left on the device
+int vxs_odom_set_resident_scan(vxs_ctx* ctx, const double* pv12_host, long long n);
 int vxs_factor_wait_uploads(vxs_factor* f);   // orders ctx->stream behind every pending upload chunk (device-side wait, no host sync)
 
 inline int vxs_fail(vxs_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) {

@@ -29,6 +29,7 @@
 #include "vxs_internal.h"
 #include "vxs_math.cuh"
 #include "vxs_sortscan.cuh"
+#include "vxs_odom_math.cuh"
 
 using namespace vxs;
 
@@ -84,6 +85,7 @@ struct vxs_map {
   DevBuf<unsigned long long> keysA, keysB, refs, rec_key;
   DevBuf<unsigned int> idxA, idxB, flagbuf, scanbuf, rec_start, node_of_rec, node_rec_start, nflag;
   DevBuf<unsigned int> sel, nent, voff, eoff;
+  DevBuf<double> odom_st;    // pose / covariance block and the 34 sums of vxs_map_odom_accumulate
   int win_count = 0;
   long long bb[6] = {0, 0, 0, 0, 0, 0}; bool bb_valid = false;
 };
@@ -680,6 +682,43 @@ __global__ void __launch_bounds__(128) k_map_rehash(NodeView nv, int n_nodes, un
   while (atomicCAS(table + h, 0u, (unsigned int)nd + 1u) != 0u) h = (h + 1u) & tmask;
 }
 
+// ---------------------------------------------------------------- odometry association against the resident map
+// match() (voxel_map.hpp:1674-1698): root cell of the world point through the root hash (surf_map holds EVERY root, also those that left the slide
+// map), OctoTree::match (:1335-1392): descend by centre comparison while the node is inner (a missing child ends the search), at the leaf the
+// 3-sigma gates on the plane row that plane_update left in the node — read in place, nothing is exported or re-sorted.
+__global__ void __launch_bounds__(256) k_map_odom(NodeView nv, const unsigned int* __restrict__ table, unsigned int tmask, const double* __restrict__ pv, long long n,
+                                                  const double* __restrict__ st /* R9 p3 rotvar9 tslvar9 */, double voxel_size, double* __restrict__ out, int* __restrict__ flags) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double acc[34];
+#pragma unroll
+  for (int k = 0; k < 34; k++) acc[k] = 0.0;
+  if (i < n) {
+    int hit = 0;
+    const double* p = pv + 12 * i;
+    const double x = p[0], y = p[1], z = p[2];
+    const d3 w = world_point(st, mk3(x, y, z));
+    const long long kx = quantise(w.x, voxel_size), ky = quantise(w.y, voxel_size), kz = quantise(w.z, voxel_size);
+    unsigned int h = table_hash(kx, ky, kz) & tmask;
+    int node = -1;
+    for (;;) {
+      const unsigned int v = table[h];
+      if (v == 0u) break;
+      const int r = int(v - 1u);
+      if (nv.rkey[r] == kx && nv.rkey[nv.cap + r] == ky && nv.rkey[2 * nv.cap + r] == kz) { node = r; break; }
+      h = (h + 1u) & tmask;
+    }
+    while (node >= 0 && (nv.flags[node] & F_INNER)) node = nv.child[size_t(octant_of(nv, node, w)) * nv.cap + node];     // leaves[leafnum] == nullptr -> no match
+    if (node >= 0 && (nv.flags[node] & F_PLANE)) {
+      double row[OD_ROW];
+#pragma unroll
+      for (int k = 0; k < OD_ROW; k++) row[k] = nv.plane[size_t(k) * nv.cap + node];
+      hit = od_contribution(row, x, y, z, w.x, w.y, w.z, p, st, acc);
+    }
+    if (flags) flags[i] = hit;
+  }
+  od_flush(acc, out);
+}
+
 // ---------------------------------------------------------------- host side
 template <class T> static int grow_soa(vxs_ctx* ctx, DevBuf<T>& b, int rows, size_t oldcap, size_t newcap, int used, int fill) {
   T* np = nullptr;
@@ -922,13 +961,13 @@ extern "C" int vxs_map_destroy(vxs_map* m) {
   m->swp.release(); m->sw_free.release(); m->scan_ptrs.release(); m->fix_pv.release(); m->fix_leaf.release(); m->fix_pv2.release(); m->fix_leaf2.release(); m->d_ring.release(); m->d_poses.release(); m->d_off.release();
   m->ss.hist.release(); m->ss.blocksums.release(); m->ss.totals.release(); m->keysA.release(); m->keysB.release(); m->refs.release(); m->rec_key.release(); m->idxA.release(); m->idxB.release();
   m->flagbuf.release(); m->scanbuf.release(); m->rec_start.release(); m->node_of_rec.release(); m->node_rec_start.release(); m->nflag.release(); m->sel.release(); m->nent.release();
-  m->voff.release(); m->eoff.release();
+  m->voff.release(); m->eoff.release(); m->odom_st.release();
   delete m;
   return VXS_OK;
 }
 
 extern "C" int vxs_map_push_scan(vxs_map* m, const double* pv12, int64_t n, const double* poses12, int win_count, vxs_factor* out) {
-  if (!m || !poses12 || n < 0 || (n > 0 && !pv12) || win_count < 1 || win_count > m->W || (out && out->ctx != m->ctx)) return VXS_ERR_ARG;
+  if (!m || !poses12 || n < 0 || win_count < 1 || win_count > m->W || (out && out->ctx != m->ctx)) return VXS_ERR_ARG;
   if (win_count != m->win_count + 1) return vxs_fail(m->ctx, VXS_ERR_ARG, "vxs_map_push_scan: win_count must be the number of resident scans + 1 (call vxs_map_margi when the window is full)");
   if (n >= (1ll << 31)) return vxs_fail(m->ctx, VXS_ERR_ARG, "more than 2^31 points in one scan");
   vxs_ctx* ctx = m->ctx;
@@ -938,7 +977,13 @@ extern "C" int vxs_map_push_scan(vxs_map* m, const double* pv12, int64_t n, cons
   // ---- the new scan becomes resident in its ring slot
   DevBuf<double>& pv = *m->scan_pv[size_t(slot)]; DevBuf<int>& lf = *m->scan_leaf[size_t(slot)];
   VXS_CUDA(ctx, pv.reserve(size_t(std::max<int64_t>(n, 1)) * 12)); VXS_CUDA(ctx, lf.reserve(size_t(std::max<int64_t>(n, 1))));
-  if (n) VXS_CUDA(ctx, cudaMemcpyAsync(pv.p, pv12, size_t(n) * 96, cudaMemcpyHostToDevice, st));
+  if (n && pv12) VXS_CUDA(ctx, cudaMemcpyAsync(pv.p, pv12, size_t(n) * 96, cudaMemcpyHostToDevice, st));
+  else if (n) {   // pv12 == NULL: the scan that vxs_var_init / vxs_pvec_update left on the device (no host round trip)
+    double* res = nullptr; long long nres = 0;
+    vxs_odom_resident_scan(ctx, &res, &nres);
+    if (nres != n || !res) return vxs_fail(ctx, VXS_ERR_ARG, "vxs_map_push_scan: pv12 is NULL and there is no resident scan of this size (vxs_var_init / vxs_pvec_update)");
+    VXS_CUDA(ctx, cudaMemcpyAsync(pv.p, res, size_t(n) * 96, cudaMemcpyDeviceToDevice, st));
+  }
   m->scan_n[size_t(slot)] = n;
   m->win_count = win_count;
   int rc = map_reserve_nodes(m, size_t(m->n_nodes) + size_t(n));
@@ -1126,5 +1171,42 @@ extern "C" int vxs_map_read_planes(vxs_map* m, double* rows52, int64_t* ids5, in
   VXS_CUDA(ctx, cudaMemcpyAsync(rows52, ctx->stage.p, size_t(np) * 52 * 8, cudaMemcpyDeviceToHost, st));
   if (ids5) VXS_CUDA(ctx, cudaMemcpyAsync(ids5, ctx->stage_i64.p, size_t(np) * 5 * 8, cudaMemcpyDeviceToHost, st));
   VXS_CUDA(ctx, cudaStreamSynchronize(st));
+  return VXS_OK;
+}
+
+// The per-point loop of the EKF update (voxelslam.cpp:876-918) against the resident map: no plane table is exported (vxs_odom_set_planes is the
+// host-octree path).  pv12 = NULL uses the scan that vxs_var_init / a previous call left on the device.
+extern "C" int vxs_map_odom_accumulate(vxs_map* m, const double* pv12, int64_t n, const double* pose12, const double* rot_var9, const double* tsl_var9, double* HTH36, double* HTz6,
+                                       double* nnt9, int64_t* match_num, int32_t* flags) {
+  if (!m || n < 0 || !pose12 || !rot_var9 || !tsl_var9 || !HTH36 || !HTz6 || !nnt9 || !match_num) return VXS_ERR_ARG;
+  vxs_ctx* ctx = m->ctx;
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  if (pv12) { int rc = vxs_odom_set_resident_scan(ctx, pv12, n); if (rc) return rc; }
+  double* pv = nullptr; long long nres = 0;
+  vxs_odom_resident_scan(ctx, &pv, &nres);
+  if (nres != n) return vxs_fail(ctx, VXS_ERR_ARG, "vxs_map_odom_accumulate: no resident scan of this size");
+  double sth[30];
+  for (int k = 0; k < 12; k++) sth[k] = pose12[k];
+  for (int k = 0; k < 9; k++) { sth[12 + k] = rot_var9[k]; sth[21 + k] = tsl_var9[k]; }
+  VXS_CUDA(ctx, m->odom_st.reserve(30 + 34));
+  double* d_st = m->odom_st.p; double* d_out = m->odom_st.p + 30;
+  VXS_CUDA(ctx, cudaMemcpyAsync(d_st, sth, sizeof sth, cudaMemcpyHostToDevice, st));
+  VXS_CUDA(ctx, cudaMemsetAsync(d_out, 0, 34 * 8, st));
+  int* dflags = nullptr;
+  if (flags && n > 0) { VXS_CUDA(ctx, m->flagbuf.reserve(size_t(n))); dflags = reinterpret_cast<int*>(m->flagbuf.p); }
+  if (n > 0 && m->n_nodes > 0)
+    VXS_LAUNCH(ctx, "k_map_odom", k_map_odom, nblk(size_t(n), 256), 256, 0, view(m), m->table.p, (unsigned int)(m->tcap - 1), pv, (long long)n, d_st, m->mp.voxel_size, d_out, dflags);
+  else if (dflags) VXS_CUDA(ctx, cudaMemsetAsync(dflags, 0, size_t(n) * 4, st));
+  double out[34];
+  VXS_CUDA(ctx, cudaMemcpyAsync(out, d_out, sizeof out, cudaMemcpyDeviceToHost, st));
+  if (dflags) VXS_CUDA(ctx, cudaMemcpyAsync(flags, dflags, size_t(n) * 4, cudaMemcpyDeviceToHost, st));
+  VXS_CUDA(ctx, cudaStreamSynchronize(st));
+  int u = 0;
+  for (int a = 0; a < 6; a++) for (int b = a; b < 6; b++) { HTH36[6 * a + b] = out[u]; HTH36[6 * b + a] = out[u]; u++; }
+  for (int a = 0; a < 6; a++) HTz6[a] = out[21 + a];
+  const int sy[9] = {27, 28, 29, 28, 30, 31, 29, 31, 32};
+  for (int k = 0; k < 9; k++) nnt9[k] = out[sy[k]];
+  *match_num = int64_t(out[33] + 0.5);
   return VXS_OK;
 }

@@ -10,6 +10,7 @@
 // key of every layer"; the octant path follows the reference's comparisons and float quarter lengths exactly (same routine as the map
 // build), so the point -> leaf assignment is bit-exact.
 #include <algorithm>
+#include <cmath>
 #include <vector>
 #include "vxs_internal.h"
 #include "vxs_math.cuh"
@@ -99,6 +100,78 @@ __global__ void __launch_bounds__(256) k_odom_accumulate(const double* __restric
     if (flags) flags[i] = hit;
   }
   od_flush(acc, out);
+}
+
+// calcBodyVar + var_init (voxelslam.hpp:163-203): per point the range / bearing noise model in the sensor frame, then the extrinsic.
+// The float intermediates of the reference are kept: `float range`, `float range_var = range_inc * range_inc` (:167-168); dir_var =
+// pow(sin(DEG2RAD(degree_inc)), 2) is the same for every point and is computed on the host with the same libm calls.
+__global__ void __launch_bounds__(256) k_var_init(const float* __restrict__ pts, int stride, long long n, const double* __restrict__ ext /* R9 p3 */, float range_inc, double dir_var,
+                                                  double* __restrict__ pv) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* ap = pts + size_t(i) * stride;
+  double pb[3] = {(double)ap[0], (double)ap[1], (double)ap[2]};
+  if (pb[2] == 0) pb[2] = 0.0001;                                              // :165-166 (modifies pv.pnt itself)
+  const double nn = (pb[0] * pb[0] + pb[1] * pb[1]) + pb[2] * pb[2];
+  const float range = __double2float_rn(sqrt(nn));
+  const float range_var = __fmul_rn(range_inc, range_inc);
+  const double inv = sqrt(nn);
+  const double d[3] = {pb[0] / inv, pb[1] / inv, pb[2] / inv};                 // direction.normalize()
+  double b1[3] = {1.0, 1.0, -(d[0] + d[1]) / d[2]};
+  { const double l = sqrt((b1[0] * b1[0] + b1[1] * b1[1]) + b1[2] * b1[2]); b1[0] /= l; b1[1] /= l; b1[2] /= l; }
+  double b2[3] = {b1[1] * d[2] - b1[2] * d[1], b1[2] * d[0] - b1[0] * d[2], b1[0] * d[1] - b1[1] * d[0]};    // base_vector1.cross(direction)
+  { const double l = sqrt((b2[0] * b2[0] + b2[1] * b2[1]) + b2[2] * b2[2]); b2[0] /= l; b2[1] /= l; b2[2] /= l; }
+  // A = range * hat(direction) * [b1 b2]:  hat(d) v = d x v
+  const double r = (double)range;
+  const double A1[3] = {r * (d[1] * b1[2] - d[2] * b1[1]), r * (d[2] * b1[0] - d[0] * b1[2]), r * (d[0] * b1[1] - d[1] * b1[0])};
+  const double A2[3] = {r * (d[1] * b2[2] - d[2] * b2[1]), r * (d[2] * b2[0] - d[0] * b2[2]), r * (d[0] * b2[1] - d[1] * b2[0])};
+  double var[9];
+  const double rv = (double)range_var;
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+#pragma unroll
+    for (int b = 0; b < 3; b++) var[3 * a + b] = d[a] * rv * d[b] + (A1[a] * dir_var * A1[b] + A2[a] * dir_var * A2[b]);
+  // pv.pnt = ext.R * pv.pnt + ext.p;  pv.var = ext.R * pv.var * ext.R^T     (:199-200)
+  double* o = pv + 12 * i;
+#pragma unroll
+  for (int a = 0; a < 3; a++) o[a] = ((ext[3 * a] * pb[0] + ext[3 * a + 1] * pb[1]) + ext[3 * a + 2] * pb[2]) + ext[9 + a];
+  double t[9];
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+#pragma unroll
+    for (int b = 0; b < 3; b++) t[3 * a + b] = (ext[3 * a] * var[b] + ext[3 * a + 1] * var[3 + b]) + ext[3 * a + 2] * var[6 + b];
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+#pragma unroll
+    for (int b = 0; b < 3; b++) o[3 + 3 * a + b] = (t[3 * a] * ext[3 * b] + t[3 * a + 1] * ext[3 * b + 1]) + t[3 * a + 2] * ext[3 * b + 2];
+}
+// pvec_update (voxelslam.hpp:205-214): pv.var = R var R^T + phat rot_var phat^T + tsl_var (in place, pv.pnt stays in the body frame), pwld = R pnt + p
+__global__ void __launch_bounds__(256) k_pvec_update(double* __restrict__ pv, long long n, const double* __restrict__ st /* R9 p3 rotvar9 tslvar9 */, double* __restrict__ pwld) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double* p = pv + 12 * i;
+  const double x = p[0], y = p[1], z = p[2];
+  const double ph[9] = {0.0, -z, y, z, 0.0, -x, -y, x, 0.0};
+  double t[9], u[9];
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+#pragma unroll
+    for (int b = 0; b < 3; b++) {
+      t[3 * a + b] = (st[3 * a] * p[3 + b] + st[3 * a + 1] * p[6 + b]) + st[3 * a + 2] * p[9 + b];                       // R var
+      u[3 * a + b] = (ph[3 * a] * st[12 + b] + ph[3 * a + 1] * st[15 + b]) + ph[3 * a + 2] * st[18 + b];                 // phat rot_var
+    }
+  double o[9];
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+#pragma unroll
+    for (int b = 0; b < 3; b++)
+      o[3 * a + b] = (((t[3 * a] * st[3 * b] + t[3 * a + 1] * st[3 * b + 1]) + t[3 * a + 2] * st[3 * b + 2]) + ((u[3 * a] * ph[3 * b] + u[3 * a + 1] * ph[3 * b + 1]) + u[3 * a + 2] * ph[3 * b + 2])) +
+                     st[21 + 3 * a + b];
+#pragma unroll
+  for (int k = 0; k < 9; k++) p[3 + k] = o[k];
+  if (pwld) {
+    pwld[3 * i] = od_dot3(st[0], st[1], st[2], x, y, z, st[9]); pwld[3 * i + 1] = od_dot3(st[3], st[4], st[5], x, y, z, st[10]); pwld[3 * i + 2] = od_dot3(st[6], st[7], st[8], x, y, z, st[11]);
+  }
 }
 
 OdomScratch* odom_scratch(vxs_ctx* c) { if (!c->odom_scratch) c->odom_scratch = new OdomScratch(); return static_cast<OdomScratch*>(c->odom_scratch); }
@@ -207,5 +280,64 @@ extern "C" int vxs_odom_accumulate(vxs_ctx* ctx, const double* pv12, int64_t n, 
   const int sy[9] = {27, 28, 29, 28, 30, 31, 29, 31, 32};
   for (int k = 0; k < 9; k++) nnt9[k] = out[sy[k]];
   *match_num = int64_t(out[33] + 0.5);
+  return VXS_OK;
+}
+
+// ---------------------------------------------------------------- the ctx's resident scan (shared with vxs_map.cu)
+int vxs_odom_resident_scan(vxs_ctx* ctx, double** pv12_dev, long long* n) {
+  OdomScratch* s = odom_scratch(ctx);
+  *pv12_dev = s->pts.p; *n = s->n_pts;
+  return VXS_OK;
+}
+int vxs_odom_set_resident_scan(vxs_ctx* ctx, const double* pv12_host, long long n) {
+  OdomScratch* s = odom_scratch(ctx);
+  VXS_CUDA(ctx, s->pts.reserve(size_t(std::max<long long>(n, 1)) * 12));
+  if (n) VXS_CUDA(ctx, cudaMemcpyAsync(s->pts.p, pv12_host, size_t(n) * 96, cudaMemcpyHostToDevice, ctx->stream));
+  s->n_pts = n;
+  return VXS_OK;
+}
+
+extern "C" int vxs_var_init(vxs_ctx* ctx, const float* pts, int stride_floats, int64_t n, const double* ext_R9, const double* ext_p3, double dept_err, double beam_err, double* pv12_out) {
+  if (!ctx || n < 0 || (n > 0 && !pts) || stride_floats < 3 || !ext_R9 || !ext_p3) return VXS_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  OdomScratch* s = odom_scratch(ctx);
+  VXS_CUDA(ctx, s->pts.reserve(size_t(std::max<int64_t>(n, 1)) * 12));
+  VXS_CUDA(ctx, s->st.reserve(30));
+  s->n_pts = n;
+  if (n == 0) return VXS_OK;
+  VXS_CUDA(ctx, ctx->stage.reserve((size_t(n) * stride_floats + 1) / 2 + 1));
+  float* raw = reinterpret_cast<float*>(ctx->stage.p);
+  VXS_CUDA(ctx, cudaMemcpyAsync(raw, pts, size_t(n) * stride_floats * 4, cudaMemcpyHostToDevice, ctx->stream));
+  double ext[12];
+  for (int k = 0; k < 9; k++) ext[k] = ext_R9[k];
+  for (int k = 0; k < 3; k++) ext[9 + k] = ext_p3[k];
+  VXS_CUDA(ctx, cudaMemcpyAsync(s->st.p, ext, sizeof ext, cudaMemcpyHostToDevice, ctx->stream));
+  // calcBodyVar takes `const float range_inc, const float degree_inc` (:163): the doubles narrow at the call; DEG2RAD(x) = ((x)*0.017453293) (pcl_macros.h)
+  const float range_inc = float(dept_err), degree_inc = float(beam_err);
+  const double dir_var = std::pow(std::sin(double(degree_inc) * 0.017453293), 2);
+  VXS_LAUNCH(ctx, "k_var_init", k_var_init, unsigned((n + 255) / 256), 256, 0, raw, stride_floats, (long long)n, s->st.p, range_inc, dir_var, s->pts.p);
+  if (pv12_out) VXS_CUDA(ctx, cudaMemcpyAsync(pv12_out, s->pts.p, size_t(n) * 96, cudaMemcpyDeviceToHost, ctx->stream));
+  VXS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return VXS_OK;
+}
+
+extern "C" int vxs_pvec_update(vxs_ctx* ctx, const double* pv12, int64_t n, const double* pose12, const double* rot_var9, const double* tsl_var9, double* pv12_out, double* pwld_out) {
+  if (!ctx || n < 0 || !pose12 || !rot_var9 || !tsl_var9) return VXS_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  OdomScratch* s = odom_scratch(ctx);
+  if (pv12) { int rc = vxs_odom_set_resident_scan(ctx, pv12, n); if (rc) return rc; }
+  else if (n != s->n_pts) return vxs_fail(ctx, VXS_ERR_ARG, "vxs_pvec_update: no resident scan of this size");
+  if (n == 0) return VXS_OK;
+  double st[30];
+  for (int k = 0; k < 12; k++) st[k] = pose12[k];
+  for (int k = 0; k < 9; k++) { st[12 + k] = rot_var9[k]; st[21 + k] = tsl_var9[k]; }
+  VXS_CUDA(ctx, s->st.reserve(30));
+  VXS_CUDA(ctx, cudaMemcpyAsync(s->st.p, st, sizeof st, cudaMemcpyHostToDevice, ctx->stream));
+  double* pw = nullptr;
+  if (pwld_out) { VXS_CUDA(ctx, ctx->stage.reserve(size_t(n) * 3)); pw = ctx->stage.p; }
+  VXS_LAUNCH(ctx, "k_pvec_update", k_pvec_update, unsigned((n + 255) / 256), 256, 0, s->pts.p, (long long)n, s->st.p, pw);
+  if (pv12_out) VXS_CUDA(ctx, cudaMemcpyAsync(pv12_out, s->pts.p, size_t(n) * 96, cudaMemcpyDeviceToHost, ctx->stream));
+  if (pwld_out) VXS_CUDA(ctx, cudaMemcpyAsync(pwld_out, pw, size_t(n) * 24, cudaMemcpyDeviceToHost, ctx->stream));
+  VXS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return VXS_OK;
 }

@@ -92,7 +92,8 @@ __global__ void __launch_bounds__(RS_TE + 32) k_residual_stream(FactorView f, co
         const unsigned int ph = (tc / unsigned(nstages)) & 1u;
         double* col = reinterpret_cast<double*>(stage_base + size_t(s) * RS_STAGE_BYTES);
         const int* frs = reinterpret_cast<const int*>(col + 10 * RS_COL);
-        mbar_wait(full + s, ph);
+        if (lane == 0) mbar_wait(full + s, ph);      // one lane polls (a polling warp costs issue slots the working warps need), the rest of the warp parks at the warp barrier
+        __syncwarp();
         // ---- phase A: transform the entry in place
         const int e = t0 + tid;
         if (e >= B0 && e < B1) {
@@ -191,7 +192,8 @@ __global__ void __launch_bounds__(RS_TE + 32) k_residual_stream(FactorView f, co
 template <bool SP, int TE>
 static int launch_resid(vxs_ctx* ctx, vxs_factor* f, const double* poses_dev, int pstride, double* residual_dev, int* ran) {
   constexpr int COL = TE + RS_COLPAD, STAGE_BYTES = 10 * COL * 8 + TE * 4;
-  const int per_sm = TE >= 512 ? 1 : (TE >= 256 ? 2 : 4);
+  // measured at the metric shape (us): TE 512 x 1 CTA/SM x 4 stages 98; 256 x 2 x 4: 81-85; 128 x 4 x 3: 79-81; 256 x 3 x 2: 76 (default); 128 x 6 x 2: 99
+  const int per_sm = TE >= 512 ? 1 : (ctx->resid_per_sm > 0 ? ctx->resid_per_sm : (TE >= 256 ? 2 : 4));
   const int G = ctx->sm_count * per_sm;
   // batches: about 96 voxels each, an equal number per CTA
   const long long V = f->V;
@@ -202,7 +204,7 @@ static int launch_resid(vxs_ctx* ctx, vxs_factor* f, const double* poses_dev, in
   ResidPlan pl; pl.V = int(V); pl.VB = int(VB); pl.nbatch = int((V + VB - 1) / VB); pl.vbcap = int((VB + 7) & ~7ll);
   const size_t fixed = size_t(pl.vbcap) * 80 + size_t(pl.vbcap + 8) * 4 + size_t(TE) * 8 + 2 * RS_MAX_STAGES * 8 + (SP ? size_t(12) * f->W * 8 : 0) + 128;
   const size_t budget = size_t(ctx->smem_optin) / per_sm - (per_sm > 1 ? 1024 : 0);   // per-CTA share (1 KB per CTA is reserved by the driver)
-  int nstages = RS_MAX_STAGES;
+  int nstages = std::min(RS_MAX_STAGES, std::max(2, ctx->resid_stages));
   while (nstages > 2 && size_t(nstages) * STAGE_BYTES + fixed > budget) nstages--;
   if (size_t(nstages) * STAGE_BYTES + fixed > budget) return VXS_OK;
   const size_t smem = size_t(nstages) * STAGE_BYTES + fixed;
