@@ -193,6 +193,24 @@ int vxs_hba_window(vxs_ctx* ctx, const vxs_map_params* coarse, const vxs_map_par
                    int stride_floats, const int64_t* kf_offsets, double* poses12, int W, int max_iter, int thread_num,
                    double* hess_out, double* resis_log, int* outer_iters);
 
+/* The BOTTOM level of the hierarchical global BA as one batch: thd_globalmapping (voxelslam.cpp:2484-2557) calls
+ *     HBA_add_edge(xs, smp_local, gba_edges1, mps, max_iter = 1, thread_num = 2, plptr)
+ * once per window of win_size = 10 keyframes (stride mgsize = 5): with max_iter = 1 that is ONE map build with the fine parameters
+ * (:2362-2372), OctreeGBA_multi_recut, Lidar_BA_Optimizer::damping_iter(up = 4) and the PGO edges (:2405-2427) — hundreds of independent
+ * 6*win_size-dof problems.  Here all windows of a chunk are built, solved (LM loop on the device, block-diagonal Hessian, one CTA per window
+ * for the solve) and read back together.  Windows are independent, so a multi-GPU run simply gives every rank its share of `win_first`.
+ *   xyz / kf_offsets / poses12: all K keyframes (clouds as in vxs_build_gba_factor, poses = the keyframes' x0); win_first[w] = first keyframe of window w.
+ *   max_points_per_chunk (<= 0: default 96 Mi): bound on the points of the windows processed together (device memory).
+ *   poses_out [nwin][win_size][12]: the windows' refined copies of the poses (the keyframes themselves are not moved, as in the reference);
+ *   resis [nwin][2]; status [nwin]: 0, VXS_WARN_SINGULAR or VXS_ERR_TOO_FEW_VOXELS (the reference would exit(0), voxel_map.hpp:345-348 — such a
+ *   window keeps its poses); is_converge / lm_iters [nwin]; edges: for pair p = (i, j), i < j in lexicographic order, P = win_size (win_size - 1) / 2
+ *   per window: edge_valid [nwin][P], edge_v6 [nwin][P][6], edge_rot [nwin][P][9], edge_tra [nwin][P][3]; hess_out (may be NULL)
+ *   [nwin][(6 win_size)^2] column-major raw Hessians.  Every output but poses_out may be NULL.
+ * The submap merge of the reference's post-step (:2428-2447) stays a per-window call (vxs_submap_merge). */
+int vxs_hba_bottom_batch(vxs_ctx* ctx, const vxs_map_params* fine, const float* xyz, int stride_floats, const int64_t* kf_offsets, const double* poses12, int K,
+                         const int32_t* win_first, int nwin, int win_size, int thread_num, int64_t max_points_per_chunk, double* poses_out, double* resis, int32_t* status,
+                         int32_t* is_converge, int32_t* lm_iters, int32_t* edge_valid, double* edge_v6, double* edge_rot, double* edge_tra, double* hess_out);
+
 /* PGO edge extraction of HBA_add_edge (voxelslam.cpp:2405-2427) from the raw Hessian of the LAST vxs_lidar_ba / vxs_hba_window
  * on this ctx, without downloading the Hessian: for every pair i<j whose six diagonal entries of block (i,j) are all >= 1e-6 in
  * magnitude, one edge with variance v6[k] = 1/|H(6i+k, 6j+k)|, rot = R_i^T R_j (row-major), tra = R_i^T (p_j - p_i).

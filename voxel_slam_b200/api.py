@@ -362,6 +362,32 @@ Context.odom_set_planes = _odom_set_planes
 Context.odom_accumulate = _odom_accumulate
 
 
+def _hba_bottom_batch(self, fine, xyz_f32, kf_offsets, poses12, win_first, win_size=10, thread_num=2, stride_floats=None, max_points_per_chunk=0, want_hess=False):
+    """vxs_hba_bottom_batch: the bottom level of the hierarchical global BA (one HBA_add_edge(max_iter=1) per window) for all windows at once."""
+    x = np.ascontiguousarray(xyz_f32, dtype=np.float32)
+    stride = int(stride_floats) if stride_floats else (x.shape[1] if x.ndim == 2 else 3)
+    off = np.ascontiguousarray(kf_offsets, dtype=np.int64)
+    p = _f64(poses12).reshape(-1, 12)
+    K = p.shape[0]
+    wf = np.ascontiguousarray(win_first, dtype=np.int32)
+    nw, P, n = wf.shape[0], win_size * (win_size - 1) // 2, 6 * win_size
+    out = dict(poses=np.zeros((nw, win_size, 12)), resis=np.zeros((nw, 2)), status=np.zeros(nw, dtype=np.int32), is_converge=np.zeros(nw, dtype=np.int32),
+               lm_iters=np.zeros(nw, dtype=np.int32), edge_valid=np.zeros((nw, P), dtype=np.int32), edge_v6=np.zeros((nw, P, 6)), edge_rot=np.zeros((nw, P, 9)),
+               edge_tra=np.zeros((nw, P, 3)), hess=np.zeros((nw, n * n)) if want_hess else None)
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+    rc = self._check(lib().vxs_hba_bottom_batch(self._p, C.byref(fine), x.ctypes.data_as(C.POINTER(C.c_float)), C.c_int(stride), off.ctypes.data_as(C.POINTER(C.c_int64)), _dp(p), C.c_int(K),
+                                                ip(wf), C.c_int(nw), C.c_int(win_size), C.c_int(thread_num), C.c_int64(max_points_per_chunk), _dp(out["poses"]), _dp(out["resis"]),
+                                                ip(out["status"]), ip(out["is_converge"]), ip(out["lm_iters"]), ip(out["edge_valid"]), _dp(out["edge_v6"]), _dp(out["edge_rot"]),
+                                                _dp(out["edge_tra"]), _dp(out["hess"])))
+    out["rc"] = rc
+    if want_hess:
+        out["hess"] = out["hess"].reshape(nw, n, n).transpose(0, 2, 1)      # column-major -> [w][row][col]
+    return out
+
+
+Context.hba_bottom_batch = _hba_bottom_batch
+
+
 def _submap_merge(self, xyz_f32, kf_offsets, poses12, voxel_size, stride_floats=None):
     """Submap merge of HBA_add_edge (voxelslam.cpp:2428-2447): clouds into the frame of keyframe 0 + down_sampling_voxel."""
     x = np.ascontiguousarray(xyz_f32, dtype=np.float32)

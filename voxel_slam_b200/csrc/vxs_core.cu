@@ -209,7 +209,7 @@ static void factor_free_arrays(vxs_factor* f) {
 }
 static void vxs_factor_release_device(vxs_factor* f) {
   factor_free_arrays(f);
-  f->X.release(); f->C.release(); f->gD.release(); f->partial.release(); f->counter.release(); f->cache_copy.release(); f->sk_tab.release(); f->vc.release();
+  f->vwin.release(); f->X.release(); f->C.release(); f->gD.release(); f->partial.release(); f->counter.release(); f->cache_copy.release(); f->sk_tab.release(); f->vc.release();
   for (int c = 0; c < vxs_factor::UP_MAX; c++) if (f->up_ev[c]) { cudaEventDestroy(f->up_ev[c]); f->up_ev[c] = nullptr; }
   if (f->up_fence) { cudaEventDestroy(f->up_fence); f->up_fence = nullptr; }
   f->up_pending = f->up_n = 0;
@@ -231,7 +231,7 @@ extern "C" int vxs_factor_destroy(vxs_factor* f) {
 extern "C" int vxs_factor_clear(vxs_factor* f) {
   if (!f || !f->ctx) return VXS_ERR_ARG;
   int rc = vxs_factor_wait_uploads(f);   // an upload still in flight targets the arrays the next push will write
-  f->V = 0; f->E = 0; f->has_fix = false;
+  f->V = 0; f->E = 0; f->has_fix = false; f->block_W = 0;
   return rc;
 }
 extern "C" int vxs_factor_set_win_size(vxs_factor* f, int w) { if (!f || w <= 0 || f->V != 0) return VXS_ERR_ARG; f->W = w; return VXS_OK; }

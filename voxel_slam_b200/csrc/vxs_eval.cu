@@ -198,7 +198,8 @@ __device__ __forceinline__ void xt_store_zero(double* X, int v, int f0, int nfra
 // handles has the same frame for (almost) every voxel, so the flush happens a handful of times per thread instead of once per
 // entry; in sparse global-BA windows it degenerates gracefully to the per-entry scatter (where contention is low anyway).
 template <int G, bool DENSE>
-__global__ void __launch_bounds__(128, 3) k_jac(FactorView f, const double* __restrict__ poses, int pstride, double* __restrict__ X, double* __restrict__ gD) {
+__global__ void __launch_bounds__(128, 3) k_jac(FactorView f, const double* __restrict__ poses, int pstride, double* __restrict__ X, double* __restrict__ gD,
+                                                const int32_t* __restrict__ vwin, const int* __restrict__ build_mask) {   // batch: voxels of windows with build_mask == 0 are skipped
   __shared__ double acc[30][128];   // per-thread running sums for the thread's current frame (column = thread: conflict-free)
   const int tid = threadIdx.x;
   const int lane = tid & (G - 1);
@@ -211,6 +212,7 @@ __global__ void __launch_bounds__(128, 3) k_jac(FactorView f, const double* __re
 #pragma unroll
   for (int i = 0; i < 30; i++) acc[i][tid] = 0.0;
   for (int v = group; v < f.V; v += ngroups) {
+    if (build_mask && !build_mask[vwin[v]]) continue;
     const int beg = f.ptr[v], end = f.ptr[v + 1];
     if (DENSE && beg == end && lane == 0) xt_store_zero(X, v, 0, W, 6 * W);
     if (beg + lane >= end) continue;
@@ -380,6 +382,43 @@ __global__ void __launch_bounds__(128) k_pairs(FactorView f, const double* __res
       atomicAdd(C + size_t(6 * fb + c) * nl + 6 * fa + r, -val);
     }
   }
+}
+
+// Batch of independent windows (vxs_hba_bottom_batch): frames are global (window * WB + slot), a voxel only touches its own window, so the
+// pair blocks go to that window's (6 WB)^2 block of a block-diagonal accumulator instead of a (6 W_total)^2 matrix.
+template <int G>
+__global__ void __launch_bounds__(128) k_pairs_bd(FactorView f, const double* __restrict__ X, double* __restrict__ Cbd, int WB, const int32_t* __restrict__ vwin, const int* __restrict__ build_mask) {
+  const int lane = threadIdx.x & (G - 1);
+  const int group = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+  const int ngroups = (gridDim.x * blockDim.x) / G;
+  const int nb = 6 * WB;
+  for (int v = group; v < f.V; v += ngroups) {
+    const int win = vwin[v];
+    if (build_mask && !build_mask[win]) continue;
+    const int beg = f.ptr[v], k = f.ptr[v + 1] - beg;
+    const int total = k * k * 36;
+    double* C = Cbd + size_t(win) * nb * nb;
+    const int fbase = win * WB;
+    for (int idx = lane; idx < total; idx += G) {
+      const int a = idx / (36 * k), rem = idx - a * 36 * k, b = rem / 36, el = rem - b * 36;
+      if (b < a) continue;
+      const int r = el / 6, c = el - r * 6;
+      const double* xa = X + size_t(beg + a) * 18 + r;
+      const double* xb = X + size_t(beg + b) * 18 + c;
+      const double val = xa[0] * xb[0] + xa[6] * xb[6] + xa[12] * xb[12];
+      const int fa = __ldg(f.frame + beg + a) - fbase, fb = __ldg(f.frame + beg + b) - fbase;
+      atomicAdd(C + size_t(6 * fb + c) * nb + 6 * fa + r, -val);
+    }
+  }
+}
+// zero the accumulators of the windows that are rebuilt: Cbd block, g (6 per frame), D (24 per frame)
+__global__ void __launch_bounds__(256) k_bd_zero(double* __restrict__ Cbd, double* __restrict__ gD, int WB, int nwin, const int* __restrict__ build_mask) {
+  const int win = blockIdx.x;
+  if (build_mask && !build_mask[win]) return;
+  const int nb = 6 * WB, Wt = nwin * WB;
+  for (int i = threadIdx.x; i < nb * nb; i += blockDim.x) Cbd[size_t(win) * nb * nb + i] = 0.0;
+  for (int i = threadIdx.x; i < WB * 6; i += blockDim.x) gD[size_t(win) * WB * 6 + i] = 0.0;
+  for (int i = threadIdx.x; i < WB * 24; i += blockDim.x) gD[size_t(Wt) * 6 + size_t(win) * WB * 24 + i] = 0.0;
 }
 
 // ------------------------------------------------------------------ Hessian part 2b: dense windows, SYRK on the fp64 tensor cores
@@ -572,7 +611,7 @@ __global__ void __launch_bounds__(SY_THREADS, 2) k_syrk(const double* __restrict
 //   * a diagonal tile stages its part once (parts I and J are the same columns).
 #define SYB_STAGES 5
 __global__ void __launch_bounds__(SY_THREADS, 2) k_syrk_bulk(const double* __restrict__ XT, double* __restrict__ C, int g_first, int ngroups_vox, int W, SyrkGeom g, int groups_per_chunk) {
-  extern __shared__ __align__(128) double smem[];
+  extern __shared__ __align__(16) double smem[];
   __shared__ __align__(8) uint64_t bars[2 * SYB_STAGES];
   uint64_t* full = bars; uint64_t* empty = bars + SYB_STAGES;
   const int tile = int(blockIdx.x % g.ntiles), chunk = int(blockIdx.x / g.ntiles);
@@ -1086,7 +1125,7 @@ int vxs_eval_hessian_dev(vxs_ctx* ctx, vxs_factor* f, const double* poses_dev, i
     const int GJ = pick_group_jac(f);
     unsigned gridj = unsigned(std::min<size_t>((size_t(f->V) * GJ + 127) / 128, size_t(ctx->sm_count) * 8));
     unsigned grid = unsigned(std::min<size_t>((size_t(f->V) * G + 127) / 128, size_t(ctx->sm_count) * 16));
-#define LAUNCH_JAC(GG, DD) { auto kp = k_jac<GG, DD>; VXS_LAUNCH(ctx, "k_jac", kp, gridj, 128, 0, fv, poses_dev, pstride, f->X.p, gD); }
+#define LAUNCH_JAC(GG, DD) { auto kp = k_jac<GG, DD>; VXS_LAUNCH(ctx, "k_jac", kp, gridj, 128, 0, fv, poses_dev, pstride, f->X.p, gD, (const int32_t*)nullptr, (const int*)nullptr); }
     // First build after vxs_factor_push_voxels_async: the clusters are still arriving in chunks of voxel groups; run the Jacobian and the
     // SYRK chunk by chunk behind the upload events so that the PCIe transfer overlaps them (both kernels only accumulate: RED into C, g, D).
     const bool chunked = f->up_pending > 0 && dense && W <= 128;
@@ -1174,6 +1213,28 @@ int vxs_eval_hessian_dev(vxs_ctx* ctx, vxs_factor* f, const double* poses_dev, i
     { auto kp = k_eig_residual<false>; VXS_LAUNCH(ctx, "k_lambda_sum", kp, blocks_v, 256, 0, fv, f->partial.p, f->counter.p, r1); }
   }
   if (ctx->nranks > 1) return vxs_comm_allreduce(ctx, C, tot);
+  return VXS_OK;
+}
+
+// Block-diagonal Hessian build of a batch of windows: Cbd = [nwin][(6 WB)^2] (upper block triangle, as C), gD = g [W_total][6] | D [W_total][24],
+// both zeroed and rebuilt only for the windows with build_mask != 0 (device flags; nullptr = all).  Uses the cached eig / sum like acc_evaluate2.
+int vxs_eval_hessian_bd_dev(vxs_ctx* ctx, vxs_factor* f, const double* poses_dev, int pstride, const int* build_mask_dev, double* Cbd, double* gD) {
+  const int WB = f->block_W;
+  if (WB <= 0 || !f->vwin.p) return vxs_fail(ctx, VXS_ERR_ARG, "not a batch factor");
+  const int nwin = f->W / WB;
+  VXS_LAUNCH(ctx, "k_bd_zero", k_bd_zero, unsigned(nwin), 256, 0, Cbd, gD, WB, nwin, build_mask_dev);
+  if (f->V == 0) return VXS_OK;
+  FactorView fv = make_view(f);
+  VXS_CUDA(ctx, f->X.reserve(size_t(f->E) * 18));
+  VXS_CUDA(ctx, f->vc.reserve(size_t(8) * f->Vcap));
+  fv.vc = f->vc.p;
+  VXS_LAUNCH(ctx, "k_voxel_consts", k_voxel_consts, nblk(size_t(f->V), 256), 256, 0, fv, f->vc.p);
+  const int G = pick_group(f);
+  const unsigned grid = unsigned(std::min<size_t>((size_t(f->V) * G + 127) / 128, size_t(ctx->sm_count) * 16));
+#define LAUNCH_BD(GG) { auto kj = k_jac<GG, false>; VXS_LAUNCH(ctx, "k_jac", kj, grid, 128, 0, fv, poses_dev, pstride, f->X.p, gD, (const int32_t*)f->vwin.p, build_mask_dev); \
+                        auto kp = k_pairs_bd<GG>; VXS_LAUNCH(ctx, "k_pairs", kp, grid, 128, 0, fv, f->X.p, Cbd, WB, (const int32_t*)f->vwin.p, build_mask_dev); }
+  if (G == 32) LAUNCH_BD(32) else if (G == 16) LAUNCH_BD(16) else LAUNCH_BD(8)
+#undef LAUNCH_BD
   return VXS_OK;
 }
 

@@ -32,6 +32,19 @@ struct DevBuf {  // grow-only device buffer
     return e;
   }
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  // grow to n elements keeping the first `used` ones
+  cudaError_t reserve_keep(size_t n, size_t used, cudaStream_t st) {
+    if (n <= cap) return cudaSuccess;
+    size_t nc = cap ? cap : 1024;
+    while (nc < n) nc *= 2;
+    T* np = nullptr;
+    cudaError_t e = cudaMalloc((void**)&np, nc * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (p && used) { e = cudaMemcpyAsync(np, p, used * sizeof(T), cudaMemcpyDeviceToDevice, st); if (e == cudaSuccess) e = cudaStreamSynchronize(st); }
+    if (p) cudaFree(p);
+    p = np; cap = nc;
+    return e;
+  }
 };
 
 struct vxs_ctx {
@@ -98,6 +111,9 @@ struct vxs_factor {
   double* eig = nullptr;         // [12][Vcap]
   double* sum = nullptr;         // [10][Vcap]
   bool has_fix = false;
+  // batch of independent windows (vxs_hba_bottom_batch): W = nwin * block_W global frames, voxel v belongs to window vwin[v] and only touches that window's frames
+  int block_W = 0;
+  DevBuf<int32_t> vwin;
   // evaluation workspaces (sized lazily)
   DevBuf<double> X;              // scaled rank-3 rows: dense-slot [V][W][18] or compact [E][18]
   DevBuf<double> C;              // lidar Hessian accumulator, (6W)^2 column-major, upper block triangle
@@ -163,8 +179,9 @@ struct vxs_eval_out {
 };
 int vxs_eval_residual_dev(vxs_ctx* ctx, vxs_factor* f, const double* poses_dev, int pose_stride, double* residual_dev);
 int vxs_eval_hessian_dev(vxs_ctx* ctx, vxs_factor* f, const double* poses_dev, int pose_stride, double* r1_dev);
+int vxs_eval_hessian_bd_dev(vxs_ctx* ctx, vxs_factor* f, const double* poses_dev, int pstride, const int* build_mask_dev, double* Cbd, double* gD);
 int vxs_comm_allreduce(vxs_ctx* ctx, double* buf, size_t n);
-int vxs_residual_stream_launch(vxs_ctx* ctx, vxs_factor* f, const double* poses_dev, int pstride, double* residual_dev, int* ran);   // vxs_resid.cu
+int vxs_residual_stream_launch(vxs_ctx* ctx, vxs_factor* f, const double* poses_dev, int pstride, double* residual_dev, int* ran, double* rvox = nullptr);   // vxs_resid.cu
 
 // solver (vxs_solve.cu)
 int vxs_solve_damped(vxs_ctx* ctx, const double* Hraw, const double* jact, int n, int gauge, double u, double* dx_dev, double* D_dev, double* rhs_dev, int* singular_flag_host);

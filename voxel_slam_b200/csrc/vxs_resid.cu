@@ -29,7 +29,7 @@ struct ResidPlan { int V, VB, nbatch, vbcap; };   // vbcap = VB rounded up to 8:
 
 template <bool SP, int RS_TE>
 __global__ void __launch_bounds__(RS_TE + 32) k_residual_stream(FactorView f, const double* __restrict__ poses, int pstride, ResidPlan pl, int nstages, double* __restrict__ partial,
-                                                                     unsigned int* __restrict__ counter, double* __restrict__ result) {
+                                                                     unsigned int* __restrict__ counter, double* __restrict__ result, double* __restrict__ rvox) {
   constexpr int RS_CONS = RS_TE, RS_THREADS = RS_TE + 32, RS_COL = RS_TE + RS_COLPAD, RS_STAGE_BYTES = 10 * RS_COL * 8 + RS_TE * 4;
   extern __shared__ __align__(128) unsigned char rs_smem[];
   __shared__ int s_va[2], s_vb[2];   // by tile parity: a fast warp writes the next tile's values while a slow one still reads this tile's
@@ -162,7 +162,9 @@ __global__ void __launch_bounds__(RS_TE + 32) k_residual_stream(FactorView f, co
         double* eo = f.eig + v;
         eo[0] = w[0]; eo[st] = w[1]; eo[2 * st] = w[2];
         eo[3 * st] = u0.x; eo[4 * st] = u1.x; eo[5 * st] = u2.x; eo[6 * st] = u0.y; eo[7 * st] = u1.y; eo[8 * st] = u2.y; eo[9 * st] = u0.z; eo[10 * st] = u1.z; eo[11 * st] = u2.z;
-        rsum += f.coe[v] * w[0];
+        const double contrib = f.coe[v] * w[0];
+        if (rvox) rvox[v] = contrib;              // per-voxel residual for the per-window sums of a batch (vxs_hba_bottom_batch)
+        rsum += contrib;
       }
       named_bar_sync(1, RS_CONS);   // acc / sp_ptr are re-initialised for the next batch
     }
@@ -190,7 +192,7 @@ __global__ void __launch_bounds__(RS_TE + 32) k_residual_stream(FactorView f, co
 
 // *ran = 1 when the streaming kernel ran, 0 when the caller should use the two-kernel form (A/B switch VXS_RESID_STREAM=0, or no room in shared memory)
 template <bool SP, int TE>
-static int launch_resid(vxs_ctx* ctx, vxs_factor* f, const double* poses_dev, int pstride, double* residual_dev, int* ran) {
+static int launch_resid(vxs_ctx* ctx, vxs_factor* f, const double* poses_dev, int pstride, double* residual_dev, int* ran, double* rvox) {
   constexpr int COL = TE + RS_COLPAD, STAGE_BYTES = 10 * COL * 8 + TE * 4;
   // measured at the metric shape (us): TE 512 x 1 CTA/SM x 4 stages 98; 256 x 2 x 4: 81-85; 128 x 4 x 3: 79-81; 256 x 3 x 2: 76 (default); 128 x 6 x 2: 99
   const int per_sm = TE >= 512 ? 1 : (ctx->resid_per_sm > 0 ? ctx->resid_per_sm : (TE >= 256 ? 2 : 4));
@@ -214,16 +216,16 @@ static int launch_resid(vxs_ctx* ctx, vxs_factor* f, const double* poses_dev, in
   FactorView fv = make_view(f);
   auto kp = k_residual_stream<SP, TE>;
   VXS_CUDA(ctx, cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  VXS_LAUNCH(ctx, "k_residual_stream", kp, grid, TE + 32, smem, fv, poses_dev, pstride, pl, nstages, f->partial.p, f->counter.p, residual_dev);
+  VXS_LAUNCH(ctx, "k_residual_stream", kp, grid, TE + 32, smem, fv, poses_dev, pstride, pl, nstages, f->partial.p, f->counter.p, residual_dev, rvox);
   *ran = 1;
   return VXS_OK;
 }
-int vxs_residual_stream_launch(vxs_ctx* ctx, vxs_factor* f, const double* poses_dev, int pstride, double* residual_dev, int* ran) {
+int vxs_residual_stream_launch(vxs_ctx* ctx, vxs_factor* f, const double* poses_dev, int pstride, double* residual_dev, int* ran, double* rvox) {
   *ran = 0;
-  if (!ctx->resid_stream || f->V <= 0 || (f->Ecap & 3)) return VXS_OK;
+  if ((!ctx->resid_stream && !rvox) || f->V <= 0 || (f->Ecap & 3)) return VXS_OK;
   const bool spm = f->W <= POSE_SMEM_MAX_W && f->W <= 256;
   const int te = ctx->resid_te;
-#define RS_GO(SPV, TEV) return launch_resid<SPV, TEV>(ctx, f, poses_dev, pstride, residual_dev, ran)
+#define RS_GO(SPV, TEV) return launch_resid<SPV, TEV>(ctx, f, poses_dev, pstride, residual_dev, ran, rvox)
   if (spm) { if (te >= 512) RS_GO(true, 512); if (te >= 256) RS_GO(true, 256); RS_GO(true, 128); }
   if (te >= 512) RS_GO(false, 512); if (te >= 256) RS_GO(false, 256); RS_GO(false, 128);
 #undef RS_GO

@@ -26,7 +26,7 @@ using namespace vxs;
 
 // ------------------------------------------------------------------ scratch
 struct VoxScratch : SortScratch {   // SortScratch: hist, blocksums, totals (vxs_sortscan.cuh)
-  DevBuf<double> pts_d; DevBuf<float> pts_f, pts_f2; DevBuf<double> poses; DevBuf<long long> offsets; DevBuf<long long> bbox;
+  DevBuf<double> pts_d; DevBuf<float> pts_f, pts_f2; DevBuf<double> poses; DevBuf<long long> offsets, src_off; DevBuf<long long> bbox;
   DevBuf<unsigned long long> keysA, keysB; DevBuf<unsigned int> idxA, idxB; DevBuf<unsigned short> pathbits;
   DevBuf<unsigned int> flags, scanbuf;
   DevBuf<unsigned int> rec_start, node_of_rec, node_rec_start, rec_node_flag;
@@ -42,7 +42,7 @@ static VoxScratch* scratch(vxs_ctx* c) { if (!c->vox_scratch) c->vox_scratch = n
 void vxs_voxelize_release(vxs_ctx* c) {
   if (!c->vox_scratch) return;
   VoxScratch* s = static_cast<VoxScratch*>(c->vox_scratch);
-  s->pts_d.release(); s->pts_f.release(); s->pts_f2.release(); s->poses.release(); s->offsets.release(); s->bbox.release(); s->keysA.release(); s->keysB.release();
+  s->pts_d.release(); s->pts_f.release(); s->pts_f2.release(); s->poses.release(); s->offsets.release(); s->src_off.release(); s->bbox.release(); s->keysA.release(); s->keysB.release();
   s->idxA.release(); s->idxB.release(); s->pathbits.release(); s->hist.release(); s->flags.release(); s->scanbuf.release(); s->blocksums.release();
   s->totals.release(); s->rec_start.release(); s->node_of_rec.release(); s->node_rec_start.release(); s->rec_node_flag.release(); s->rec_key.release();
   s->rec_local.release(); s->rec_world.release();
@@ -95,8 +95,13 @@ struct PointSrc {
   const double* poses;                             // [nframes][12]
   int nframes;
   long long n;
+  // batch mode (many independent windows in one build, vxs_hba_bottom_batch): a "frame" is a (window, slot) pair, frame = window * win_size + slot;
+  // the index space is the concatenation of the windows' clouds, src_off[frame] = first point of that keyframe in the point array (keyframes
+  // shared by overlapping windows are stored once).  win_size == 0: one window, the index space IS the point array.
+  const long long* src_off; int win_size;
 };
-__device__ __forceinline__ d3 load_point(const PointSrc& s, long long i) {
+__device__ __forceinline__ d3 load_point(const PointSrc& s, long long i, int fr) {
+  if (s.src_off) i = s.src_off[fr] + (i - s.offsets[fr]);
   if (s.pd) return mk3(s.pd[3 * i], s.pd[3 * i + 1], s.pd[3 * i + 2]);
   const float* p = s.pf + size_t(i) * s.fstride;
   return mk3((double)p[0], (double)p[1], (double)p[2]);
@@ -119,7 +124,7 @@ __global__ void __launch_bounds__(256) k_bbox(PointSrc s, double voxel_size, lon
   long long mn[3] = {LLONG_MAX, LLONG_MAX, LLONG_MAX}, mx[3] = {LLONG_MIN, LLONG_MIN, LLONG_MIN};
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < s.n; i += (long long)gridDim.x * blockDim.x) {
     const int fr = frame_of(s, i);
-    const d3 w = world_point(s.poses + 12 * fr, load_point(s, i));
+    const d3 w = world_point(s.poses + 12 * fr, load_point(s, i, fr));
     const long long k[3] = {quantise(w.x, voxel_size), quantise(w.y, voxel_size), quantise(w.z, voxel_size)};
     for (int a = 0; a < 3; a++) { mn[a] = min(mn[a], k[a]); mx[a] = max(mx[a], k[a]); }
   }
@@ -131,15 +136,17 @@ __global__ void __launch_bounds__(256) k_bbox(PointSrc s, double voxel_size, lon
 
 // key0 = (linear root id << FB) | frame ; pathbits = octants of the deeper layers
 __global__ void __launch_bounds__(256) k_point_keys(PointSrc s, double voxel_size, int max_layer, long long minx, long long miny, long long minz, long long ey, long long ez,
-                                                    int FB, unsigned long long* __restrict__ keys, unsigned int* __restrict__ idx, unsigned short* __restrict__ pathbits,
+                                                    long long cells, int FB, unsigned long long* __restrict__ keys, unsigned int* __restrict__ idx, unsigned short* __restrict__ pathbits,
                                                     int shard_rank, int shard_n, unsigned int* __restrict__ owned) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= s.n) return;
   const int fr = frame_of(s, i);
-  const d3 w = world_point(s.poses + 12 * fr, load_point(s, i));
+  const d3 w = world_point(s.poses + 12 * fr, load_point(s, i, fr));
   const long long kx = quantise(w.x, voxel_size), ky = quantise(w.y, voxel_size), kz = quantise(w.z, voxel_size);
-  const unsigned long long lin = (unsigned long long)(((kx - minx) * ey + (ky - miny)) * ez + (kz - minz));
-  keys[i] = (lin << FB) | (unsigned long long)fr;
+  unsigned long long lin = (unsigned long long)(((kx - minx) * ey + (ky - miny)) * ez + (kz - minz));
+  int slot = fr;
+  if (s.win_size > 0) { const int win = fr / s.win_size; slot = fr - win * s.win_size; lin += (unsigned long long)win * (unsigned long long)cells; }   // every window has its own copy of the cell space
+  keys[i] = (lin << FB) | (unsigned long long)slot;
   idx[i] = (unsigned int)i;
   pathbits[i] = (unsigned short)octant_bits(w, kx, ky, kz, voxel_size, max_layer);
   // multi-GPU: a root cell (and its whole octree) belongs to rank hash(VOXEL_LOC) mod n  
@@ -166,12 +173,13 @@ __global__ void __launch_bounds__(256) k_rec_clusters(PointSrc s, const unsigned
     const bool valid = r < R;
     unsigned int beg = 0, end = 0; int fr = 0;
     if (valid) { beg = rec_start[r]; end = rec_start[r + 1]; fr = int(rec_key[r] & ((1ull << FB) - 1ull)); }
+    if (valid && s.win_size > 0 && end > beg) fr = frame_of(s, idx[beg]);        // batch mode: the key holds the slot, the (window, slot) frame follows from any point of the record
     const double* pose = s.poses + 12 * fr;
     double a[20];
 #pragma unroll
     for (int k = 0; k < 20; k++) a[k] = 0.0;
     for (unsigned int j = beg + lane; j < end; j += G) {
-      const d3 p = load_point(s, idx[j]);
+      const d3 p = load_point(s, idx[j], fr);
       const d3 w = world_point(pose, p);
       a[0] += p.x * p.x; a[1] += p.x * p.y; a[2] += p.x * p.z; a[3] += p.y * p.y; a[4] += p.y * p.z; a[5] += p.z * p.z; a[6] += p.x; a[7] += p.y; a[8] += p.z; a[9] += 1.0;
       a[10] += w.x * w.x; a[11] += w.x * w.y; a[12] += w.x * w.z; a[13] += w.y * w.y; a[14] += w.y * w.z; a[15] += w.z * w.z; a[16] += w.x; a[17] += w.y; a[18] += w.z; a[19] += 1.0;
@@ -245,6 +253,7 @@ __global__ void __launch_bounds__(128) k_node_decide(DecideParams dp, unsigned i
 struct FactorOut {
   int32_t* ptr; int32_t* frame; int32_t* vox; double* cl; size_t Ecap; double* fix; double* coe; double* eig; double* sum; size_t Vcap;
   long long V0, E0;
+  int32_t* vwin; long long cells; int win_size;      // batch mode: window of every voxel; entry frames become window * win_size + slot
 };
 // LidarFactor::push_voxel for every selected node, straight into the device CSR
 __global__ void __launch_bounds__(128) k_emit_factor(FactorOut fo, unsigned int Nn, int W, int FB, const unsigned int* __restrict__ sel, const unsigned int* __restrict__ voff,
@@ -259,10 +268,12 @@ __global__ void __launch_bounds__(128) k_emit_factor(FactorOut fo, unsigned int 
   long long e = fo.E0 + eoff[nd];
   fo.ptr[v] = int32_t(e);
   const unsigned long long fmask = (1ull << FB) - 1ull;
+  int fbase = 0;
+  if (fo.win_size > 0) { const int win = int(root[nd] / fo.cells); fbase = win * fo.win_size; fo.vwin[v] = win; }
   for (unsigned int r = node_rec_start[nd]; r < node_rec_start[nd + 1]; r++) {
     const int fr = int(rec_key[r] & fmask);
     if (fr >= W) continue;
-    fo.frame[e] = fr; fo.vox[e] = int32_t(v);
+    fo.frame[e] = fbase + fr; fo.vox[e] = int32_t(v);
     for (int k = 0; k < 10; k++) fo.cl[size_t(k) * fo.Ecap + e] = rec_local[size_t(k) * Rcap + r];
     e++;
   }
@@ -270,7 +281,7 @@ __global__ void __launch_bounds__(128) k_emit_factor(FactorOut fo, unsigned int 
   for (int k = 0; k < 12; k++) fo.eig[size_t(k) * fo.Vcap + v] = eig[size_t(k) * Ncap + nd];
   fo.coe[v] = 1.0;   // voxel_map.hpp:1316, loop_refine.hpp:380
   if (ids) {
-    const long long lin = root[nd];
+    const long long lin = fo.win_size > 0 ? root[nd] % fo.cells : root[nd];
     const long long kz = lin % ez, ky = (lin / ez) % ey, kx = lin / (ez * ey);
     vxs_voxel_id id; id.x = kx + minx; id.y = ky + miny; id.z = kz + minz; id.layer = layer; id.path = path[nd];
     ids[v - fo.V0 + 0] = id;
@@ -300,8 +311,11 @@ __global__ void k_next_keys(const unsigned long long* __restrict__ keys, const u
 
 
 // ------------------------------------------------------------------ driver shared by the local map and the GBA map
+// Batch mode (bs != nullptr): `nframes` = nwin * win_size virtual frames; offsets_host = prefix over the virtual frames' point counts, bs->src_off_host = first point
+// of every virtual frame's keyframe in the uploaded point array (npts_total points), poses12_host = the nwin * win_size virtual-frame poses, W = win_size.
+struct BatchSpec { int nwin, win_size; const int64_t* src_off_host; int64_t npts_total; };
 static int build_factor(vxs_ctx* ctx, const vxs_map_params* mp, bool gba, const double* pts_d_host, const float* pts_f_host, int fstride, const int64_t* offsets_host, int nframes,
-                        const double* poses12_host, int W, vxs_factor* out, vxs_voxel_id* ids_out, int64_t ids_cap, int64_t* n_out) {
+                        const double* poses12_host, int W, vxs_factor* out, vxs_voxel_id* ids_out, int64_t ids_cap, int64_t* n_out, const BatchSpec* bs = nullptr) {
   if (!ctx || !mp || !out || !offsets_host || !poses12_host || out->ctx != ctx) return VXS_ERR_ARG;
   if (mp->max_layer < 0 || mp->max_layer > 3 || !(mp->voxel_size > 0)) return vxs_fail(ctx, VXS_ERR_ARG, "max_layer must be 0..3 and voxel_size > 0");
   cudaSetDevice(ctx->device);
@@ -310,18 +324,25 @@ static int build_factor(vxs_ctx* ctx, const vxs_map_params* mp, bool gba, const 
   const long long N = offsets_host[nframes];
   if (N >= (1ll << 32)) return vxs_fail(ctx, VXS_ERR_ARG, "more than 2^32 points in one build");
   vxs_factor_clear(out);
-  out->W = W;
+  out->W = bs ? bs->nwin * bs->win_size : W;        // batch: entry frames are global (window * win_size + slot)
+  out->block_W = bs ? bs->win_size : 0;
   if (n_out) *n_out = 0;
   VXS_CUDA(ctx, s->totals.reserve(16));
   if (N == 0) return VXS_OK;
-  const int FB = bits_for((unsigned long long)nframes);
+  const int FB = bits_for((unsigned long long)(bs ? bs->win_size : nframes));
   // ---- upload
-  PointSrc ps; ps.pd = nullptr; ps.pf = nullptr; ps.fstride = fstride; ps.nframes = nframes; ps.n = N;
-  if (pts_d_host) { VXS_CUDA(ctx, s->pts_d.reserve(size_t(N) * 3)); VXS_CUDA(ctx, cudaMemcpyAsync(s->pts_d.p, pts_d_host, size_t(N) * 24, cudaMemcpyHostToDevice, st)); ps.pd = s->pts_d.p; }
-  else { VXS_CUDA(ctx, s->pts_f.reserve(size_t(N) * fstride)); VXS_CUDA(ctx, cudaMemcpyAsync(s->pts_f.p, pts_f_host, size_t(N) * fstride * 4, cudaMemcpyHostToDevice, st)); ps.pf = s->pts_f.p; }
+  PointSrc ps; ps.pd = nullptr; ps.pf = nullptr; ps.fstride = fstride; ps.nframes = nframes; ps.n = N; ps.src_off = nullptr; ps.win_size = 0;
+  const long long Nup = bs ? bs->npts_total : N;     // points to upload (batch: every keyframe once, although most belong to two windows)
+  if (pts_d_host) { VXS_CUDA(ctx, s->pts_d.reserve(size_t(Nup) * 3)); VXS_CUDA(ctx, cudaMemcpyAsync(s->pts_d.p, pts_d_host, size_t(Nup) * 24, cudaMemcpyHostToDevice, st)); ps.pd = s->pts_d.p; }
+  else { VXS_CUDA(ctx, s->pts_f.reserve(size_t(Nup) * fstride)); VXS_CUDA(ctx, cudaMemcpyAsync(s->pts_f.p, pts_f_host, size_t(Nup) * fstride * 4, cudaMemcpyHostToDevice, st)); ps.pf = s->pts_f.p; }
+  if (bs) {
+    VXS_CUDA(ctx, s->src_off.reserve(size_t(nframes)));
+    VXS_CUDA(ctx, cudaMemcpyAsync(s->src_off.p, bs->src_off_host, size_t(nframes) * 8, cudaMemcpyHostToDevice, st));
+    ps.src_off = s->src_off.p; ps.win_size = bs->win_size;
+  }
   VXS_CUDA(ctx, s->poses.reserve(size_t(nframes) * 12));
-  VXS_CUDA(ctx, cudaMemcpyAsync(s->poses.p, poses12_host, size_t(W) * 96, cudaMemcpyHostToDevice, st));
-  if (nframes > W) { const double ident[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0}; VXS_CUDA(ctx, cudaMemcpyAsync(s->poses.p + size_t(W) * 12, ident, 96, cudaMemcpyHostToDevice, st)); }
+  VXS_CUDA(ctx, cudaMemcpyAsync(s->poses.p, poses12_host, size_t(bs ? nframes : W) * 96, cudaMemcpyHostToDevice, st));
+  if (!bs && nframes > W) { const double ident[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0}; VXS_CUDA(ctx, cudaMemcpyAsync(s->poses.p + size_t(W) * 12, ident, 96, cudaMemcpyHostToDevice, st)); }
   VXS_CUDA(ctx, s->offsets.reserve(size_t(nframes) + 1));
   VXS_CUDA(ctx, cudaMemcpyAsync(s->offsets.p, offsets_host, (size_t(nframes) + 1) * 8, cudaMemcpyHostToDevice, st));
   ps.offsets = s->offsets.p; ps.poses = s->poses.p;
@@ -334,17 +355,19 @@ static int build_factor(vxs_ctx* ctx, const vxs_map_params* mp, bool gba, const 
   VXS_CUDA(ctx, cudaMemcpyAsync(bb, s->bbox.p, sizeof bb, cudaMemcpyDeviceToHost, st));
   VXS_CUDA(ctx, cudaStreamSynchronize(st));
   const long double ex = (long double)bb[3] - bb[0] + 1, ey = (long double)bb[4] - bb[1] + 1, ez = (long double)bb[5] - bb[2] + 1;
-  if (ex * ey * ez >= (long double)(1ull << 40)) return vxs_fail(ctx, VXS_ERR_RANGE, "root-cell bounding box exceeds 2^40 cells");
+  const long double nw = bs ? (long double)bs->nwin : 1.0L;
+  if (ex * ey * ez * nw >= (long double)(1ull << 40)) return vxs_fail(ctx, VXS_ERR_RANGE, "root-cell bounding box (x windows) exceeds 2^40 cells");
   const long long eyl = (long long)ey, ezl = (long long)ez;
-  const int root_bits = bits_for((unsigned long long)(ex * ey * ez));
+  const long long cells = (long long)(ex * ey * ez);
+  const int root_bits = bits_for((unsigned long long)(ex * ey * ez * nw));
   // ---- layer-0 keys
   VXS_CUDA(ctx, s->keysA.reserve(size_t(N))); VXS_CUDA(ctx, s->keysB.reserve(size_t(N)));
   VXS_CUDA(ctx, s->idxA.reserve(size_t(N))); VXS_CUDA(ctx, s->idxB.reserve(size_t(N)));
   VXS_CUDA(ctx, s->pathbits.reserve(size_t(N)));
-  const bool sharded = ctx->nranks > 1;
+  const bool sharded = ctx->nranks > 1 && !bs;      // a batch of whole windows is distributed by window, not by voxel
   unsigned int* owned = nullptr;
   if (sharded) { VXS_CUDA(ctx, s->flags.reserve(size_t(N))); VXS_CUDA(ctx, s->scanbuf.reserve(size_t(N))); owned = s->flags.p; }
-  VXS_LAUNCH(ctx, "k_point_keys", k_point_keys, nblk(size_t(N), 256), 256, 0, ps, mp->voxel_size, int(mp->max_layer), bb[0], bb[1], bb[2], eyl, ezl, FB, s->keysA.p, s->idxA.p, s->pathbits.p,
+  VXS_LAUNCH(ctx, "k_point_keys", k_point_keys, nblk(size_t(N), 256), 256, 0, ps, mp->voxel_size, int(mp->max_layer), bb[0], bb[1], bb[2], eyl, ezl, cells, FB, s->keysA.p, s->idxA.p, s->pathbits.p,
              ctx->rank, ctx->nranks, owned);
 
   size_t m = size_t(N);
@@ -435,6 +458,8 @@ static int build_factor(vxs_ctx* ctx, const vxs_map_params* mp, bool gba, const 
       if (rc) return rc;
       FactorOut fo; fo.ptr = out->ptr; fo.frame = out->frame; fo.vox = out->vox; fo.cl = out->cl; fo.Ecap = out->Ecap; fo.fix = out->fix; fo.coe = out->coe; fo.eig = out->eig;
       fo.sum = out->sum; fo.Vcap = out->Vcap; fo.V0 = Vtot; fo.E0 = Etot;
+      fo.vwin = nullptr; fo.cells = cells; fo.win_size = 0;
+      if (bs) { VXS_CUDA(ctx, out->vwin.reserve_keep(size_t(Vtot + selV), size_t(Vtot), ctx->stream)); fo.vwin = out->vwin.p; fo.win_size = bs->win_size; }
       vxs_voxel_id* ids_dev = nullptr;
       if (ids_out) { VXS_CUDA(ctx, s->ids.reserve(selV)); ids_dev = s->ids.p; }
       VXS_LAUNCH(ctx, "k_emit_factor", k_emit_factor, nblk(Nn, 128), 128, 0, fo, Nn, W, FB, s->node_sel.p, s->node_voff.p, s->node_eoff.p, s->node_rec_start.p, s->rec_key.p,
@@ -458,7 +483,7 @@ static int build_factor(vxs_ctx* ctx, const vxs_map_params* mp, bool gba, const 
   if (Vtot > 0) {
     VXS_LAUNCH(ctx, "k_set_last_ptr", k_set_last_ptr, 1, 1, 0, out->ptr, Vtot, Etot);
     // fix clusters present?  (only when fixed map points were supplied)
-    out->has_fix = nframes > W;
+    out->has_fix = !bs && nframes > W;
   }
   out->V = Vtot; out->E = Etot;
   VXS_CUDA(ctx, cudaStreamSynchronize(st));
@@ -746,6 +771,25 @@ extern "C" int vxs_build_gba_factor(vxs_ctx* ctx, const vxs_map_params* mp, cons
 }
 
 // HBA_add_edge BA loop, voxelslam.cpp:2360-2399
+// Map build of a chunk of independent windows (vxs_hba_bottom_batch): OctreeGBA::cut_voxel of every (window, keyframe) + OctreeGBA_multi_recut, one pass.
+// win_first[w] = first keyframe of window w; keyframes [kf_lo, kf_hi) cover the chunk and are uploaded once.
+int vxs_build_gba_batch(vxs_ctx* ctx, const vxs_map_params* mp, const float* xyz, int stride_floats, const int64_t* kf_offsets, const double* poses12, const int32_t* win_first, int nwin,
+                        int win_size, int kf_lo, int kf_hi, vxs_factor* out) {
+  const int nf = nwin * win_size;
+  std::vector<int64_t> voff(size_t(nf) + 1, 0), soff(size_t(nf), 0);
+  std::vector<double> vposes(size_t(nf) * 12);
+  const int64_t base = kf_offsets[kf_lo];
+  for (int w = 0; w < nwin; w++)
+    for (int j = 0; j < win_size; j++) {
+      const int kf = win_first[w] + j, vf = w * win_size + j;
+      voff[size_t(vf) + 1] = voff[size_t(vf)] + (kf_offsets[kf + 1] - kf_offsets[kf]);
+      soff[size_t(vf)] = kf_offsets[kf] - base;
+      memcpy(vposes.data() + size_t(vf) * 12, poses12 + size_t(kf) * 12, 96);
+    }
+  BatchSpec bs; bs.nwin = nwin; bs.win_size = win_size; bs.src_off_host = soff.data(); bs.npts_total = kf_offsets[kf_hi] - base;
+  return build_factor(ctx, mp, true, nullptr, xyz + size_t(base) * stride_floats, stride_floats, voff.data(), nf, vposes.data(), win_size, out, nullptr, 0, nullptr, &bs);
+}
+
 extern "C" int vxs_hba_window(vxs_ctx* ctx, const vxs_map_params* coarse, const vxs_map_params* fine, const float* xyz, int stride_floats, const int64_t* kf_offsets,
                               double* poses12, int W, int max_iter, int thread_num, double* hess_out, double* resis_log, int* outer_iters) {
   if (!ctx || !coarse || !fine || !poses12 || W <= 0) return VXS_ERR_ARG;
