@@ -311,9 +311,15 @@ def run_ours(args):
     gba = None
     if not args.no_gba:
         try:
-            gba = gba_sharded_leg(vx, local, rank, world, dist, args)
+            gba = hba_leg(vx, local, rank, world, dist, args)
         except Exception as e:
-            gba = {"error": repr(e)}
+            import traceback
+            gba = {"error": repr(e), "trace": traceback.format_exc()[-1500:]}
+        if args.gba_window_leg:
+            try:
+                gba["dense_window"] = gba_sharded_leg(vx, local, rank, world, dist, args)
+            except Exception as e:
+                gba["dense_window"] = {"error": repr(e)}
 
     if rank == 0:
         line = {
@@ -424,6 +430,88 @@ def local_mapping_leg(vx, ctx, W, pts, L, steps):
            "kernel_ms_per_step": {k: v / max(len(walls), 1) for k, v in sorted(stage_ms.items(), key=lambda kv: -kv[1])[:14]},
            "round1_from_scratch_rebuild_ms": 120.0, "fill_s": time.perf_counter() - t_fill}
     dm.close(); f.close()
+    return res
+
+
+def hba_leg(vx, local, rank, world, dist, args):
+    """The hierarchical global-BA step (north_star; thd_globalmapping voxelslam.cpp:2484-2557) on K keyframes, STRONG scaling:
+      bottom : every window of 10 keyframes (stride 5) = HBA_add_edge(max_iter 1): map build + Lidar_BA damping_iter(up 4) + PGO edges — vxs_hba_bottom_batch on this rank's
+               share of the windows (windows are independent: no collective) — then the submap merge + down-sampling of those windows (vxs_submap_merge_batch);
+      gather : the merged submap clouds go to every rank (NCCL all-gather through torch.distributed, device buffers);
+      top    : ONE BA over all submaps (W = number of windows), HBA_add_edge(total_max_iter 1): the voxel map is sharded over the ranks by the hash of the root cell and
+               [C | g | D | r] is all-reduced by libvxs' own NCCL communicator once per Hessian build; the 6W-dof LDLT is replicated.
+    A step is one full pass; time = max over ranks."""
+    import torch
+    from voxel_slam_b200 import api
+    K, n, per_row = args.hba_keyframes, args.hba_pts, args.hba_per_row
+    ws, stride_w = 10, 5
+    ctx = vx.Context(local)
+    if world > 1:
+        uid = [vx.Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(uid[0], rank, world)
+    t0 = time.time()
+    tr = np.stack([synth.lawnmower_pose(i, per_row) for i in range(K)])
+    est = np.stack([tr[0]] + [synth.perturb_pose(tr[i], 100 + i, 1e-3, 1e-2) for i in range(1, K)])
+    xyz = api.pinned_array((K * n, 3), np.float32)
+    for i in range(K):
+        synth.gen_scan_city(i, n, tr[i], rng_m=args.hba_range, out=xyz[i * n:(i + 1) * n])
+    off = np.arange(K + 1, dtype=np.int64) * n
+    t_gen = time.time() - t0
+    fine = vx.MapParams.make(voxel_size=1.0, min_eigen_value=0.0025, max_layer=2)
+    win_first = np.arange(0, K - ws + 1, stride_w, dtype=np.int32)
+    nwin = len(win_first)
+    lo, hi = nwin * rank // world, nwin * (rank + 1) // world
+    mine = win_first[lo:hi]
+    dev = f"cuda:{local}"
+    ph = {}
+    per_step = []
+
+    coarse = fine      # total_max_iter = 1 (GBA/total_max_iter default, voxelslam.cpp:2493): the single outer iteration already uses the fine parameters
+
+    def step():
+        t0_ = time.perf_counter()
+        o = ctx.hba_pass(coarse, fine, xyz, off, est, win_size=ws, win_stride=stride_w, top_max_iter=1, nranks=world, rank=rank)
+        wall = (time.perf_counter() - t0_) * 1e3
+        for k, name in enumerate(("bottom_ms", "merge_ms", "exchange_ms", "top_ms")):
+            ph[name] = ph.get(name, 0.0) + float(o["phase_ms"][k])
+        ph["wall_ms"] = ph.get("wall_ms", 0.0) + wall
+        per_step.append([round(float(x), 2) for x in o["phase_ms"][:4]] + [round(wall, 2)])
+        return o
+
+    o = step()
+    step()
+    ph.clear()
+    barrier(dist, local)
+    steps = args.hba_steps
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o = step()
+    ms = (time.perf_counter() - t0) * 1e3
+    ms = barrier_max(dist, local, ms)
+    mine_ph = [ph[k] / steps for k in ("bottom_ms", "merge_ms", "exchange_ms", "top_ms", "wall_ms")]
+    per_rank = [mine_ph]
+    if dist is not None:
+        g = [torch.zeros(5, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(g, torch.tensor(mine_ph, dtype=torch.float64, device=dev))
+        per_rank = [x.cpu().tolist() for x in g]
+    # sanity: the bottom windows move their keyframes towards the truth (relative to the window's fixed first keyframe)
+    k0 = int(win_first[lo]) if hi > lo else 0
+    e0 = float(np.abs(est[k0 + 1:k0 + ws, 9:] - tr[k0 + 1:k0 + ws, 9:]).max()); e1 = float(np.abs(o["bottom_poses"][0][1:, 9:] - tr[k0 + 1:k0 + ws, 9:]).max())
+    res = {"metric": "hierarchical global-BA passes/sec (bottom windows distributed + top level voxel-sharded; strong scaling)", "value": steps / (ms * 1e-3), "unit": "passes/s",
+           "keyframes_per_s": K * steps / (ms * 1e-3), "ms_per_step": ms / steps, "steps": steps, "scaling": "strong", "n_gpus": world,
+           "workload": f"C4-like: {K} keyframes x {n} pts (city grid, lawn-mower path, {args.hba_range} m sensor range), {nwin} bottom windows of {ws} (stride {stride_w}), top level W={nwin} (n={6 * nwin}); "
+                       f"{int(o['submap_sizes'].sum())} submap points after the merge",
+           "call": "vxs_hba_pass: host keyframe clouds (pinned) in; bottom BA + merge on this rank's windows, submaps exchanged device to device (NCCL), top level sharded; poses / edges out",
+           "per_rank_[bottom,merge,exchange,top,wall]_ms": [[round(x, 2) for x in r] for r in per_rank],
+           "per_step_[bottom,merge,exchange,top,wall]_ms_rank0": per_step[-steps:],
+           "bottom": {"windows_this_rank": int(hi - lo), "plane_voxels_this_rank": int(o["phase_ms"][4]), "clusters_this_rank": int(o["phase_ms"][5]), "status_ok": int(np.sum(o["bottom_status"][: hi - lo] == 0)), "edges_mean": float(np.mean(np.sum(o["edge_valid"][: hi - lo], axis=1))),
+                      "pos_err_first_window_before_after": [e0, e1]},
+           "top": {"outer_iters": int(o["top_outer_iters"]), "resis": [float(x) for x in o["top_resis"][:2]],
+                   "pos_err_submaps_before_after": [float(np.abs(est[win_first][1:, 9:] - tr[win_first][1:, 9:]).max()), float(np.abs(o["top_poses"][1:, 9:] - tr[win_first][1:, 9:]).max())]},
+           "comm": "libvxs' own NCCL communicator (vxs_ctx_comm_init): sizes all-reduce + grouped broadcasts of the submaps + all-reduce of [C | g | D | r] per top-level Hessian build" if world > 1 else "single GPU: no collective",
+           "scene_gen_s": t_gen}
+    ctx.close()
     return res
 
 
@@ -820,6 +908,12 @@ def main():
     ap.add_argument("--no-local-mapping", action="store_true")
     ap.add_argument("--lm-steps", type=int, default=6)
     ap.add_argument("--no-gba", action="store_true")
+    ap.add_argument("--hba-keyframes", type=int, default=2000)
+    ap.add_argument("--hba-pts", type=int, default=100000)
+    ap.add_argument("--hba-per-row", type=int, default=50)
+    ap.add_argument("--hba-range", type=float, default=35.0)
+    ap.add_argument("--hba-steps", type=int, default=5)
+    ap.add_argument("--gba-window-leg", action="store_true")
     ap.add_argument("--gba-win", type=int, default=100)
     ap.add_argument("--gba-win-pts", type=int, default=200000)
     ap.add_argument("--gba-L", type=float, default=260.0)

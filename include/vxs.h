@@ -211,6 +211,19 @@ int vxs_hba_bottom_batch(vxs_ctx* ctx, const vxs_map_params* fine, const float* 
                          const int32_t* win_first, int nwin, int win_size, int thread_num, int64_t max_points_per_chunk, double* poses_out, double* resis, int32_t* status,
                          int32_t* is_converge, int32_t* lm_iters, int32_t* edge_valid, double* edge_v6, double* edge_rot, double* edge_tra, double* hess_out);
 
+/* One PASS of the hierarchical global BA (thd_globalmapping, voxelslam.cpp:2484-2557) over K keyframes, single- or multi-GPU (the ranks of vxs_ctx_comm_init):
+ *   windows w = 0 .. nwin-1, nwin = (K - win_size) / win_stride + 1, first keyframe w * win_stride (the reference: win_size 10, stride 5, :2501-2502);
+ *   rank r of n takes the contiguous share [nwin r / n, nwin (r + 1) / n) of the bottom level: vxs_hba_bottom_batch + vxs_submap_merge_batch on keyframe clouds that are
+ *   uploaded once and on merged submaps that STAY on the device; the submaps are exchanged between the ranks' device buffers over NCCL; the top level
+ *   (HBA_add_edge over all submaps, W = nwin, top_max_iter = GBA/total_max_iter, thread_num 5, :2538) runs voxel-sharded with the all-reduced Hessian.
+ * Outputs (host): bottom_* for THIS rank's windows only (layouts of vxs_hba_bottom_batch; *my_first_window / *my_window_count say which), top_poses [nwin][12]
+ * (identical on every rank), top_resis_log [2 top_max_iter], submap_sizes [nwin] (cells per merged submap), phase_ms [6] = device time of
+ * {upload + bottom BA, merge, exchange, top}, then the plane voxels and (voxel, keyframe) clusters of this rank's bottom windows.  Every bottom_* / top_resis_log / submap_sizes / phase_ms pointer but bottom_poses may be NULL. */
+int vxs_hba_pass(vxs_ctx* ctx, const vxs_map_params* coarse, const vxs_map_params* fine, const float* xyz, int stride_floats, const int64_t* kf_offsets, const double* poses12, int K,
+                 int win_size, int win_stride, int bottom_thread_num, int top_thread_num, int top_max_iter, int64_t max_points_per_chunk, double* bottom_poses, double* bottom_resis,
+                 int32_t* bottom_status, int32_t* bottom_edge_valid, double* bottom_edge_v6, double* bottom_edge_rot, double* bottom_edge_tra, int32_t* my_first_window,
+                 int32_t* my_window_count, double* top_poses, double* top_resis_log, int* top_outer_iters, int64_t* submap_sizes, double* phase_ms);
+
 /* PGO edge extraction of HBA_add_edge (voxelslam.cpp:2405-2427) from the raw Hessian of the LAST vxs_lidar_ba / vxs_hba_window
  * on this ctx, without downloading the Hessian: for every pair i<j whose six diagonal entries of block (i,j) are all >= 1e-6 in
  * magnitude, one edge with variance v6[k] = 1/|H(6i+k, 6j+k)|, rot = R_i^T R_j (row-major), tra = R_i^T (p_j - p_i).
@@ -247,6 +260,13 @@ int vxs_down_sampling_pvec(vxs_ctx* ctx, const double* pv, int stride_doubles, i
  * `intensity`) follows from kf_offsets.  voxel_size < 0.001: the merged cloud is returned as it is (count 0). */
 int vxs_submap_merge(vxs_ctx* ctx, const float* xyz, int stride_floats, const int64_t* kf_offsets, const double* poses12, int W,
                      double voxel_size, float* xyz_out, float* count_out, int64_t* first_index_out, int64_t cap, int64_t* n_out);
+
+/* The same for MANY windows at once (the post-step of every bottom-level HBA_add_edge, after vxs_hba_bottom_batch): poses_win [nwin][win_size][12] are the
+ * windows' refined poses, window w merges keyframes win_first[w] .. win_first[w] + win_size - 1 into the frame of its first keyframe and down-samples.
+ * Outputs are the windows' clouds back to back, win_offsets[nwin + 1] delimits them (cells of a window in ascending cell order); first_index_out indexes the
+ * window's own concatenated input.  *n_out = total cells (may exceed cap: truncated).  voxel_size >= 0.001 (the reference's voxel_size / 8). */
+int vxs_submap_merge_batch(vxs_ctx* ctx, const float* xyz, int stride_floats, const int64_t* kf_offsets, int K, const double* poses_win, const int32_t* win_first, int nwin, int win_size,
+                           double voxel_size, int64_t max_points_per_chunk, float* xyz_out, float* count_out, int64_t* first_index_out, int64_t cap, int64_t* win_offsets, int64_t* n_out);
 
 /* ---------------------------------------------------------------- odometry association
  * The per-point loop of the EKF update (voxelslam.cpp:876-918): world point and its covariance, match() against the voxel map

@@ -79,6 +79,26 @@ def main():
         ok = g["outer_iters"] == r["outer_iters"] and e_pose < 1e-5 and e_h < 1e-6
         print(f"[multi-gpu x{world}] sharded HBA window: outer iters {g['outer_iters']}/{r['outer_iters']}  pose {e_pose:.2e}  hess {e_h:.2e} -> {'OK' if ok else 'FAIL'}", flush=True)
         ok_all = ok_all and ok
+    # the whole hierarchical pass (vxs_hba_pass): bottom windows distributed over the ranks, merged submaps exchanged device to device over NCCL, top level voxel-sharded —
+    # compared with the same pass run by ONE extra single-GPU context through the separate host-buffer calls
+    K, ws, stp = 30, 10, 5
+    tr, est = scenes.poses_true_est(K, 8.0, 99, rot_sigma=3e-3, pos_sigma=2e-2)
+    xyz, off = scenes.make_points(K, 3000, 8.0, 99, tr, dtype=np.float32)
+    p = ctx.hba_pass(fine, fine, xyz, off, est, win_size=ws, win_stride=stp, nranks=world, rank=rank)
+    solo = vx.Context(local)
+    wf = np.arange(0, K - ws + 1, stp, dtype=np.int32)
+    b = solo.hba_bottom_batch(fine, xyz, off, est, wf, win_size=ws)
+    m = solo.submap_merge_batch(xyz, off, b["poses"], wf, 0.125)
+    top = solo.hba_window(fine, fine, m["xyz"], m["win_offsets"], est[wf], max_iter=1, thread_num=5)
+    lo, n_mine = p["first_window"], p["window_count"]
+    inc = np.max(np.abs(top["poses"] - est[wf]))
+    ok = (np.max(np.abs(p["bottom_poses"][:n_mine] - b["poses"][lo:lo + n_mine])) < 1e-10 and np.array_equal(p["submap_sizes"], np.diff(m["win_offsets"]))
+          and np.max(np.abs(p["top_poses"] - top["poses"])) < 1e-6 * inc and abs(p["top_resis"][1] - top["resis_log"][1]) / top["resis_log"][1] < 1e-9)
+    print(f"[multi-gpu x{world}] rank {rank} hierarchical pass: windows {lo}..{lo + n_mine - 1}, top pose err {np.max(np.abs(p['top_poses'] - top['poses'])) / inc:.2e} -> {'OK' if ok else 'FAIL'}", flush=True)
+    okt = torch.tensor([1 if ok else 0], device=f"cuda:{local}")
+    dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+    ok_all = ok_all and int(okt.item()) == 1
+    solo.close()
     flag = torch.tensor([1 if ok_all else 0], device=f"cuda:{local}")
     dist.broadcast(flag, src=0)
     dist.barrier()

@@ -84,3 +84,42 @@ def test_bottom_batch_too_few_voxels_is_a_status_not_an_exit(ctx):
     g = ctx.hba_bottom_batch(fine, xyz, off, est, np.array([0, 6], dtype=np.int32), win_size=ws)
     assert g["status"][0] == 0 and g["status"][1] == -3
     assert np.array_equal(g["poses"][1], est[6:12])
+
+
+def test_submap_merge_batch_vs_per_window_oracle(ctx):
+    """merge + down_sampling_voxel(voxel_size / 8) of every window in one pass: bit-exact float means, cells grouped by window in cell order"""
+    K, ws = 20, 10
+    tr, est, xyz, off = trajectory(K, 3000, 8.0, 97, stride=12)
+    win_first = np.array([0, 5, 10], dtype=np.int32)
+    poses_win = np.stack([est[k:k + ws] for k in win_first])
+    for chunk in (0, 35000):
+        g = ctx.submap_merge_batch(xyz, off, poses_win, win_first, 0.125, max_points_per_chunk=chunk)
+        assert g["win_offsets"][0] == 0 and g["win_offsets"][-1] == g["n"] == len(g["xyz"])
+        for w, k0 in enumerate(win_first):
+            lo, hi = off[k0], off[k0 + ws]
+            o = oa.submap_merge(xyz[lo:hi], off[k0:k0 + ws + 1] - lo, est[k0:k0 + ws], 0.125, stride_floats=12)
+            a, b = g["win_offsets"][w], g["win_offsets"][w + 1]
+            assert b - a == len(o["xyz"]) > 1000
+            # the oracle reports cells in its hash-map order: match them through the index of the cell's first point
+            ko, kg = np.argsort(o["index"]), np.argsort(g["index"][a:b])
+            assert np.array_equal(o["index"][ko], g["index"][a:b][kg])
+            assert np.array_equal(o["xyz"][ko].view(np.uint32), g["xyz"][a:b][kg].view(np.uint32)) and np.array_equal(o["count"][ko], g["count"][a:b][kg])
+
+
+def test_hba_pass_equals_the_separate_calls(ctx):
+    """vxs_hba_pass (device-resident clouds and submaps) == vxs_hba_bottom_batch + vxs_submap_merge_batch + vxs_hba_window through host buffers"""
+    K, ws, st = 30, 10, 5
+    tr, est, xyz, off = trajectory(K, 3000, 8.0, 99)
+    fine = vx.MapParams.make(voxel_size=1.0, min_eigen_value=0.0025, max_layer=2)
+    p = ctx.hba_pass(fine, fine, xyz, off, est, win_size=ws, win_stride=st)
+    wf = np.arange(0, K - ws + 1, st, dtype=np.int32)
+    b = ctx.hba_bottom_batch(fine, xyz, off, est, wf, win_size=ws)
+    m = ctx.submap_merge_batch(xyz, off, b["poses"], wf, 0.125)
+    top = ctx.hba_window(fine, fine, m["xyz"], m["win_offsets"], est[wf], max_iter=1, thread_num=5)
+    # (the Hessian / gradient accumulators are fp64 REDs: two runs agree to rounding, not bit for bit)
+    assert p["nwin"] == len(wf) and np.max(np.abs(p["bottom_poses"] - b["poses"])) < 1e-10 and np.array_equal(p["edge_valid"], b["edge_valid"])
+    assert np.array_equal(p["submap_sizes"], np.diff(m["win_offsets"]))
+    inc = np.max(np.abs(top["poses"] - est[wf]))
+    assert inc > 0 and np.max(np.abs(p["top_poses"] - top["poses"])) < 1e-9 * max(inc, 1e-6) + 1e-13
+    assert np.max(np.abs(p["top_resis"][:2] - top["resis_log"][:2]) / top["resis_log"][:2]) < 1e-10
+    assert np.all(p["phase_ms"][[0, 1, 3, 4, 5]] > 0)

@@ -385,7 +385,54 @@ def _hba_bottom_batch(self, fine, xyz_f32, kf_offsets, poses12, win_first, win_s
     return out
 
 
+def _submap_merge_batch(self, xyz_f32, kf_offsets, poses_win, win_first, voxel_size, stride_floats=None, max_points_per_chunk=0, cap=None):
+    """vxs_submap_merge_batch: the submap merge + down-sampling of every window (voxelslam.cpp:2428-2447) in one pass."""
+    x = np.ascontiguousarray(xyz_f32, dtype=np.float32)
+    stride = int(stride_floats) if stride_floats else (x.shape[1] if x.ndim == 2 else 3)
+    off = np.ascontiguousarray(kf_offsets, dtype=np.int64)
+    pw = _f64(poses_win)
+    wf = np.ascontiguousarray(win_first, dtype=np.int32)
+    nw, ws = pw.shape[0], pw.shape[1]
+    if cap is None:
+        cap = int(sum(off[k + ws] - off[k] for k in wf))
+    xyz = np.zeros((max(cap, 1), 3), dtype=np.float32); cnt = np.zeros(max(cap, 1), dtype=np.float32); idx = np.zeros(max(cap, 1), dtype=np.int64)
+    woff = np.zeros(nw + 1, dtype=np.int64)
+    n = C.c_int64(0)
+    self._check(lib().vxs_submap_merge_batch(self._p, x.ctypes.data_as(C.POINTER(C.c_float)), C.c_int(stride), off.ctypes.data_as(C.POINTER(C.c_int64)), C.c_int(off.shape[0] - 1), _dp(pw),
+                                             wf.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int(nw), C.c_int(ws), C.c_double(voxel_size), C.c_int64(max_points_per_chunk),
+                                             xyz.ctypes.data_as(C.POINTER(C.c_float)), cnt.ctypes.data_as(C.POINTER(C.c_float)), idx.ctypes.data_as(C.POINTER(C.c_int64)), C.c_int64(cap),
+                                             woff.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(n)))
+    m = min(n.value, cap)
+    return dict(xyz=xyz[:m], count=cnt[:m], index=idx[:m], win_offsets=woff, n=n.value)
+
+
+def _hba_pass(self, coarse, fine, xyz_f32, kf_offsets, poses12, win_size=10, win_stride=5, top_max_iter=1, stride_floats=None, max_points_per_chunk=0, nranks=1, rank=0):
+    """vxs_hba_pass: bottom windows (this rank's share) + submap merge + exchange + top level, clouds and submaps device-resident."""
+    x = xyz_f32 if (isinstance(xyz_f32, np.ndarray) and xyz_f32.dtype == np.float32 and xyz_f32.flags["C_CONTIGUOUS"]) else np.ascontiguousarray(xyz_f32, dtype=np.float32)
+    stride = int(stride_floats) if stride_floats else (x.shape[1] if x.ndim == 2 else 3)
+    off = np.ascontiguousarray(kf_offsets, dtype=np.int64)
+    p = _f64(poses12).reshape(-1, 12)
+    K = p.shape[0]
+    nwin = (K - win_size) // win_stride + 1
+    lo, hi = nwin * rank // nranks, nwin * (rank + 1) // nranks
+    nm, P = max(hi - lo, 1), win_size * (win_size - 1) // 2
+    out = dict(bottom_poses=np.zeros((nm, win_size, 12)), bottom_resis=np.zeros((nm, 2)), bottom_status=np.zeros(nm, dtype=np.int32), edge_valid=np.zeros((nm, P), dtype=np.int32),
+               edge_v6=np.zeros((nm, P, 6)), edge_rot=np.zeros((nm, P, 9)), edge_tra=np.zeros((nm, P, 3)), top_poses=np.zeros((nwin, 12)), top_resis=np.zeros(2 * max(top_max_iter, 1)),
+               submap_sizes=np.zeros(nwin, dtype=np.int64), phase_ms=np.zeros(6))
+    first, cnt, outer = C.c_int32(0), C.c_int32(0), C.c_int(0)
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+    self._check(lib().vxs_hba_pass(self._p, C.byref(coarse), C.byref(fine), x.ctypes.data_as(C.POINTER(C.c_float)), C.c_int(stride), off.ctypes.data_as(C.POINTER(C.c_int64)), _dp(p), C.c_int(K),
+                                   C.c_int(win_size), C.c_int(win_stride), C.c_int(2), C.c_int(5), C.c_int(top_max_iter), C.c_int64(max_points_per_chunk), _dp(out["bottom_poses"]),
+                                   _dp(out["bottom_resis"]), ip(out["bottom_status"]), ip(out["edge_valid"]), _dp(out["edge_v6"]), _dp(out["edge_rot"]), _dp(out["edge_tra"]), C.byref(first),
+                                   C.byref(cnt), _dp(out["top_poses"]), _dp(out["top_resis"]), C.byref(outer), out["submap_sizes"].ctypes.data_as(C.POINTER(C.c_int64)), _dp(out["phase_ms"])))
+    assert first.value == lo and cnt.value == hi - lo, (first.value, cnt.value, lo, hi)
+    out.update(first_window=lo, window_count=hi - lo, top_outer_iters=outer.value, nwin=nwin)
+    return out
+
+
+Context.hba_pass = _hba_pass
 Context.hba_bottom_batch = _hba_bottom_batch
+Context.submap_merge_batch = _submap_merge_batch
 
 
 def _submap_merge(self, xyz_f32, kf_offsets, poses12, voxel_size, stride_floats=None):

@@ -55,6 +55,7 @@ extern "C" int vxs_ctx_destroy(vxs_ctx* c) {
   vxs_ctx_comm_destroy(c);
   vxs_voxelize_release(c);
   vxs_odom_release(c);
+  vxs_hba_release(c);
   for (auto& p : c->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (auto ev : c->event_pool) cudaEventDestroy(ev);
   c->Hraw.release(); c->Mp.release(); c->Lm.release(); c->himu.release(); c->gimu.release(); c->jact.release(); c->dvec.release();

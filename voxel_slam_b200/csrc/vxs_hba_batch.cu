@@ -19,8 +19,15 @@
 
 using namespace vxs;
 
+// vxs_voxelize.cu
 int vxs_build_gba_batch(vxs_ctx* ctx, const vxs_map_params* mp, const float* xyz, int stride_floats, const int64_t* kf_offsets, const double* poses12, const int32_t* win_first, int nwin,
-                        int win_size, int kf_lo, int kf_hi, vxs_factor* out);   // vxs_voxelize.cu
+                        int win_size, int kf_lo, int kf_hi, vxs_factor* out, const float* xyz_dev, int64_t dev_first_point);
+int vxs_submap_merge_batch_impl(vxs_ctx* ctx, const float* xyz, const float* xyz_dev, int64_t dev_first_point, int stride_floats, const int64_t* kf_offsets, int K, const double* poses_win,
+                                const int32_t* win_first, int nwin, int win_size, double voxel_size, int64_t max_points_per_chunk, float* xyz_out, float* count_out,
+                                int64_t* first_index_out, int64_t cap, int64_t* win_offsets, int64_t* n_out, DevBuf<float>* dev_out);
+int vxs_hba_window_impl(vxs_ctx* ctx, const vxs_map_params* coarse, const vxs_map_params* fine, const float* xyz, const float* xyz_dev, int stride_floats, const int64_t* kf_offsets,
+                        double* poses12, int W, int max_iter, int thread_num, double* hess_out, double* resis_log, int* outer_iters, long long own_lo, long long own_hi);
+int vxs_comm_allgatherv_f32(vxs_ctx* ctx, const float* mine, size_t my_count, float* all, const size_t* counts, const size_t* displs, float* pad, size_t slot);   // vxs_lm.cu
 
 namespace {
 
@@ -224,29 +231,43 @@ __global__ void __launch_bounds__(128) k_bd_init(BdState S, const int* __restric
   S.calc[w] = 1; S.conv[w] = 1; S.done[w] = 0; S.iters[w] = 0; S.status[w] = 0; S.nvox[w] = win_ptr[w + 1] - win_ptr[w];
 }
 
-struct BatchScratch {
+struct BatchScratch {    // one per ctx, grow-only: a pass must not pay cudaMalloc / cudaFree of GB-sized buffers (each is a device-wide synchronisation)
   DevBuf<double> d; DevBuf<int> i; DevBuf<unsigned long long> kA, kB; DevBuf<unsigned int> iA, iB; DevBuf<double> rvox, Cbd, gD, out_d; DevBuf<int> out_i;
   SortScratch ss;
+  DevBuf<float> pts, sub_mine, sub_all, sub_pad;   // vxs_hba_pass: this rank's keyframe clouds, its merged submaps, all ranks' submaps, the padded all-gather slots
+  vxs_factor* f = nullptr;                // the chunk factor, kept between calls
+  long long last_voxels = 0, last_entries = 0;   // plane voxels / (voxel, keyframe) clusters of the last bottom batch (all chunks)
 };
+BatchScratch* hba_scratch(vxs_ctx* c) { if (!c->hba_scratch) c->hba_scratch = new BatchScratch(); return static_cast<BatchScratch*>(c->hba_scratch); }
 
 }  // namespace
 
-extern "C" int vxs_hba_bottom_batch(vxs_ctx* ctx, const vxs_map_params* fine, const float* xyz, int stride_floats, const int64_t* kf_offsets, const double* poses12, int K,
-                                    const int32_t* win_first, int nwin, int win_size, int thread_num, int64_t max_points_per_chunk, double* poses_out, double* resis, int32_t* status,
-                                    int32_t* is_converge, int32_t* lm_iters, int32_t* edge_valid, double* edge_v6, double* edge_rot, double* edge_tra, double* hess_out) {
+void vxs_hba_release(vxs_ctx* c) {
+  if (!c->hba_scratch) return;
+  BatchScratch* B = static_cast<BatchScratch*>(c->hba_scratch);
+  B->d.release(); B->i.release(); B->kA.release(); B->kB.release(); B->iA.release(); B->iB.release(); B->rvox.release(); B->Cbd.release(); B->gD.release(); B->out_d.release();
+  B->out_i.release(); B->ss.hist.release(); B->ss.blocksums.release(); B->ss.totals.release(); B->pts.release(); B->sub_mine.release(); B->sub_all.release(); B->sub_pad.release();
+  // B->f is owned by the ctx's factor list (released with it)
+  delete B;
+  c->hba_scratch = nullptr;
+}
+
+static int hba_bottom_batch_impl(vxs_ctx* ctx, const vxs_map_params* fine, const float* xyz, const float* xyz_dev, int64_t dev_first_point, int stride_floats, const int64_t* kf_offsets,
+                                 const double* poses12, int K, const int32_t* win_first, int nwin, int win_size, int thread_num, int64_t max_points_per_chunk, double* poses_out, double* resis,
+                                 int32_t* status, int32_t* is_converge, int32_t* lm_iters, int32_t* edge_valid, double* edge_v6, double* edge_rot, double* edge_tra, double* hess_out) {
   if (!ctx || !fine || !xyz || !kf_offsets || !poses12 || !win_first || K <= 0 || nwin <= 0 || win_size < 2 || 6 * win_size > HB_MAXN || stride_floats < 3 || !poses_out) return VXS_ERR_ARG;
   for (int w = 0; w < nwin; w++) if (win_first[w] < 0 || win_first[w] + win_size > K) return vxs_fail(ctx, VXS_ERR_ARG, "vxs_hba_bottom_batch: a window reaches beyond the keyframes");
   cudaSetDevice(ctx->device);
   cudaStream_t st = ctx->stream;
   const int WB = win_size, n = 6 * WB, npairs = WB * (WB - 1) / 2, up = 4;
   if (max_points_per_chunk <= 0) max_points_per_chunk = 96ll << 20;
-  BatchScratch B;
-  vxs_factor* f = nullptr;
-  int rc = vxs_factor_create(ctx, WB, &f);
-  if (rc) return rc;
-  auto fail = [&](int code) { vxs_factor_destroy(f); B.d.release(); B.i.release(); B.kA.release(); B.kB.release(); B.iA.release(); B.iB.release(); B.rvox.release(); B.Cbd.release(); B.gD.release();
-                              B.out_d.release(); B.out_i.release(); B.ss.hist.release(); B.ss.blocksums.release(); B.ss.totals.release(); return code; };
+  BatchScratch& B = *hba_scratch(ctx);
+  int rc = VXS_OK;
+  if (!B.f) { rc = vxs_factor_create(ctx, WB, &B.f); if (rc) return rc; }
+  vxs_factor* f = B.f;
+  auto fail = [&](int code) { return code; };
   int warn = VXS_OK;
+  B.last_voxels = 0; B.last_entries = 0;
   for (int w0 = 0; w0 < nwin;) {
     // ---- chunk of windows bounded by its number of (virtual) points
     int w1 = w0; int64_t vp = 0;
@@ -258,9 +279,10 @@ extern "C" int vxs_hba_bottom_batch(vxs_ctx* ctx, const vxs_map_params* fine, co
     const int nw = w1 - w0;
     int kf_lo = K, kf_hi = 0;
     for (int w = w0; w < w1; w++) { kf_lo = std::min(kf_lo, int(win_first[w])); kf_hi = std::max(kf_hi, int(win_first[w]) + WB); }
-    rc = vxs_build_gba_batch(ctx, fine, xyz, stride_floats, kf_offsets, poses12, win_first + w0, nw, WB, kf_lo, kf_hi, f);
+    rc = vxs_build_gba_batch(ctx, fine, xyz, stride_floats, kf_offsets, poses12, win_first + w0, nw, WB, kf_lo, kf_hi, f, xyz_dev, dev_first_point);
     if (rc < 0) return fail(rc);
     const int V = int(f->V);
+    B.last_voxels += f->V; B.last_entries += f->E;
     // ---- per-window state
     const size_t nd = size_t(nw) * WB * 12 * 2 + size_t(nw) * 7 + size_t(nw) * n * n + size_t(nw) * n;
     VXS_CUDA(ctx, B.d.reserve(nd)); VXS_CUDA(ctx, B.i.reserve(size_t(nw) * 6 + size_t(nw) + 2));
@@ -327,4 +349,109 @@ extern "C" int vxs_hba_bottom_batch(vxs_ctx* ctx, const vxs_map_params* fine, co
   }
   fail(0);
   return warn;
+}
+
+extern "C" int vxs_hba_bottom_batch(vxs_ctx* ctx, const vxs_map_params* fine, const float* xyz, int stride_floats, const int64_t* kf_offsets, const double* poses12, int K,
+                                    const int32_t* win_first, int nwin, int win_size, int thread_num, int64_t max_points_per_chunk, double* poses_out, double* resis, int32_t* status,
+                                    int32_t* is_converge, int32_t* lm_iters, int32_t* edge_valid, double* edge_v6, double* edge_rot, double* edge_tra, double* hess_out) {
+  return hba_bottom_batch_impl(ctx, fine, xyz, nullptr, 0, stride_floats, kf_offsets, poses12, K, win_first, nwin, win_size, thread_num, max_points_per_chunk, poses_out, resis, status,
+                               is_converge, lm_iters, edge_valid, edge_v6, edge_rot, edge_tra, hess_out);
+}
+
+// One pass of the hierarchical global BA (thd_globalmapping, voxelslam.cpp:2484-2557) with everything between the keyframe clouds and the results on the device:
+//   windows  w = 0 .. nwin-1 of win_size keyframes, first keyframe w * win_stride; rank r of n handles the contiguous share [nwin r / n, nwin (r+1) / n);
+//   bottom   hba_bottom_batch_impl on the rank's windows (the keyframes it needs are uploaded ONCE), then the submap merge + down-sampling, output left on the device;
+//   exchange the merged submaps go to every rank over NCCL (sizes by an all-reduce, clouds by grouped broadcasts), straight between device buffers;
+//   top      HBA_add_edge over all submaps (W = nwin, max_iter = top_max_iter): voxel-sharded map + all-reduced Hessian + replicated solve, reading the device-resident clouds.
+extern "C" int vxs_hba_pass(vxs_ctx* ctx, const vxs_map_params* coarse, const vxs_map_params* fine, const float* xyz, int stride_floats, const int64_t* kf_offsets, const double* poses12, int K,
+                            int win_size, int win_stride, int bottom_thread_num, int top_thread_num, int top_max_iter, int64_t max_points_per_chunk, double* bottom_poses, double* bottom_resis,
+                            int32_t* bottom_status, int32_t* bottom_edge_valid, double* bottom_edge_v6, double* bottom_edge_rot, double* bottom_edge_tra, int32_t* my_first_window,
+                            int32_t* my_window_count, double* top_poses, double* top_resis_log, int* top_outer_iters, int64_t* submap_sizes, double* phase_ms) {
+  if (!ctx || !coarse || !fine || !xyz || !kf_offsets || !poses12 || K <= 0 || win_size < 2 || win_stride < 1 || K < win_size || !bottom_poses || !top_poses) return VXS_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  const int nwin = (K - win_size) / win_stride + 1;
+  std::vector<int32_t> win_first(static_cast<size_t>(nwin));
+  for (int w = 0; w < nwin; w++) win_first[size_t(w)] = w * win_stride;
+  const int lo = int((long long)nwin * ctx->rank / ctx->nranks), hi = int((long long)nwin * (ctx->rank + 1) / ctx->nranks), nmine = hi - lo;
+  if (my_first_window) *my_first_window = lo;
+  if (my_window_count) *my_window_count = nmine;
+  cudaEvent_t ev[5];
+  for (auto& e : ev) cudaEventCreate(&e);
+  auto cleanup = [&](int code) { for (auto& e : ev) cudaEventDestroy(e); return code; };
+  BatchScratch& PB = *hba_scratch(ctx);
+  DevBuf<float>& pts = PB.pts; DevBuf<float>& sub_mine = PB.sub_mine; DevBuf<float>& sub_all = PB.sub_all;
+  auto release = [&]() {};
+  int rc = VXS_OK;
+  cudaEventRecord(ev[0], st);
+  // ---- this rank's keyframes, uploaded once
+  std::vector<int64_t> woff(size_t(nmine) + 1, 0);
+  std::vector<double> sizes_d(static_cast<size_t>(nwin), 0.0);
+  if (nmine > 0) {
+    const int kf_lo = win_first[size_t(lo)], kf_hi = win_first[size_t(hi) - 1] + win_size;
+    const int64_t p0 = kf_offsets[kf_lo], np = kf_offsets[kf_hi] - p0;
+    if (pts.reserve(size_t(std::max<int64_t>(np, 1)) * stride_floats) != cudaSuccess) { release(); return cleanup(vxs_fail(ctx, VXS_ERR_NOMEM, "vxs_hba_pass: keyframe clouds do not fit")); }
+    if (np > 0) cudaMemcpyAsync(pts.p, xyz + size_t(p0) * stride_floats, size_t(np) * stride_floats * 4, cudaMemcpyHostToDevice, st);
+    rc = hba_bottom_batch_impl(ctx, fine, xyz, pts.p, p0, stride_floats, kf_offsets, poses12, K, win_first.data() + lo, nmine, win_size, bottom_thread_num, max_points_per_chunk, bottom_poses,
+                               bottom_resis, bottom_status, nullptr, nullptr, bottom_edge_valid, bottom_edge_v6, bottom_edge_rot, bottom_edge_tra, nullptr);
+    if (rc < 0) { release(); return cleanup(rc); }
+    cudaEventRecord(ev[1], st);
+    int64_t ntot = 0;
+    rc = vxs_submap_merge_batch_impl(ctx, xyz, pts.p, p0, stride_floats, kf_offsets, K, bottom_poses, win_first.data() + lo, nmine, win_size, fine->voxel_size / 8, max_points_per_chunk, nullptr,
+                                     nullptr, nullptr, 0, woff.data(), &ntot, &sub_mine);
+    if (rc < 0) { release(); return cleanup(rc); }
+    for (int w = 0; w < nmine; w++) sizes_d[size_t(lo + w)] = double(woff[size_t(w) + 1] - woff[size_t(w)]);
+  } else cudaEventRecord(ev[1], st);
+  cudaEventRecord(ev[2], st);
+  // ---- submaps of all ranks on every rank
+  const float* sub_dev = sub_mine.p;
+  if (ctx->nranks > 1) {
+    if (ctx->stage.reserve(size_t(nwin)) != cudaSuccess) { release(); return cleanup(VXS_ERR_NOMEM); }
+    cudaMemcpyAsync(ctx->stage.p, sizes_d.data(), size_t(nwin) * 8, cudaMemcpyHostToDevice, st);
+    rc = vxs_comm_allreduce(ctx, ctx->stage.p, size_t(nwin));              // every rank contributed its own windows' sizes, zeros elsewhere
+    if (rc) { release(); return cleanup(rc); }
+    cudaMemcpyAsync(sizes_d.data(), ctx->stage.p, size_t(nwin) * 8, cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    std::vector<size_t> counts(size_t(ctx->nranks), 0), displs(size_t(ctx->nranks), 0);
+    size_t tot = 0;
+    for (int r = 0; r < ctx->nranks; r++) {
+      const int rlo = int((long long)nwin * r / ctx->nranks), rhi = int((long long)nwin * (r + 1) / ctx->nranks);
+      size_t c = 0;
+      for (int w = rlo; w < rhi; w++) c += size_t(sizes_d[size_t(w)]);
+      counts[size_t(r)] = c * 3; displs[size_t(r)] = tot * 3; tot += c;
+    }
+    // head room of 1/8: the merged clouds differ by a few cells from pass to pass (the poses of the bottom level agree to rounding only), and a buffer that
+    // is a few bytes short costs a cudaFree + cudaMalloc of gigabytes (measured: 370 ms once every few passes)
+    if (sub_all.cap < std::max<size_t>(tot, 1) * 3 && sub_all.reserve((std::max<size_t>(tot, 1) + tot / 8) * 3) != cudaSuccess) { release(); return cleanup(vxs_fail(ctx, VXS_ERR_NOMEM, "vxs_hba_pass: submaps do not fit")); }
+    size_t slot = 0;
+    for (size_t c : counts) slot = std::max(slot, c);
+    slot = (slot + 3) & ~size_t(3);
+    // the padded all-gather reads `slot` floats from this rank's buffer: make sure they exist
+    const size_t slot_cap = std::max<size_t>(slot, 1) + slot / 8;
+    if ((sub_mine.cap < std::max<size_t>(slot, 1) && sub_mine.reserve_keep(slot_cap, counts[size_t(ctx->rank)], st) != cudaSuccess) ||
+        (PB.sub_pad.cap < std::max<size_t>(slot, 1) * size_t(ctx->nranks) && PB.sub_pad.reserve(slot_cap * size_t(ctx->nranks)) != cudaSuccess)) {
+      release(); return cleanup(vxs_fail(ctx, VXS_ERR_NOMEM, "vxs_hba_pass: exchange buffers do not fit"));
+    }
+    rc = vxs_comm_allgatherv_f32(ctx, sub_mine.p, counts[size_t(ctx->rank)], sub_all.p, counts.data(), displs.data(), PB.sub_pad.p, slot);
+    if (rc) { release(); return cleanup(rc); }
+    sub_dev = sub_all.p;
+  }
+  cudaEventRecord(ev[3], st);
+  // ---- top level
+  std::vector<int64_t> sub_off(size_t(nwin) + 1, 0);
+  for (int w = 0; w < nwin; w++) { sub_off[size_t(w) + 1] = sub_off[size_t(w)] + int64_t(sizes_d[size_t(w)]); if (submap_sizes) submap_sizes[w] = int64_t(sizes_d[size_t(w)]); }
+  for (int w = 0; w < nwin; w++) memcpy(top_poses + size_t(w) * 12, poses12 + size_t(win_first[size_t(w)]) * 12, 96);
+  int outer = 0;
+  if (sub_off[size_t(nwin)] > 0)
+    rc = vxs_hba_window_impl(ctx, coarse, fine, nullptr, sub_dev, 3, sub_off.data(), top_poses, nwin, top_max_iter, top_thread_num, nullptr, top_resis_log, &outer,
+                             ctx->nranks > 1 ? (long long)sub_off[size_t(lo)] : -1, ctx->nranks > 1 ? (long long)sub_off[size_t(hi)] : -1);
+  if (top_outer_iters) *top_outer_iters = outer;
+  cudaEventRecord(ev[4], st);
+  cudaStreamSynchronize(st);
+  if (phase_ms) {
+    for (int k = 0; k < 4; k++) { float ms = 0; cudaEventElapsedTime(&ms, ev[k], ev[k + 1]); phase_ms[k] = ms; }
+    phase_ms[4] = double(PB.last_voxels); phase_ms[5] = double(PB.last_entries);
+  }
+  release();
+  return cleanup(rc);
 }

@@ -25,10 +25,14 @@ struct DevBuf {  // grow-only device buffer
   size_t cap = 0;
   cudaError_t reserve(size_t n) {
     if (n <= cap) return cudaSuccess;
+    // a buffer that has to grow AGAIN gets 25 % head room: sizes that creep up from call to call (record / node counts of successive map builds) must not
+    // cost a cudaFree + cudaMalloc pair — each a device-wide synchronisation, hundreds of ms for GB-sized buffers — every time
+    const size_t want = p ? n + n / 4 : n;
     if (p) cudaFree(p);
     p = nullptr; cap = 0;
-    cudaError_t e = cudaMalloc((void**)&p, n * sizeof(T));
-    if (e == cudaSuccess) cap = n;
+    cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
+    if (e != cudaSuccess && want > n) { cudaGetLastError(); e = cudaMalloc((void**)&p, n * sizeof(T)); if (e == cudaSuccess) cap = n; return e; }
+    if (e == cudaSuccess) cap = want;
     return e;
   }
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
@@ -94,6 +98,7 @@ struct vxs_ctx {
   size_t h_pin_cap = 0;
   // voxeliser scratch lives in vxs_voxelize.cu (opaque)
   void* vox_scratch = nullptr;
+  void* hba_scratch = nullptr;       // vxs_hba_batch.cu: persistent buffers of the batched / hierarchical global-BA calls (grow-only, no malloc per pass)
   std::vector<struct vxs_factor*> factors;   // live factors created on this ctx (released with it)
 };
 
@@ -135,6 +140,7 @@ struct vxs_factor {
   cudaEvent_t up_fence = nullptr;
 };
 void vxs_odom_release(vxs_ctx* c);
+void vxs_hba_release(vxs_ctx* c);
 int vxs_odom_resident_scan(vxs_ctx* ctx, double** pv12_dev, long long* n);            // the scan var_init / odom_accumulate / pvec_update left on the device
 int vxs_odom_set_resident_scan(vxs_ctx* ctx, const double* pv12_host, long long n);
 int vxs_factor_wait_uploads(vxs_factor* f);   // orders ctx->stream behind every pending upload chunk (device-side wait, no host sync)

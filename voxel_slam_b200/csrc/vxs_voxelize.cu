@@ -37,8 +37,10 @@ struct VoxScratch : SortScratch {   // SortScratch: hist, blocksums, totals (vxs
   DevBuf<double> node_eig, node_sum, node_fix; DevBuf<unsigned int> node_nent, node_sel, node_voff, node_eoff;
   DevBuf<vxs_voxel_id> ids;
   std::vector<vxs_voxel_id> ids_host;
+  vxs_factor* hba_factor = nullptr;   // vxs_hba_window's factor, kept between calls (owned by the ctx's factor list)
 };
 static VoxScratch* scratch(vxs_ctx* c) { if (!c->vox_scratch) c->vox_scratch = new VoxScratch(); return static_cast<VoxScratch*>(c->vox_scratch); }
+int vxs_comm_allreduce_max_i64(vxs_ctx* ctx, long long* buf, size_t n);   // vxs_lm.cu
 void vxs_voxelize_release(vxs_ctx* c) {
   if (!c->vox_scratch) return;
   VoxScratch* s = static_cast<VoxScratch*>(c->vox_scratch);
@@ -120,9 +122,10 @@ __global__ void k_voxel_keys(const double* __restrict__ pw, long long n, double 
   hash[i] = voxel_hash(x, y, z);
 }
 
-__global__ void __launch_bounds__(256) k_bbox(PointSrc s, double voxel_size, long long* __restrict__ bbox) {
+__global__ void k_bbox_negate_min(long long* bbox) { if (threadIdx.x < 3) bbox[threadIdx.x] = -bbox[threadIdx.x]; }   // [min | max] <-> [-min | max] around the MAX all-reduce
+__global__ void __launch_bounds__(256) k_bbox(PointSrc s, double voxel_size, long long* __restrict__ bbox, long long i0, long long i1) {   // points [i0, i1)
   long long mn[3] = {LLONG_MAX, LLONG_MAX, LLONG_MAX}, mx[3] = {LLONG_MIN, LLONG_MIN, LLONG_MIN};
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < s.n; i += (long long)gridDim.x * blockDim.x) {
+  for (long long i = i0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += (long long)gridDim.x * blockDim.x) {
     const int fr = frame_of(s, i);
     const d3 w = world_point(s.poses + 12 * fr, load_point(s, i, fr));
     const long long k[3] = {quantise(w.x, voxel_size), quantise(w.y, voxel_size), quantise(w.z, voxel_size)};
@@ -315,7 +318,8 @@ __global__ void k_next_keys(const unsigned long long* __restrict__ keys, const u
 // of every virtual frame's keyframe in the uploaded point array (npts_total points), poses12_host = the nwin * win_size virtual-frame poses, W = win_size.
 struct BatchSpec { int nwin, win_size; const int64_t* src_off_host; int64_t npts_total; };
 static int build_factor(vxs_ctx* ctx, const vxs_map_params* mp, bool gba, const double* pts_d_host, const float* pts_f_host, int fstride, const int64_t* offsets_host, int nframes,
-                        const double* poses12_host, int W, vxs_factor* out, vxs_voxel_id* ids_out, int64_t ids_cap, int64_t* n_out, const BatchSpec* bs = nullptr) {
+                        const double* poses12_host, int W, vxs_factor* out, vxs_voxel_id* ids_out, int64_t ids_cap, int64_t* n_out, const BatchSpec* bs = nullptr,
+                        const float* pts_f_dev = nullptr /* the float points are already on the device (vxs_hba_pass): no upload */, long long own_lo = -1, long long own_hi = -1) {
   if (!ctx || !mp || !out || !offsets_host || !poses12_host || out->ctx != ctx) return VXS_ERR_ARG;
   if (mp->max_layer < 0 || mp->max_layer > 3 || !(mp->voxel_size > 0)) return vxs_fail(ctx, VXS_ERR_ARG, "max_layer must be 0..3 and voxel_size > 0");
   cudaSetDevice(ctx->device);
@@ -334,6 +338,7 @@ static int build_factor(vxs_ctx* ctx, const vxs_map_params* mp, bool gba, const 
   PointSrc ps; ps.pd = nullptr; ps.pf = nullptr; ps.fstride = fstride; ps.nframes = nframes; ps.n = N; ps.src_off = nullptr; ps.win_size = 0;
   const long long Nup = bs ? bs->npts_total : N;     // points to upload (batch: every keyframe once, although most belong to two windows)
   if (pts_d_host) { VXS_CUDA(ctx, s->pts_d.reserve(size_t(Nup) * 3)); VXS_CUDA(ctx, cudaMemcpyAsync(s->pts_d.p, pts_d_host, size_t(Nup) * 24, cudaMemcpyHostToDevice, st)); ps.pd = s->pts_d.p; }
+  else if (pts_f_dev) ps.pf = pts_f_dev;
   else { VXS_CUDA(ctx, s->pts_f.reserve(size_t(Nup) * fstride)); VXS_CUDA(ctx, cudaMemcpyAsync(s->pts_f.p, pts_f_host, size_t(Nup) * fstride * 4, cudaMemcpyHostToDevice, st)); ps.pf = s->pts_f.p; }
   if (bs) {
     VXS_CUDA(ctx, s->src_off.reserve(size_t(nframes)));
@@ -350,7 +355,17 @@ static int build_factor(vxs_ctx* ctx, const vxs_map_params* mp, bool gba, const 
   VXS_CUDA(ctx, s->bbox.reserve(6));
   const long long bb0[6] = {LLONG_MAX, LLONG_MAX, LLONG_MAX, LLONG_MIN, LLONG_MIN, LLONG_MIN};
   VXS_CUDA(ctx, cudaMemcpyAsync(s->bbox.p, bb0, sizeof bb0, cudaMemcpyHostToDevice, st));
-  VXS_LAUNCH(ctx, "k_bbox", k_bbox, std::min<unsigned>(nblk(size_t(N), 256), unsigned(ctx->sm_count) * 8), 256, 0, ps, mp->voxel_size, s->bbox.p);
+  // multi-GPU with a known own share of the points (vxs_hba_pass: the rank's own submaps): every rank boxes its share only and the boxes are combined by one
+  // 6-element MAX all-reduce, instead of every rank reading all points a first time just for the box
+  const bool part_bbox = ctx->nranks > 1 && !bs && own_lo >= 0 && own_hi >= own_lo && own_hi <= N;
+  const long long b0 = part_bbox ? own_lo : 0, b1 = part_bbox ? own_hi : N;
+  if (b1 > b0) VXS_LAUNCH(ctx, "k_bbox", k_bbox, std::min<unsigned>(nblk(size_t(b1 - b0), 256), unsigned(ctx->sm_count) * 8), 256, 0, ps, mp->voxel_size, s->bbox.p, b0, b1);
+  if (part_bbox) {
+    k_bbox_negate_min<<<1, 32, 0, st>>>(s->bbox.p);
+    int rcb = vxs_comm_allreduce_max_i64(ctx, s->bbox.p, 6);
+    if (rcb) return rcb;
+    k_bbox_negate_min<<<1, 32, 0, st>>>(s->bbox.p);
+  }
   long long bb[6];
   VXS_CUDA(ctx, cudaMemcpyAsync(bb, s->bbox.p, sizeof bb, cudaMemcpyDeviceToHost, st));
   VXS_CUDA(ctx, cudaStreamSynchronize(st));
@@ -727,6 +742,168 @@ extern "C" int vxs_submap_merge(vxs_ctx* ctx, const float* xyz, int stride_float
   return down_sample_dev(ctx, 0, s->pts_f2.p, 3, n, voxel_size, xyz_out, count_out, first_index_out, cap, n_out);
 }
 
+// ------------------------------------------------------------------ submap merge of MANY windows at once (the post-step of every bottom-level HBA_add_edge, voxelslam.cpp:2428-2447)
+// Same arithmetic as vxs_submap_merge per window; the windows only share the sort: a point's key is (window, cell), the stable sort keeps the
+// keyframe-by-keyframe input order inside a cell (the running float mean is order dependent), and the cells come out grouped by window.
+__global__ void __launch_bounds__(256) k_merge_transform_batch(const float* __restrict__ pts, int stride, const long long* __restrict__ voff, const long long* __restrict__ soff, int nf,
+                                                               const double* __restrict__ rel12, long long n, float* __restrict__ out, int* __restrict__ vf_out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int lo = 0, hi = nf;
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (voff[mid] <= i) lo = mid; else hi = mid; }
+  const double* T = rel12 + 12 * lo;
+  const float* p = pts + size_t(soff[lo] + (i - voff[lo])) * stride;
+  const double x = (double)p[0], y = (double)p[1], z = (double)p[2];
+  out[3 * i] = __double2float_rn(dot3_rn(T[0], T[1], T[2], x, y, z, T[9]));
+  out[3 * i + 1] = __double2float_rn(dot3_rn(T[3], T[4], T[5], x, y, z, T[10]));
+  out[3 * i + 2] = __double2float_rn(dot3_rn(T[6], T[7], T[8], x, y, z, T[11]));
+  vf_out[i] = lo;
+}
+__global__ void __launch_bounds__(256) k_ds_keys_batch(const float* __restrict__ pts, const int* __restrict__ vf, int win_size, long long n, double voxel_size, long long minx, long long miny,
+                                                       long long minz, unsigned long long ey, unsigned long long ez, unsigned long long cells, unsigned long long* __restrict__ keys,
+                                                       unsigned int* __restrict__ idx) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = pts + 3 * size_t(i);
+  const unsigned long long x = (unsigned long long)(quantise((double)p[0], voxel_size) - minx), y = (unsigned long long)(quantise((double)p[1], voxel_size) - miny),
+                           z = (unsigned long long)(quantise((double)p[2], voxel_size) - minz);
+  keys[i] = (unsigned long long)(vf[i] / win_size) * cells + (x * ey + y) * ez + z;
+  idx[i] = (unsigned int)i;
+}
+__global__ void __launch_bounds__(256) k_merge_win_ptr(const unsigned long long* __restrict__ rec_key, unsigned int R, unsigned long long cells, int nwin, long long* __restrict__ win_ptr) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w > nwin) return;
+  unsigned int lo = 0, hi = R;
+  const unsigned long long want = (unsigned long long)w * cells;
+  while (lo < hi) { const unsigned int mid = (lo + hi) >> 1; if (rec_key[mid] < want) lo = mid + 1; else hi = mid; }
+  win_ptr[w] = (long long)lo;
+}
+__global__ void __launch_bounds__(256) k_merge_local_index(long long* __restrict__ pick, const unsigned long long* __restrict__ rec_key, unsigned int R, unsigned long long cells, int win_size,
+                                                           const long long* __restrict__ voff) {
+  const unsigned int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < R) pick[r] -= voff[size_t(rec_key[r] / cells) * win_size];     // index inside the window's concatenated clouds
+}
+
+// xyz_dev / dev_first_point: device copy of the input points (or NULL: upload from xyz).  dev_out: when given the merged points of all windows are appended to it on the
+// device (3 floats each) instead of being copied to the host arrays.
+int vxs_submap_merge_batch_impl(vxs_ctx* ctx, const float* xyz, const float* xyz_dev, int64_t dev_first_point, int stride_floats, const int64_t* kf_offsets, int K, const double* poses_win,
+                                const int32_t* win_first, int nwin, int win_size, double voxel_size, int64_t max_points_per_chunk, float* xyz_out, float* count_out,
+                                int64_t* first_index_out, int64_t cap, int64_t* win_offsets, int64_t* n_out, DevBuf<float>* dev_out) {
+  if (!ctx || (!xyz && !xyz_dev) || !kf_offsets || !poses_win || !win_first || !win_offsets || !n_out || K <= 0 || nwin <= 0 || win_size <= 0 || stride_floats < 3 || !(voxel_size >= 0.001)) return VXS_ERR_ARG;
+  for (int w = 0; w < nwin; w++) if (win_first[w] < 0 || win_first[w] + win_size > K) return vxs_fail(ctx, VXS_ERR_ARG, "vxs_submap_merge_batch: a window reaches beyond the keyframes");
+  cudaSetDevice(ctx->device);
+  VoxScratch* s = scratch(ctx);
+  cudaStream_t st = ctx->stream;
+  if (max_points_per_chunk <= 0) max_points_per_chunk = 96ll << 20;
+  VXS_CUDA(ctx, s->totals.reserve(16)); VXS_CUDA(ctx, s->bbox.reserve(6));
+  int64_t total = 0;
+  win_offsets[0] = 0;
+  for (int w0 = 0; w0 < nwin;) {
+    int w1 = w0; int64_t vp = 0;
+    while (w1 < nwin) {
+      const int64_t np = kf_offsets[win_first[w1] + win_size] - kf_offsets[win_first[w1]];
+      if (w1 > w0 && vp + np > max_points_per_chunk) break;
+      vp += np; w1++;
+    }
+    const int nw = w1 - w0, nf = nw * win_size;
+    int kf_lo = K, kf_hi = 0;
+    for (int w = w0; w < w1; w++) { kf_lo = std::min(kf_lo, int(win_first[w])); kf_hi = std::max(kf_hi, int(win_first[w]) + win_size); }
+    const int64_t base = kf_offsets[kf_lo], nup = kf_offsets[kf_hi] - base;
+    std::vector<long long> voff(size_t(nf) + 1, 0), soff(size_t(nf), 0);
+    std::vector<double> rel(size_t(nf) * 12);
+    for (int w = 0; w < nw; w++) {
+      const double* P0 = poses_win + size_t(w0 + w) * win_size * 12;
+      for (int j = 0; j < win_size; j++) {
+        const int kf = win_first[w0 + w] + j, vf = w * win_size + j;
+        voff[size_t(vf) + 1] = voff[size_t(vf)] + (kf_offsets[kf + 1] - kf_offsets[kf]);
+        soff[size_t(vf)] = kf_offsets[kf] - base;
+        const double* Pi = P0 + 12 * size_t(j);
+        const double d[3] = {Pi[9] - P0[9], Pi[10] - P0[10], Pi[11] - P0[11]};
+        for (int r = 0; r < 3; r++) {
+          for (int c = 0; c < 3; c++) rel[12 * size_t(vf) + 3 * r + c] = (P0[r] * Pi[c] + P0[3 + r] * Pi[3 + c]) + P0[6 + r] * Pi[6 + c];
+          rel[12 * size_t(vf) + 9 + r] = (P0[r] * d[0] + P0[3 + r] * d[1]) + P0[6 + r] * d[2];
+        }
+      }
+    }
+    const long long n = voff[size_t(nf)];
+    if (n >= (1ll << 32)) return vxs_fail(ctx, VXS_ERR_ARG, "more than 2^32 points in one merge chunk");
+    long long R = 0;
+    if (n > 0) {
+      const float* in_dev = nullptr;
+      if (xyz_dev) in_dev = xyz_dev + size_t(base - dev_first_point) * stride_floats;
+      else {
+        VXS_CUDA(ctx, s->pts_f.reserve(size_t(nup) * stride_floats));
+        VXS_CUDA(ctx, cudaMemcpyAsync(s->pts_f.p, xyz + size_t(base) * stride_floats, size_t(nup) * stride_floats * 4, cudaMemcpyHostToDevice, st));
+        in_dev = s->pts_f.p;
+      }
+      VXS_CUDA(ctx, s->poses.reserve(size_t(nf) * 12)); VXS_CUDA(ctx, s->offsets.reserve(size_t(nf) + 1)); VXS_CUDA(ctx, s->src_off.reserve(size_t(nf)));
+      VXS_CUDA(ctx, cudaMemcpyAsync(s->poses.p, rel.data(), rel.size() * 8, cudaMemcpyHostToDevice, st));
+      VXS_CUDA(ctx, cudaMemcpyAsync(s->offsets.p, voff.data(), voff.size() * 8, cudaMemcpyHostToDevice, st));
+      VXS_CUDA(ctx, cudaMemcpyAsync(s->src_off.p, soff.data(), soff.size() * 8, cudaMemcpyHostToDevice, st));
+      VXS_CUDA(ctx, s->pts_f2.reserve(size_t(n) * 3)); VXS_CUDA(ctx, s->flags.reserve(size_t(n))); VXS_CUDA(ctx, s->scanbuf.reserve(size_t(n)));
+      int* vf_dev = reinterpret_cast<int*>(s->scanbuf.p);       // (window, slot) of every virtual point; consumed by the key kernel before the scan reuses the buffer
+      VXS_LAUNCH(ctx, "k_merge_transform", k_merge_transform_batch, nblk(size_t(n), 256), 256, 0, in_dev, stride_floats, s->offsets.p, s->src_off.p, nf, s->poses.p, n, s->pts_f2.p, vf_dev);
+      const long long bb0[6] = {LLONG_MAX, LLONG_MAX, LLONG_MAX, LLONG_MIN, LLONG_MIN, LLONG_MIN};
+      VXS_CUDA(ctx, cudaMemcpyAsync(s->bbox.p, bb0, sizeof bb0, cudaMemcpyHostToDevice, st));
+      { auto kb = k_ds_bbox<float>; VXS_LAUNCH(ctx, "k_ds_bbox", kb, std::min<unsigned>(nblk(size_t(n), 256), unsigned(ctx->sm_count) * 8), 256, 0, s->pts_f2.p, 3, n, voxel_size, s->bbox.p); }
+      long long bb[6];
+      VXS_CUDA(ctx, cudaMemcpyAsync(bb, s->bbox.p, sizeof bb, cudaMemcpyDeviceToHost, st));
+      VXS_CUDA(ctx, cudaStreamSynchronize(st));      // also: the host vectors above are no longer read
+      const long double ex = (long double)bb[3] - bb[0] + 1, ey = (long double)bb[4] - bb[1] + 1, ez = (long double)bb[5] - bb[2] + 1;
+      if (ex * ey * ez * nw >= (long double)(1ull << 62)) return vxs_fail(ctx, VXS_ERR_RANGE, "merge grid exceeds 2^62 cells");
+      const unsigned long long cells = (unsigned long long)(ex * ey * ez);
+      const int key_bits = bits_for((unsigned long long)(ex * ey * ez * nw));
+      VXS_CUDA(ctx, s->keysA.reserve(size_t(n))); VXS_CUDA(ctx, s->keysB.reserve(size_t(n))); VXS_CUDA(ctx, s->idxA.reserve(size_t(n))); VXS_CUDA(ctx, s->idxB.reserve(size_t(n)));
+      VXS_LAUNCH(ctx, "k_ds_keys", k_ds_keys_batch, nblk(size_t(n), 256), 256, 0, s->pts_f2.p, vf_dev, win_size, n, voxel_size, bb[0], bb[1], bb[2], (unsigned long long)ey, (unsigned long long)ez,
+                 cells, s->keysA.p, s->idxA.p);
+      unsigned long long* ks; unsigned int* vs;
+      int rc = radix_sort(ctx, s, s->keysA.p, s->idxA.p, s->keysB.p, s->idxB.p, size_t(n), key_bits, &ks, &vs);
+      if (rc) return rc;
+      VXS_LAUNCH(ctx, "k_flag_heads", k_flag_heads, nblk(size_t(n), 256), 256, 0, ks, size_t(n), s->flags.p);
+      rc = scan_u32(ctx, s, s->flags.p, s->scanbuf.p, size_t(n), s->totals.p + 0);
+      if (rc) return rc;
+      unsigned int Ru = 0;
+      VXS_CUDA(ctx, cudaMemcpyAsync(&Ru, s->totals.p + 0, 4, cudaMemcpyDeviceToHost, st));
+      VXS_CUDA(ctx, cudaStreamSynchronize(st));
+      R = Ru;
+      VXS_CUDA(ctx, s->rec_start.reserve(size_t(R) + 1)); VXS_CUDA(ctx, s->rec_key.reserve(size_t(R)));
+      VXS_LAUNCH(ctx, "k_write_records", k_write_records, nblk(size_t(n), 256), 256, 0, ks, s->flags.p, s->scanbuf.p, size_t(n), s->rec_start.p, s->rec_key.p, s->totals.p + 0);
+      VXS_CUDA(ctx, s->rec_local.reserve(size_t(R) * 4 + 4)); VXS_CUDA(ctx, s->rec_world.reserve(size_t(R) + size_t(nw) + 2));
+      float* d_xyz = reinterpret_cast<float*>(s->rec_local.p); float* d_cnt = d_xyz + 3 * size_t(R);
+      long long* d_pick = reinterpret_cast<long long*>(s->rec_world.p); long long* d_wptr = d_pick + R;
+      VXS_LAUNCH(ctx, "k_ds_reduce", k_ds_reduce, nblk(size_t(R), 128), 128, 0, s->pts_f2.p, 3, vs, s->rec_start.p, Ru, 0, d_xyz, d_cnt, d_pick);
+      VXS_LAUNCH(ctx, "k_merge_win_ptr", k_merge_win_ptr, nblk(size_t(nw) + 1, 256), 256, 0, s->rec_key.p, Ru, cells, nw, d_wptr);
+      VXS_LAUNCH(ctx, "k_merge_local_index", k_merge_local_index, nblk(size_t(R), 256), 256, 0, d_pick, s->rec_key.p, Ru, cells, win_size, s->offsets.p);
+      std::vector<long long> wp(size_t(nw) + 1);
+      VXS_CUDA(ctx, cudaMemcpyAsync(wp.data(), d_wptr, wp.size() * 8, cudaMemcpyDeviceToHost, st));
+      if (dev_out && R > 0) {   // keep the merged cloud on the device
+        VXS_CUDA(ctx, dev_out->reserve_keep(size_t(total + R) * 3, size_t(total) * 3, st));
+        VXS_CUDA(ctx, cudaMemcpyAsync(dev_out->p + size_t(total) * 3, d_xyz, size_t(R) * 12, cudaMemcpyDeviceToDevice, st));
+      }
+      const int64_t room = dev_out ? 0 : std::max<int64_t>(0, cap - total);
+      const size_t ncopy = size_t(std::min<int64_t>(room, R));
+      if (xyz_out && ncopy) VXS_CUDA(ctx, cudaMemcpyAsync(xyz_out + size_t(total) * 3, d_xyz, ncopy * 12, cudaMemcpyDeviceToHost, st));
+      if (count_out && ncopy) VXS_CUDA(ctx, cudaMemcpyAsync(count_out + size_t(total), d_cnt, ncopy * 4, cudaMemcpyDeviceToHost, st));
+      if (first_index_out && ncopy) VXS_CUDA(ctx, cudaMemcpyAsync(first_index_out + size_t(total), d_pick, ncopy * 8, cudaMemcpyDeviceToHost, st));
+      VXS_CUDA(ctx, cudaStreamSynchronize(st));
+      for (int w = 0; w < nw; w++) win_offsets[w0 + w + 1] = total + wp[size_t(w) + 1];
+    } else {
+      for (int w = 0; w < nw; w++) win_offsets[w0 + w + 1] = total;
+    }
+    total += R;
+    w0 = w1;
+  }
+  *n_out = total;
+  return VXS_OK;
+}
+extern "C" int vxs_submap_merge_batch(vxs_ctx* ctx, const float* xyz, int stride_floats, const int64_t* kf_offsets, int K, const double* poses_win, const int32_t* win_first, int nwin,
+                                      int win_size, double voxel_size, int64_t max_points_per_chunk, float* xyz_out, float* count_out, int64_t* first_index_out, int64_t cap,
+                                      int64_t* win_offsets, int64_t* n_out) {
+  if (!xyz) return VXS_ERR_ARG;
+  return vxs_submap_merge_batch_impl(ctx, xyz, nullptr, 0, stride_floats, kf_offsets, K, poses_win, win_first, nwin, win_size, voxel_size, max_points_per_chunk, xyz_out, count_out,
+                                     first_index_out, cap, win_offsets, n_out, nullptr);
+}
+
 extern "C" int vxs_down_sampling_voxel(vxs_ctx* ctx, const float* pts, int stride_floats, int64_t n, double voxel_size, float* xyz_out, float* count_out, int64_t* first_index_out,
                                        int64_t cap, int64_t* n_out) {
   return down_sample(ctx, 0, pts, stride_floats, n, voxel_size, xyz_out, count_out, first_index_out, cap, n_out);
@@ -774,7 +951,7 @@ extern "C" int vxs_build_gba_factor(vxs_ctx* ctx, const vxs_map_params* mp, cons
 // Map build of a chunk of independent windows (vxs_hba_bottom_batch): OctreeGBA::cut_voxel of every (window, keyframe) + OctreeGBA_multi_recut, one pass.
 // win_first[w] = first keyframe of window w; keyframes [kf_lo, kf_hi) cover the chunk and are uploaded once.
 int vxs_build_gba_batch(vxs_ctx* ctx, const vxs_map_params* mp, const float* xyz, int stride_floats, const int64_t* kf_offsets, const double* poses12, const int32_t* win_first, int nwin,
-                        int win_size, int kf_lo, int kf_hi, vxs_factor* out) {
+                        int win_size, int kf_lo, int kf_hi, vxs_factor* out, const float* xyz_dev, int64_t dev_first_point) {   // xyz_dev: device copy of the points from global index dev_first_point on (or NULL)
   const int nf = nwin * win_size;
   std::vector<int64_t> voff(size_t(nf) + 1, 0), soff(size_t(nf), 0);
   std::vector<double> vposes(size_t(nf) * 12);
@@ -787,23 +964,27 @@ int vxs_build_gba_batch(vxs_ctx* ctx, const vxs_map_params* mp, const float* xyz
       memcpy(vposes.data() + size_t(vf) * 12, poses12 + size_t(kf) * 12, 96);
     }
   BatchSpec bs; bs.nwin = nwin; bs.win_size = win_size; bs.src_off_host = soff.data(); bs.npts_total = kf_offsets[kf_hi] - base;
-  return build_factor(ctx, mp, true, nullptr, xyz + size_t(base) * stride_floats, stride_floats, voff.data(), nf, vposes.data(), win_size, out, nullptr, 0, nullptr, &bs);
+  return build_factor(ctx, mp, true, nullptr, xyz + size_t(base) * stride_floats, stride_floats, voff.data(), nf, vposes.data(), win_size, out, nullptr, 0, nullptr, &bs,
+                      xyz_dev ? xyz_dev + size_t(base - dev_first_point) * stride_floats : nullptr);
 }
 
-extern "C" int vxs_hba_window(vxs_ctx* ctx, const vxs_map_params* coarse, const vxs_map_params* fine, const float* xyz, int stride_floats, const int64_t* kf_offsets,
-                              double* poses12, int W, int max_iter, int thread_num, double* hess_out, double* resis_log, int* outer_iters) {
+int vxs_hba_window_impl(vxs_ctx* ctx, const vxs_map_params* coarse, const vxs_map_params* fine, const float* xyz, const float* xyz_dev, int stride_floats, const int64_t* kf_offsets,
+                        double* poses12, int W, int max_iter, int thread_num, double* hess_out, double* resis_log, int* outer_iters, long long own_lo, long long own_hi) {
   if (!ctx || !coarse || !fine || !poses12 || W <= 0) return VXS_ERR_ARG;
   vxs_map_params gp = *coarse;
   const int up = 4;
   int converge_flag = 0, iters = 0, warn = 0;
   double converge_thre = 0.05;
-  vxs_factor* f = nullptr;
-  int rc = vxs_factor_create(ctx, W, &f);
-  if (rc) return rc;
+  // the factor (and its (6W)^2 accumulators) is kept on the ctx between calls: an HBA pass per submap must not pay its cudaMalloc / cudaFree every time
+  VoxScratch* vs_ = scratch(ctx);
+  int rc = VXS_OK;
+  if (!vs_->hba_factor) { rc = vxs_factor_create(ctx, W, &vs_->hba_factor); if (rc) return rc; }
+  vxs_factor* f = vs_->hba_factor;
   for (int iterCnt = 0; iterCnt < max_iter; iterCnt++) {
     if (converge_flag == 1 || iterCnt == max_iter - 1) { const int ml = gp.max_layer; gp = *fine; gp.max_layer = ml; }   // :2362-2372 (max_layer is the shared global)
     int64_t nv = 0;
-    rc = vxs_build_gba_factor(ctx, &gp, xyz, stride_floats, kf_offsets, poses12, W, f, nullptr, 0, &nv);
+    rc = xyz_dev ? build_factor(ctx, &gp, true, nullptr, nullptr, stride_floats, kf_offsets, W, poses12, W, f, nullptr, 0, &nv, nullptr, xyz_dev, own_lo, own_hi)
+                 : vxs_build_gba_factor(ctx, &gp, xyz, stride_floats, kf_offsets, poses12, W, f, nullptr, 0, &nv);
     if (rc < 0) break;
     double resis[2] = {0, 0};
     int is_converge = 0;
@@ -818,7 +999,10 @@ extern "C" int vxs_hba_window(vxs_ctx* ctx, const vxs_map_params* coarse, const 
       else if (converge_flag == 1) break;
     }
   }
-  vxs_factor_destroy(f);
   if (outer_iters) *outer_iters = iters;
   return rc < 0 ? rc : warn;
+}
+extern "C" int vxs_hba_window(vxs_ctx* ctx, const vxs_map_params* coarse, const vxs_map_params* fine, const float* xyz, int stride_floats, const int64_t* kf_offsets,
+                              double* poses12, int W, int max_iter, int thread_num, double* hess_out, double* resis_log, int* outer_iters) {
+  return vxs_hba_window_impl(ctx, coarse, fine, xyz, nullptr, stride_floats, kf_offsets, poses12, W, max_iter, thread_num, hess_out, resis_log, outer_iters, -1, -1);
 }
