@@ -262,8 +262,12 @@ def run_ours(args):
     bytes_hess = E * 80 + V * 176 + 8 * (nl * nl + nl + 1)
     flops_hess = V * (700.0 * kv + 110.0 * kv * kv)
     roof_hess = roof(["k_jac", "k_syrk"], bytes_hess, flops_hess)
-    roof_resid = roof(["k_cluster_sum", "k_eig_residual"], bytes_resid)
+    resid_names = ["k_residual_stream"] if "k_residual_stream" in kern else ["k_cluster_sum", "k_eig_residual"]
+    roof_resid = roof(resid_names, bytes_resid)
     roof_jac = roof(["k_jac"], E * 80 + V * 176 + E * 144)
+    if roof_jac is not None:   # SURVEY §8(d) counts only the cluster reads (k*80 + 176 B / voxel); the 144 B / entry of rank-3 rows written for the SYRK are this design's own intermediate
+        roof_jac["bytes_counted"] = "k*80 + 176 B read + k*144 B written per voxel (the X rows the SYRK consumes)"
+        roof_jac["frac_survey_8d_bytes_only"] = (E * 80 + V * 176) / (roof_jac["ms"] * 1e-3) / 1e9 / hbm
     # the dominant kernel (k_syrk: H -= X^T X on the fp64 tensor path) is compute-bound for k >~ 4 (SURVEY.md §7.3 / §8d "report both"):
     # its roofline is the fp64 mma.sync (DMMA) throughput measured in this process; the HBM view of the whole Hessian build rides along
     roof_main = roof_hess
@@ -277,12 +281,12 @@ def run_ours(args):
         roof_main = {"kernel": "k_syrk", "bound": "tensor", "achieved": fl_sy / t_sy / 1e12, "peak": dmma_peak, "unit": "TFLOP/s", "frac": fl_sy / t_sy / 1e12 / dmma_peak,
                      "traffic": ncu_traffic(["k_syrk"]), "peak_source": "vxs_diag_dmma_tflops: mma.sync.m8n8k4.f64 (SASS DMMA) throughput measured in this process; "
                      "MEASURED_PEAKS.json carries no fp64 figure", "algorithmic_flops": fl_sy, "us_per_launch": t_sy * 1e6,
-                     "traffic_source": "profiles/r01_ncu_full_ba_kernels.txt (ncu --set full of this command, DRAM read + write per launch)",
+                     "traffic_source": "profiles/r02_ncu_full_ba_kernels.txt (ncu --set full of this command, DRAM read + write per launch)",
                      "hbm_view_of_hessian_build": roof_hess}
-    for r_, names_ in ((roof_hess, ["k_jac_slab", "k_syrk"]), (roof_resid, ["k_cluster_sum", "k_eig_residual"]), (roof_jac, ["k_jac_slab"])):
+    for r_, names_ in ((roof_hess, ["k_jac_slab", "k_syrk"]), (roof_resid, resid_names), (roof_jac, ["k_jac_slab"])):
         if r_ is not None:
             r_["traffic"] = ncu_traffic(names_)
-            r_["traffic_source"] = "profiles/r01_ncu_full_ba_kernels.txt (ncu --set full of this command, DRAM read + write per launch)"
+            r_["traffic_source"] = "profiles/r02_ncu_full_ba_kernels.txt (ncu --set full of this command, DRAM read + write per launch)"
     dom = max(kern.items(), key=lambda kv_: kv_[1]["ms_per_step"])[0] if kern else None
 
     c2 = ds = None
@@ -441,8 +445,9 @@ def hba_leg(vx, local, rank, world, dist, args):
       top    : ONE BA over all submaps (W = number of windows), HBA_add_edge(total_max_iter 1): the voxel map is sharded over the ranks by the hash of the root cell and
                [C | g | D | r] is all-reduced by libvxs' own NCCL communicator once per Hessian build; the 6W-dof LDLT is replicated.
     A step is one full pass; time = max over ranks."""
-    import torch
     from voxel_slam_b200 import api
+    if world > 1:
+        import torch
     K, n, per_row = args.hba_keyframes, args.hba_pts, args.hba_per_row
     ws, stride_w = 10, 5
     ctx = vx.Context(local)
@@ -459,9 +464,10 @@ def hba_leg(vx, local, rank, world, dist, args):
     off = np.arange(K + 1, dtype=np.int64) * n
     t_gen = time.time() - t0
     fine = vx.MapParams.make(voxel_size=1.0, min_eigen_value=0.0025, max_layer=2)
-    win_first = np.arange(0, K - ws + 1, stride_w, dtype=np.int32)
+    from voxel_slam_b200 import sharding
+    win_first = sharding.hba_windows(K, ws, stride_w)
     nwin = len(win_first)
-    lo, hi = nwin * rank // world, nwin * (rank + 1) // world
+    lo, hi = sharding.window_share(nwin, rank, world)
     mine = win_first[lo:hi]
     dev = f"cuda:{local}"
     ph = {}
@@ -479,7 +485,8 @@ def hba_leg(vx, local, rank, world, dist, args):
         per_step.append([round(float(x), 2) for x in o["phase_ms"][:4]] + [round(wall, 2)])
         return o
 
-    o = step()
+    o = step()          # warm-up passes: allocations settle (buffers keep 1/8 head room), NCCL opens its peer channels on first use
+    step()
     step()
     ph.clear()
     barrier(dist, local)
@@ -571,8 +578,8 @@ def gba_sharded_leg(vx, local, rank, world, dist, args):
 
 def ncu_traffic(kernels):
     """DRAM bytes per launch (read + write) of the named kernels from the committed `ncu --set full` summary of this same command
-    (profiles/r01_ncu_full_ba_kernels.txt); None when the summary is absent."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_ncu_full_ba_kernels.txt")
+    (profiles/r02_ncu_full_ba_kernels.txt); None when the summary is absent."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_ncu_full_ba_kernels.txt")
     try:
         txt = open(path).read()
     except OSError:
@@ -904,7 +911,7 @@ def main():
     ap.add_argument("--pts-per-scan", type=int, default=1000000)
     ap.add_argument("--L", type=float, default=130.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="local_ba", choices=["local_ba", "gba", "gba_window"])
+    ap.add_argument("--workload", default="local_ba", choices=["local_ba", "gba", "gba_window", "hba"])
     ap.add_argument("--no-local-mapping", action="store_true")
     ap.add_argument("--lm-steps", type=int, default=6)
     ap.add_argument("--no-gba", action="store_true")
@@ -923,6 +930,15 @@ def main():
     ap.add_argument("--gba-per-row", type=int, default=20)
     ap.add_argument("--gba-voxel", type=float, default=1.0)
     args = ap.parse_args()
+    if args.workload == "hba":     # the hierarchical global-BA leg alone (same JSON block as the `gba` key of the default run)
+        import voxel_slam_b200 as vx
+        rank, world, local, dist = dist_setup(args)
+        res = hba_leg(vx, local, rank, world, dist, args)
+        if rank == 0:
+            print(json.dumps(res), flush=True)
+        if dist is not None:
+            dist.barrier(); dist.destroy_process_group()
+        return
     if args.workload == "gba":
         return run_gba(args)
     if args.workload == "gba_window":

@@ -61,3 +61,49 @@ def test_shard_csr_helper():
     p2, f2, c2, (e2,) = sharding.shard_csr(ptr, fr, cl, [np.array([10, 11, 12])], [True, False, True])
     assert p2.tolist() == [0, 2, 5] and f2.tolist() == [0, 1, 0, 1, 2] and e2.tolist() == [10, 12] and c2[2, 0] == 30.0
     assert sharding.voxel_hash(-3, 0, -5) == 5254958208       # matches tests/golden/voxel_keys.json
+
+
+def _hba_worker(rank, world, port, q):
+    """bottom level of the hierarchical global BA over `world` ranks: every rank takes its share of the windows, solves them with the ORACLE (the windows are
+    independent problems), and the per-window results gathered over gloo equal the single-process pass"""
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import oracle_api as oa
+    import scenes
+    import voxel_slam_b200 as vx
+    from voxel_slam_b200 import sharding
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    K, ws, st = 14, 6, 2
+    tr, est = scenes.poses_true_est(K, 8.0, 71, rot_sigma=3e-3, pos_sigma=2e-2)
+    xyz, off = scenes.make_points(K, 1500, 8.0, 71, tr, dtype=np.float32)
+    fine = vx.MapParams.make(voxel_size=1.0, min_eigen_value=0.0025, max_layer=2)
+    wf = sharding.hba_windows(K, ws, st)
+    lo, hi = sharding.window_share(len(wf), rank, world)
+
+    def solve(k0):
+        a, b = off[k0], off[k0 + ws]
+        return oa.hba_window(fine, fine, xyz[a:b], off[k0:k0 + ws + 1] - a, est[k0:k0 + ws], max_iter=1, thread_num=2)["poses"]
+
+    mine = torch.zeros((len(wf), ws, 12), dtype=torch.float64)
+    for w in range(lo, hi):
+        mine[w] = torch.from_numpy(solve(int(wf[w])))
+    dist.all_reduce(mine)                                   # disjoint shares: the sum is the concatenation
+    if rank == 0:
+        shares = [sharding.window_share(len(wf), r, world) for r in range(world)]
+        ok = shares[0][0] == 0 and shares[-1][1] == len(wf) and all(shares[r][1] == shares[r + 1][0] for r in range(world - 1)) and len(wf) == 5
+        ok = ok and all(np.array_equal(mine[w].numpy(), solve(int(wf[w]))) for w in range(len(wf)))
+        q.put(bool(ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_hba_bottom_windows_distributed_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_hba_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    [p.join(240) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    assert q.get(timeout=5) is True

@@ -37,6 +37,7 @@ extern "C" int vxs_ctx_create(int device, vxs_ctx** out) {
   { const char* e = getenv("VXS_RESID_STAGES"); if (e) c->resid_stages = atoi(e); }
   { const char* e = getenv("VXS_RESID_PER_SM"); if (e) c->resid_per_sm = atoi(e); }
   cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  { const char* e = getenv("VXS_HBA_ROUTE"); c->hba_route = (e && e[0] == '0') ? 0 : 1; }
   { const char* e = getenv("VXS_SYRK_BULK"); c->syrk_bulk = (e && e[0] == '1') ? 1 : 0; }
   { const char* e = getenv("VXS_SYRK_STREAMK"); c->syrk_streamk = (e && e[0] == '1') ? 1 : 0; }
   *out = c;

@@ -27,6 +27,8 @@ int vxs_submap_merge_batch_impl(vxs_ctx* ctx, const float* xyz, const float* xyz
                                 int64_t* first_index_out, int64_t cap, int64_t* win_offsets, int64_t* n_out, DevBuf<float>* dev_out);
 int vxs_hba_window_impl(vxs_ctx* ctx, const vxs_map_params* coarse, const vxs_map_params* fine, const float* xyz, const float* xyz_dev, int stride_floats, const int64_t* kf_offsets,
                         double* poses12, int W, int max_iter, int thread_num, double* hess_out, double* resis_log, int* outer_iters, long long own_lo, long long own_hi);
+int vxs_hba_top_routed(vxs_ctx* ctx, const vxs_map_params* coarse, const vxs_map_params* fine, const float* sub_mine, const int64_t* woff_host, int first_window, int nmine, int nwin,
+                       double* poses12, int max_iter, int thread_num, double* resis_log, int* outer_iters, DevBuf<float>* sendbuf, DevBuf<float>* recvbuf);
 int vxs_comm_allgatherv_f32(vxs_ctx* ctx, const float* mine, size_t my_count, float* all, const size_t* counts, const size_t* displs, float* pad, size_t slot);   // vxs_lm.cu
 
 namespace {
@@ -403,7 +405,9 @@ extern "C" int vxs_hba_pass(vxs_ctx* ctx, const vxs_map_params* coarse, const vx
     for (int w = 0; w < nmine; w++) sizes_d[size_t(lo + w)] = double(woff[size_t(w) + 1] - woff[size_t(w)]);
   } else cudaEventRecord(ev[1], st);
   cudaEventRecord(ev[2], st);
-  // ---- submaps of all ranks on every rank
+  // ---- multi-GPU: either every point goes straight to the rank that owns its root cell (all-to-all, default), or the submaps of all ranks go to every rank (all-gather,
+  //      VXS_HBA_ROUTE=0) and every rank picks its points out of all of them
+  const bool routed = ctx->nranks > 1 && ctx->hba_route;
   const float* sub_dev = sub_mine.p;
   if (ctx->nranks > 1) {
     if (ctx->stage.reserve(size_t(nwin)) != cudaSuccess) { release(); return cleanup(VXS_ERR_NOMEM); }
@@ -412,29 +416,31 @@ extern "C" int vxs_hba_pass(vxs_ctx* ctx, const vxs_map_params* coarse, const vx
     if (rc) { release(); return cleanup(rc); }
     cudaMemcpyAsync(sizes_d.data(), ctx->stage.p, size_t(nwin) * 8, cudaMemcpyDeviceToHost, st);
     cudaStreamSynchronize(st);
+    if (!routed) {
     std::vector<size_t> counts(size_t(ctx->nranks), 0), displs(size_t(ctx->nranks), 0);
-    size_t tot = 0;
-    for (int r = 0; r < ctx->nranks; r++) {
-      const int rlo = int((long long)nwin * r / ctx->nranks), rhi = int((long long)nwin * (r + 1) / ctx->nranks);
-      size_t c = 0;
-      for (int w = rlo; w < rhi; w++) c += size_t(sizes_d[size_t(w)]);
-      counts[size_t(r)] = c * 3; displs[size_t(r)] = tot * 3; tot += c;
+      size_t tot = 0;
+      for (int r = 0; r < ctx->nranks; r++) {
+        const int rlo = int((long long)nwin * r / ctx->nranks), rhi = int((long long)nwin * (r + 1) / ctx->nranks);
+        size_t c = 0;
+        for (int w = rlo; w < rhi; w++) c += size_t(sizes_d[size_t(w)]);
+        counts[size_t(r)] = c * 3; displs[size_t(r)] = tot * 3; tot += c;
+      }
+      // head room of 1/8: the merged clouds differ by a few cells from pass to pass (the poses of the bottom level agree to rounding only), and a buffer that
+      // is a few bytes short costs a cudaFree + cudaMalloc of gigabytes (measured: 370 ms once every few passes)
+      if (sub_all.cap < std::max<size_t>(tot, 1) * 3 && sub_all.reserve((std::max<size_t>(tot, 1) + tot / 8) * 3) != cudaSuccess) { release(); return cleanup(vxs_fail(ctx, VXS_ERR_NOMEM, "vxs_hba_pass: submaps do not fit")); }
+      size_t slot = 0;
+      for (size_t c : counts) slot = std::max(slot, c);
+      slot = (slot + 3) & ~size_t(3);
+      // the padded all-gather reads `slot` floats from this rank's buffer: make sure they exist
+      const size_t slot_cap = std::max<size_t>(slot, 1) + slot / 8;
+      if ((sub_mine.cap < std::max<size_t>(slot, 1) && sub_mine.reserve_keep(slot_cap, counts[size_t(ctx->rank)], st) != cudaSuccess) ||
+          (PB.sub_pad.cap < std::max<size_t>(slot, 1) * size_t(ctx->nranks) && PB.sub_pad.reserve(slot_cap * size_t(ctx->nranks)) != cudaSuccess)) {
+        release(); return cleanup(vxs_fail(ctx, VXS_ERR_NOMEM, "vxs_hba_pass: exchange buffers do not fit"));
+      }
+      rc = vxs_comm_allgatherv_f32(ctx, sub_mine.p, counts[size_t(ctx->rank)], sub_all.p, counts.data(), displs.data(), PB.sub_pad.p, slot);
+      if (rc) { release(); return cleanup(rc); }
+      sub_dev = sub_all.p;
     }
-    // head room of 1/8: the merged clouds differ by a few cells from pass to pass (the poses of the bottom level agree to rounding only), and a buffer that
-    // is a few bytes short costs a cudaFree + cudaMalloc of gigabytes (measured: 370 ms once every few passes)
-    if (sub_all.cap < std::max<size_t>(tot, 1) * 3 && sub_all.reserve((std::max<size_t>(tot, 1) + tot / 8) * 3) != cudaSuccess) { release(); return cleanup(vxs_fail(ctx, VXS_ERR_NOMEM, "vxs_hba_pass: submaps do not fit")); }
-    size_t slot = 0;
-    for (size_t c : counts) slot = std::max(slot, c);
-    slot = (slot + 3) & ~size_t(3);
-    // the padded all-gather reads `slot` floats from this rank's buffer: make sure they exist
-    const size_t slot_cap = std::max<size_t>(slot, 1) + slot / 8;
-    if ((sub_mine.cap < std::max<size_t>(slot, 1) && sub_mine.reserve_keep(slot_cap, counts[size_t(ctx->rank)], st) != cudaSuccess) ||
-        (PB.sub_pad.cap < std::max<size_t>(slot, 1) * size_t(ctx->nranks) && PB.sub_pad.reserve(slot_cap * size_t(ctx->nranks)) != cudaSuccess)) {
-      release(); return cleanup(vxs_fail(ctx, VXS_ERR_NOMEM, "vxs_hba_pass: exchange buffers do not fit"));
-    }
-    rc = vxs_comm_allgatherv_f32(ctx, sub_mine.p, counts[size_t(ctx->rank)], sub_all.p, counts.data(), displs.data(), PB.sub_pad.p, slot);
-    if (rc) { release(); return cleanup(rc); }
-    sub_dev = sub_all.p;
   }
   cudaEventRecord(ev[3], st);
   // ---- top level
@@ -442,7 +448,9 @@ extern "C" int vxs_hba_pass(vxs_ctx* ctx, const vxs_map_params* coarse, const vx
   for (int w = 0; w < nwin; w++) { sub_off[size_t(w) + 1] = sub_off[size_t(w)] + int64_t(sizes_d[size_t(w)]); if (submap_sizes) submap_sizes[w] = int64_t(sizes_d[size_t(w)]); }
   for (int w = 0; w < nwin; w++) memcpy(top_poses + size_t(w) * 12, poses12 + size_t(win_first[size_t(w)]) * 12, 96);
   int outer = 0;
-  if (sub_off[size_t(nwin)] > 0)
+  if (routed)
+    rc = vxs_hba_top_routed(ctx, coarse, fine, sub_mine.p, woff.data(), lo, nmine, nwin, top_poses, top_max_iter, top_thread_num, top_resis_log, &outer, &PB.sub_pad, &sub_all);
+  else if (sub_off[size_t(nwin)] > 0)
     rc = vxs_hba_window_impl(ctx, coarse, fine, nullptr, sub_dev, 3, sub_off.data(), top_poses, nwin, top_max_iter, top_thread_num, nullptr, top_resis_log, &outer,
                              ctx->nranks > 1 ? (long long)sub_off[size_t(lo)] : -1, ctx->nranks > 1 ? (long long)sub_off[size_t(hi)] : -1);
   if (top_outer_iters) *top_outer_iters = outer;

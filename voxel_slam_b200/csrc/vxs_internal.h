@@ -81,6 +81,7 @@ struct vxs_ctx {
   int resid_te = 256;             // VXS_RESID_TE: entries per tile (= consumer threads per CTA) of k_residual_stream: 512 (1 CTA/SM), 256 (2), 128 (4)
   int resid_stages = 2, resid_per_sm = 3;   // VXS_RESID_STAGES (2..4), VXS_RESID_PER_SM (CTAs per SM the batches are cut for; 0 = by tile size)
   int smem_optin = 0;             // cudaDevAttrMaxSharedMemoryPerBlockOptin
+  int hba_route = 1;              // VXS_HBA_ROUTE=0: multi-GPU top level of vxs_hba_pass through the all-gather of the submaps instead of the owner-routed all-to-all
   int syrk_bulk = 0;              // VXS_SYRK_BULK=1: the bulk-copy / mbarrier form of k_syrk (A/B switch; measured 0.796 vs 0.737 ms for the cp.async form at the metric shape)
   int syrk_streamk = 0;           // VXS_SYRK_STREAMK=1: one-wave stream-K plan instead of the (tile, chunk) grid of k_syrk (A/B switch; measured SLOWER at the metric
                                   // shape, 1.06 vs 0.74 ms: tiles of one voxel chunk no longer run together, so every tile re-reads its XT columns from HBM instead of L2)

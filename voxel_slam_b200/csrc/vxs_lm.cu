@@ -33,6 +33,8 @@ struct NcclApi {
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
   int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 };
 static NcclApi* nccl_api() {
@@ -50,6 +52,8 @@ static NcclApi* nccl_api() {
       api.GroupStart = (int (*)())dlsym(api.lib, "ncclGroupStart");
       api.GroupEnd = (int (*)())dlsym(api.lib, "ncclGroupEnd");
       api.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(api.lib, "ncclAllGather");
+      api.Send = (int (*)(const void*, size_t, int, int, void*, cudaStream_t))dlsym(api.lib, "ncclSend");
+      api.Recv = (int (*)(void*, size_t, int, int, void*, cudaStream_t))dlsym(api.lib, "ncclRecv");
       api.GetErrorString = (const char* (*)(int))dlsym(api.lib, "ncclGetErrorString");
       if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy) api.lib = nullptr;
     }
@@ -118,6 +122,25 @@ int vxs_comm_allgatherv_f32(vxs_ctx* ctx, const float* mine, size_t my_count, fl
   if (ctx->timing) vxs_stage_end(ctx);
   (void)my_count;
   if (rc != 0 || rc2 != 0) return vxs_fail(ctx, VXS_ERR_COMM, (rc && a->GetErrorString) ? a->GetErrorString(rc) : "all-gather of the submaps failed");
+  return VXS_OK;
+}
+// all-to-all with per-peer counts / displacements (in floats): grouped ncclSend / ncclRecv, the own part by a device copy
+int vxs_comm_alltoallv_f32(vxs_ctx* ctx, const float* send, const size_t* scount, const size_t* sdispl, float* recv, const size_t* rcount, const size_t* rdispl) {
+  NcclApi* a = nccl_api();
+  if (!a || !ctx->comm || !a->Send || !a->Recv || !a->GroupStart || !a->GroupEnd) return vxs_fail(ctx, VXS_ERR_COMM, "communicator not initialised / ncclSend missing");
+  if (ctx->timing) vxs_stage_begin(ctx, vxs_stage_id(ctx, "nccl_alltoallv"));
+  const int me = ctx->rank;
+  int rc = 0;
+  if (rcount[me]) { if (cudaMemcpyAsync(recv + rdispl[me], send + sdispl[me], rcount[me] * 4, cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess) rc = 1; }
+  int rg = a->GroupStart();
+  for (int p = 0; p < ctx->nranks && rc == 0 && rg == 0; p++) {
+    if (p == me) continue;
+    if (scount[p]) rc = a->Send(send + sdispl[p], scount[p], /*ncclFloat32*/ 7, p, ctx->comm, ctx->stream);
+    if (rc == 0 && rcount[p]) rc = a->Recv(recv + rdispl[p], rcount[p], /*ncclFloat32*/ 7, p, ctx->comm, ctx->stream);
+  }
+  const int rg2 = a->GroupEnd();
+  if (ctx->timing) vxs_stage_end(ctx);
+  if (rc || rg || rg2) return vxs_fail(ctx, VXS_ERR_COMM, "all-to-all of the routed points failed");
   return VXS_OK;
 }
 // element-wise MAX all-reduce of a few int64 (bounding boxes: [-min | max])

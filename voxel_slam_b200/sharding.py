@@ -25,3 +25,14 @@ def shard_csr(ptr, frame, clusters, per_voxel_arrays, keep):
     ent_keep = np.repeat(keep, counts)
     new_ptr = np.concatenate([[0], np.cumsum(counts[keep])]).astype(np.int64)
     return new_ptr, frame[ent_keep], clusters[ent_keep], [a[keep] for a in per_voxel_arrays]
+
+
+# ---------------------------------------------------------------------------------------------- bottom level of the hierarchical global BA
+def hba_windows(K, win_size=10, win_stride=5):
+    """first keyframe of every bottom-level window (thd_globalmapping: wdsize 10, mgsize 5, voxelslam.cpp:2501-2502) — the rule vxs_hba_pass uses"""
+    return np.arange(0, (K - win_size) // win_stride + 1, dtype=np.int32) * win_stride if K >= win_size else np.zeros(0, dtype=np.int32)
+
+
+def window_share(nwin, rank, nranks):
+    """contiguous share [lo, hi) of the bottom-level windows that rank `rank` of `nranks` solves (windows are independent problems: no collective)"""
+    return nwin * rank // nranks, nwin * (rank + 1) // nranks
