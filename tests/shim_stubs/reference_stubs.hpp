@@ -9,7 +9,7 @@
 #include <vector>
 #define DIM 15                                            // tools.hpp:16
 namespace Eigen {
-struct Vector3d { double d[3] = {0, 0, 0}; double& operator[](int i) { return d[i]; } const double& operator[](int i) const { return d[i]; } void setZero() { d[0] = d[1] = d[2] = 0; } };
+struct Vector3d { double d[3] = {0, 0, 0}; Vector3d() = default; Vector3d(double a, double b, double c) { d[0] = a; d[1] = b; d[2] = c; } double& operator[](int i) { return d[i]; } const double& operator[](int i) const { return d[i]; } void setZero() { d[0] = d[1] = d[2] = 0; } };
 struct Matrix3d { double d[9] = {0}; double& operator()(int r, int c) { return d[3 * c + r]; } const double& operator()(int r, int c) const { return d[3 * c + r]; } };
 struct MatrixXd {
   std::vector<double> a; int r_ = 0, c_ = 0;
@@ -19,10 +19,10 @@ struct MatrixXd {
   double* data() { return a.data(); } const double* data() const { return a.data(); }
 };
 struct VectorXd { std::vector<double> a; VectorXd() = default; explicit VectorXd(int n) : a(n) {} void setZero() { std::fill(a.begin(), a.end(), 0.0); } double* data() { return a.data(); } };
-template <class T, int R, int C> struct Matrix { T d[R * C]; };
+template <class T, int R, int C> struct Matrix { T d[R * C]; T& operator()(int r, int c) { return d[R * c + r]; } const T& operator()(int r, int c) const { return d[R * c + r]; } T& operator[](int i) { return d[i]; } };
 template <class M> struct Map { const double* p; explicit Map(const double* q) : p(q) {} operator Matrix<double, DIM, 1>() const { Matrix<double, DIM, 1> m; std::memcpy(m.d, p, sizeof m.d); return m; } };
 }  // namespace Eigen
-struct IMUST { Eigen::Matrix3d R; Eigen::Vector3d p, v, bg, ba, g; };                                  // tools.hpp:135-199
+struct IMUST { Eigen::Matrix3d R; Eigen::Vector3d p, v, bg, ba, g; Eigen::Matrix<double, DIM, DIM> cov; };   // tools.hpp:135-199
 struct PointCluster { Eigen::Matrix3d P; Eigen::Vector3d v; int N = 0; };                              // tools.hpp:304-365
 struct IMU_PRE {                                                                                          // preintegration.hpp:20-300
   Eigen::Vector3d dbg, dba, dbg_buf, dba_buf;                                                            // :25-26

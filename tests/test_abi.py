@@ -35,6 +35,13 @@ void use(std::vector<IMUST>& xs, std::deque<IMU_PRE*>& imus, std::vector<Keyfram
   vxs_shim::down_sampling_close(c, pl, 0.1);
   vxs_shim::down_sampling_pvec(c, pvec, 0.1, pl);
   vxs_shim::submap_merge(c, xs, smps, 1.0, pl);
+  vxs_shim::var_init(c, xs[0], pl, pptr, 0.02, 0.05);                          // voxelslam.cpp:1246, 1584
+  vxs_shim::pvec_update(c, pptr, xs[0], pwld);                                 // voxelslam.cpp:1250, 1594
+  Eigen::Matrix<double, 6, 6> HTH; Eigen::Matrix<double, 6, 1> HTz; Eigen::Matrix3d nnt;
+  int match_num = vxs_shim::odom_accumulate(surf_map, pptr, xs[0], true, HTH, HTz, nnt);   // voxelslam.cpp:876-918
+  (void)match_num;
+  std::vector<std::vector<IMUST>> win_xs; std::vector<int32_t> wf{0}, st;
+  vxs_shim::hba_bottom_batch(c, mpar, smps, wf, 10, win_xs, st);               // voxelslam.cpp:2540-2557 (every HBA_add_edge(..., 1, 2, plptr) at once)
 }
 int main() { return 0; }
 '''

@@ -400,5 +400,76 @@ inline void OctreeGBA_multi_recut(GbaMap& feat_map, LidarFactor& voxhess, int /*
   feat_map.clear();          // the reference consumes (deletes) the octrees here too (loop_refine.hpp:503-509)
 }
 
+// ---------------------------------------------------------------- scan pre-processing and odometry association (voxelslam.hpp:187-214, voxelslam.cpp:876-918)
+//   var_init(extrin_para, pl_down, pptr, dept_err, beam_err);   voxelslam.cpp:1246, 1584      pvec_update(pptr, x_curr, pwld);   voxelslam.cpp:611, 1250, 1594
+// The records also stay on the device (the ctx's resident scan): the EKF passes and the later vxs_map_push_scan can take them from there.
+inline void var_init(Context& ctx, IMUST& ext, pcl::PointCloud<PointType>& pl_cur, PVecPtr pptr, double dept_err, double beam_err) {
+  static_assert(sizeof(pointVar) == 12 * sizeof(double), "pointVar is handed over as 12 doubles");
+  const int64_t n = int64_t(pl_cur.size());
+  pptr->clear(); pptr->resize(size_t(n));
+  double R[9], p[3];
+  for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) R[3 * r + c] = ext.R(r, c); p[r] = ext.p[r]; }
+  std::vector<double> rec(size_t(n) * 12);
+  check(ctx.get(), vxs_var_init(ctx.get(), reinterpret_cast<const float*>(pl_cur.points.data()), int(sizeof(PointType) / sizeof(float)), n, R, p, dept_err, beam_err, rec.data()), "vxs_var_init");
+  for (int64_t i = 0; i < n; i++) {          // var comes back row-major; pointVar::var is an Eigen matrix (symmetric, so the storage order does not matter, but stay explicit)
+    pointVar& pv = (*pptr)[size_t(i)];
+    const double* q = &rec[12 * size_t(i)];
+    pv.pnt = Eigen::Vector3d(q[0], q[1], q[2]);
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) pv.var(r, c) = q[3 + 3 * r + c];
+  }
+}
+inline void pvec_update(Context& ctx, PVecPtr pptr, IMUST& x_curr, PLV(3)& pwld) {
+  const int64_t n = int64_t(pptr->size());
+  std::vector<double> rec(size_t(n) * 12), out(size_t(n) * 12), pw(size_t(n) * 3);
+  for (int64_t i = 0; i < n; i++) { const pointVar& pv = (*pptr)[size_t(i)]; double* q = &rec[12 * size_t(i)]; for (int k = 0; k < 3; k++) q[k] = pv.pnt[k]; for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) q[3 + 3 * r + c] = pv.var(r, c); }
+  double st[24], rv[9], tv[9];
+  pack_state(x_curr, st);
+  for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) { rv[3 * r + c] = x_curr.cov(r, c); tv[3 * r + c] = x_curr.cov(3 + r, 3 + c); }
+  check(ctx.get(), vxs_pvec_update(ctx.get(), rec.data(), n, st, rv, tv, out.data(), pw.data()), "vxs_pvec_update");
+  for (int64_t i = 0; i < n; i++) {
+    pointVar& pv = (*pptr)[size_t(i)];
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) pv.var(r, c) = out[12 * size_t(i) + 3 + 3 * r + c];
+    pwld.push_back(Eigen::Vector3d(pw[3 * size_t(i)], pw[3 * size_t(i) + 1], pw[3 * size_t(i) + 2]));
+  }
+}
+// the per-point loop of one EKF iteration (voxelslam.cpp:876-918) against the resident map: HTH, HTz, nnt, match_num.  first_pass uploads the scan, later passes reuse it.
+inline int odom_accumulate(SurfMap& surf_map, PVecPtr pptr, IMUST& x_curr, bool first_pass, Eigen::Matrix<double, 6, 6>& HTH, Eigen::Matrix<double, 6, 1>& HTz, Eigen::Matrix3d& nnt) {
+  const int64_t n = int64_t(pptr->size());
+  std::vector<double> rec;
+  if (first_pass) { rec.resize(size_t(n) * 12); for (int64_t i = 0; i < n; i++) { const pointVar& pv = (*pptr)[size_t(i)]; double* q = &rec[12 * size_t(i)]; for (int k = 0; k < 3; k++) q[k] = pv.pnt[k]; for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) q[3 + 3 * r + c] = pv.var(r, c); } }
+  double st[24], rv[9], tv[9], h[36], z[6], nn[9];
+  pack_state(x_curr, st);
+  for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) { rv[3 * r + c] = x_curr.cov(r, c); tv[3 * r + c] = x_curr.cov(3 + r, 3 + c); }
+  int64_t m = 0;
+  check(surf_map.ctx(), vxs_map_odom_accumulate(surf_map.get(), first_pass ? rec.data() : nullptr, n, st, rv, tv, h, z, nn, &m, nullptr), "vxs_map_odom_accumulate");
+  for (int r = 0; r < 6; r++) { for (int c = 0; c < 6; c++) HTH(r, c) = h[6 * r + c]; HTz[r] = z[r]; }
+  for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) nnt(r, c) = nn[3 * r + c];
+  return int(m);
+}
+
+// ---------------------------------------------------------------- bottom level of the hierarchical global BA in one call (thd_globalmapping, voxelslam.cpp:2484-2557)
+// every window w solves HBA_add_edge(xs, smp_local, gba_edges1, mps, 1, 2, plptr) on keyframes win_first[w] .. +win_size-1; poses_out[w] are the window's refined xs
+template <class KeyframePtrVec>
+inline void hba_bottom_batch(Context& ctx, const vxs_map_params& fine, const KeyframePtrVec& keyframes, const std::vector<int32_t>& win_first, int win_size,
+                             std::vector<std::vector<IMUST>>& poses_out, std::vector<int32_t>& status) {
+  const int K = int(keyframes.size()), nwin = int(win_first.size());
+  std::vector<int64_t> off(size_t(K) + 1, 0);
+  for (int i = 0; i < K; i++) off[size_t(i) + 1] = off[size_t(i)] + int64_t(keyframes[i]->plptr->size());
+  std::vector<PointType, PinnedAllocator<PointType>> all; all.reserve(size_t(off[size_t(K)]));
+  std::vector<double> p(size_t(K) * 12), st(24), out(size_t(nwin) * win_size * 12);
+  for (int i = 0; i < K; i++) { all.insert(all.end(), keyframes[i]->plptr->points.begin(), keyframes[i]->plptr->points.end()); pack_state(keyframes[i]->x0, st.data()); std::memcpy(&p[12 * size_t(i)], st.data(), 96); }
+  status.assign(size_t(nwin), 0);
+  check(ctx.get(), vxs_hba_bottom_batch(ctx.get(), &fine, reinterpret_cast<const float*>(all.data()), int(sizeof(PointType) / sizeof(float)), off.data(), p.data(), K, win_first.data(), nwin, win_size,
+                                        2, 0, out.data(), nullptr, status.data(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr), "vxs_hba_bottom_batch");
+  poses_out.assign(size_t(nwin), std::vector<IMUST>(size_t(win_size)));
+  for (int w = 0; w < nwin; w++)
+    for (int j = 0; j < win_size; j++) {
+      poses_out[size_t(w)][size_t(j)] = keyframes[win_first[size_t(w)] + j]->x0;
+      double s24[24] = {0}; std::memcpy(s24, &out[(size_t(w) * win_size + j) * 12], 96);
+      IMUST& x = poses_out[size_t(w)][size_t(j)];
+      for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) x.R(r, c) = s24[3 * r + c]; x.p[r] = s24[9 + r]; }
+    }
+}
+
 }  // namespace vxs_shim
 #endif  // VXS_SHIM_WITH_REFERENCE_TYPES
