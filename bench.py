@@ -397,6 +397,7 @@ def local_mapping_leg(vx, ctx, W, pts, L, steps):
     t_fill = time.perf_counter()
     stage_ms = {}
     walls, iters = [], 0
+    odom, odom_err = [], []
     for i in range(nscan):
         tr = synth.true_pose(L, i)
         est = synth.perturb_pose(tr, 77000 + i, 1e-4, 5e-3) if i else tr
@@ -406,6 +407,24 @@ def local_mapping_leg(vx, ctx, W, pts, L, steps):
         timed = i >= W - 1 + 4                              # window full and four warm steps behind us (the map's pools have reached their steady size)
         if timed:
             ctx.timing(True); ctx.timing_reset()
+        if timed:
+            # side measurement on the same scan (the step BEFORE the map update): var_init -> 4 EKF association passes against the resident map
+            # (voxelslam.cpp:860-918 runs up to num_max_iter = 4) -> pvec_update, the scan staying on the device in between.  Own try block: it must never cost the main leg.
+            try:
+                cloud32 = np.ascontiguousarray(xyz_tmp, dtype=np.float32)
+                rot_var, tsl_var = np.eye(3) * 1e-6, np.eye(3) * 1e-4
+                ta = time.perf_counter()
+                ctx.var_init(cloud32, np.eye(3), np.zeros(3), 0.02, 0.05, want_out=False)
+                tb = time.perf_counter()
+                matched = 0
+                for _ in range(4):
+                    matched = dm.odom_accumulate(None, est, rot_var, tsl_var, n=pts, want_flags=False)["n"]
+                tc = time.perf_counter()
+                ctx.pvec_update(None, est, rot_var, tsl_var, n=pts, want_pv=False, want_pwld=False)
+                td = time.perf_counter()
+                odom.append(((tb - ta) * 1e3, (tc - tb) * 1e3 / 4, (td - tc) * 1e3, matched / float(pts)))
+            except Exception as e:          # noqa: BLE001
+                odom_err.append(repr(e))
         t0 = time.perf_counter()
         dm.push_scan(pv, np.stack(x_buf), f)
         t1 = time.perf_counter()
@@ -434,6 +453,14 @@ def local_mapping_leg(vx, ctx, W, pts, L, steps):
            "h2d_bytes_per_step": int(pts * 96), "timing": "host wall clock around the three synchronous C-ABI calls (pinned host scan; includes the 96 MB H2D)",
            "kernel_ms_per_step": {k: v / max(len(walls), 1) for k, v in sorted(stage_ms.items(), key=lambda kv: -kv[1])[:14]},
            "round1_from_scratch_rebuild_ms": 120.0, "fill_s": time.perf_counter() - t_fill}
+    if odom:
+        o_ = np.array(odom)
+        res["odometry_front"] = {"what": "per scan, host wall around the C-ABI calls: vxs_var_init (12 MB float cloud up, records stay resident), one EKF association pass of vxs_map_odom_accumulate "
+                                         "(mean of 4, against the resident map's plane rows), vxs_pvec_update (resident)",
+                                 "ms_var_init": float(o_[:, 0].mean()), "ms_ekf_pass": float(o_[:, 1].mean()), "ms_pvec_update": float(o_[:, 2].mean()), "matched_fraction": float(o_[:, 3].mean()),
+                                 "points": int(pts)}
+    elif odom_err:
+        res["odometry_front"] = {"error": odom_err[0]}
     dm.close(); f.close()
     return res
 
