@@ -337,7 +337,18 @@ static int build_factor(vxs_ctx* ctx, const vxs_map_params* mp, bool gba, const 
   out->block_W = bs ? bs->win_size : 0;
   if (n_out) *n_out = 0;
   VXS_CUDA(ctx, s->totals.reserve(16));
-  if (N == 0) return VXS_OK;
+  if (N == 0) {
+    // a rank that received no point at all (routed multi-GPU build) must still take part in the bounding-box all-reduce its peers run below
+    if (ctx->nranks > 1 && !bs && own_lo == 0 && own_hi == 0) {   // the same condition as part_bbox below, at N = 0
+      VXS_CUDA(ctx, s->bbox.reserve(6));
+      const long long nb[6] = {-LLONG_MAX, -LLONG_MAX, -LLONG_MAX, LLONG_MIN, LLONG_MIN, LLONG_MIN};     // [-min | max] of an empty set: neutral for MAX
+      VXS_CUDA(ctx, cudaMemcpyAsync(s->bbox.p, nb, sizeof nb, cudaMemcpyHostToDevice, ctx->stream));
+      int rcb = vxs_comm_allreduce_max_i64(ctx, s->bbox.p, 6);
+      if (rcb) return rcb;
+      VXS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return VXS_OK;
+  }
   const int FB = bits_for((unsigned long long)(bs ? bs->win_size : nframes));
   // ---- upload
   PointSrc ps; ps.pd = nullptr; ps.pf = nullptr; ps.fstride = fstride; ps.nframes = nframes; ps.n = N; ps.src_off = nullptr; ps.win_size = 0; ps.frame_in_w = routed ? 1 : 0;
