@@ -388,21 +388,27 @@ extern "C" int vxs_hba_pass(vxs_ctx* ctx, const vxs_map_params* coarse, const vx
   cudaEventRecord(ev[0], st);
   // ---- this rank's keyframes, uploaded once
   std::vector<int64_t> woff(size_t(nmine) + 1, 0);
-  std::vector<double> sizes_d(static_cast<size_t>(nwin), 0.0);
+  std::vector<double> sizes_d(static_cast<size_t>(nwin) + 1, 0.0);      // [nwin] = error flag: a rank whose bottom level failed must not leave its peers waiting in the exchange
+  int my_err = 0;
+  const bool multi = ctx->nranks > 1;
   if (nmine > 0) {
     const int kf_lo = win_first[size_t(lo)], kf_hi = win_first[size_t(hi) - 1] + win_size;
     const int64_t p0 = kf_offsets[kf_lo], np = kf_offsets[kf_hi] - p0;
-    if (pts.reserve(size_t(std::max<int64_t>(np, 1)) * stride_floats) != cudaSuccess) { release(); return cleanup(vxs_fail(ctx, VXS_ERR_NOMEM, "vxs_hba_pass: keyframe clouds do not fit")); }
-    if (np > 0) cudaMemcpyAsync(pts.p, xyz + size_t(p0) * stride_floats, size_t(np) * stride_floats * 4, cudaMemcpyHostToDevice, st);
-    rc = hba_bottom_batch_impl(ctx, fine, xyz, pts.p, p0, stride_floats, kf_offsets, poses12, K, win_first.data() + lo, nmine, win_size, bottom_thread_num, max_points_per_chunk, bottom_poses,
+    if (pts.reserve(size_t(std::max<int64_t>(np, 1)) * stride_floats) != cudaSuccess) {
+      my_err = vxs_fail(ctx, VXS_ERR_NOMEM, "vxs_hba_pass: keyframe clouds do not fit");
+      if (!multi) { release(); return cleanup(my_err); }
+    }
+    if (!my_err && np > 0) cudaMemcpyAsync(pts.p, xyz + size_t(p0) * stride_floats, size_t(np) * stride_floats * 4, cudaMemcpyHostToDevice, st);
+    if (!my_err) rc = hba_bottom_batch_impl(ctx, fine, xyz, pts.p, p0, stride_floats, kf_offsets, poses12, K, win_first.data() + lo, nmine, win_size, bottom_thread_num, max_points_per_chunk, bottom_poses,
                                bottom_resis, bottom_status, nullptr, nullptr, bottom_edge_valid, bottom_edge_v6, bottom_edge_rot, bottom_edge_tra, nullptr);
-    if (rc < 0) { release(); return cleanup(rc); }
+    if (rc < 0 && !my_err) { if (!multi) { release(); return cleanup(rc); } my_err = rc; }
     cudaEventRecord(ev[1], st);
     int64_t ntot = 0;
-    rc = vxs_submap_merge_batch_impl(ctx, xyz, pts.p, p0, stride_floats, kf_offsets, K, bottom_poses, win_first.data() + lo, nmine, win_size, fine->voxel_size / 8, max_points_per_chunk, nullptr,
+    if (!my_err) rc = vxs_submap_merge_batch_impl(ctx, xyz, pts.p, p0, stride_floats, kf_offsets, K, bottom_poses, win_first.data() + lo, nmine, win_size, fine->voxel_size / 8, max_points_per_chunk, nullptr,
                                      nullptr, nullptr, 0, woff.data(), &ntot, &sub_mine);
-    if (rc < 0) { release(); return cleanup(rc); }
-    for (int w = 0; w < nmine; w++) sizes_d[size_t(lo + w)] = double(woff[size_t(w) + 1] - woff[size_t(w)]);
+    if (rc < 0 && !my_err) { if (!multi) { release(); return cleanup(rc); } my_err = rc; }
+    if (!my_err) for (int w = 0; w < nmine; w++) sizes_d[size_t(lo + w)] = double(woff[size_t(w) + 1] - woff[size_t(w)]);
+    else sizes_d[size_t(nwin)] = 1.0;
   } else cudaEventRecord(ev[1], st);
   cudaEventRecord(ev[2], st);
   // ---- multi-GPU: either every point goes straight to the rank that owns its root cell (all-to-all, default), or the submaps of all ranks go to every rank (all-gather,
@@ -410,12 +416,16 @@ extern "C" int vxs_hba_pass(vxs_ctx* ctx, const vxs_map_params* coarse, const vx
   const bool routed = ctx->nranks > 1 && ctx->hba_route;
   const float* sub_dev = sub_mine.p;
   if (ctx->nranks > 1) {
-    if (ctx->stage.reserve(size_t(nwin)) != cudaSuccess) { release(); return cleanup(VXS_ERR_NOMEM); }
-    cudaMemcpyAsync(ctx->stage.p, sizes_d.data(), size_t(nwin) * 8, cudaMemcpyHostToDevice, st);
-    rc = vxs_comm_allreduce(ctx, ctx->stage.p, size_t(nwin));              // every rank contributed its own windows' sizes, zeros elsewhere
+    if (ctx->stage.reserve(size_t(nwin) + 1) != cudaSuccess) { release(); return cleanup(VXS_ERR_NOMEM); }
+    cudaMemcpyAsync(ctx->stage.p, sizes_d.data(), (size_t(nwin) + 1) * 8, cudaMemcpyHostToDevice, st);
+    rc = vxs_comm_allreduce(ctx, ctx->stage.p, size_t(nwin) + 1);          // every rank contributed its own windows' sizes (+ its error flag), zeros elsewhere
     if (rc) { release(); return cleanup(rc); }
-    cudaMemcpyAsync(sizes_d.data(), ctx->stage.p, size_t(nwin) * 8, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(sizes_d.data(), ctx->stage.p, (size_t(nwin) + 1) * 8, cudaMemcpyDeviceToHost, st);
     cudaStreamSynchronize(st);
+    if (sizes_d[size_t(nwin)] > 0.0) {       // all ranks leave together, before any further collective
+      release();
+      return cleanup(my_err ? my_err : vxs_fail(ctx, VXS_ERR_COMM, "vxs_hba_pass: the bottom level failed on another rank"));
+    }
     if (!routed) {
     std::vector<size_t> counts(size_t(ctx->nranks), 0), displs(size_t(ctx->nranks), 0);
       size_t tot = 0;
