@@ -10,6 +10,8 @@
 // lines each where a test needs them, each with its file:line: the from-scratch build sequence (:611-625), the per-scan map sequence
 // (:1599-1615, 1669-1712 with multi_recut :1398-1453 and multi_margi :1321-1395 in their single-thread form) and the EKF accumulation loop
 // (:876-918).  Everything numerical they call is the reference's own code.
+// Two pieces are NOT restated but cut out of their files at build time (oracle/Makefile) and compiled as they are: calcBodyVar / var_init / pvec_update
+// (voxelslam.hpp:163-214) and the member function HBA_add_edge (voxelslam.cpp:2319-2482).
 #include <chrono>
 #include <cstdint>
 #include <cstring>
@@ -22,6 +24,9 @@
 #define DEG2RAD(x) ((x)*0.017453293)   // pcl/pcl_macros.h (PCL 1.10), used by calcBodyVar
 #endif
 #include "_ref/vh_pointvar.inc"         // calcBodyVar / var_init / pvec_update cut out of voxelslam.hpp:163-214 by the Makefile (see there)
+struct RefHbaHost {                     // stands for the reference's node class around its member function HBA_add_edge (voxelslam.cpp:2319-2482)
+#include "_ref/vc_hba_add_edge.inc"     // cut out of voxelslam.cpp by the Makefile (see there)
+};
 
 namespace {
 
@@ -354,6 +359,42 @@ void* vxr_build_gba_factor(const vxs_map_params* mpar, const float* xyz, int str
   OctreeGBA_multi_recut(oct_map, rf->f, threads);
   if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   return rf;
+}
+
+// The reference's own HBA_add_edge on W keyframe clouds (body frame) and poses: the outer coarse -> fine loop, the PGO edges of the final Hessian and (want_submap) the
+// merged, down-sampled submap cloud in the frame of keyframe 0.  The function optimises a private copy of the poses (voxelslam.cpp:2326-2348): they are visible through
+// the edges' relative poses only.  Returns the number of edges (all in map 0); *n_submap = points of the merged cloud.
+int64_t vxr_hba_add_edge(const vxs_map_params* coarse, const vxs_map_params* fine, const float* xyz, int stride_floats, const int64_t* kf_offsets, const double* poses12, int W, int max_iter,
+                         int thread_num, int want_submap, int64_t edge_cap, int32_t* eij, double* v6, double* rot, double* tra, int64_t sub_cap, float* sub_xyz, int64_t* n_submap) {
+  set_gba_params(coarse);
+  voxel_size = fine->voxel_size; min_eigen_value = fine->min_eigen_value;        // the globals the last outer iteration switches to (:2368-2371)
+  plane_eigen_value_thre.assign(8, fine->plane_thre[3]);
+  for (int k = 0; k < 4; k++) plane_eigen_value_thre[k] = fine->plane_thre[k];
+  vector<IMUST> xs = states12(poses12, W);
+  vector<Keyframe*> smps;
+  for (int i = 0; i < W; i++) {
+    Keyframe* kf = new Keyframe(xs[i]);
+    kf->id = i; kf->mp = 0;
+    for (int64_t k = kf_offsets[i]; k < kf_offsets[i + 1]; k++) { PointType ap; ap.x = xyz[size_t(k) * stride_floats]; ap.y = xyz[size_t(k) * stride_floats + 1]; ap.z = xyz[size_t(k) * stride_floats + 2]; kf->plptr->push_back(ap); }
+    smps.push_back(kf);
+  }
+  PGO_Edges edges;
+  vector<int> maps = {0};
+  pcl::PointCloud<PointType>::Ptr sub;
+  if (want_submap) sub.reset(new pcl::PointCloud<PointType>());
+  RefHbaHost host;
+  host.HBA_add_edge(xs, smps, edges, maps, max_iter, thread_num, sub);
+  int64_t m = 0;
+  for (PGO_Edge& e : edges.edges) for (size_t k = 0; k < e.ids1.size(); k++, m++) {
+    if (m >= edge_cap) continue;
+    eij[2 * m] = e.ids1[k]; eij[2 * m + 1] = e.ids2[k];
+    for (int a = 0; a < 6; a++) v6[6 * m + a] = e.covs[k][a];
+    for (int a = 0; a < 3; a++) { tra[3 * m + a] = e.tras[k][a]; for (int b = 0; b < 3; b++) rot[9 * m + 3 * a + b] = e.rots[k](a, b); }
+  }
+  if (n_submap) *n_submap = sub ? int64_t(sub->size()) : 0;
+  if (sub) for (int64_t i = 0; i < int64_t(sub->size()) && i < sub_cap; i++) { const PointType& p = (*sub)[size_t(i)]; sub_xyz[3 * i] = p.x; sub_xyz[3 * i + 1] = p.y; sub_xyz[3 * i + 2] = p.z; }
+  for (Keyframe* kf : smps) delete kf;
+  return m;
 }
 
 // ---------------------------------------------------------------- down-sampling (tools.hpp:201-302, voxel_map.hpp:23-64); the cloud's first point index rides in `intensity`

@@ -262,6 +262,26 @@ def hba_window(coarse, fine, xyz_f32, kf_offsets, poses12, max_iter, thread_num=
     return dict(poses=p, hess=H, resis_log=log[: 2 * it.value], outer_iters=it.value, status=rc)
 
 
+def hba_add_edge(coarse, fine, xyz_f32, kf_offsets, poses12, max_iter, thread_num=2, stride_floats=3, want_submap=True):
+    """ref backend only: the reference's own HBA_add_edge (voxelslam.cpp:2319-2482, cut out at build time) -> its PGO edges and merged submap."""
+    if BACKEND != "ref":
+        raise RuntimeError("hba_add_edge exists for the reference build only; the oracle exposes hba_window / hba_edges / submap_merge")
+    x = np.ascontiguousarray(xyz_f32, dtype=np.float32)
+    off = np.ascontiguousarray(kf_offsets, dtype=np.int64)
+    W = off.shape[0] - 1
+    n = int(off[-1])
+    p = _f64(poses12)
+    cap = W * (W - 1) // 2
+    eij = np.zeros((cap, 2), dtype=np.int32); v6 = np.zeros((cap, 6)); rot = np.zeros((cap, 9)); tra = np.zeros((cap, 3))
+    sub = np.zeros((max(n, 1), 3), dtype=np.float32)
+    nsub = C.c_int64(0)
+    lib().vxo_hba_add_edge.restype = C.c_int64
+    m = lib().vxo_hba_add_edge(C.byref(coarse), C.byref(fine), x.ctypes.data_as(C.POINTER(C.c_float)), C.c_int(stride_floats), off.ctypes.data_as(C.POINTER(C.c_int64)), _dp(p), C.c_int(W),
+                               C.c_int(max_iter), C.c_int(thread_num), C.c_int(int(want_submap)), C.c_int64(cap), eij.ctypes.data_as(C.POINTER(C.c_int32)), _dp(v6), _dp(rot), _dp(tra),
+                               C.c_int64(n), sub.ctypes.data_as(C.POINTER(C.c_float)), C.byref(nsub))
+    return dict(n=m, ij=eij[:m], v6=v6[:m], rot=rot[:m], tra=tra[:m], submap=sub[: nsub.value])
+
+
 def var_init(pts_f32, ext_R, ext_p, dept_err, beam_err, stride_floats=None):
     """var_init (voxelslam.hpp:187-203) -> n x 12 pointVar records (pnt | var row-major)"""
     x = np.ascontiguousarray(pts_f32, dtype=np.float32)

@@ -342,3 +342,28 @@ def test_var_init_and_pvec_update_against_the_reference_functions():
     assert np.array_equal(pa[:, :3], a[:, :3])                      # pnt stays in the body frame
     assert np.max(np.abs(wa - wb)) < 1e-12
     assert np.max(np.abs(pa[:, 3:] - pb[:, 3:]) / np.max(np.abs(pb[:, 3:]), axis=1, keepdims=True)) < 1e-12
+
+
+@pytest.mark.parametrize("max_iter", [1, 4])
+def test_hba_add_edge_against_the_reference_member_function(max_iter):
+    """The reference's own HBA_add_edge (voxelslam.cpp:2319-2482, cut out of the ROS node class at build time): coarse -> fine outer loop over OctreeGBA map
+    builds and Lidar_BA_Optimizer solves, the PGO edges of the final Hessian and the merged + down-sampled submap — against the oracle's hba_window /
+    hba_edges / submap_merge chain that the GPU tests (vxs_hba_window, vxs_hba_edges, vxs_submap_merge, vxs_hba_bottom_batch, vxs_hba_pass) compare with.
+    The reference optimises a private copy of the poses, so they are pinned through the edges' relative poses and the merged cloud."""
+    W = 8
+    tr, est = scenes.poses_true_est(W, 8.0, 43, rot_sigma=3e-3, pos_sigma=2e-2)
+    xyz, off = scenes.make_points(W, 4000, 8.0, 43, tr, dtype=np.float32)
+    coarse = vx.MapParams.make(voxel_size=2.0, min_eigen_value=0.1, max_layer=2)
+    fine = vx.MapParams.make(voxel_size=1.0, min_eigen_value=0.0025, max_layer=2)
+    a = ra.hba_add_edge(coarse, fine, xyz, off, est, max_iter, thread_num=2)
+    w = oa.hba_window(coarse, fine, xyz, off, est, max_iter, thread_num=2)
+    assert w["status"] == 0 and w["outer_iters"] == max_iter
+    e = oa.hba_edges(w["hess"], W, w["poses"])
+    assert a["n"] == e["n"] == W * (W - 1) // 2 and np.array_equal(a["ij"], e["ij"])      # lexicographic (i, j), voxelslam.cpp:2405-2406
+    assert np.max(np.abs(a["v6"] - e["v6"]) / np.abs(e["v6"])) < 1e-10
+    assert np.max(np.abs(a["rot"] - e["rot"])) < 1e-12 and np.max(np.abs(a["tra"] - e["tra"])) < 1e-12
+    assert np.max(np.abs(w["poses"] - est)) > 1e-4                                       # the solve moved the poses: the edges above are not the input's
+    m = oa.submap_merge(xyz, off, w["poses"], fine.voxel_size / 8)
+    assert len(a["submap"]) == len(m["xyz"]) > 1000
+    ka, kb = np.lexsort(a["submap"].T), np.lexsort(m["xyz"].T)
+    assert np.array_equal(a["submap"][ka].view(np.uint32), m["xyz"][kb].view(np.uint32))  # float running means of the same cells, bit-exact
