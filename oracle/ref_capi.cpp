@@ -8,7 +8,7 @@
 //
 // Pieces of voxelslam.cpp (one 2600-line ROS translation unit that cannot be compiled here) that drive these classes are restated in a few
 // lines each where a test needs them, each with its file:line: the from-scratch build sequence (:611-625), the per-scan map sequence
-// (:1599-1615, 1669-1712 with multi_recut :1398-1453 and multi_margi :1321-1395 in their single-thread form) and the EKF accumulation loop
+// (:1599-1615, 1669-1712; multi_recut :1398-1453 and multi_margi :1321-1395 are the reference's own member functions, see below) and the EKF accumulation loop
 // (:876-918).  Everything numerical they call is the reference's own code.
 // Two pieces are NOT restated but cut out of their files at build time (oracle/Makefile) and compiled as they are: calcBodyVar / var_init / pvec_update
 // (voxelslam.hpp:163-214) and the member function HBA_add_edge (voxelslam.cpp:2319-2482).
@@ -25,7 +25,9 @@
 #endif
 #include "_ref/vh_pointvar.inc"         // calcBodyVar / var_init / pvec_update cut out of voxelslam.hpp:163-214 by the Makefile (see there)
 struct RefHbaHost {                     // stands for the reference's node class around its member function HBA_add_edge (voxelslam.cpp:2319-2482)
+  int thread_num = 1;                   // the node's thread count (voxelslam.cpp:805 reads it from the launch file); 1 = deterministic push order
 #include "_ref/vc_hba_add_edge.inc"     // cut out of voxelslam.cpp by the Makefile (see there)
+#include "_ref/vc_multi_margi_recut.inc"   // multi_margi + multi_recut (voxelslam.cpp:1321-1453), likewise
 };
 
 namespace {
@@ -545,16 +547,15 @@ static void ref_sim_add(RefSlidingSim* s, PVecPtr pv, const double* pose12, int 
   PLV(3) pwld;
   for (pointVar& p : *pv) pwld.push_back(x.R * p.pnt + x.p);
   cut_voxel(s->surf_map, pv, s->win_count - 1, s->surf_map_slide, s->win_size, pwld, s->sws);   // :1611 (the single-thread form of :1612)
-  for (auto& kv : s->surf_map_slide) kv.second->recut(s->win_count, s->x_buf, s->sws);     // multi_recut :1420-1424
-  for (auto& kv : s->surf_map_slide) kv.second->tras_opt(s->voxhess);                      // :1450-1451
+  RefHbaHost host;                                                                          // thread_num = 1
+  { vector<vector<SlideWindow*>> sws(1); sws[0].swap(s->sws); host.multi_recut(s->surf_map_slide, s->win_count, s->x_buf, s->voxhess, sws); s->sws.swap(sws[0]); }   // :1615, the reference's own function
   if (s->win_count >= s->win_size) {
     if (ba_iters > 0 && s->voxhess.plvec_voxels.size() >= 2) {                               // the BA between recut and margi (:1637-1654), pose-only flavour
       Lidar_BA_Optimizer opt; opt.thd_num = 2;
       Eigen::MatrixXd hess; vector<double> resis;
       opt.damping_iter(s->x_buf, s->voxhess, &hess, resis, ba_iters, false);
     }
-    for (auto& kv : s->surf_map_slide) kv.second->margi(s->win_count, 1, s->x_buf, s->voxhess);   // multi_margi :1356-1362
-    for (auto it = s->surf_map_slide.begin(); it != s->surf_map_slide.end();) { if (it->second->isexist) it++; else { it->second->clear_slwd(s->sws); s->surf_map_slide.erase(it++); } }   // :1379-1388
+    host.multi_margi(s->surf_map_slide, 0.0, s->win_count, s->x_buf, s->voxhess, s->sws);         // :1669, the reference's own function (jour only stamps the octrees)
     for (int i = 0; i < s->win_size; i++) { s->ring[size_t(i)] += s->mgsize; if (s->ring[size_t(i)] >= s->win_size) s->ring[size_t(i)] -= s->win_size; }                              // :1689-1693
     for (int i = s->mgsize; i < s->win_count; i++) s->x_buf[size_t(i - s->mgsize)] = s->x_buf[size_t(i)];                                                                             // :1695-1701
     for (int i = s->win_count - s->mgsize; i < s->win_count; i++) s->x_buf.pop_back();
