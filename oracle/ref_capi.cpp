@@ -11,7 +11,7 @@
 // (:1599-1615, 1669-1712; multi_recut :1398-1453 and multi_margi :1321-1395 are the reference's own member functions, see below) and the EKF accumulation loop
 // (:876-918).  Everything numerical they call is the reference's own code.
 // Two pieces are NOT restated but cut out of their files at build time (oracle/Makefile) and compiled as they are: calcBodyVar / var_init / pvec_update
-// (voxelslam.hpp:163-214) and the member function HBA_add_edge (voxelslam.cpp:2319-2482).
+// (voxelslam.hpp:163-214) and the member functions HBA_add_edge (voxelslam.cpp:2319-2482), multi_margi / multi_recut (:1321-1453) and lio_state_estimation (:856-954).
 #include <chrono>
 #include <cstdint>
 #include <cstring>
@@ -28,6 +28,9 @@ struct RefHbaHost {                     // stands for the reference's node class
   int thread_num = 1;                   // the node's thread count (voxelslam.cpp:805 reads it from the launch file); 1 = deterministic push order
 #include "_ref/vc_hba_add_edge.inc"     // cut out of voxelslam.cpp by the Makefile (see there)
 #include "_ref/vc_multi_margi_recut.inc"   // multi_margi + multi_recut (voxelslam.cpp:1321-1453), likewise
+  IMUST x_curr;                            // the node's current state and its map, as lio_state_estimation uses them (voxelslam.cpp:737, 741)
+  unordered_map<VOXEL_LOC, OctoTree*> surf_map;
+#include "_ref/vc_lio_state_estimation.inc"   // lio_state_estimation (voxelslam.cpp:856-954), likewise
 };
 
 namespace {
@@ -513,6 +516,24 @@ int vxr_local_map_odom_accumulate(void* hh, const double* pv12, int64_t n, const
   RefLocalMap* h = static_cast<RefLocalMap*>(hh);
   set_local_params(&h->mp);
   return odom_accum_impl(h->map, pv12, n, pose12, rot_var9, tsl_var9, passes, HTH36, HTz6, nnt9, flags);
+}
+
+// The reference's own lio_state_estimation (up to 4 EKF iterations: association with the per-point leaf cache, 15x15 update, re-match rule, degeneracy test on nnt)
+// on the local map.  state24 = R | p | v | bg | ba | g, cov225 row-major; both updated in place.  Returns the function's bool (1 = not degenerate).
+int vxr_local_map_lio_state_estimation(void* hh, const double* pv12, int64_t n, double* state24, double* cov225) {
+  RefLocalMap* h = static_cast<RefLocalMap*>(hh);
+  set_local_params(&h->mp);
+  PVecPtr pv(new PVec(size_t(n)));
+  for (int64_t k = 0; k < n; k++) { const double* p = pv12 + 12 * k; (*pv)[size_t(k)].pnt = Eigen::Vector3d(p[0], p[1], p[2]); for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) (*pv)[size_t(k)].var(r, c) = p[3 + 3 * r + c]; }
+  RefHbaHost host;
+  host.x_curr = state_from24(state24);
+  for (int r = 0; r < DIM; r++) for (int c = 0; c < DIM; c++) host.x_curr.cov(r, c) = cov225[DIM * r + c];
+  host.surf_map.swap(h->map);
+  const bool ok = host.lio_state_estimation(pv);
+  host.surf_map.swap(h->map);
+  state_to24(host.x_curr, state24);
+  for (int r = 0; r < DIM; r++) for (int c = 0; c < DIM; c++) cov225[DIM * r + c] = host.x_curr.cov(r, c);
+  return ok ? 1 : 0;
 }
 
 // ---------------------------------------------------------------- the per-scan map sequence of thd_odometry_localmapping (voxelslam.cpp:1599-1615, 1669-1712), poses given

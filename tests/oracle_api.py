@@ -360,6 +360,16 @@ class LocalMap:
         return dict(n=m, HTH=HTH, HTz=HTz, nnt=nnt, flags=flags)
 
 
+    def lio_state_estimation(self, pv12, state24, cov):
+        """ref backend only: the reference's own lio_state_estimation (voxelslam.cpp:856-954, cut out at build time) on this map -> (ok, state24, cov 15x15)."""
+        if BACKEND != "ref":
+            raise RuntimeError("lio_state_estimation exists for the reference build only")
+        pv = _f64(pv12).reshape(-1, 12)
+        st, cv = _f64(state24).copy(), _f64(cov).copy()
+        ok = lib().vxo_local_map_lio_state_estimation(C.c_void_p(self._h), _dp(pv), C.c_int64(pv.shape[0]), _dp(st), _dp(cv))
+        return bool(ok), st, cv.reshape(15, 15)
+
+
 class SlidingSim:
     """Map side of the sliding-window loop (voxelslam.cpp:1599-1686): cut + recut + tras_opt per scan, margi + ring rotation when full."""
 
