@@ -267,7 +267,6 @@ static int hba_bottom_batch_impl(vxs_ctx* ctx, const vxs_map_params* fine, const
   int rc = VXS_OK;
   if (!B.f) { rc = vxs_factor_create(ctx, WB, &B.f); if (rc) return rc; }
   vxs_factor* f = B.f;
-  auto fail = [&](int code) { return code; };
   int warn = VXS_OK;
   B.last_voxels = 0; B.last_entries = 0;
   for (int w0 = 0; w0 < nwin;) {
@@ -282,7 +281,7 @@ static int hba_bottom_batch_impl(vxs_ctx* ctx, const vxs_map_params* fine, const
     int kf_lo = K, kf_hi = 0;
     for (int w = w0; w < w1; w++) { kf_lo = std::min(kf_lo, int(win_first[w])); kf_hi = std::max(kf_hi, int(win_first[w]) + WB); }
     rc = vxs_build_gba_batch(ctx, fine, xyz, stride_floats, kf_offsets, poses12, win_first + w0, nw, WB, kf_lo, kf_hi, f, xyz_dev, dev_first_point);
-    if (rc < 0) return fail(rc);
+    if (rc < 0) return rc;
     const int V = int(f->V);
     B.last_voxels += f->V; B.last_entries += f->E;
     // ---- per-window state
@@ -308,7 +307,7 @@ static int hba_bottom_batch_impl(vxs_ctx* ctx, const vxs_map_params* fine, const
       VXS_LAUNCH(ctx, "k_bd_vwin_keys", k_bd_vwin_keys, unsigned((V + 255) / 256), 256, 0, (const int32_t*)f->vwin.p, V, B.kA.p, B.iA.p);
       unsigned long long* ks; unsigned int* vs;
       rc = radix_sort(ctx, &B.ss, B.kA.p, B.iA.p, B.kB.p, B.iB.p, size_t(V), bits_for((unsigned long long)nw), &ks, &vs);
-      if (rc) return fail(rc);
+      if (rc) return rc;
       win_vox = vs;
       VXS_LAUNCH(ctx, "k_bd_win_ptr", k_bd_win_ptr, unsigned((nw + 256) / 256), 256, 0, ks, V, nw, win_ptr);
     } else VXS_CUDA(ctx, cudaMemsetAsync(win_ptr, 0, size_t(nw + 1) * 4, st));
@@ -320,14 +319,14 @@ static int hba_bottom_batch_impl(vxs_ctx* ctx, const vxs_map_params* fine, const
     // ---- Lidar_BA_Optimizer::damping_iter(xs, voxhess, &hess, resis, up) for all windows, no host synchronisation inside
     for (int it = 0; it < up && V > 0; it++) {
       rc = vxs_eval_hessian_bd_dev(ctx, f, S.x, 12, S.calc, B.Cbd.p, B.gD.p);      // windows with is_calc_hess (the others keep their accumulators)
-      if (rc) return fail(rc);
+      if (rc) return rc;
       VXS_LAUNCH(ctx, "k_bd_lambda", k_bd_lambda, unsigned((V + 255) / 256), 256, 0, (const double*)f->eig, (const double*)f->coe, V, B.rvox.p);
       VXS_LAUNCH(ctx, "k_bd_winsum", k_bd_winsum, unsigned(nw), 128, 0, (const double*)B.rvox.p, (const int*)win_ptr, (const unsigned int*)win_vox, (const int*)S.calc, 1, S.r1);
       VXS_LAUNCH(ctx, "k_bd_solve", k_bd_solve, unsigned(nw), 128, smem, S, (const double*)B.Cbd.p, (const double*)B.gD.p, WB, nw);
       int ran = 0;
       rc = vxs_residual_stream_launch(ctx, f, S.xt, 12, ctx->scal.p, &ran, B.rvox.p);     // evaluate_only_residual at x_temp: overwrites the cached eig / pcr_adds (:271-273)
-      if (rc) return fail(rc);
-      if (!ran) return fail(vxs_fail(ctx, VXS_ERR_CUDA, "vxs_hba_bottom_batch: the streaming residual kernel could not be launched"));
+      if (rc) return rc;
+      if (!ran) return vxs_fail(ctx, VXS_ERR_CUDA, "vxs_hba_bottom_batch: the streaming residual kernel could not be launched");
       VXS_LAUNCH(ctx, "k_bd_winsum", k_bd_winsum, unsigned(nw), 128, 0, (const double*)B.rvox.p, (const int*)win_ptr, (const unsigned int*)win_vox, (const int*)S.done, 0, S.r2);
       VXS_LAUNCH(ctx, "k_bd_accept", k_bd_accept, unsigned((nw + 127) / 128), 128, 0, S, nw, WB, up, thread_num);
     }
@@ -349,7 +348,6 @@ static int hba_bottom_batch_impl(vxs_ctx* ctx, const vxs_map_params* fine, const
     if (V == 0 && status) for (int w = 0; w < nw; w++) status[w0 + w] = VXS_ERR_TOO_FEW_VOXELS;
     w0 = w1;
   }
-  fail(0);
   return warn;
 }
 
@@ -383,7 +381,6 @@ extern "C" int vxs_hba_pass(vxs_ctx* ctx, const vxs_map_params* coarse, const vx
   auto cleanup = [&](int code) { for (auto& e : ev) cudaEventDestroy(e); return code; };
   BatchScratch& PB = *hba_scratch(ctx);
   DevBuf<float>& pts = PB.pts; DevBuf<float>& sub_mine = PB.sub_mine; DevBuf<float>& sub_all = PB.sub_all;
-  auto release = [&]() {};
   int rc = VXS_OK;
   cudaEventRecord(ev[0], st);
   // ---- this rank's keyframes, uploaded once
@@ -396,17 +393,17 @@ extern "C" int vxs_hba_pass(vxs_ctx* ctx, const vxs_map_params* coarse, const vx
     const int64_t p0 = kf_offsets[kf_lo], np = kf_offsets[kf_hi] - p0;
     if (pts.reserve(size_t(std::max<int64_t>(np, 1)) * stride_floats) != cudaSuccess) {
       my_err = vxs_fail(ctx, VXS_ERR_NOMEM, "vxs_hba_pass: keyframe clouds do not fit");
-      if (!multi) { release(); return cleanup(my_err); }
+      if (!multi) { return cleanup(my_err); }
     }
     if (!my_err && np > 0) cudaMemcpyAsync(pts.p, xyz + size_t(p0) * stride_floats, size_t(np) * stride_floats * 4, cudaMemcpyHostToDevice, st);
     if (!my_err) rc = hba_bottom_batch_impl(ctx, fine, xyz, pts.p, p0, stride_floats, kf_offsets, poses12, K, win_first.data() + lo, nmine, win_size, bottom_thread_num, max_points_per_chunk, bottom_poses,
                                bottom_resis, bottom_status, nullptr, nullptr, bottom_edge_valid, bottom_edge_v6, bottom_edge_rot, bottom_edge_tra, nullptr);
-    if (rc < 0 && !my_err) { if (!multi) { release(); return cleanup(rc); } my_err = rc; }
+    if (rc < 0 && !my_err) { if (!multi) { return cleanup(rc); } my_err = rc; }
     cudaEventRecord(ev[1], st);
     int64_t ntot = 0;
     if (!my_err) rc = vxs_submap_merge_batch_impl(ctx, xyz, pts.p, p0, stride_floats, kf_offsets, K, bottom_poses, win_first.data() + lo, nmine, win_size, fine->voxel_size / 8, max_points_per_chunk, nullptr,
                                      nullptr, nullptr, 0, woff.data(), &ntot, &sub_mine);
-    if (rc < 0 && !my_err) { if (!multi) { release(); return cleanup(rc); } my_err = rc; }
+    if (rc < 0 && !my_err) { if (!multi) { return cleanup(rc); } my_err = rc; }
     if (!my_err) for (int w = 0; w < nmine; w++) sizes_d[size_t(lo + w)] = double(woff[size_t(w) + 1] - woff[size_t(w)]);
     else sizes_d[size_t(nwin)] = 1.0;
   } else cudaEventRecord(ev[1], st);
@@ -416,14 +413,13 @@ extern "C" int vxs_hba_pass(vxs_ctx* ctx, const vxs_map_params* coarse, const vx
   const bool routed = ctx->nranks > 1 && ctx->hba_route;
   const float* sub_dev = sub_mine.p;
   if (ctx->nranks > 1) {
-    if (ctx->stage.reserve(size_t(nwin) + 1) != cudaSuccess) { release(); return cleanup(VXS_ERR_NOMEM); }
+    if (ctx->stage.reserve(size_t(nwin) + 1) != cudaSuccess) { return cleanup(VXS_ERR_NOMEM); }
     cudaMemcpyAsync(ctx->stage.p, sizes_d.data(), (size_t(nwin) + 1) * 8, cudaMemcpyHostToDevice, st);
     rc = vxs_comm_allreduce(ctx, ctx->stage.p, size_t(nwin) + 1);          // every rank contributed its own windows' sizes (+ its error flag), zeros elsewhere
-    if (rc) { release(); return cleanup(rc); }
+    if (rc) { return cleanup(rc); }
     cudaMemcpyAsync(sizes_d.data(), ctx->stage.p, (size_t(nwin) + 1) * 8, cudaMemcpyDeviceToHost, st);
     cudaStreamSynchronize(st);
     if (sizes_d[size_t(nwin)] > 0.0) {       // all ranks leave together, before any further collective
-      release();
       return cleanup(my_err ? my_err : vxs_fail(ctx, VXS_ERR_COMM, "vxs_hba_pass: the bottom level failed on another rank"));
     }
     if (!routed) {
@@ -437,7 +433,7 @@ extern "C" int vxs_hba_pass(vxs_ctx* ctx, const vxs_map_params* coarse, const vx
       }
       // head room of 1/8: the merged clouds differ by a few cells from pass to pass (the poses of the bottom level agree to rounding only), and a buffer that
       // is a few bytes short costs a cudaFree + cudaMalloc of gigabytes (measured: 370 ms once every few passes)
-      if (sub_all.cap < std::max<size_t>(tot, 1) * 3 && sub_all.reserve((std::max<size_t>(tot, 1) + tot / 8) * 3) != cudaSuccess) { release(); return cleanup(vxs_fail(ctx, VXS_ERR_NOMEM, "vxs_hba_pass: submaps do not fit")); }
+      if (sub_all.cap < std::max<size_t>(tot, 1) * 3 && sub_all.reserve((std::max<size_t>(tot, 1) + tot / 8) * 3) != cudaSuccess) { return cleanup(vxs_fail(ctx, VXS_ERR_NOMEM, "vxs_hba_pass: submaps do not fit")); }
       size_t slot = 0;
       for (size_t c : counts) slot = std::max(slot, c);
       slot = (slot + 3) & ~size_t(3);
@@ -445,10 +441,10 @@ extern "C" int vxs_hba_pass(vxs_ctx* ctx, const vxs_map_params* coarse, const vx
       const size_t slot_cap = std::max<size_t>(slot, 1) + slot / 8;
       if ((sub_mine.cap < std::max<size_t>(slot, 1) && sub_mine.reserve_keep(slot_cap, counts[size_t(ctx->rank)], st) != cudaSuccess) ||
           (PB.sub_pad.cap < std::max<size_t>(slot, 1) * size_t(ctx->nranks) && PB.sub_pad.reserve(slot_cap * size_t(ctx->nranks)) != cudaSuccess)) {
-        release(); return cleanup(vxs_fail(ctx, VXS_ERR_NOMEM, "vxs_hba_pass: exchange buffers do not fit"));
+        return cleanup(vxs_fail(ctx, VXS_ERR_NOMEM, "vxs_hba_pass: exchange buffers do not fit"));
       }
       rc = vxs_comm_allgatherv_f32(ctx, sub_mine.p, counts[size_t(ctx->rank)], sub_all.p, counts.data(), displs.data(), PB.sub_pad.p, slot);
-      if (rc) { release(); return cleanup(rc); }
+      if (rc) { return cleanup(rc); }
       sub_dev = sub_all.p;
     }
   }
@@ -470,6 +466,5 @@ extern "C" int vxs_hba_pass(vxs_ctx* ctx, const vxs_map_params* coarse, const vx
     for (int k = 0; k < 4; k++) { float ms = 0; cudaEventElapsedTime(&ms, ev[k], ev[k + 1]); phase_ms[k] = ms; }
     phase_ms[4] = double(PB.last_voxels); phase_ms[5] = double(PB.last_entries);
   }
-  release();
   return cleanup(rc);
 }
