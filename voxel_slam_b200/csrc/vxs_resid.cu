@@ -1,9 +1,10 @@
 // evaluate_only_residual (voxel_map.hpp:243-279) as ONE streaming kernel (sm_100a):
 //
-//   k_residual_stream   persistent, one CTA per SM.  A producer warp streams the SoA cluster columns (80 B per (voxel, frame) entry, + the
+//   k_residual_stream   persistent, per_sm CTAs per SM (default: 3 CTAs of TE = 256 consumer threads + one producer warp, 2 stages each; tuned on the
+//                       metric shape, see launch_resid).  The producer warp streams the SoA cluster columns (80 B per (voxel, frame) entry, + the
 //                       4-B frame index) of the CTA's voxel batches through a ring of shared-memory stages with 1-D bulk copies
 //                       (cp.async.bulk + mbarrier complete_tx — TMA without a tensor map: every column of a tile is one contiguous run),
-//                       so ~130-170 KB per SM are in flight whatever the consumers do.  16 consumer warps, per tile of 512 entries:
+//                       so ~130 KB per SM are in flight whatever the consumers do.  TE / 32 consumer warps, per tile of TE entries:
 //                         A  thread per entry: PointCluster::transform with the entry's pose (tools.hpp:357-363), result written back in place;
 //                         B  thread per (voxel, component, quarter): fixed-order sum of the voxel's run inside the tile into the batch's
 //                            accumulators in shared memory (the order depends only on the factor and the launch shape: bit-stable run to run);
