@@ -377,10 +377,10 @@ static int build_factor(vxs_ctx* ctx, const vxs_map_params* mp, bool gba, const 
   const long long b0 = part_bbox ? own_lo : 0, b1 = part_bbox ? own_hi : N;
   if (b1 > b0) VXS_LAUNCH(ctx, "k_bbox", k_bbox, std::min<unsigned>(nblk(size_t(b1 - b0), 256), unsigned(ctx->sm_count) * 8), 256, 0, ps, mp->voxel_size, s->bbox.p, b0, b1);
   if (part_bbox) {
-    k_bbox_negate_min<<<1, 32, 0, st>>>(s->bbox.p);
+    VXS_LAUNCH(ctx, "k_bbox_negate_min", k_bbox_negate_min, 1, 32, 0, s->bbox.p);
     int rcb = vxs_comm_allreduce_max_i64(ctx, s->bbox.p, 6);
     if (rcb) return rcb;
-    k_bbox_negate_min<<<1, 32, 0, st>>>(s->bbox.p);
+    VXS_LAUNCH(ctx, "k_bbox_negate_min", k_bbox_negate_min, 1, 32, 0, s->bbox.p);
   }
   long long bb[6];
   VXS_CUDA(ctx, cudaMemcpyAsync(bb, s->bbox.p, sizeof bb, cudaMemcpyDeviceToHost, st));
@@ -1082,7 +1082,7 @@ int vxs_hba_top_routed(vxs_ctx* ctx, const vxs_map_params* coarse, const vxs_map
       unsigned long long* ks;
       rc = radix_sort(ctx, s, s->keysA.p, s->idxA.p, s->keysB.p, s->idxB.p, size_t(n), bits_for((unsigned long long)R), &ks, &sidx);
       if (rc) return rc;
-      k_route_counts<<<1, 32, 0, st>>>(ks, n, R, s->flags.p);
+      VXS_LAUNCH(ctx, "k_route_counts", k_route_counts, 1, 32, 0, ks, n, R, s->flags.p);
       VXS_CUDA(ctx, sendbuf->reserve((size_t(n) + size_t(n) / 8) * 4));
       VXS_LAUNCH(ctx, "k_route_pack", k_route_pack, nblk(size_t(n), 256), 256, 0, sub_mine, s->offsets.p, nmine, first_window, sidx, n, reinterpret_cast<float4*>(sendbuf->p));
       VXS_CUDA(ctx, cudaMemcpyAsync(hist.data(), s->flags.p, size_t(R) * 4, cudaMemcpyDeviceToHost, st));
