@@ -51,6 +51,27 @@ def main():
         tot.update(c)
         print("%-44s %7d " % (d[:44], n) + " ".join("%7d" % c[k] for k in keys))
     print("\n%-44s %7d " % ("total (%d kernels)" % len(rows), sum(size.values())) + " ".join("%7d" % tot[k] for k in keys))
+    # ---- registers / stack / static shared memory per kernel (cuobjdump -res-usage)
+    res = subprocess.run(["cuobjdump", "-res-usage", LIB], capture_output=True, text=True, check=True).stdout.splitlines()
+    rr = []
+    for i, l in enumerate(res):
+        m = re.match(r"\s*Function (\S+):", l)
+        if m and i + 1 < len(res):
+            r = dict(re.findall(r"(REG|STACK|SHARED|LOCAL):(\d+)", res[i + 1]))
+            rr.append((m.group(1), int(r.get("REG", 0)), int(r.get("STACK", 0)), int(r.get("SHARED", 0))))
+    dem = subprocess.run(["c++filt"], input="\n".join(n for n, *_ in rr), capture_output=True, text=True).stdout.splitlines()
+    seen, out = set(), []
+    for (n, reg, stack, sh), d in zip(rr, dem):
+        d = re.sub(r"^void ", "", d.replace("(anonymous namespace)::", ""))
+        d = re.sub(r"\((?:[^()]|\([^()]*\))*\)\s*$", "", d)
+        if (d, reg, stack, sh) not in seen:
+            seen.add((d, reg, stack, sh)); out.append((d, reg, stack, sh))
+    out.sort(key=lambda x: -x[1])
+    print("\n\nResource usage (cuobjdump -res-usage): registers per thread, stack bytes per thread (local arrays / spills), STATIC shared memory bytes\n")
+    print("%-44s %5s %6s %8s" % ("kernel", "REG", "STACK", "SHARED"))
+    for d, reg, stack, sh in out:
+        if reg >= 64 or stack:
+            print("%-44s %5d %6d %8d" % (d[:44], reg, stack, sh))
     return 0
 
 
