@@ -181,6 +181,25 @@ def test_window_map_build(W, pts, L, ml):
     compare_factor_sets(a.export(), b.export(), W)
 
 
+@pytest.mark.parametrize("vs,me,thre,minp,ml", [(0.5, 0.0025, (0.25, 0.25, 0.25, 0.25), (5, 5, 5, 5), 2), (2.0, 0.01, (0.1, 0.15, 0.2, 0.3), (20, 12, 8, 5), 3),
+                                                (1.0, 0.001, (1 / 16.0, 1 / 9.0, 1 / 4.0, 1.0), (30, 20, 10, 5), 2), (1.5, 0.05, (0.5, 0.5, 0.5, 0.5), (5, 5, 5, 5), 1)])
+def test_window_map_build_nondefault_parameters(vs, me, thre, minp, ml):
+    """The same sequence under parameter sets away from the launch-file defaults: voxel size, min_eigen_value, per-layer plane thresholds
+    (plane_eigen_value_thre, already inverted as voxelslam.cpp:825 leaves them) and per-layer min_point — every branch of plane_judge / recut keyed on them."""
+    W, pts, L = 5, 8000, 9.0
+    tr, est = scenes.poses_true_est(W, L, 23)
+    p, off = scenes.make_points(W, pts, L, 23, tr)
+    mp = vx.MapParams.make(voxel_size=vs, min_eigen_value=me, plane_thre=thre, min_point=tuple(float(x) for x in minp), max_layer=ml)
+    a, b = ra.build_window_factor(mp, p, off, est), oa.build_window_factor(mp, p, off, est)
+    assert a.size() == b.size() > 5
+    compare_factor_sets(a.export(), b.export(), W)
+    ga, gb = ra.build_gba_factor(mp, p.astype(np.float32), off, est, threads=2).export(), oa.build_gba_factor(mp, p.astype(np.float32), off, est, threads=2).export()
+    assert len(ga["sum10"]) == len(gb["sum10"]) > 5
+    ka = np.lexsort(np.round(ga["sum10"][:, [8, 7, 6, 9]], 6).T); kb = np.lexsort(np.round(gb["sum10"][:, [8, 7, 6, 9]], 6).T)
+    assert np.array_equal(ga["clusters10"][ka][:, :, 9], gb["clusters10"][kb][:, :, 9])
+    assert np.max(np.abs(ga["sum10"][ka] - gb["sum10"][kb]) / (np.abs(gb["sum10"][kb]) + 1e-6)) < 1e-12
+
+
 def test_gba_map_build():
     W = 6
     tr, est = scenes.poses_true_est(W, 8.0, 41, rot_sigma=3e-3, pos_sigma=2e-2)
