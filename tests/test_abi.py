@@ -144,3 +144,34 @@ def test_bench_reference_arm_contract_on_cpu():
         assert k in d, k
     assert d["impl"] == "reference" and d["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] == 0 and d["cpu_baseline"]["kind"] in ("reference", "port")
     assert d["cpu_baseline"]["all_cores_variant"].get("value", 0) > 0
+
+
+def test_every_entry_point_rejects_null_arguments_without_a_gpu():
+    """Error behaviour of the boundary: every function of include/vxs.h called with all-NULL / zero arguments returns (VXS_ERR_ARG or another negative
+    code; destroy / free of NULL are no-ops) instead of dereferencing anything — on a box without a GPU, so no compute call is involved.  One subprocess:
+    a crash must fail this test, not take the suite down."""
+    import json
+    import re
+    import subprocess
+    import sys
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "vxs.h")).read()
+    calls = []
+    for s in vx.declared_symbols():
+        m = re.search(r"\b" + s + r"\s*\(([^;]*?)\)\s*;", hdr, re.S)
+        assert m, s
+        a = m.group(1).strip()
+        n, depth = (0 if a in ("", "void") else 1), 0
+        for ch in a:
+            depth += ch == "("; depth -= ch == ")"
+            n += ch == "," and depth == 0
+        calls.append((s, n))
+    assert len(calls) >= 60
+    code = "import ctypes as C, sys, json\nsys.path.insert(0, %r)\nimport voxel_slam_b200 as vx\nL = vx.lib()\nout = {}\nfor s, n in %r:\n    f = getattr(L, s); f.restype = C.c_int32\n" \
+           "    print('CALL', s, flush=True)\n    out[s] = f(*([C.c_void_p(0)] * n))\nprint('RESULT', json.dumps(out))\n" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), calls)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    last = [l for l in r.stdout.splitlines() if l.startswith("CALL")][-1:]
+    assert r.returncode == 0, (r.returncode, last, r.stderr[-400:])
+    res = json.loads([l for l in r.stdout.splitlines() if l.startswith("RESULT")][-1][7:])
+    benign = {"vxs_version", "vxs_ctx_destroy", "vxs_factor_destroy", "vxs_map_destroy", "vxs_ctx_launch_count", "vxs_ctx_last_error", "vxs_host_free"}
+    wrong = {s: v for s, v in res.items() if s not in benign and not v < 0}
+    assert not wrong, wrong
