@@ -200,6 +200,29 @@ def test_window_map_build_nondefault_parameters(vs, me, thre, minp, ml):
     assert np.max(np.abs(ga["sum10"][ka] - gb["sum10"][kb]) / (np.abs(gb["sum10"][kb]) + 1e-6)) < 1e-12
 
 
+def test_ragged_and_empty_scans():
+    """Edge cases of the map builds and the down-sampling: scans of very different sizes, an EMPTY scan and a one-point scan inside the window; empty and
+    one-point clouds through down_sampling_voxel."""
+    W, L = 6, 7.0
+    tr, est = scenes.poses_true_est(W, L, 31)
+    sizes = [5000, 0, 1, 7000, 37, 2500]
+    scans = [synth.gen_scan(L, i, max(n, 1), tr[i], seed=0x5EED0000 + 31)[:n] for i, n in enumerate(sizes)]
+    p = np.concatenate(scans); off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    mp = vx.MapParams.make(voxel_size=1.0, max_layer=2)
+    a, b = ra.build_window_factor(mp, p, off, est), oa.build_window_factor(mp, p, off, est)
+    assert a.size() == b.size() > 50
+    ea, eb = a.export(), b.export()
+    compare_factor_sets(ea, eb, W)
+    assert np.all(eb["clusters10"][:, 1, 9] == 0) and np.sum(eb["clusters10"][:, 2, 9]) <= 1            # the empty scan observes nothing, the one-point scan at most one voxel
+    ga, gb = ra.build_gba_factor(mp, p.astype(np.float32), off, est, threads=2).export(), oa.build_gba_factor(mp, p.astype(np.float32), off, est, threads=2).export()
+    assert len(ga["sum10"]) == len(gb["sum10"]) > 50
+    ka = np.lexsort(np.round(ga["sum10"][:, [8, 7, 6, 9]], 6).T); kb = np.lexsort(np.round(gb["sum10"][:, [8, 7, 6, 9]], 6).T)
+    assert np.array_equal(ga["clusters10"][ka][:, :, 9], gb["clusters10"][kb][:, :, 9])
+    for cloud in (np.zeros((0, 3), dtype=np.float32), np.array([[1.25, -2.5, 0.75]], dtype=np.float32)):
+        da, db = ra.down_sampling(cloud, 0.5), oa.down_sampling(cloud, 0.5)
+        assert len(da["xyz"]) == len(db["xyz"]) == len(cloud) and np.array_equal(da["xyz"], db["xyz"]) and np.array_equal(da["count"], db["count"])
+
+
 def test_gba_map_build():
     W = 6
     tr, est = scenes.poses_true_est(W, 8.0, 41, rot_sigma=3e-3, pos_sigma=2e-2)
